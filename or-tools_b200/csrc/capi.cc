@@ -1,0 +1,399 @@
+// capi.cc -- the extern "C" boundary declared in include/pdlp_b200.h.
+// No exception crosses the boundary: CUDA / allocation failures become
+// PDLP_B200_STATUS_* codes (and TERMINATION_REASON_OTHER for the solve).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include "device_problem.h"
+#include "solver.h"
+
+using namespace pdlp_b200;
+
+struct PdlpDeviceProblem {
+  std::unique_ptr<DeviceProblem> p;
+  PdlpParams default_params;
+};
+struct PdlpDistributedContext {
+  int rank = 0, world = 1, device = 0;
+};
+
+namespace {
+
+char* DupString(const std::string& s) {
+  char* p = static_cast<char*>(std::malloc(s.size() + 1));
+  std::memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+double* DupVec(const std::vector<double>& v) {
+  if (v.empty()) return nullptr;
+  double* p = static_cast<double*>(std::malloc(v.size() * sizeof(double)));
+  std::memcpy(p, v.data(), v.size() * sizeof(double));
+  return p;
+}
+void FillResult(SolverResultCpp&& r, PdlpResult* out) {
+  std::memset(out, 0, sizeof(*out));
+  out->primal_size = static_cast<int64_t>(r.primal_solution.size());
+  out->dual_size = static_cast<int64_t>(r.dual_solution.size());
+  out->primal_solution = DupVec(r.primal_solution);
+  out->dual_solution = DupVec(r.dual_solution);
+  out->reduced_costs = DupVec(r.reduced_costs);
+  const SolveLogCpp& l = r.solve_log;
+  out->instance_name = l.instance_name ? DupString(*l.instance_name) : nullptr;
+  out->termination_reason = l.termination_reason;
+  out->termination_string = l.termination_string ? DupString(*l.termination_string) : nullptr;
+  out->iteration_count = l.iteration_count;
+  out->solve_time_sec = l.solve_time_sec;
+  out->preprocessing_time_sec = l.preprocessing_time_sec;
+  out->solution_type = l.solution_type;
+  out->has_solution_stats = l.has_solution_stats;
+  out->solution_stats = l.solution_stats;
+  out->has_original_problem_stats = l.has_original_stats;
+  out->has_preprocessed_problem_stats = l.has_preprocessed_stats;
+  out->original_problem_stats = l.original_stats;
+  out->preprocessed_problem_stats = l.preprocessed_stats;
+  out->num_iteration_stats = static_cast<int64_t>(l.iteration_stats.size());
+  if (!l.iteration_stats.empty()) {
+    out->iteration_stats = static_cast<PdlpIterationStats*>(std::malloc(l.iteration_stats.size() * sizeof(PdlpIterationStats)));
+    std::memcpy(out->iteration_stats, l.iteration_stats.data(), l.iteration_stats.size() * sizeof(PdlpIterationStats));
+  }
+  out->params = l.params;
+  out->gpu_kernel_launches = l.gpu_kernel_launches;
+  out->device_iteration_time_sec = l.device_iteration_time_sec;
+}
+
+// Runs `body`, mapping exceptions to status codes.
+template <class F>
+int32_t Guard(F body) {
+  try {
+    if (Device::DeviceCount() <= 0) return PDLP_B200_STATUS_NO_DEVICE;
+    body();
+    return PDLP_B200_STATUS_OK;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "pdlp_b200: %s\n", e.what());
+    return PDLP_B200_STATUS_CUDA_ERROR;
+  }
+}
+
+// RAII device vector uploaded from a host pointer (position order of `p`).
+struct PrimalVec {
+  DeviceProblem& p; double* d;
+  PrimalVec(DeviceProblem& p_, const double* host) : p(p_), d(p_.NewPrimal()) { if (host != nullptr) p.UploadPrimal(d, host); }
+  ~PrimalVec() { p.dev().Free(d); }
+};
+struct DualVec {
+  DeviceProblem& p; double* d;
+  DualVec(DeviceProblem& p_, const double* host) : p(p_), d(p_.NewDual()) { if (host != nullptr) p.UploadDual(d, host); }
+  ~DualVec() { p.dev().Free(d); }
+};
+struct PlainVec {  // natural order
+  Device& dev; double* d; int64_t n;
+  PlainVec(Device& dv, const double* host, int64_t n_) : dev(dv), d(dv.AllocF64(n_)), n(n_) { if (host != nullptr) dev.Upload(d, host, n); }
+  ~PlainVec() { dev.Free(d); }
+};
+
+}  // namespace
+
+extern "C" {
+
+void pdlp_b200_params_set_defaults(PdlpParams* params) { SetDefaultParams(params); }
+
+int32_t pdlp_b200_params_validate(const PdlpParams* params, char* message, int64_t capacity) {
+  const std::string e = ValidateParams(*params);
+  if (message != nullptr && capacity > 0) {
+    std::strncpy(message, e.c_str(), static_cast<size_t>(capacity - 1));
+    message[capacity - 1] = 0;
+  }
+  return e.empty() ? 1 : 0;
+}
+
+int32_t pdlp_b200_device_count(void) { return Device::DeviceCount(); }
+const char* pdlp_b200_version(void) { return "pdlp_b200 0.1.0 (sm_100a)"; }
+
+int32_t pdlp_b200_primal_dual_hybrid_gradient(const PdlpProblemView* qp, const PdlpParams* params, const double* initial_primal,
+                                              int64_t initial_primal_size, const double* initial_dual, int64_t initial_dual_size,
+                                              const volatile int32_t* interrupt_solve, PdlpMessageCallback message_callback,
+                                              PdlpIterationStatsCallback stats_callback, void* user_data, PdlpResult* result) {
+  if (qp == nullptr || params == nullptr || result == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  std::memset(result, 0, sizeof(*result));
+  if (Device::DeviceCount() <= 0) return PDLP_B200_STATUS_NO_DEVICE;
+  Logger logger{message_callback, user_data};
+  std::optional<InitialSolution> init;
+  if (initial_primal != nullptr || initial_dual != nullptr) {
+    init.emplace();
+    if (initial_primal != nullptr) init->primal.assign(initial_primal, initial_primal + initial_primal_size);
+    if (initial_dual != nullptr) init->dual.assign(initial_dual, initial_dual + initial_dual_size);
+  }
+  StatsCallback cb;
+  if (stats_callback != nullptr) cb = [=](const PdlpIterationCallbackInfo& info) { stats_callback(&info, user_data); };
+  try {
+    FillResult(PrimalDualHybridGradient(*qp, *params, std::move(init), interrupt_solve, logger, std::move(cb), 0), result);
+    return PDLP_B200_STATUS_OK;
+  } catch (const std::exception& e) {
+    SolverResultCpp r;
+    r.solve_log.termination_reason = PDLP_TERMINATION_REASON_OTHER;
+    r.solve_log.termination_string = std::string("device failure: ") + e.what();
+    FillResult(std::move(r), result);
+    return PDLP_B200_STATUS_CUDA_ERROR;
+  }
+}
+
+void pdlp_b200_result_free(PdlpResult* r) {
+  if (r == nullptr) return;
+  std::free(r->primal_solution); std::free(r->dual_solution); std::free(r->reduced_costs);
+  std::free(r->instance_name); std::free(r->termination_string); std::free(r->iteration_stats);
+  std::memset(r, 0, sizeof(*r));
+}
+
+// ---- multi-GPU (implemented in distributed.cc when NCCL is wired in) -------
+int32_t pdlp_b200_nccl_unique_id(const char*, uint8_t*) { return PDLP_B200_STATUS_BAD_ARGUMENT; }
+int32_t pdlp_b200_distributed_init(const char*, int32_t, int32_t, int32_t, const uint8_t*, PdlpDistributedContext**) { return PDLP_B200_STATUS_BAD_ARGUMENT; }
+void pdlp_b200_distributed_destroy(PdlpDistributedContext* c) { delete c; }
+int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(PdlpDistributedContext*, const PdlpProblemView*, const PdlpParams*, const double*, int64_t,
+                                                          const double*, int64_t, const volatile int32_t*, PdlpMessageCallback,
+                                                          PdlpIterationStatsCallback, void*, PdlpResult*) {
+  return PDLP_B200_STATUS_BAD_ARGUMENT;
+}
+
+// ---- device-resident problem -----------------------------------------------
+int32_t pdlp_b200_problem_create(const PdlpProblemView* qp, int32_t cuda_device, PdlpDeviceProblem** out) {
+  if (qp == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  *out = nullptr;
+  return Guard([&] {
+    auto h = std::make_unique<PdlpDeviceProblem>();
+    h->p.reset(new DeviceProblem(*qp, cuda_device));
+    SetDefaultParams(&h->default_params);
+    *out = h.release();
+  });
+}
+void pdlp_b200_problem_destroy(PdlpDeviceProblem* h) { delete h; }
+
+int32_t pdlp_b200_transposed_matrix_vector_product(PdlpDeviceProblem* h, const double* y, double* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    DualVec yv(p, y);
+    PrimalVec o(p, nullptr);
+    p.KTy(yv.d, o.d);
+    p.DownloadPrimal(out, o.d);
+  });
+}
+int32_t pdlp_b200_matrix_vector_product(PdlpDeviceProblem* h, const double* x, double* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec xv(p, x);
+    DualVec o(p, nullptr);
+    p.Kx(xv.d, o.d);
+    p.DownloadDual(out, o.d);
+  });
+}
+int32_t pdlp_b200_apply_rescaling(PdlpDeviceProblem* h, int32_t ruiz, int32_t l2, double* row_scaling, double* col_scaling) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    double *r = nullptr, *c = nullptr;
+    p.ApplyRescaling(ruiz, l2 != 0, &r, &c);
+    p.DownloadDual(row_scaling, r);
+    p.DownloadPrimal(col_scaling, c);
+    p.dev().Free(r);
+    p.dev().Free(c);
+  });
+}
+int32_t pdlp_b200_scaling_iterations(PdlpDeviceProblem* h, int32_t norm, int32_t iters, double* row_scaling, double* col_scaling) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    DualVec r(p, row_scaling);
+    PrimalVec c(p, col_scaling);
+    p.ApplyScalingIterationsForNorm(iters, norm, r.d, c.d);
+    p.DownloadDual(row_scaling, r.d);
+    p.DownloadPrimal(col_scaling, c.d);
+  });
+}
+int32_t pdlp_b200_scaled_col_norm(PdlpDeviceProblem* h, int32_t norm, const double* row_scaling, const double* col_scaling, double* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    DualVec r(p, row_scaling);
+    PrimalVec c(p, col_scaling), o(p, nullptr);
+    p.dev().ScaledRowNorm(p.cols(), norm, r.d, c.d, o.d);
+    p.DownloadPrimal(out, o.d);
+  });
+}
+int32_t pdlp_b200_scaled_row_norm(PdlpDeviceProblem* h, int32_t norm, const double* row_scaling, const double* col_scaling, double* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    DualVec r(p, row_scaling), o(p, nullptr);
+    PrimalVec c(p, col_scaling);
+    p.dev().ScaledRowNorm(p.rows(), norm, c.d, r.d, o.d);
+    p.DownloadDual(out, o.d);
+  });
+}
+int32_t pdlp_b200_rescale_quadratic_program(PdlpDeviceProblem* h, const double* col_scaling, const double* row_scaling) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec c(p, col_scaling);
+    DualVec r(p, row_scaling);
+    p.RescaleQuadraticProgram(c.d, r.d);
+    p.dev().Sync();
+  });
+}
+int32_t pdlp_b200_problem_download(PdlpDeviceProblem* h, double* values, double* objective_vector, double* objective_matrix_diagonal,
+                                   double* clb, double* cub, double* vlb, double* vub) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    if (values) p.DownloadValuesCsc(values);
+    if (objective_vector) p.DownloadPrimal(objective_vector, p.c());
+    if (objective_matrix_diagonal && p.q() != nullptr) p.DownloadPrimal(objective_matrix_diagonal, p.q());
+    if (clb) p.DownloadDual(clb, p.lc());
+    if (cub) p.DownloadDual(cub, p.uc());
+    if (vlb) p.DownloadPrimal(vlb, p.lv());
+    if (vub) p.DownloadPrimal(vub, p.uv());
+  });
+}
+int32_t pdlp_b200_compute_stats(PdlpDeviceProblem* h, PdlpQuadraticProgramStats* out) {
+  return Guard([&] { *out = h->p->ComputeStats(); });
+}
+int32_t pdlp_b200_project_to_primal_variable_bounds(PdlpDeviceProblem* h, double* primal, int32_t use_feasibility_bounds) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal);
+    p.dev().ClampPrimal(x.d, p.lv(), p.uv(), use_feasibility_bounds != 0, p.n());
+    p.DownloadPrimal(primal, x.d);
+  });
+}
+int32_t pdlp_b200_project_to_dual_variable_bounds(PdlpDeviceProblem* h, double* dual) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    DualVec y(p, dual);
+    p.dev().ClampDual(y.d, p.lc(), p.uc(), p.m());
+    p.DownloadDual(dual, y.d);
+  });
+}
+int32_t pdlp_b200_compute_primal_gradient(PdlpDeviceProblem* h, const double* primal, const double* dual_product, double* gradient, double* value) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal), dp(p, dual_product), g(p, nullptr);
+    *value = p.dev().LagrangianPrimalGradient(x.d, dp.d, p.c(), p.q(), g.d, p.n());
+    p.DownloadPrimal(gradient, g.d);
+  });
+}
+int32_t pdlp_b200_compute_dual_gradient(PdlpDeviceProblem* h, const double* dual, const double* primal_product, double* gradient, double* value) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    DualVec y(p, dual), pp(p, primal_product), g(p, nullptr);
+    *value = p.dev().LagrangianDualGradient(y.d, pp.d, p.lc(), p.uc(), g.d, p.m());
+    p.DownloadDual(gradient, g.d);
+  });
+}
+int32_t pdlp_b200_compute_convergence_information(PdlpDeviceProblem* h, const PdlpParams* params, const double* col_scaling, const double* row_scaling,
+                                                  const double* primal, const double* dual, double cw_primal_offset, double cw_dual_offset,
+                                                  int32_t candidate_type, PdlpConvergenceInformation* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal), cs(p, col_scaling);
+    DualVec y(p, dual), rs(p, row_scaling);
+    *out = p.ComputeConvergenceInformation(params->handle_some_primal_gradients_on_finite_bounds_as_residuals != 0, col_scaling ? cs.d : nullptr,
+                                           row_scaling ? rs.d : nullptr, x.d, y.d, nullptr, cw_primal_offset, cw_dual_offset, candidate_type);
+  });
+}
+int32_t pdlp_b200_compute_infeasibility_information(PdlpDeviceProblem* h, const PdlpParams* params, const double* col_scaling,
+                                                    const double* row_scaling, const double* primal_ray, const double* dual_ray,
+                                                    const double* primal_for_residual_tests, int32_t candidate_type, PdlpInfeasibilityInformation* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal_ray), xr(p, primal_for_residual_tests), cs(p, col_scaling);
+    DualVec y(p, dual_ray), rs(p, row_scaling);
+    *out = p.ComputeInfeasibilityInformation(params->handle_some_primal_gradients_on_finite_bounds_as_residuals != 0, col_scaling ? cs.d : nullptr,
+                                             row_scaling ? rs.d : nullptr, x.d, y.d, xr.d, nullptr, candidate_type);
+  });
+}
+int32_t pdlp_b200_reduced_costs(PdlpDeviceProblem* h, const PdlpParams*, const double* primal, const double* dual, int32_t use_zero_primal_objective,
+                                double* out) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal), o(p, nullptr);
+    DualVec y(p, dual);
+    p.ReducedCosts(x.d, y.d, use_zero_primal_objective != 0, o.d);
+    p.DownloadPrimal(out, o.d);
+  });
+}
+int32_t pdlp_b200_compute_localized_lagrangian_bounds(PdlpDeviceProblem* h, const double* primal, const double* dual, double primal_weight,
+                                                      double radius, const double* primal_product, const double* dual_product,
+                                                      int32_t use_diagonal_solver, double diagonal_tol, double out[4]) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal), dp(p, dual_product);
+    DualVec y(p, dual), pp(p, primal_product);
+    p.ComputeLocalizedLagrangianBounds(x.d, y.d, primal_weight, radius, primal_product ? pp.d : nullptr, dual_product ? dp.d : nullptr,
+                                       use_diagonal_solver != 0, diagonal_tol, out);
+  });
+}
+
+// ---- problem-free vector entry points ---------------------------------------
+int32_t pdlp_b200_solve_trust_region(int32_t cuda_device, int64_t size, const double* objective, const double* lb, const double* ub,
+                                     const double* center, const double* weights, double target_radius, double* solution, double* step_size,
+                                     double* objective_value) {
+  return Guard([&] {
+    Device dev(cuda_device);
+    PlainVec o(dev, objective, size), l(dev, lb, size), u(dev, ub, size), c(dev, center, size), w(dev, weights, size), s(dev, nullptr, size);
+    dev.SolveTrustRegion(o.d, l.d, u.d, c.d, w.d, target_radius, size, s.d, step_size, objective_value);
+    dev.Download(solution, s.d, size);
+  });
+}
+int32_t pdlp_b200_solve_diagonal_trust_region(int32_t cuda_device, int64_t size, const double* objective, const double* qdiag, const double* lb,
+                                              const double* ub, const double* center, const double* weights, double target_radius, double tol,
+                                              double* solution, double* step_size, double* objective_value) {
+  return Guard([&] {
+    Device dev(cuda_device);
+    PlainVec o(dev, objective, size), q(dev, qdiag, size), l(dev, lb, size), u(dev, ub, size), c(dev, center, size), w(dev, weights, size),
+        s(dev, nullptr, size);
+    dev.SolveDiagonalTrustRegion(o.d, q.d, l.d, u.d, c.d, w.d, target_radius, tol, size, s.d, step_size, objective_value);
+    dev.Download(solution, s.d, size);
+  });
+}
+int32_t pdlp_b200_weighted_average(int32_t cuda_device, int64_t size, int64_t count, const double* datapoints, const double* weights,
+                                   double* out_average, double* out_sum_weights, int32_t* out_num_terms) {
+  return Guard([&] {
+    Device dev(cuda_device);
+    PlainVec avg(dev, nullptr, size), v(dev, nullptr, size);
+    dev.Fill(avg.d, 0.0, size);
+    double sum = 0.0;
+    int32_t terms = 0;
+    for (int64_t k = 0; k < count; ++k) {  // ShardedWeightedAverage::Add, sou.cc:54-66
+      const double w = weights[k];
+      if (w > 0.0) {
+        dev.Upload(v.d, datapoints + k * size, size);
+        dev.WeightedAverageAdd(avg.d, v.d, w / (sum + w), size);
+        sum += w;
+      }
+      ++terms;
+    }
+    dev.Download(out_average, avg.d, size);
+    if (out_sum_weights) *out_sum_weights = sum;
+    if (out_num_terms) *out_num_terms = terms;
+  });
+}
+int32_t pdlp_b200_vector_reduce(int32_t cuda_device, int32_t op, int64_t size, const double* a, const double* b, double* out) {
+  int32_t bad = 0;
+  const int32_t rc = Guard([&] {
+    Device dev(cuda_device);
+    PlainVec va(dev, a, size), vb(dev, b, size);
+    switch (op) {
+      case PDLP_VECOP_DOT: *out = dev.Dot(va.d, vb.d, size); break;
+      case PDLP_VECOP_LINF_NORM: *out = dev.LInf(va.d, size); break;
+      case PDLP_VECOP_L1_NORM: *out = dev.L1(va.d, size); break;
+      case PDLP_VECOP_SQUARED_NORM: *out = dev.SumSq(va.d, size); break;
+      case PDLP_VECOP_NORM: *out = std::sqrt(dev.SumSq(va.d, size)); break;
+      case PDLP_VECOP_SQUARED_DISTANCE: *out = dev.SumSqDiff(va.d, vb.d, size); break;
+      case PDLP_VECOP_DISTANCE: *out = std::sqrt(dev.SumSqDiff(va.d, vb.d, size)); break;
+      case PDLP_VECOP_SCALED_LINF_NORM: *out = dev.ScaledLInf(va.d, vb.d, size); break;
+      case PDLP_VECOP_SCALED_SQUARED_NORM: *out = dev.ScaledSumSq(va.d, vb.d, size); break;
+      case PDLP_VECOP_SCALED_NORM: *out = std::sqrt(dev.ScaledSumSq(va.d, vb.d, size)); break;
+      default: bad = 1;
+    }
+  });
+  return bad ? PDLP_B200_STATUS_BAD_ARGUMENT : rc;
+}
+
+}  // extern "C"

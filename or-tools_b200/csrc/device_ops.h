@@ -1,0 +1,249 @@
+// device_ops.h -- C++ interface between the host PDHG driver (solver.cc) and
+// the hand-written sm_100a kernels (device_ops.cu). Plain pointers + PODs; no
+// CUDA types leak into the host translation units.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//  * K is stored twice, as sliced-ELL with 32-row slices ("SELL-32"): once
+//    row-major (rows of K; used for K x) and once column-major (rows of K^T;
+//    used for K^T y), so neither product needs atomics -- the device
+//    equivalent of ShardedQuadraticProgram's matrix + explicit transpose
+//    (sharded_quadratic_program.cc:79-107).
+//  * Every vector lives in "position order": dual-length vectors in the slot
+//    order of the row-major copy, primal-length vectors in the slot order of
+//    the column-major copy. Column indices stored in one copy are positions of
+//    the other copy's vector order, so all epilogue accesses are coalesced.
+//    Permutations are applied only at upload / download.
+#ifndef PDLP_B200_DEVICE_OPS_H_
+#define PDLP_B200_DEVICE_OPS_H_
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/pdlp_b200.h"
+
+namespace pdlp_b200 {
+
+// ---------------------------------------------------------------------------
+// Host-side image of one SELL-32 orientation (built by sell_builder.cc).
+// ---------------------------------------------------------------------------
+struct SellHost {
+  int64_t num_rows = 0;      // logical rows of this orientation (= positions)
+  int64_t num_cols = 0;      // length of the gathered vector
+  int64_t num_split = 0;     // rows longer than split_len, cut into virtual slots
+  int64_t num_virtual = 0;   // virtual slots in use
+  int64_t num_virtual_padded = 0;  // rounded up to 32
+  int64_t num_slots = 0;     // all slots, multiple of 32
+  int64_t padded_nnz = 0;
+  int32_t split_len = 0;
+  std::vector<int64_t> slice_ptr;    // [num_slots/32 + 1]
+  std::vector<int32_t> slot_len;     // [num_slots]
+  std::vector<int32_t> col;          // [padded_nnz] position in the other order
+  std::vector<double> val;           // [padded_nnz]
+  std::vector<int32_t> split_first;  // [num_split+1] first virtual slot of split row
+  std::vector<int32_t> virt_pos;     // [num_virtual_padded] position of the row a virtual slot belongs to (-1 pad)
+  std::vector<int32_t> row_of_pos;   // [num_rows] original row index at a position
+  std::vector<int32_t> pos_of_row;   // [num_rows]
+};
+
+struct QpHost {  // device-ready problem image
+  int64_t n = 0, m = 0, nnz = 0;
+  SellHost rows;  // K   : m logical rows, gathers primal positions
+  SellHost cols;  // K^T : n logical rows, gathers dual positions
+  bool has_q = false;
+};
+
+// Builds both SELL copies from the CSC view. `row_begin/row_end` restrict the
+// image to a contiguous block of constraint rows (multi-GPU row sharding);
+// pass 0 / m for the whole problem. Throws std::runtime_error on bad input.
+QpHost BuildQpHost(const PdlpProblemView& view, int64_t row_begin, int64_t row_end,
+                   int sigma = 4096);
+
+// ---------------------------------------------------------------------------
+// Device objects
+// ---------------------------------------------------------------------------
+struct SellDev {
+  int64_t num_rows = 0, num_cols = 0, num_split = 0, num_virtual_padded = 0, num_slots = 0, padded_nnz = 0;
+  int64_t* slice_ptr = nullptr;
+  int32_t* slot_len = nullptr;
+  int32_t* col = nullptr;
+  double* val = nullptr;
+  int32_t* split_first = nullptr;
+  int32_t* virt_pos = nullptr;
+  double* virt_partial = nullptr;  // [num_virtual_padded] scratch for split rows
+};
+
+// State of the device-resident adaptive / constant step loop
+// (Solver::TakeAdaptiveStep / TakeConstantSizeStep, pdhg.cc:2558-2675). It
+// lives in device memory; kernels read it at launch so that a rejected step
+// needs no host round trip. The host mirrors it at checkpoints.
+struct StepState {
+  double step_size;
+  double primal_weight;
+  int32_t cur, prev, cand;          // buffer indices of x/y/K^T y
+  int32_t iterations_completed;
+  int32_t num_rejected_steps;
+  int32_t inner_iterations;
+  int32_t halt;                     // kHalt*
+  int32_t k_stop;
+  double kkt_pass_limit;
+  double avg_weight_sum;
+  int32_t avg_num_terms;
+  int32_t rule;                     // PDLP_ADAPTIVE_LINESEARCH_RULE / PDLP_CONSTANT_STEP_SIZE_RULE
+  double pending_ratio;             // deferred average update of the current iterate
+  double reduction_exponent, growth_exponent;
+  double last_dx2, last_dy2, last_nonlinearity, last_movement;
+  int64_t attempts;                 // attempts actually executed (not no-ops)
+};
+enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent = 3, kHaltInnerLimit = 4 };
+
+struct MSideStats {  // reductions over the dual (row) side
+  double linf_residual, sumsq_residual, cw_residual;  // PrimalResidualNorms
+  double bounds_term;                                 // DualObjectiveBoundsTerm
+  double linf_scaled, sumsq_scaled;                   // ||y o d_r||
+};
+struct NSideStats {  // reductions over the primal (column) side
+  double correction, full_correction, linf_residual, sumsq_residual, cw_residual;  // DualResidualNorms
+  double objective_dot, quadratic, linf_scaled, sumsq_scaled, linf_qx;
+};
+struct VectorInfoDev { double num_finite_nonzero, num_infinite, num_zero, largest, smallest, sum, sumsq; };
+
+class Device {
+ public:
+  // Picks the CUDA device; throws std::runtime_error if none is usable.
+  explicit Device(int cuda_device);
+  ~Device();
+  Device(const Device&) = delete;
+  Device& operator=(const Device&) = delete;
+
+  static int DeviceCount();  // 0 if no driver / device
+
+  int64_t launches() const { return launches_; }
+  void* stream() const { return stream_; }
+  void Sync();
+
+  // raw memory
+  double* AllocF64(int64_t n);
+  void Free(void* p);
+  void Upload(double* dst, const double* src, int64_t n);
+  void Download(double* dst, const double* src, int64_t n);
+  void CopyD2D(double* dst, const double* src, int64_t n);
+  void Fill(double* dst, double value, int64_t n);
+  // dst[p] = src_host[row_of_pos[p]] and inverse; perm lives on device.
+  void UploadPermuted(double* dst, const double* src_host, const int32_t* row_of_pos_dev, int64_t n);
+  void DownloadPermuted(double* dst_host, const double* src, const int32_t* row_of_pos_dev, int64_t n);
+  int32_t* UploadI32(const std::vector<int32_t>& v);
+
+  SellDev UploadSell(const SellHost& h);
+  void FreeSell(SellDev& s);
+  void DownloadSellValues(const SellDev& s, std::vector<double>& out);
+
+  // ---- SpMV + generic vector kernels (positions order) -------------------
+  void SpMV(const SellDev& a, const double* x, double* out);           // out = A x
+  // out[pos] = norm over the row of |a_ij * other_scale[col]| * |own_scale[pos]|; norm 0 LInf, 1 L2
+  // (ScaledColLInfNorm / ScaledColL2Norm, sharder.cc:288-332).
+  void ScaledRowNorm(const SellDev& a, int norm, const double* other_scale, const double* own_scale, double* out);
+  void ScaleMatrix(SellDev& a, const double* own_scale, const double* other_scale);  // a_ij *= own[i]*other[j]
+  void DivideBySqrt(double* vec, const double* divisor, int64_t n);                   // skip zeros (sou.cc:354-365)
+  void Mul(double* dst, const double* a, int64_t n);                                  // dst *= a
+  void Div(double* dst, const double* a, int64_t n);                                  // dst /= a
+  void MulSq(double* dst, const double* a, int64_t n);                                // dst *= a*a
+  void Axpy(double* dst, double s, const double* a, int64_t n);                       // dst += s*a
+  void Sub(double* dst, const double* a, const double* b, int64_t n);                 // dst = a - b
+  void ReplaceLargeWithInf(double* v, double threshold, int64_t n);
+  void ClampPrimal(double* x, const double* lb, const double* ub, bool feasibility_bounds, int64_t n);
+  void ClampDual(double* y, const double* lc, const double* uc, int64_t m);
+  void WeightedAverageAdd(double* avg, const double* v, double ratio, int64_t n);     // avg += ratio*(v-avg)
+
+  // reductions (deterministic: fixed grid + fixed-order final pass); host result
+  double Dot(const double* a, const double* b, int64_t n);
+  double SumSq(const double* a, int64_t n);
+  double SumSqDiff(const double* a, const double* b, int64_t n);
+  double LInf(const double* a, int64_t n);
+  double L1(const double* a, int64_t n);
+  double ScaledLInf(const double* a, const double* s, int64_t n);
+  double ScaledSumSq(const double* a, const double* s, int64_t n);
+  void DistancesSq(const double* x, const double* x0, int64_t n, const double* y, const double* y0, int64_t m, double out[2]);
+  VectorInfoDev VectorInfo(const double* v, int64_t n);                       // ComputeVectorInfo (sou.cc:179-191)
+  VectorInfoDev CombinedBoundsInfo(const double* a, const double* b, int64_t n);  // sou.cc:223-238
+  VectorInfoDev GapInfo(const double* lb, const double* ub, int64_t n);       // sou.cc:193-205
+  VectorInfoDev MatrixInfo(const SellDev& a);                                 // sou.cc:207-221
+  bool BoundsValid(const double* lb, const double* ub, int64_t n);           // HasValidBounds
+  bool AllNonNegative(const double* v, int64_t n);
+
+  // KKT reductions (iteration_stats.cc:66-350). dr/dc may be null (= ones).
+  MSideStats DualSideStats(const double* y, const double* kx, const double* lc, const double* uc, const double* dr,
+                           double cw_offset, bool homogeneous_bounds, int64_t m);
+  NSideStats PrimalSideStats(const double* x, const double* x_for_bounds, const double* kty, const double* c, const double* q,
+                             const double* lv, const double* uv, const double* dc, double cw_offset, bool zero_objective,
+                             bool handle_as_residuals, int64_t n);
+  // out = (zero_objective ? 0 : q*x + c) - kty   (PrimalGradientFromObjectiveProduct)
+  void PrimalGradient(const double* x, const double* kty, const double* c, const double* q, bool zero_objective, double* out, int64_t n);
+  // ComputePrimalGradient / ComputeDualGradient (sou.cc:446-527): gradient + value
+  double LagrangianPrimalGradient(const double* x, const double* kty, const double* c, const double* q, double* grad, int64_t n);
+  double LagrangianDualGradient(const double* y, const double* kx, const double* lc, const double* uc, double* grad, int64_t m);
+  // SetActiveSetInformation (pdhg.cc:1476-1545): out = {count, change}
+  void ActiveSetPrimal(const double* x, const double* x0, const double* lv, const double* uv, int64_t n, int64_t out[2]);
+  void ActiveSetDual(const double* y, const double* y0, const double* lc, const double* uc, int64_t m, int64_t out[2]);
+  double RandomProjection(const double* v, int64_t n, uint32_t seed, uint32_t stream_id);
+
+  // ---- trust region (trust_region.cc) ------------------------------------
+  // Joint problem (trust_region.cc:115-162) over (x, y): returns lagrangian
+  // value, lower, upper (ComputeLocalizedLagrangianBounds, Euclidean norm).
+  void LocalizedLagrangianBounds(const double* x, const double* y, const double* kx, const double* kty, const double* c, const double* q,
+                                 const double* lv, const double* uv, const double* lc, const double* uc, double primal_weight,
+                                 double radius, bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t m, double out[3]);
+  // Explicit-vector problems (SolveTrustRegion / SolveDiagonalTrustRegion).
+  void SolveTrustRegion(const double* obj, const double* lb, const double* ub, const double* center, const double* w, double radius,
+                        int64_t n, double* solution, double* step_size, double* objective_value);
+  void SolveDiagonalTrustRegion(const double* obj, const double* qdiag, const double* lb, const double* ub, const double* center,
+                                const double* w, double radius, double tol, int64_t n, double* solution, double* step_size,
+                                double* objective_value);
+
+  // ---- PDHG step (hot path) ----------------------------------------------
+  struct StepBuffers {
+    int64_t n = 0, m = 0;
+    double* x[3] = {nullptr, nullptr, nullptr};
+    double* y[3] = {nullptr, nullptr, nullptr};
+    double* kty[3] = {nullptr, nullptr, nullptr};
+    double* x_tilde = nullptr;
+    double* avg_x = nullptr;
+    double* avg_y = nullptr;
+    const double *c = nullptr, *q = nullptr, *lv = nullptr, *uv = nullptr, *lc = nullptr, *uc = nullptr;
+    StepState* state = nullptr;  // device
+  };
+  StepState* AllocState();
+  void UploadState(StepState* dev, const StepState& host);
+  void DownloadState(StepState& host, const StepState* dev);
+  // Enqueues `count` attempts of the fused 3-kernel step; attempts after the
+  // device sets `halt` are no-ops. Does not synchronise.
+  void EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count);
+  // Applies the deferred average update (if any) for both averages.
+  void FlushAverages(const StepBuffers& b);
+
+  // Unfused pieces for the Malitsky-Pock rule (pdhg.cc:2463-2556).
+  void PrimalStep(const double* x, const double* kty, const double* c, const double* q, const double* lv, const double* uv,
+                  double tau, double* x_next, int64_t n);
+  void DualStepFromProducts(const double* y, const double* kx_cur, const double* kx_next, const double* lc, const double* uc,
+                            double sigma, double theta, double* y_next, int64_t m);
+
+ private:
+  friend struct DeviceImpl;
+  int device_ = 0;
+  void* stream_ = nullptr;
+  double* partials_ = nullptr;   // reduction scratch
+  double* results_ = nullptr;    // small device result vector
+  double* host_results_ = nullptr;  // pinned
+  int64_t launches_ = 0;
+  int num_sms_ = 148;
+  // trust-region scratch (grown on demand)
+  double* tr_scratch_ = nullptr;
+  int64_t tr_scratch_size_ = 0;
+  double* step_partials_ = nullptr;
+  int64_t step_partials_size_ = 0;
+  double* TrScratch(int64_t doubles);
+};
+
+}  // namespace pdlp_b200
+
+#endif  // PDLP_B200_DEVICE_OPS_H_

@@ -1,0 +1,255 @@
+// device_problem.cc -- see device_problem.h.
+#include "device_problem.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+namespace pdlp_b200 {
+
+namespace {
+constexpr double kInf = std::numeric_limits<double>::infinity();
+}
+
+DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device) : dev_(new Device(cuda_device)) {
+  QpHost h = BuildQpHost(view, 0, view.num_constraints);
+  n_ = h.n;
+  m_ = h.m;
+  nnz_ = h.nnz;
+  objective_offset_ = view.objective_offset;
+  objective_scaling_factor_ = view.objective_scaling_factor;
+  rows_ = dev_->UploadSell(h.rows);
+  cols_ = dev_->UploadSell(h.cols);
+  primal_perm_ = dev_->UploadI32(h.cols.row_of_pos);
+  dual_perm_ = dev_->UploadI32(h.rows.row_of_pos);
+  col_starts_.assign(view.col_starts, view.col_starts + n_ + 1);
+  cols_meta_ = std::move(h.cols);
+  std::vector<int32_t>().swap(cols_meta_.col);
+  std::vector<double>().swap(cols_meta_.val);
+  auto up_primal = [&](const double* src) { double* d = NewPrimal(); UploadPrimal(d, src); return d; };
+  auto up_dual = [&](const double* src) { double* d = NewDual(); UploadDual(d, src); return d; };
+  c_ = up_primal(view.objective_vector);
+  if (view.objective_matrix_diagonal != nullptr) q_ = up_primal(view.objective_matrix_diagonal);
+  lv_ = up_primal(view.variable_lower_bounds);
+  uv_ = up_primal(view.variable_upper_bounds);
+  lc_ = up_dual(view.constraint_lower_bounds);
+  uc_ = up_dual(view.constraint_upper_bounds);
+  for (int k = 0; k < 4; ++k) {
+    tmp_n_[k] = NewPrimal();
+    tmp_m_[k] = NewDual();
+  }
+  ones_n_ = NewPrimal();
+  ones_m_ = NewDual();
+  dev_->Fill(ones_n_, 1.0, n_);
+  dev_->Fill(ones_m_, 1.0, m_);
+  dev_->Sync();
+}
+
+DeviceProblem::~DeviceProblem() {
+  for (double* p : {c_, q_, lv_, uv_, lc_, uc_, ones_n_, ones_m_}) dev_->Free(p);
+  for (int k = 0; k < 4; ++k) { dev_->Free(tmp_n_[k]); dev_->Free(tmp_m_[k]); }
+  dev_->Free(primal_perm_);
+  dev_->Free(dual_perm_);
+  dev_->FreeSell(rows_);
+  dev_->FreeSell(cols_);
+}
+
+void DeviceProblem::RescaleQuadraticProgram(const double* col_scaling, const double* row_scaling) {
+  Device& d = *dev_;
+  d.Mul(c_, col_scaling, n_);
+  d.Div(lv_, col_scaling, n_);
+  d.Div(uv_, col_scaling, n_);
+  if (q_ != nullptr) d.MulSq(q_, col_scaling, n_);
+  d.Mul(lc_, row_scaling, m_);
+  d.Mul(uc_, row_scaling, m_);
+  d.ScaleMatrix(rows_, row_scaling, col_scaling);
+  d.ScaleMatrix(cols_, col_scaling, row_scaling);
+}
+
+void DeviceProblem::ReplaceLargeConstraintBoundsWithInfinity(double threshold) {
+  dev_->ReplaceLargeWithInf(lc_, threshold, m_);
+  dev_->ReplaceLargeWithInf(uc_, threshold, m_);
+}
+
+bool DeviceProblem::HasValidBounds() { return dev_->BoundsValid(lc_, uc_, m_) && dev_->BoundsValid(lv_, uv_, n_); }
+bool DeviceProblem::ObjectiveMatrixIsNonNegative() { return q_ == nullptr || dev_->AllNonNegative(q_, n_); }
+
+namespace {
+struct Info { double largest, smallest, average, l2; int64_t nfn, nzero; };
+Info Finish(const VectorInfoDev& v) {  // VectorInfoAccumulator::operator VectorInfo, sou.cc:155-167
+  Info r;
+  r.nfn = static_cast<int64_t>(v.num_finite_nonzero);
+  r.nzero = static_cast<int64_t>(v.num_zero);
+  r.largest = r.nfn > 0 ? v.largest : 0.0;
+  r.smallest = r.nfn > 0 ? v.smallest : 0.0;
+  r.average = (r.nfn + r.nzero > 0) ? v.sum / static_cast<double>(r.nfn + r.nzero) : std::numeric_limits<double>::quiet_NaN();
+  r.l2 = std::sqrt(v.sumsq);
+  return r;
+}
+}  // namespace
+
+PdlpQuadraticProgramStats DeviceProblem::ComputeStats() {
+  Device& d = *dev_;
+  // row / column LInf norms with unit scaling (sou.cc:240-266)
+  d.ScaledRowNorm(rows_, 0, ones_n_, ones_m_, tmp_m_[0]);
+  d.ScaledRowNorm(cols_, 0, ones_m_, ones_n_, tmp_n_[0]);
+  const Info row_info = Finish(d.VectorInfo(tmp_m_[0], m_));
+  const Info col_info = Finish(d.VectorInfo(tmp_n_[0], n_));
+  const Info mat = Finish(d.MatrixInfo(cols_));
+  const Info bounds = Finish(d.CombinedBoundsInfo(uc_, lc_, m_));
+  const Info var_bounds = Finish(d.CombinedBoundsInfo(uv_, lv_, n_));
+  const Info obj = Finish(d.VectorInfo(c_, n_));
+  const Info gaps = Finish(d.GapInfo(lv_, uv_, n_));
+  PdlpQuadraticProgramStats s;
+  std::memset(&s, 0, sizeof(s));
+  s.num_variables = n_;
+  s.num_constraints = m_;
+  s.constraint_matrix_col_min_l_inf_norm = col_info.smallest;
+  s.constraint_matrix_row_min_l_inf_norm = row_info.smallest;
+  s.constraint_matrix_num_nonzeros = mat.nfn;
+  s.constraint_matrix_abs_max = mat.largest; s.constraint_matrix_abs_min = mat.smallest;
+  s.constraint_matrix_abs_avg = mat.average; s.constraint_matrix_l2_norm = mat.l2;
+  s.combined_bounds_max = bounds.largest; s.combined_bounds_min = bounds.smallest;
+  s.combined_bounds_avg = bounds.average; s.combined_bounds_l2_norm = bounds.l2;
+  s.combined_variable_bounds_max = var_bounds.largest; s.combined_variable_bounds_min = var_bounds.smallest;
+  s.combined_variable_bounds_avg = var_bounds.average; s.combined_variable_bounds_l2_norm = var_bounds.l2;
+  s.variable_bound_gaps_num_finite = gaps.nfn + gaps.nzero;
+  s.variable_bound_gaps_max = gaps.largest; s.variable_bound_gaps_min = gaps.smallest;
+  s.variable_bound_gaps_avg = gaps.average; s.variable_bound_gaps_l2_norm = gaps.l2;
+  s.objective_vector_abs_max = obj.largest; s.objective_vector_abs_min = obj.smallest;
+  s.objective_vector_abs_avg = obj.average; s.objective_vector_l2_norm = obj.l2;
+  if (q_ == nullptr) {
+    s.objective_matrix_abs_avg = std::numeric_limits<double>::quiet_NaN();
+  } else {
+    const Info qi = Finish(d.VectorInfo(q_, n_));
+    s.objective_matrix_num_nonzeros = qi.nfn;
+    s.objective_matrix_abs_max = qi.largest; s.objective_matrix_abs_min = qi.smallest;
+    s.objective_matrix_abs_avg = qi.average; s.objective_matrix_l2_norm = qi.l2;
+  }
+  return s;
+}
+
+// sou.cc:367-405: both norms are computed from the same (old) scaling vectors.
+void DeviceProblem::ApplyScalingIterationsForNorm(int num_iterations, int norm, double* row_scaling, double* col_scaling) {
+  Device& d = *dev_;
+  for (int it = 0; it < num_iterations; ++it) {
+    d.ScaledRowNorm(cols_, norm, row_scaling, col_scaling, tmp_n_[0]);  // column norms of D_r K D_c
+    d.ScaledRowNorm(rows_, norm, col_scaling, row_scaling, tmp_m_[0]);  // row norms
+    d.DivideBySqrt(col_scaling, tmp_n_[0], n_);
+    d.DivideBySqrt(row_scaling, tmp_m_[0], m_);
+  }
+}
+
+void DeviceProblem::ApplyRescaling(int l_inf_ruiz_iterations, bool l2_norm_rescaling, double** row_scaling, double** col_scaling) {
+  Device& d = *dev_;
+  double* r = NewDual();
+  double* c = NewPrimal();
+  d.Fill(r, 1.0, m_);
+  d.Fill(c, 1.0, n_);
+  bool do_rescale = false;
+  if (l_inf_ruiz_iterations > 0) { do_rescale = true; ApplyScalingIterationsForNorm(l_inf_ruiz_iterations, 0, r, c); }
+  if (l2_norm_rescaling) { do_rescale = true; ApplyScalingIterationsForNorm(1, 1, r, c); }
+  if (do_rescale) RescaleQuadraticProgram(c, r);
+  *row_scaling = r;
+  *col_scaling = c;
+}
+
+PdlpConvergenceInformation DeviceProblem::ComputeConvergenceInformation(bool handle_as_residuals, const double* dc, const double* dr, const double* x,
+                                                                        const double* y, const double* kty_or_null, double cw_primal_offset,
+                                                                        double cw_dual_offset, int candidate_type) {
+  Device& d = *dev_;
+  PdlpConvergenceInformation r;
+  std::memset(&r, 0, sizeof(r));
+  Kx(x, tmp_m_[0]);
+  const double* kty = kty_or_null;
+  if (kty == nullptr) { KTy(y, tmp_n_[0]); kty = tmp_n_[0]; }
+  const MSideStats ms = d.DualSideStats(y, tmp_m_[0], lc_, uc_, dr, cw_primal_offset, /*homogeneous=*/false, m_);
+  const NSideStats ns = d.PrimalSideStats(x, x, kty, c_, q_, lv_, uv_, dc, cw_dual_offset, /*zero_objective=*/false, handle_as_residuals, n_);
+  r.l_inf_primal_residual = ms.linf_residual;
+  r.l2_primal_residual = std::sqrt(ms.sumsq_residual);
+  r.l_inf_componentwise_primal_residual = ms.cw_residual;
+  r.l_inf_primal_variable = ns.linf_scaled;
+  r.l2_primal_variable = std::sqrt(ns.sumsq_scaled);
+  r.l_inf_dual_variable = ms.linf_scaled;
+  r.l2_dual_variable = std::sqrt(ms.sumsq_scaled);
+  const double quadratic_objective = 0.5 * ns.quadratic;
+  r.primal_objective = ApplyObjectiveScalingAndOffset(quadratic_objective + ns.objective_dot);
+  const double dual_objective_piece = -quadratic_objective + ms.bounds_term;
+  r.dual_objective = ApplyObjectiveScalingAndOffset(dual_objective_piece + ns.correction);
+  r.corrected_dual_objective = ApplyObjectiveScalingAndOffset(dual_objective_piece + ns.full_correction);
+  r.l_inf_dual_residual = ns.linf_residual;
+  r.l2_dual_residual = std::sqrt(ns.sumsq_residual);
+  r.l_inf_componentwise_dual_residual = ns.cw_residual;
+  r.candidate_type = candidate_type;
+  return r;
+}
+
+PdlpInfeasibilityInformation DeviceProblem::ComputeInfeasibilityInformation(bool handle_as_residuals, const double* dc, const double* dr,
+                                                                            const double* primal_ray, const double* dual_ray,
+                                                                            const double* primal_for_residual_tests,
+                                                                            const double* kty_of_dual_ray_or_null, int candidate_type) {
+  Device& d = *dev_;
+  PdlpInfeasibilityInformation r;
+  std::memset(&r, 0, sizeof(r));
+  const double* kty = kty_of_dual_ray_or_null;
+  if (kty == nullptr) { KTy(dual_ray, tmp_n_[1]); kty = tmp_n_[1]; }
+  Kx(primal_ray, tmp_m_[1]);
+  // dual ray side: gradient = -K^T ray; DualResidualNorms against the bounds at
+  // `primal_for_residual_tests`; primal ray side: objective terms + norms.
+  const NSideStats ns_dual = d.PrimalSideStats(primal_ray, primal_for_residual_tests, kty, c_, q_, lv_, uv_, dc, 0.0, /*zero_objective=*/true,
+                                               handle_as_residuals, n_);
+  const MSideStats ms = d.DualSideStats(dual_ray, tmp_m_[1], lc_, uc_, dr, 0.0, /*homogeneous=*/true, m_);
+  const double l_inf_primal = ns_dual.linf_scaled;
+  const double l_inf_dual = ms.linf_scaled;
+  const double dual_ray_objective = ms.bounds_term + ns_dual.correction;
+  if (l_inf_dual > 0) {
+    r.dual_ray_objective = dual_ray_objective / l_inf_dual;
+    r.max_dual_ray_infeasibility = ns_dual.linf_residual / l_inf_dual;
+  }
+  if (l_inf_primal > 0.0) {
+    r.primal_ray_quadratic_norm = ns_dual.linf_qx / l_inf_primal;
+    r.max_primal_ray_infeasibility = ms.linf_residual / l_inf_primal;
+    r.primal_ray_linear_objective = ns_dual.objective_dot / l_inf_primal;
+  }
+  r.candidate_type = candidate_type;
+  return r;
+}
+
+void DeviceProblem::ReducedCosts(const double* x, const double* y, bool use_zero_primal_objective, double* out) {
+  KTy(y, tmp_n_[0]);
+  dev_->PrimalGradient(x, tmp_n_[0], c_, q_, use_zero_primal_objective, out, n_);
+}
+
+void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const double* y, double primal_weight, double radius, const double* kx,
+                                                     const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4]) {
+  if (kx == nullptr) { Kx(x, tmp_m_[2]); kx = tmp_m_[2]; }
+  if (kty == nullptr) { KTy(y, tmp_n_[2]); kty = tmp_n_[2]; }
+  double r3[3];
+  dev_->LocalizedLagrangianBounds(x, y, kx, kty, c_, q_, lv_, uv_, lc_, uc_, primal_weight, radius, use_diagonal_solver, diagonal_tol, n_, m_, r3);
+  out[0] = r3[0]; out[1] = r3[1]; out[2] = r3[2]; out[3] = radius;
+}
+
+void DeviceProblem::DownloadValuesCsc(double* values) {
+  std::vector<double> sell;
+  dev_->DownloadSellValues(cols_, sell);
+  const SellHost& s = cols_meta_;
+  const int32_t T = s.split_len;
+  for (int64_t pos = 0; pos < n_; ++pos) {
+    const int32_t col = s.row_of_pos[pos];
+    const int64_t dst = col_starts_[col];
+    if (pos < s.num_split) {
+      int64_t off = 0;
+      for (int32_t v = s.split_first[pos]; v < s.split_first[pos + 1]; ++v, off += T) {
+        const int64_t base = s.slice_ptr[v >> 5] + (v & 31);
+        for (int32_t j = 0; j < s.slot_len[v]; ++j) values[dst + off + j] = sell[base + static_cast<int64_t>(j) * 32];
+      }
+    } else {
+      const int64_t slot = s.num_virtual_padded + (pos - s.num_split);
+      const int64_t base = s.slice_ptr[slot >> 5] + (slot & 31);
+      for (int32_t j = 0; j < s.slot_len[slot]; ++j) values[dst + j] = sell[base + static_cast<int64_t>(j) * 32];
+    }
+  }
+}
+
+}  // namespace pdlp_b200

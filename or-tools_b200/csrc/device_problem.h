@@ -1,0 +1,104 @@
+// device_problem.h -- the device-resident QP: B200 counterpart of
+// ShardedQuadraticProgram (sharded_quadratic_program.h:37-124) plus the
+// operators of sharded_optimization_utils / iteration_stats / trust_region on
+// device vectors. All device vectors are in "position order" (device_ops.h).
+#ifndef PDLP_B200_DEVICE_PROBLEM_H_
+#define PDLP_B200_DEVICE_PROBLEM_H_
+
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device_ops.h"
+
+namespace pdlp_b200 {
+
+class DeviceProblem {
+ public:
+  // Uploads the QP and builds both sparse orientations. Throws
+  // std::runtime_error on CUDA failure / no device.
+  DeviceProblem(const PdlpProblemView& view, int cuda_device);
+  ~DeviceProblem();
+  DeviceProblem(const DeviceProblem&) = delete;
+  DeviceProblem& operator=(const DeviceProblem&) = delete;
+
+  Device& dev() { return *dev_; }
+  int64_t n() const { return n_; }
+  int64_t m() const { return m_; }
+  int64_t nnz() const { return nnz_; }
+  bool is_lp() const { return q_ == nullptr; }
+
+  // problem data (device, position order)
+  double *c() const { return c_; }
+  double *q() const { return q_; }
+  double *lv() const { return lv_; }
+  double *uv() const { return uv_; }
+  double *lc() const { return lc_; }
+  double *uc() const { return uc_; }
+  const SellDev& rows() const { return rows_; }
+  const SellDev& cols() const { return cols_; }
+  double objective_offset() const { return objective_offset_; }
+  double objective_scaling_factor() const { return objective_scaling_factor_; }
+  double ApplyObjectiveScalingAndOffset(double v) const { return objective_scaling_factor_ * (v + objective_offset_); }
+
+  // vectors
+  double* NewPrimal() { return dev_->AllocF64(n_); }
+  double* NewDual() { return dev_->AllocF64(m_); }
+  void UploadPrimal(double* dst, const double* host) { dev_->UploadPermuted(dst, host, primal_perm_, n_); }
+  void UploadDual(double* dst, const double* host) { dev_->UploadPermuted(dst, host, dual_perm_, m_); }
+  void DownloadPrimal(double* host, const double* src) { dev_->DownloadPermuted(host, src, primal_perm_, n_); }
+  void DownloadDual(double* host, const double* src) { dev_->DownloadPermuted(host, src, dual_perm_, m_); }
+
+  void Kx(const double* x, double* out) { dev_->SpMV(rows_, x, out); }    // K x    (pdhg.cc:1912-1916)
+  void KTy(const double* y, double* out) { dev_->SpMV(cols_, y, out); }   // K^T y  (sharder.cc:160-173)
+
+  // sharded_quadratic_program.cc:148-189
+  void RescaleQuadraticProgram(const double* col_scaling, const double* row_scaling);
+  void ReplaceLargeConstraintBoundsWithInfinity(double threshold);
+  // sharded_optimization_utils.cc
+  PdlpQuadraticProgramStats ComputeStats();
+  void ApplyScalingIterationsForNorm(int num_iterations, int norm /*0 LInf, 1 L2*/, double* row_scaling, double* col_scaling);
+  // ApplyRescaling: allocates and returns the scaling vectors (device).
+  void ApplyRescaling(int l_inf_ruiz_iterations, bool l2_norm_rescaling, double** row_scaling, double** col_scaling);
+  bool HasValidBounds();
+  bool ObjectiveMatrixIsNonNegative();
+
+  // iteration_stats.cc; dc / dr may be null (ones). tmp vectors are owned here.
+  PdlpConvergenceInformation ComputeConvergenceInformation(bool handle_as_residuals, const double* dc, const double* dr, const double* x,
+                                                           const double* y, const double* kty_or_null, double cw_primal_offset,
+                                                           double cw_dual_offset, int candidate_type);
+  // primal_ray must already be projected to the feasibility bounds and dual_ray
+  // to the dual bounds where required (pdhg.cc:1704-1722).
+  PdlpInfeasibilityInformation ComputeInfeasibilityInformation(bool handle_as_residuals, const double* dc, const double* dr,
+                                                               const double* primal_ray, const double* dual_ray,
+                                                               const double* primal_for_residual_tests, const double* kty_of_dual_ray_or_null,
+                                                               int candidate_type);
+  void ReducedCosts(const double* x, const double* y, bool use_zero_primal_objective, double* out);
+  // trust_region.cc:978-1016 (Euclidean). kx / kty may be null (computed).
+  void ComputeLocalizedLagrangianBounds(const double* x, const double* y, double primal_weight, double radius, const double* kx,
+                                        const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4]);
+
+  // download of the (possibly rescaled) problem in the caller's CSC order
+  void DownloadValuesCsc(double* values);
+
+  // scratch vectors (position order)
+  double* tmp_n(int k) { return tmp_n_[k]; }
+  double* tmp_m(int k) { return tmp_m_[k]; }
+
+ private:
+  std::unique_ptr<Device> dev_;
+  int64_t n_ = 0, m_ = 0, nnz_ = 0;
+  double objective_offset_ = 0, objective_scaling_factor_ = 1;
+  double *c_ = nullptr, *q_ = nullptr, *lv_ = nullptr, *uv_ = nullptr, *lc_ = nullptr, *uc_ = nullptr;
+  SellDev rows_, cols_;
+  SellHost cols_meta_;                 // structure only (col/val released)
+  std::vector<int64_t> col_starts_;    // caller's CSC column starts
+  int32_t *primal_perm_ = nullptr, *dual_perm_ = nullptr;
+  double* tmp_n_[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* tmp_m_[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *ones_n_ = nullptr, *ones_m_ = nullptr;
+};
+
+}  // namespace pdlp_b200
+
+#endif  // PDLP_B200_DEVICE_PROBLEM_H_

@@ -1,0 +1,964 @@
+// solver.cc -- host driver of the device-resident PDHG solve.
+//
+// Mirrors PrimalDualHybridGradient() / PreprocessSolver / Solver of
+// ortools/pdlp/primal_dual_hybrid_gradient.cc, restructured for the GPU:
+//  * every vector stays in HBM; the host only sees reduced scalars;
+//  * the adaptive / constant step loop (pdhg.cc:2558-2675) runs on the device:
+//    accept test and step-size rule are evaluated by k_step_decide, so a
+//    rejected step costs no host round trip. The host enqueues attempts up to
+//    the next *checkpoint* -- the next iteration at which the reference's
+//    MajorIterationAndTerminationCheck (pdhg.cc:2360-2435) would do anything
+//    (termination check, major iteration, artificial restart, iteration or
+//    KKT-pass limit) -- and replays that function there.
+//  * the Malitsky-Pock rule (pdhg.cc:2463-2556) is host-driven per inner step.
+#include "solver.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+#include "device_problem.h"
+
+namespace pdlp_b200 {
+
+void Logger::Log(const std::string& s) const {
+  if (cb != nullptr) cb(s.c_str(), user);
+  else { std::fputs(s.c_str(), stdout); std::fputc('\n', stdout); }
+}
+
+namespace {
+
+constexpr double kInf = std::numeric_limits<double>::infinity();
+inline double Sq(double v) { return v * v; }
+
+std::string Fmt(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  std::vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return buf;
+}
+std::string G(double v) { return Fmt("%g", v); }
+
+struct WallTimer {
+  std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
+  void Start() { start = std::chrono::steady_clock::now(); }
+  double Get() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); }
+};
+
+SolverResultCpp ErrorSolverResult(int reason, const std::string& message, const Logger& logger) {  // pdhg.cc:776-785
+  SolverResultCpp r;
+  r.solve_log.termination_reason = reason;
+  r.solve_log.termination_string = message;
+  logger.Log("The solver did not run because of invalid input: " + message);
+  return r;
+}
+
+// ---- termination.cc (scalar logic, host) -----------------------------------
+struct DetailedCriteria { double primal_abs, primal_rel, dual_abs, dual_rel, gap_abs, gap_rel; };
+DetailedCriteria EffectiveOptimalityCriteria(const PdlpTerminationCriteria& c) {  // termination.cc:126-159
+  if (c.optimality_criteria_case == PDLP_DETAILED_OPTIMALITY_CRITERIA)
+    return {c.eps_optimal_primal_residual_absolute, c.eps_optimal_primal_residual_relative, c.eps_optimal_dual_residual_absolute,
+            c.eps_optimal_dual_residual_relative, c.eps_optimal_objective_gap_absolute, c.eps_optimal_objective_gap_relative};
+  const bool simple = c.optimality_criteria_case == PDLP_SIMPLE_OPTIMALITY_CRITERIA;
+  const double a = simple ? c.simple_eps_optimal_absolute : c.eps_optimal_absolute;
+  const double r = simple ? c.simple_eps_optimal_relative : c.eps_optimal_relative;
+  return {a, r, a, r, a, r};
+}
+double EpsilonRatio(double a, double r) { return a == r ? 1.0 : a / r; }  // termination.cc:230-237
+bool ObjectiveGapMet(const DetailedCriteria& oc, const PdlpConvergenceInformation& s) {  // termination.cc:26-41
+  if (std::isinf(oc.gap_abs) || std::isinf(oc.gap_rel)) return true;
+  const double abs_obj = std::abs(s.primal_objective) + std::abs(s.dual_objective);
+  const double gap = std::abs(s.primal_objective - s.dual_objective);
+  return std::isfinite(abs_obj) && gap <= oc.gap_abs + oc.gap_rel * abs_obj;
+}
+bool OptimalityCriteriaMet(const DetailedCriteria& oc, const PdlpConvergenceInformation& s, int norm, const PdlpBoundNorms& bn) {  // :43-97
+  double perr, pbase, derr, dbase, pabs = oc.primal_abs, dabs = oc.dual_abs;
+  if (norm == PDLP_OPTIMALITY_NORM_L_INF) {
+    perr = s.l_inf_primal_residual; pbase = bn.l_inf_norm_constraint_bounds; derr = s.l_inf_dual_residual; dbase = bn.l_inf_norm_primal_linear_objective;
+  } else if (norm == PDLP_OPTIMALITY_NORM_L_INF_COMPONENTWISE) {
+    perr = s.l_inf_componentwise_primal_residual; pbase = 1.0; pabs = 0.0; derr = s.l_inf_componentwise_dual_residual; dbase = 1.0; dabs = 0.0;
+  } else {
+    perr = s.l2_primal_residual; pbase = bn.l2_norm_constraint_bounds; derr = s.l2_dual_residual; dbase = bn.l2_norm_primal_linear_objective;
+  }
+  const bool p_ok = std::isinf(oc.primal_abs) || std::isinf(oc.primal_rel) || perr <= pabs + oc.primal_rel * pbase;
+  const bool d_ok = std::isinf(oc.dual_abs) || std::isinf(oc.dual_rel) || derr <= dabs + oc.dual_rel * dbase;
+  return p_ok && d_ok && ObjectiveGapMet(oc, s);
+}
+struct ReasonAndType { int reason, type; };
+std::optional<ReasonAndType> CheckSimpleTerminationCriteria(const PdlpTerminationCriteria& c, const PdlpIterationStats& st,
+                                                            const volatile int32_t* interrupt) {  // termination.cc:161-184
+  if (st.iteration_number >= c.iteration_limit) return ReasonAndType{PDLP_TERMINATION_REASON_ITERATION_LIMIT, PDLP_POINT_TYPE_NONE};
+  if (st.cumulative_kkt_matrix_passes >= c.kkt_matrix_pass_limit) return ReasonAndType{PDLP_TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT, PDLP_POINT_TYPE_NONE};
+  if (st.cumulative_time_sec >= c.time_sec_limit) return ReasonAndType{PDLP_TERMINATION_REASON_TIME_LIMIT, PDLP_POINT_TYPE_NONE};
+  if (interrupt != nullptr && *interrupt != 0) return ReasonAndType{PDLP_TERMINATION_REASON_INTERRUPTED_BY_USER, PDLP_POINT_TYPE_NONE};
+  return std::nullopt;
+}
+std::optional<ReasonAndType> CheckIterateTerminationCriteria(const PdlpTerminationCriteria& c, const PdlpIterationStats& st,
+                                                             const PdlpBoundNorms& bn, bool force_numerical) {  // termination.cc:186-219
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(c);
+  for (int i = 0; i < st.num_convergence_information; ++i)
+    if (OptimalityCriteriaMet(oc, st.convergence_information[i], c.optimality_norm, bn))
+      return ReasonAndType{PDLP_TERMINATION_REASON_OPTIMAL, st.convergence_information[i].candidate_type};
+  for (int i = 0; i < st.num_infeasibility_information; ++i) {
+    const PdlpInfeasibilityInformation& s = st.infeasibility_information[i];
+    if (s.dual_ray_objective > 0.0 && s.max_dual_ray_infeasibility / s.dual_ray_objective <= c.eps_primal_infeasible)
+      return ReasonAndType{PDLP_TERMINATION_REASON_PRIMAL_INFEASIBLE, s.candidate_type};
+    if (s.primal_ray_linear_objective < 0.0 && s.max_primal_ray_infeasibility / -s.primal_ray_linear_objective <= c.eps_dual_infeasible &&
+        s.primal_ray_quadratic_norm / -s.primal_ray_linear_objective <= c.eps_dual_infeasible)
+      return ReasonAndType{PDLP_TERMINATION_REASON_DUAL_INFEASIBLE, s.candidate_type};
+  }
+  if (force_numerical) return ReasonAndType{PDLP_TERMINATION_REASON_NUMERICAL_ERROR, PDLP_POINT_TYPE_NONE};
+  return std::nullopt;
+}
+PdlpBoundNorms BoundNormsFromProblemStats(const PdlpQuadraticProgramStats& s) {  // termination.cc:221-228
+  return {s.objective_vector_l2_norm, s.combined_bounds_l2_norm, s.objective_vector_abs_max, s.combined_bounds_max};
+}
+
+const PdlpConvergenceInformation* GetConvergenceInformation(const PdlpIterationStats& s, int type) {
+  for (int i = 0; i < s.num_convergence_information; ++i)
+    if (s.convergence_information[i].candidate_type == type) return &s.convergence_information[i];
+  return nullptr;
+}
+
+// ---- log table (pdhg.cc:127-318) --------------------------------------------
+void LogIterationStatsHeader(int verbosity, const Logger& logger) {
+  const std::string work = verbosity >= 3 ? Fmt("%6s %8s %6s", "iter#", "kkt_pass", "time") : Fmt("%6s %6s", "iter#", "time");
+  const std::string conv = verbosity >= 3
+      ? Fmt("%12s %12s %12s | %12s %12s %12s | %12s %12s | %12s %12s", "rel_prim_res", "rel_dual_res", "rel_gap", "prim_resid", "dual_resid",
+            "obj_gap", "prim_obj", "dual_obj", "prim_var_l2", "dual_var_l2")
+      : Fmt("%10s %10s %10s | %10s %10s", "rel_p_res", "rel_d_res", "rel_gap", "prim_obj", "dual_obj");
+  logger.Log(std::string(verbosity >= 4 ? "I " : "") + work + " | " + conv);
+}
+void LogIterationStats(int verbosity, const PdlpIterationStats& st, const PdlpTerminationCriteria& tc, const PdlpBoundNorms& bn, int preferred,
+                       const Logger& logger) {
+  const std::string iter = verbosity >= 3 ? Fmt("%6d %8.1f %6.1f", st.iteration_number, st.cumulative_kkt_matrix_passes, st.cumulative_time_sec)
+                                          : Fmt("%6d %6.1f", st.iteration_number, st.cumulative_time_sec);
+  const PdlpConvergenceInformation* ci = GetConvergenceInformation(st, preferred);
+  if (ci == nullptr && st.num_convergence_information > 0) ci = &st.convergence_information[0];
+  if (ci == nullptr) { logger.Log(std::string(verbosity >= 4 ? "? " : "") + iter); return; }
+  const char* tag = "";
+  if (verbosity >= 4)
+    tag = ci->candidate_type == PDLP_POINT_TYPE_CURRENT_ITERATE ? "C " : ci->candidate_type == PDLP_POINT_TYPE_AVERAGE_ITERATE ? "A "
+        : ci->candidate_type == PDLP_POINT_TYPE_ITERATE_DIFFERENCE ? "D " : "? ";
+  // ComputeRelativeResiduals, termination.cc:239-271
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(tc);
+  const double rp = EpsilonRatio(oc.primal_abs, oc.primal_rel), rd = EpsilonRatio(oc.dual_abs, oc.dual_rel), rg = EpsilonRatio(oc.gap_abs, oc.gap_rel);
+  const double abs_obj = std::abs(ci->primal_objective) + std::abs(ci->dual_objective);
+  const double rel_gap = (ci->primal_objective - ci->dual_objective) / (rg + abs_obj);
+  double relp, reld, absp, absd;
+  if (tc.optimality_norm == PDLP_OPTIMALITY_NORM_L_INF) {
+    relp = ci->l_inf_primal_residual / (rp + bn.l_inf_norm_constraint_bounds); reld = ci->l_inf_dual_residual / (rd + bn.l_inf_norm_primal_linear_objective);
+    absp = ci->l_inf_primal_residual; absd = ci->l_inf_dual_residual;
+  } else if (tc.optimality_norm == PDLP_OPTIMALITY_NORM_L_INF_COMPONENTWISE) {
+    relp = ci->l_inf_componentwise_primal_residual; reld = ci->l_inf_componentwise_dual_residual; absp = ci->l_inf_primal_residual; absd = ci->l_inf_dual_residual;
+  } else {
+    relp = ci->l2_primal_residual / (rp + bn.l2_norm_constraint_bounds); reld = ci->l2_dual_residual / (rd + bn.l2_norm_primal_linear_objective);
+    absp = ci->l2_primal_residual; absd = ci->l2_dual_residual;
+  }
+  const std::string conv = verbosity >= 3
+      ? Fmt("%#12.6g %#12.6g %#12.6g | %#12.6g %#12.6g %#12.6g | %#12.6g %#12.6g | %#12.6g %#12.6g", relp, reld, rel_gap, absp, absd,
+            ci->primal_objective - ci->dual_objective, ci->primal_objective, ci->dual_objective, ci->l2_primal_variable, ci->l2_dual_variable)
+      : Fmt("%#10.4g %#10.4g %#10.4g | %#10.4g %#10.4g", relp, reld, rel_gap, ci->primal_objective, ci->dual_objective);
+  logger.Log(std::string(tag) + iter + " | " + conv);
+}
+
+// pdhg.cc:791-983
+std::optional<SolverResultCpp> CheckProblemStats(const PdlpQuadraticProgramStats& s, double objective_offset, bool check_small, const Logger& logger) {
+  const double kBig = 1e50, kSmall = 1e-50, kRange = 1e20;
+  auto err = [&](const std::string& m) { return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, m, logger); };
+  auto warn_range = [&](const char* what, double mx, double mn) {
+    if (mx > kRange * mn) logger.Log(std::string("WARNING: ") + what + " has largest absolute value " + G(mx) + " and smallest non-zero absolute value " + G(mn) + "; performance may suffer.");
+  };
+  if (std::isnan(s.constraint_matrix_l2_norm)) return err("Constraint matrix has a NAN.");
+  if (s.constraint_matrix_abs_max > kBig) return err("Constraint matrix has a non-zero with absolute value " + G(s.constraint_matrix_abs_max) + " which exceeds limit of " + G(kBig) + ".");
+  warn_range("Constraint matrix", s.constraint_matrix_abs_max, s.constraint_matrix_abs_min);
+  if (s.constraint_matrix_col_min_l_inf_norm > 0 && s.constraint_matrix_col_min_l_inf_norm < kSmall)
+    return err("Constraint matrix has a column with Linf norm " + G(s.constraint_matrix_col_min_l_inf_norm) + " which is less than limit of " + G(kSmall) + ".");
+  if (s.constraint_matrix_row_min_l_inf_norm > 0 && s.constraint_matrix_row_min_l_inf_norm < kSmall)
+    return err("Constraint matrix has a row with Linf norm " + G(s.constraint_matrix_row_min_l_inf_norm) + " which is less than limit of " + G(kSmall) + ".");
+  if (std::isnan(s.combined_bounds_l2_norm)) return err("Constraint bounds vector has a NAN.");
+  if (s.combined_bounds_max > kBig) return err("Combined constraint bounds vector has a non-zero with absolute value " + G(s.combined_bounds_max) + " which exceeds limit of " + G(kBig) + ".");
+  if (check_small && s.combined_bounds_min > 0 && s.combined_bounds_min < kSmall)
+    return err("Combined constraint bounds vector has a non-zero with absolute value " + G(s.combined_bounds_min) + " which is less than the limit of " + G(kSmall) + ".");
+  warn_range("Combined constraint bounds vector", s.combined_bounds_max, s.combined_bounds_min);
+  if (std::isnan(s.combined_variable_bounds_l2_norm)) return err("Variable bounds vector has a NAN.");
+  if (s.combined_variable_bounds_max > kBig) return err("Combined variable bounds vector has a non-zero with absolute value " + G(s.combined_variable_bounds_max) + " which exceeds limit of " + G(kBig) + ".");
+  if (check_small && s.combined_variable_bounds_min > 0 && s.combined_variable_bounds_min < kSmall)
+    return err("Combined variable bounds vector has a non-zero with absolute value " + G(s.combined_variable_bounds_min) + " which is less than the limit of " + G(kSmall) + ".");
+  warn_range("Combined variable bounds vector", s.combined_variable_bounds_max, s.combined_variable_bounds_min);
+  warn_range("Variable bound gap vector", s.variable_bound_gaps_max, s.variable_bound_gaps_min);
+  if (std::isnan(objective_offset)) return err("Objective offset is NAN.");
+  if (std::abs(objective_offset) > kBig) return err("Objective offset " + G(objective_offset) + " has absolute value which exceeds limit of " + G(kBig) + ".");
+  if (std::isnan(s.objective_vector_l2_norm)) return err("Objective vector has a NAN.");
+  if (s.objective_vector_abs_max > kBig) return err("Objective vector has a non-zero with absolute value " + G(s.objective_vector_abs_max) + " which exceeds limit of " + G(kBig) + ".");
+  if (check_small && s.objective_vector_abs_min > 0 && s.objective_vector_abs_min < kSmall)
+    return err("Objective vector has a non-zero with absolute value " + G(s.objective_vector_abs_min) + " which is less than the limit of " + G(kSmall) + ".");
+  warn_range("Objective vector", s.objective_vector_abs_max, s.objective_vector_abs_min);
+  if (std::isnan(s.objective_matrix_l2_norm)) return err("Objective matrix has a NAN.");
+  if (s.objective_matrix_abs_max > kBig) return err("Objective matrix has a non-zero with absolute value " + G(s.objective_matrix_abs_max) + " which exceeds limit of " + G(kBig) + ".");
+  warn_range("Objective matrix", s.objective_matrix_abs_max, s.objective_matrix_abs_min);
+  return std::nullopt;
+}
+
+std::string ValidateDimensions(const PdlpProblemView& v) {  // quadratic_program.cc:38-97
+  auto sz = [](int64_t given, int64_t dflt) { return given < 0 ? dflt : given; };
+  const long long n = v.num_variables, m = v.num_constraints;
+  const long long var_lb = sz(v.variable_lower_bounds_size, n), var_ub = sz(v.variable_upper_bounds_size, n), obj = sz(v.objective_vector_size, n);
+  const long long con_lb = sz(v.constraint_lower_bounds_size, m), con_ub = sz(v.constraint_upper_bounds_size, m);
+  if (var_lb != var_ub) return Fmt("Inconsistent dimensions: variable lower bound vector has size %lld while variable upper bound vector has size %lld", var_lb, var_ub);
+  if (var_lb != obj) return Fmt("Inconsistent dimensions: variable lower bound vector has size %lld while objective vector has size %lld", var_lb, obj);
+  if (var_lb != n) return Fmt("Inconsistent dimensions: variable lower bound vector has size %lld while constraint matrix has %lld columns", var_lb, n);
+  if (v.objective_matrix_diagonal != nullptr && var_lb != sz(v.objective_matrix_size, n))
+    return Fmt("Inconsistent dimensions: variable lower bound vector has size %lld while objective matrix has %lld rows", var_lb, (long long)sz(v.objective_matrix_size, n));
+  if (con_lb != con_ub) return Fmt("Inconsistent dimensions: constraint lower bound vector has size %lld while constraint upper bound vector has size %lld", con_lb, con_ub);
+  if (con_lb != m) return Fmt("Inconsistent dimensions: constraint lower bound vector has size %lld while constraint matrix has %lld rows ", con_lb, m);
+  return "";
+}
+
+struct LocalizedBounds { double lagrangian_value, lower_bound, upper_bound, radius; };
+inline double BoundGap(const LocalizedBounds& b) { return b.upper_bound - b.lower_bound; }
+
+// ---------------------------------------------------------------------------
+// The device solve. One object plays both PreprocessSolver (original-problem
+// bookkeeping, scaling vectors, termination checks) and Solver (iterate state).
+// ---------------------------------------------------------------------------
+class DeviceSolve {
+ public:
+  DeviceSolve(DeviceProblem& p, const PdlpParams& params, const Logger& logger, StatsCallback cb)
+      : P(p), D(p.dev()), params_(params), logger_(logger), callback_(std::move(cb)) {}
+  ~DeviceSolve() {
+    for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); }
+    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, dc_, dr_, delta_x_, delta_y_}) D.Free(v);
+    D.Free(buf_.state);
+  }
+
+  SolverResultCpp PreprocessAndSolve(std::optional<InitialSolution> initial_solution, const volatile int32_t* interrupt_solve, const std::string* name);
+
+ private:
+  enum class Outcome { kSuccessful, kForceNumericalTermination };
+
+  // ---- state helpers --------------------------------------------------------
+  double* X() const { return buf_.x[hs_.cur]; }
+  double* Y() const { return buf_.y[hs_.cur]; }
+  double* Kty() const { return buf_.kty[hs_.cur]; }
+  bool PrimalAvgHasWeight() const { return avg_x_weight_ > 0.0; }
+  bool DualAvgHasWeight() const { return avg_y_weight_ > 0.0; }
+  const double* PrimalAverage() const { return PrimalAvgHasWeight() ? buf_.avg_x : X(); }  // pdhg.cc:2172-2186
+  const double* DualAverage() const { return DualAvgHasWeight() ? buf_.avg_y : Y(); }
+  void PushState() { D.UploadState(buf_.state, hs_); }
+  void ClearAverages() {
+    D.Fill(buf_.avg_x, 0.0, P.n());
+    D.Fill(buf_.avg_y, 0.0, P.m());
+    avg_x_weight_ = avg_y_weight_ = 0.0;
+    avg_x_terms_ = avg_y_terms_ = 0;
+    hs_.avg_weight_sum = 0.0;
+    hs_.avg_num_terms = 0;
+    hs_.pending_ratio = 0.0;
+  }
+  void AverageAdd(bool primal, const double* v, double weight) {  // ShardedWeightedAverage::Add, sou.cc:54-66
+    double& w = primal ? avg_x_weight_ : avg_y_weight_;
+    int& terms = primal ? avg_x_terms_ : avg_y_terms_;
+    if (weight > 0.0) {
+      D.WeightedAverageAdd(primal ? buf_.avg_x : buf_.avg_y, v, weight / (w + weight), primal ? P.n() : P.m());
+      w += weight;
+    }
+    ++terms;
+  }
+  void ResetAverageToCurrent() {  // pdhg.cc:2437-2442
+    ClearAverages();
+    AverageAdd(true, X(), 1.0);
+    AverageAdd(false, Y(), 1.0);
+    hs_.avg_weight_sum = 1.0;
+    hs_.avg_num_terms = 1;
+  }
+  void SetCurrentPrimalAndDualProducts() {  // pdhg.cc:1961-1974
+    if (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE) P.Kx(X(), kx_cur_);
+    P.KTy(Y(), Kty());
+  }
+  double DistanceTraveledFromLastStart(const double* x, const double* y) {  // pdhg.cc:1998-2007
+    double d[2];
+    D.DistancesSq(x, x0_, P.n(), y, y0_, P.m(), d);
+    return std::sqrt((0.5 * hs_.primal_weight) * d[0] + (0.5 / hs_.primal_weight) * d[1]);
+  }
+  LocalizedBounds BoundsAt(const double* x, const double* y, const double* kx, const double* kty) {
+    const double radius = DistanceTraveledFromLastStart(x, y);
+    double out[4];
+    P.ComputeLocalizedLagrangianBounds(x, y, hs_.primal_weight, radius, kx, kty, params_.use_diagonal_qp_trust_region_solver != 0,
+                                       params_.diagonal_qp_trust_region_solver_tolerance, out);
+    return {out[0], out[1], out[2], out[3]};
+  }
+  LocalizedBounds ComputeLocalizedBoundsAtCurrent() {  // pdhg.cc:2009-2021
+    return BoundsAt(X(), Y(), params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE ? kx_cur_ : nullptr, Kty());
+  }
+  LocalizedBounds ComputeLocalizedBoundsAtAverage() { return BoundsAt(PrimalAverage(), DualAverage(), nullptr, nullptr); }  // :2023-2039
+  static bool AverageHasBetterPotential(const LocalizedBounds& avg, const LocalizedBounds& cur) {  // :2041-2048
+    return BoundGap(avg) / Sq(avg.radius) < BoundGap(cur) / Sq(cur.radius);
+  }
+  bool ShouldDoAdaptiveRestartHeuristic(double gap) const {  // :2058-2072
+    const double ratio = gap / normalized_gap_at_last_restart_;
+    if (ratio < params_.sufficient_reduction_for_restart) return true;
+    return ratio < params_.necessary_reduction_for_restart && gap > normalized_gap_at_last_trial_;
+  }
+  int DetermineDistanceBasedRestartChoice();
+  int ChooseRestartToApply(bool is_major_iteration);
+  double ComputeNewPrimalWeight();
+  void ApplyRestartChoice(int restart);
+  PdlpIterationStats CreateSimpleIterationStats(int restart_used) const;
+  std::optional<SolverResultCpp> MajorIterationAndTerminationCheck(bool force_numerical, const volatile int32_t* interrupt, SolveLogCpp& log);
+  std::optional<ReasonAndType> UpdateIterationStatsAndCheckTermination(bool force_numerical, const volatile int32_t* interrupt,
+                                                                       const PdlpIterationStats& full_stats, PdlpIterationStats& stats);
+  void ConvergenceAndInfeasibility(const double* x, const double* y, const double* kty_or_null, int type, PdlpConvergenceInformation* conv,
+                                   PdlpInfeasibilityInformation* infeas);
+  void AddPointMetadata(const double* x, const double* y, int type, PdlpIterationStats& stats);
+  SolverResultCpp PickSolutionAndConstructSolverResult(const double* avg_x, const double* avg_y, const PdlpIterationStats& stats, int reason,
+                                                       int output_type, SolveLogCpp log);
+  SolverResultCpp ConstructOriginalSolverResult(SolverResultCpp result);
+  void MaterializeDeltas();
+  int NextCheckpoint(int k) const;
+  Outcome RunDeviceSteps(int k, const volatile int32_t* interrupt);
+  Outcome TakeMalitskyPockStep();
+  SolverResultCpp Solve(const volatile int32_t* interrupt_solve, SolveLogCpp solve_log);
+  void LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) const;
+
+  DeviceProblem& P;
+  Device& D;
+  const PdlpParams params_;
+  const Logger& logger_;
+  StatsCallback callback_;
+  PdlpBoundNorms original_bound_norms_{};
+  double *dc_ = nullptr, *dr_ = nullptr;  // col / row scaling vectors
+  Device::StepBuffers buf_;
+  StepState hs_{};
+  double *x0_ = nullptr, *y0_ = nullptr;            // last restart point
+  double *kx_cur_ = nullptr, *kx_next_ = nullptr;    // Malitsky-Pock product cache
+  double *delta_x_ = nullptr, *delta_y_ = nullptr;   // materialised iterate difference
+  bool have_delta_ = false;
+  double avg_x_weight_ = 0, avg_y_weight_ = 0;
+  int avg_x_terms_ = 0, avg_y_terms_ = 0;
+  double ratio_last_two_step_sizes_ = 1;
+  double normalized_gap_at_last_trial_ = kInf, normalized_gap_at_last_restart_ = kInf;
+  struct { double distance_moved_last_restart_period = kInf; int length_of_last_restart_period = 1; } distance_info_;
+  double preprocessing_time_sec_ = 0;
+  WallTimer timer_;
+  WallTimer log_clock_;
+  double time_of_last_log_ = -kInf;
+  int log_counter_ = 0;
+  int iterations_completed_ = 0;
+  int num_rejected_steps_ = 0;
+  double device_time_sec_ = 0;
+};
+
+int DeviceSolve::DetermineDistanceBasedRestartChoice() {  // pdhg.cc:2074-2107
+  if (avg_x_terms_ == 0) return PDLP_RESTART_CHOICE_NO_RESTART;
+  if (distance_info_.length_of_last_restart_period == 0) return PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE;
+  const int period = avg_x_terms_;
+  const double dist_avg = DistanceTraveledFromLastStart(buf_.avg_x, buf_.avg_y);
+  if ((dist_avg / period) < params_.sufficient_reduction_for_restart *
+                                (distance_info_.distance_moved_last_restart_period / distance_info_.length_of_last_restart_period)) {
+    const LocalizedBounds avg = ComputeLocalizedBoundsAtAverage();
+    const LocalizedBounds cur = ComputeLocalizedBoundsAtCurrent();
+    return AverageHasBetterPotential(avg, cur) ? PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE : PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
+  }
+  return PDLP_RESTART_CHOICE_NO_RESTART;
+}
+
+int DeviceSolve::ChooseRestartToApply(bool is_major) {  // pdhg.cc:2109-2170
+  if (!PrimalAvgHasWeight() && !DualAvgHasWeight()) return PDLP_RESTART_CHOICE_NO_RESTART;
+  const int restart_length = avg_x_terms_;
+  if (restart_length >= iterations_completed_ / 2 && params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
+    const LocalizedBounds avg = ComputeLocalizedBoundsAtAverage();
+    const LocalizedBounds cur = ComputeLocalizedBoundsAtCurrent();
+    return AverageHasBetterPotential(avg, cur) ? PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE : PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
+  }
+  if (!is_major) return PDLP_RESTART_CHOICE_NO_RESTART;
+  switch (params_.restart_strategy) {
+    case PDLP_NO_RESTARTS: return PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
+    case PDLP_EVERY_MAJOR_ITERATION: return PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE;
+    case PDLP_ADAPTIVE_HEURISTIC: {
+      const LocalizedBounds avg = ComputeLocalizedBoundsAtAverage();
+      const LocalizedBounds cur = ComputeLocalizedBoundsAtCurrent();
+      double gap;
+      int choice;
+      if (AverageHasBetterPotential(avg, cur)) { gap = BoundGap(avg) / avg.radius; choice = PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE; }
+      else { gap = BoundGap(cur) / cur.radius; choice = PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET; }
+      if (ShouldDoAdaptiveRestartHeuristic(gap)) return choice;
+      normalized_gap_at_last_trial_ = gap;
+      return PDLP_RESTART_CHOICE_NO_RESTART;
+    }
+    case PDLP_ADAPTIVE_DISTANCE_BASED: return DetermineDistanceBasedRestartChoice();
+    default: return PDLP_RESTART_CHOICE_UNSPECIFIED;
+  }
+}
+
+double DeviceSolve::ComputeNewPrimalWeight() {  // pdhg.cc:2188-2214
+  double d[2];
+  D.DistancesSq(X(), x0_, P.n(), Y(), y0_, P.m(), d);
+  const double primal_distance = std::sqrt(d[0]), dual_distance = std::sqrt(d[1]);
+  constexpr double kNonzeroTol = 1.0e-10;
+  if (primal_distance <= kNonzeroTol || primal_distance >= 1.0 / kNonzeroTol || dual_distance <= kNonzeroTol || dual_distance >= 1.0 / kNonzeroTol)
+    return hs_.primal_weight;
+  const double s = params_.primal_weight_update_smoothing;
+  const double w = std::exp(s * std::log(dual_distance / primal_distance) + (1.0 - s) * std::log(hs_.primal_weight));
+  if (params_.verbosity_level >= 4) logger_.Log(Fmt("New computed primal weight is %g at iteration %d", w, iterations_completed_));
+  return w;
+}
+
+void DeviceSolve::ApplyRestartChoice(int restart) {  // pdhg.cc:2246-2296
+  switch (restart) {
+    case PDLP_RESTART_CHOICE_UNSPECIFIED:
+    case PDLP_RESTART_CHOICE_NO_RESTART: return;
+    case PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET:
+      if (params_.verbosity_level >= 4) logger_.Log(Fmt("Restarted to current on iteration %d after %d iterations", iterations_completed_, avg_x_terms_));
+      break;
+    case PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE:
+      if (params_.verbosity_level >= 4) logger_.Log(Fmt("Restarted to average on iteration %d after %d iterations", iterations_completed_, avg_x_terms_));
+      D.CopyD2D(X(), buf_.avg_x, P.n());
+      D.CopyD2D(Y(), buf_.avg_y, P.m());
+      SetCurrentPrimalAndDualProducts();
+      break;
+  }
+  hs_.primal_weight = ComputeNewPrimalWeight();
+  ratio_last_two_step_sizes_ = 1;
+  if (params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
+    const LocalizedBounds b = ComputeLocalizedBoundsAtCurrent();
+    normalized_gap_at_last_restart_ = BoundGap(b) / b.radius;
+    normalized_gap_at_last_trial_ = kInf;
+  } else if (params_.restart_strategy == PDLP_ADAPTIVE_DISTANCE_BASED) {
+    distance_info_.distance_moved_last_restart_period = DistanceTraveledFromLastStart(X(), Y());
+    distance_info_.length_of_last_restart_period = avg_x_terms_;
+  }
+  ClearAverages();
+  D.CopyD2D(x0_, X(), P.n());
+  D.CopyD2D(y0_, Y(), P.m());
+}
+
+PdlpIterationStats DeviceSolve::CreateSimpleIterationStats(int restart_used) const {  // pdhg.cc:1976-1996
+  PdlpIterationStats s;
+  std::memset(&s, 0, sizeof(s));
+  const double per_rejected = params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE ? 0.5 : 1.0;
+  s.iteration_number = iterations_completed_;
+  s.cumulative_rejected_steps = num_rejected_steps_;
+  s.cumulative_kkt_matrix_passes = iterations_completed_ + per_rejected * num_rejected_steps_;
+  s.cumulative_time_sec = preprocessing_time_sec_ + timer_.Get();
+  s.restart_used = restart_used;
+  s.step_size = hs_.step_size;
+  s.primal_weight = hs_.primal_weight;
+  return s;
+}
+
+// pdhg.cc:1655-1724 (no presolve)
+void DeviceSolve::ConvergenceAndInfeasibility(const double* x, const double* y, const double* kty_or_null, int type, PdlpConvergenceInformation* conv,
+                                              PdlpInfeasibilityInformation* infeas) {
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(params_.termination_criteria);
+  const bool har = params_.handle_some_primal_gradients_on_finite_bounds_as_residuals != 0;
+  if (conv != nullptr)
+    *conv = P.ComputeConvergenceInformation(har, dc_, dr_, x, y, kty_or_null, EpsilonRatio(oc.primal_abs, oc.primal_rel),
+                                            EpsilonRatio(oc.dual_abs, oc.dual_rel), type);
+  if (infeas != nullptr) {
+    double* primal_copy = P.tmp_n(3);
+    D.CopyD2D(primal_copy, x, P.n());
+    D.ClampPrimal(primal_copy, P.lv(), P.uv(), /*feasibility_bounds=*/true, P.n());
+    if (type == PDLP_POINT_TYPE_ITERATE_DIFFERENCE) {
+      double* dual_copy = P.tmp_m(3);
+      D.CopyD2D(dual_copy, y, P.m());
+      D.ClampDual(dual_copy, P.lc(), P.uc(), P.m());
+      *infeas = P.ComputeInfeasibilityInformation(har, dc_, dr_, primal_copy, dual_copy, x, nullptr, type);
+    } else {
+      // the dual ray is y itself: reuse K^T y when the caller has it
+      const double* kty = kty_or_null;
+      if (kty == nullptr && conv != nullptr) kty = P.tmp_n(0);  // left there by ComputeConvergenceInformation
+      *infeas = P.ComputeInfeasibilityInformation(har, dc_, dr_, primal_copy, y, x, kty, type);
+    }
+  }
+}
+
+void DeviceSolve::AddPointMetadata(const double* x, const double* y, int type, PdlpIterationStats& stats) {  // pdhg.cc:1547-1565
+  PdlpPointMetadata md;
+  std::memset(&md, 0, sizeof(md));
+  md.point_type = type;
+  md.num_random_projections = std::min<int>(params_.num_random_projection_seeds, PDLP_MAX_RANDOM_PROJECTION_SEEDS);
+  for (int k = 0; k < md.num_random_projections; ++k) {
+    const uint32_t seed = static_cast<uint32_t>(params_.random_projection_seeds[k]);
+    md.random_primal_projections[k] = D.RandomProjection(x, P.n(), seed, 0);
+    md.random_dual_projections[k] = D.RandomProjection(y, P.m(), seed, 1);
+  }
+  if (type != PDLP_POINT_TYPE_ITERATE_DIFFERENCE) {  // SetActiveSetInformation, pdhg.cc:1476-1545
+    int64_t pc[2], dcnt[2];
+    D.ActiveSetPrimal(x, x0_, P.lv(), P.uv(), P.n(), pc);
+    D.ActiveSetDual(y, y0_, P.lc(), P.uc(), P.m(), dcnt);
+    md.has_active_set_information = 1;
+    md.active_primal_variable_count = pc[0];
+    md.active_primal_variable_change = pc[1];
+    md.active_dual_variable_count = dcnt[0];
+    md.active_dual_variable_change = dcnt[1];
+  }
+  stats.point_metadata[stats.num_point_metadata++] = md;
+}
+
+void DeviceSolve::MaterializeDeltas() {
+  // current_primal_delta_ / current_dual_delta_ of the last accepted step
+  // (pdhg.cc:2604-2605) are x[cur]-x[prev] and y[cur]-y[prev]: the third
+  // buffer keeps `prev` intact across rejected candidates. Called right after
+  // the steps of a chunk so that a later restart (which overwrites x[cur])
+  // cannot disturb them.
+  D.Sub(delta_x_, buf_.x[hs_.cur], buf_.x[hs_.prev], P.n());
+  D.Sub(delta_y_, buf_.y[hs_.cur], buf_.y[hs_.prev], P.m());
+  have_delta_ = true;
+}
+
+// pdhg.cc:1567-1653
+std::optional<ReasonAndType> DeviceSolve::UpdateIterationStatsAndCheckTermination(bool force_numerical, const volatile int32_t* interrupt,
+                                                                                  const PdlpIterationStats& full_stats, PdlpIterationStats& stats) {
+  ConvergenceAndInfeasibility(X(), Y(), Kty(), PDLP_POINT_TYPE_CURRENT_ITERATE, &stats.convergence_information[stats.num_convergence_information],
+                              &stats.infeasibility_information[stats.num_infeasibility_information]);
+  stats.num_convergence_information++;
+  stats.num_infeasibility_information++;
+  AddPointMetadata(X(), Y(), PDLP_POINT_TYPE_CURRENT_ITERATE, stats);
+  if (PrimalAvgHasWeight() && DualAvgHasWeight()) {
+    ConvergenceAndInfeasibility(buf_.avg_x, buf_.avg_y, nullptr, PDLP_POINT_TYPE_AVERAGE_ITERATE,
+                                &stats.convergence_information[stats.num_convergence_information],
+                                &stats.infeasibility_information[stats.num_infeasibility_information]);
+    stats.num_convergence_information++;
+    stats.num_infeasibility_information++;
+    AddPointMetadata(buf_.avg_x, buf_.avg_y, PDLP_POINT_TYPE_AVERAGE_ITERATE, stats);
+  }
+  if (have_delta_) {
+    ConvergenceAndInfeasibility(delta_x_, delta_y_, nullptr, PDLP_POINT_TYPE_ITERATE_DIFFERENCE, nullptr,
+                                &stats.infeasibility_information[stats.num_infeasibility_information]);
+    stats.num_infeasibility_information++;
+    AddPointMetadata(delta_x_, delta_y_, PDLP_POINT_TYPE_ITERATE_DIFFERENCE, stats);
+  }
+  constexpr int kLogEvery = 15;
+  const double now = log_clock_.Get();
+  if (params_.verbosity_level >= 2 && (params_.log_interval_seconds == 0.0 || now - time_of_last_log_ >= params_.log_interval_seconds)) {
+    if (log_counter_ == 0) LogIterationStatsHeader(params_.verbosity_level, logger_);
+    LogIterationStats(params_.verbosity_level, stats, params_.termination_criteria, original_bound_norms_, PDLP_POINT_TYPE_AVERAGE_ITERATE, logger_);
+    if (params_.verbosity_level >= 4 && GetConvergenceInformation(stats, PDLP_POINT_TYPE_AVERAGE_ITERATE) != nullptr)
+      LogIterationStats(params_.verbosity_level, stats, params_.termination_criteria, original_bound_norms_, PDLP_POINT_TYPE_CURRENT_ITERATE, logger_);
+    time_of_last_log_ = now;
+    if (++log_counter_ >= kLogEvery) log_counter_ = 0;
+  }
+  if (callback_) {
+    PdlpIterationCallbackInfo info{PDLP_ITERATION_TYPE_NORMAL, &params_.termination_criteria, &stats, original_bound_norms_};
+    callback_(info);
+  }
+  if (const auto t = CheckIterateTerminationCriteria(params_.termination_criteria, stats, original_bound_norms_, force_numerical); t.has_value()) return t;
+  return CheckSimpleTerminationCriteria(params_.termination_criteria, full_stats, interrupt);
+}
+
+// pdhg.cc:2216-2244 + 329-342. Downloads the chosen point (still scaled).
+SolverResultCpp DeviceSolve::PickSolutionAndConstructSolverResult(const double* avg_x, const double* avg_y, const PdlpIterationStats& stats, int reason,
+                                                                  int output_type, SolveLogCpp log) {
+  const double *px = avg_x, *py = avg_y;
+  switch (output_type) {
+    case PDLP_POINT_TYPE_CURRENT_ITERATE: px = X(); py = Y(); break;
+    case PDLP_POINT_TYPE_ITERATE_DIFFERENCE: px = delta_x_; py = delta_y_; break;
+    case PDLP_POINT_TYPE_AVERAGE_ITERATE:
+    case PDLP_POINT_TYPE_PRESOLVER_SOLUTION: break;
+    default: output_type = PDLP_POINT_TYPE_AVERAGE_ITERATE; break;
+  }
+  // keep the chosen point on the device in tmp vectors for the unscaling step
+  D.CopyD2D(P.tmp_n(1), px, P.n());
+  D.CopyD2D(P.tmp_m(1), py, P.m());
+  log.iteration_count = stats.iteration_number;
+  log.termination_reason = reason;
+  log.solution_type = output_type;
+  log.solve_time_sec = stats.cumulative_time_sec;
+  log.solution_stats = stats;
+  log.has_solution_stats = true;
+  SolverResultCpp r;
+  r.solve_log = std::move(log);
+  return r;
+}
+
+// pdhg.cc:1728-1818 (no presolve); the chosen scaled point is in tmp_n(1)/tmp_m(1).
+SolverResultCpp DeviceSolve::ConstructOriginalSolverResult(SolverResultCpp result) {
+  double* x = P.tmp_n(1);
+  double* y = P.tmp_m(1);
+  const int reason = result.solve_log.termination_reason;
+  const bool use_zero_primal_objective = reason == PDLP_TERMINATION_REASON_PRIMAL_INFEASIBLE;
+  if (reason == PDLP_TERMINATION_REASON_DUAL_INFEASIBLE) D.ClampPrimal(x, P.lv(), P.uv(), true, P.n());
+  if (reason == PDLP_TERMINATION_REASON_PRIMAL_INFEASIBLE) D.ClampDual(y, P.lc(), P.uc(), P.m());
+  double* rc = P.tmp_n(2);
+  P.ReducedCosts(x, y, use_zero_primal_objective, rc);
+  D.Mul(x, dc_, P.n());
+  D.Mul(y, dr_, P.m());
+  D.Div(rc, dc_, P.n());
+  result.primal_solution.resize(P.n());
+  result.dual_solution.resize(P.m());
+  result.reduced_costs.resize(P.n());
+  P.DownloadPrimal(result.primal_solution.data(), x);
+  P.DownloadDual(result.dual_solution.data(), y);
+  P.DownloadPrimal(result.reduced_costs.data(), rc);
+  if (callback_) {
+    PdlpIterationCallbackInfo info{PDLP_ITERATION_TYPE_NORMAL_TERMINATION, &params_.termination_criteria, &result.solve_log.solution_stats, original_bound_norms_};
+    callback_(info);
+  }
+  if (params_.verbosity_level >= 1) {
+    logger_.Log(Fmt("Termination reason: %d", result.solve_log.termination_reason));
+    logger_.Log(Fmt("Solution point type: %d", result.solve_log.solution_type));
+    logger_.Log("Final solution stats:");
+    LogIterationStatsHeader(params_.verbosity_level, logger_);
+    LogIterationStats(params_.verbosity_level, result.solve_log.solution_stats, params_.termination_criteria, original_bound_norms_,
+                      result.solve_log.solution_type, logger_);
+    const PdlpConvergenceInformation* ci = GetConvergenceInformation(result.solve_log.solution_stats, result.solve_log.solution_type);
+    if (ci != nullptr && std::isfinite(ci->corrected_dual_objective)) logger_.Log(Fmt("Dual objective after infeasibility correction: %g", ci->corrected_dual_objective));
+  }
+  return result;
+}
+
+// pdhg.cc:2360-2435
+std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bool force_numerical, const volatile int32_t* interrupt, SolveLogCpp& log) {
+  const int cycle = iterations_completed_ % params_.major_iteration_frequency;
+  const bool is_major = cycle == 0 && iterations_completed_ > 0;
+  const int restart = force_numerical ? PDLP_RESTART_CHOICE_NO_RESTART : ChooseRestartToApply(is_major);
+  PdlpIterationStats stats = CreateSimpleIterationStats(restart);
+  const PdlpIterationStats full_work_stats = stats;
+  const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_work_stats, interrupt);
+  const bool check_termination = cycle % params_.termination_check_frequency == 0 || simple.has_value() || force_numerical;
+  if (check_termination) {
+    const double* avg_x = PrimalAverage();
+    const double* avg_y = DualAverage();
+    const auto maybe = UpdateIterationStatsAndCheckTermination(force_numerical, interrupt, full_work_stats, stats);
+    if (params_.record_iteration_stats) log.iteration_stats.push_back(stats);
+    if (maybe.has_value()) return PickSolutionAndConstructSolverResult(avg_x, avg_y, stats, maybe->reason, maybe->type, std::move(log));
+  } else if (params_.record_iteration_stats) {
+    log.iteration_stats.push_back(stats);
+  }
+  ApplyRestartChoice(restart);
+  return std::nullopt;
+}
+
+// Smallest k' > k at which MajorIterationAndTerminationCheck does something.
+int DeviceSolve::NextCheckpoint(int k) const {
+  const PdlpTerminationCriteria& tc = params_.termination_criteria;
+  if (params_.record_iteration_stats) return k + 1;
+  const int major = params_.major_iteration_frequency, check = params_.termination_check_frequency;
+  int best = std::numeric_limits<int>::max();
+  auto consider = [&](int64_t v) { if (v > k && v < best) best = static_cast<int>(std::min<int64_t>(v, std::numeric_limits<int>::max())); };
+  consider((static_cast<int64_t>(k) / major + 1) * major);  // next major iteration (also a termination check)
+  {  // next termination check inside the current major cycle
+    const int cyc = k % major;
+    const int next_cyc = (cyc / check + 1) * check;
+    if (next_cyc < major) consider(static_cast<int64_t>(k) - cyc + next_cyc);
+  }
+  consider(tc.iteration_limit);
+  if (params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
+    // artificial restart (pdhg.cc:2120-2130): first k' with terms + (k'-k) >= k'/2
+    const int terms = avg_x_terms_;
+    for (int64_t j = 1;; ++j) {
+      if (terms + j >= (static_cast<int64_t>(k) + j) / 2) { consider(static_cast<int64_t>(k) + j); break; }
+      if (k + j >= best) break;
+    }
+  }
+  // time limit / interrupt are polled at checkpoints: keep them close.
+  if (std::isfinite(tc.time_sec_limit)) consider(static_cast<int64_t>(k) + 32);
+  return best;
+}
+
+DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* interrupt) {
+  hs_.iterations_completed = k;
+  hs_.num_rejected_steps = num_rejected_steps_;
+  hs_.inner_iterations = 0;
+  hs_.halt = kHaltNone;
+  int k_stop = NextCheckpoint(k);
+  if (interrupt != nullptr) k_stop = std::min(k_stop, k + 32);
+  hs_.k_stop = k_stop;
+  hs_.kkt_pass_limit = params_.termination_criteria.kkt_matrix_pass_limit;
+  hs_.avg_weight_sum = avg_x_weight_;
+  hs_.avg_num_terms = avg_x_terms_;
+  hs_.pending_ratio = 0.0;
+  PushState();
+  WallTimer t;
+  for (;;) {
+    const int remaining = std::max(1, hs_.k_stop - hs_.iterations_completed);
+    D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining + 1, 4096));
+    D.DownloadState(hs_, buf_.state);
+    if (hs_.halt != kHaltNone) break;
+  }
+  D.FlushAverages(buf_);
+  D.DownloadState(hs_, buf_.state);
+  device_time_sec_ += t.Get();
+  if (hs_.iterations_completed > k) MaterializeDeltas();
+  avg_x_weight_ = avg_y_weight_ = hs_.avg_weight_sum;
+  avg_x_terms_ = avg_y_terms_ = hs_.avg_num_terms;
+  num_rejected_steps_ = hs_.num_rejected_steps;
+  iterations_completed_ = hs_.iterations_completed;
+  if (hs_.halt == kHaltCheckpoint) return Outcome::kSuccessful;
+  // kForceNumericalTermination (pdhg.cc:2562-2587, 2653-2662)
+  if (params_.verbosity_level >= 2 && hs_.halt != kHaltInnerLimit)
+    logger_.Log(Fmt("Forced numerical termination at iteration %d with primal delta squared norm %g dual delta squared norm %g primal weight %g",
+                    iterations_completed_, hs_.last_dx2, hs_.last_dy2, hs_.primal_weight));
+  if (hs_.halt == kHaltInnerLimit) logger_.Log(Fmt("WARNING: Inner iteration limit reached at iteration %d", iterations_completed_));
+  if (hs_.halt == kHaltZeroMovement || hs_.halt == kHaltInnerLimit) ResetAverageToCurrent();
+  // the reference's outer loop still increments iterations_completed_
+  iterations_completed_ += 1;
+  return Outcome::kForceNumericalTermination;
+}
+
+// pdhg.cc:2463-2556, host-driven (one sync per inner step).
+DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
+  Outcome outcome = Outcome::kSuccessful;
+  const int64_t n = P.n(), m = P.m();
+  const double omega = hs_.primal_weight;
+  const double primal_step_size = hs_.step_size / omega;
+  double* x_next = buf_.x[hs_.cand];
+  double* y_next = buf_.y[hs_.cand];
+  double* kty_next = buf_.kty[hs_.cand];
+  D.PrimalStep(X(), Kty(), P.c(), P.q(), P.lv(), P.uv(), primal_step_size, x_next, n);
+  const double dilating = 1 + (params_.malitsky_pock_step_size_interpolation * (std::sqrt(1 + ratio_last_two_step_sizes_) - 1));
+  double new_primal_step_size = primal_step_size * dilating;
+  const double downscaling = params_.malitsky_pock_step_size_downscaling_factor;
+  const double contraction = params_.malitsky_pock_linesearch_contraction_factor;
+  const double dual_weight = omega * omega;
+  int inner_iterations = 0;
+  P.Kx(x_next, kx_next_);
+  for (bool accepted = false; !accepted; ++inner_iterations) {
+    if (inner_iterations >= 60) {
+      logger_.Log(Fmt("WARNING: Inner iteration limit reached at iteration %d", iterations_completed_));
+      ResetAverageToCurrent();
+      outcome = Outcome::kForceNumericalTermination;
+      break;
+    }
+    const double new_ratio = new_primal_step_size / primal_step_size;
+    D.DualStepFromProducts(Y(), kx_cur_, kx_next_, P.lc(), P.uc(), dual_weight * new_primal_step_size, new_ratio, y_next, m);
+    P.KTy(y_next, kty_next);
+    const double delta_dual_norm = std::sqrt(D.SumSqDiff(y_next, Y(), m));
+    const double delta_dual_prod_norm = std::sqrt(D.SumSqDiff(Kty(), kty_next, n));
+    if (omega * new_primal_step_size * delta_dual_prod_norm <= contraction * delta_dual_norm) {
+      hs_.step_size = new_primal_step_size * omega;
+      ratio_last_two_step_sizes_ = new_ratio;
+      if (!PrimalAvgHasWeight()) AverageAdd(true, X(), new_primal_step_size * new_ratio);
+      const double dx2 = D.SumSqDiff(x_next, X(), n);
+      const double dy2 = delta_dual_norm * delta_dual_norm;
+      const int old_prev = hs_.prev;
+      hs_.prev = hs_.cur;
+      hs_.cur = hs_.cand;
+      hs_.cand = old_prev;
+      std::swap(kx_cur_, kx_next_);
+      MaterializeDeltas();
+      AverageAdd(true, X(), new_primal_step_size);
+      AverageAdd(false, Y(), new_primal_step_size);
+      const double movement = (0.5 * omega * dx2) + (0.5 / omega) * dy2;
+      if (movement == 0.0 || movement > 1.0e100) {
+        if (params_.verbosity_level >= 2)
+          logger_.Log(Fmt("Forced numerical termination at iteration %d with primal delta squared norm %g dual delta squared norm %g primal weight %g",
+                          iterations_completed_, dx2, dy2, omega));
+        if (movement == 0.0) ResetAverageToCurrent();
+        outcome = Outcome::kForceNumericalTermination;
+      }
+      break;
+    } else {
+      new_primal_step_size = downscaling * new_primal_step_size;
+    }
+  }
+  num_rejected_steps_ += inner_iterations;
+  iterations_completed_ += 1;
+  return outcome;
+}
+
+// pdhg.cc:3017-3092
+SolverResultCpp DeviceSolve::Solve(const volatile int32_t* interrupt_solve, SolveLogCpp solve_log) {
+  preprocessing_time_sec_ = solve_log.preprocessing_time_sec;
+  timer_.Start();
+  D.CopyD2D(x0_, X(), P.n());
+  D.CopyD2D(y0_, Y(), P.m());
+  ratio_last_two_step_sizes_ = 1;
+  SetCurrentPrimalAndDualProducts();
+  bool force_numerical = false;
+  num_rejected_steps_ = 0;
+  iterations_completed_ = 0;
+  const bool device_loop = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE;
+  for (;;) {
+    auto maybe = MajorIterationAndTerminationCheck(force_numerical, interrupt_solve, solve_log);
+    if (maybe.has_value()) {
+      maybe->solve_log.gpu_kernel_launches = D.launches();
+      maybe->solve_log.device_iteration_time_sec = device_time_sec_;
+      return std::move(*maybe);
+    }
+    const Outcome outcome = device_loop ? RunDeviceSteps(iterations_completed_, interrupt_solve) : TakeMalitskyPockStep();
+    if (outcome == Outcome::kForceNumericalTermination) force_numerical = true;
+  }
+}
+
+void DeviceSolve::LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) const {  // pdhg.cc:1341-1399
+  logger_.Log(Fmt("There are %lld variables, %lld constraints, and %lld constraint matrix nonzeros.", (long long)s.num_variables,
+                  (long long)s.num_constraints, (long long)s.constraint_matrix_num_nonzeros));
+  if (s.constraint_matrix_num_nonzeros > 0) {
+    logger_.Log(Fmt("Absolute values of nonzero constraint matrix elements: largest=%f, smallest=%f, avg=%f", s.constraint_matrix_abs_max,
+                    s.constraint_matrix_abs_min, s.constraint_matrix_abs_avg));
+    logger_.Log(Fmt("Constraint matrix, infinity norm: max(row & col)=%f, min_col=%f, min_row=%f", s.constraint_matrix_abs_max,
+                    s.constraint_matrix_col_min_l_inf_norm, s.constraint_matrix_row_min_l_inf_norm));
+    logger_.Log(Fmt("Constraint bounds statistics (max absolute value per row): largest=%f, smallest=%f, avg=%f, l2_norm=%f", s.combined_bounds_max,
+                    s.combined_bounds_min, s.combined_bounds_avg, s.combined_bounds_l2_norm));
+  }
+  if (!P.is_lp()) {
+    logger_.Log(Fmt("There are %lld nonzero diagonal coefficients in the objective matrix.", (long long)s.objective_matrix_num_nonzeros));
+    logger_.Log(Fmt("Absolute values of nonzero objective matrix elements: largest=%f, smallest=%f, avg=%f", s.objective_matrix_abs_max,
+                    s.objective_matrix_abs_min, s.objective_matrix_abs_avg));
+  }
+  logger_.Log(Fmt("Absolute values of objective vector elements: largest=%f, smallest=%f, avg=%f, l2_norm=%f", s.objective_vector_abs_max,
+                  s.objective_vector_abs_min, s.objective_vector_abs_avg, s.objective_vector_l2_norm));
+  logger_.Log(Fmt("Gaps between variable upper and lower bounds: #finite=%lld of %lld, largest=%f, smallest=%f, avg=%f",
+                  (long long)s.variable_bound_gaps_num_finite, (long long)s.num_variables, s.variable_bound_gaps_max, s.variable_bound_gaps_min,
+                  s.variable_bound_gaps_avg));
+}
+
+// pdhg.cc:1039-1221
+SolverResultCpp DeviceSolve::PreprocessAndSolve(std::optional<InitialSolution> initial_solution, const volatile int32_t* interrupt_solve,
+                                                const std::string* name) {
+  WallTimer timer;
+  SolveLogCpp solve_log;
+  if (params_.verbosity_level >= 1) logger_.Log("Solving with PDLP parameters: (PdlpParams POD)");
+  if (name != nullptr) solve_log.instance_name = *name;
+  solve_log.params = params_;
+  const int64_t n = P.n(), m = P.m();
+  P.ReplaceLargeConstraintBoundsWithInfinity(params_.infinite_constraint_bound_threshold);
+  if (!P.HasValidBounds())
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
+                             "The input problem has invalid bounds (after replacing large constraint bounds with infinity): some variable or "
+                             "constraint has lower_bound > upper_bound, lower_bound == inf, or upper_bound == -inf.", logger_);
+  if (!P.ObjectiveMatrixIsNonNegative())
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
+                             "The objective is not convex (i.e., the objective matrix contains negative or NAN entries).", logger_);
+  solve_log.original_stats = P.ComputeStats();
+  solve_log.has_original_stats = true;
+  if (auto r = CheckProblemStats(solve_log.original_stats, P.objective_offset(), params_.presolve_use_glop != 0, logger_); r.has_value()) return std::move(*r);
+
+  // iterate buffers
+  buf_.n = n;
+  buf_.m = m;
+  for (int k = 0; k < 3; ++k) { buf_.x[k] = P.NewPrimal(); buf_.y[k] = P.NewDual(); buf_.kty[k] = P.NewPrimal(); }
+  buf_.x_tilde = P.NewPrimal();
+  buf_.avg_x = P.NewPrimal();
+  buf_.avg_y = P.NewDual();
+  x0_ = P.NewPrimal();
+  y0_ = P.NewDual();
+  delta_x_ = P.NewPrimal();
+  delta_y_ = P.NewDual();
+  if (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE) { kx_cur_ = P.NewDual(); kx_next_ = P.NewDual(); }
+  buf_.c = P.c(); buf_.q = P.q(); buf_.lv = P.lv(); buf_.uv = P.uv(); buf_.lc = P.lc(); buf_.uc = P.uc();
+  buf_.state = D.AllocState();
+  std::memset(&hs_, 0, sizeof(hs_));
+  hs_.cur = 0; hs_.prev = 1; hs_.cand = 2;
+
+  if (initial_solution.has_value()) {  // CheckInitialSolution, pdhg.cc:985-1037
+    const double kBig = 1e50;
+    auto err = [&](const std::string& msg) { return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_INITIAL_SOLUTION, msg, logger_); };
+    if (static_cast<int64_t>(initial_solution->primal.size()) != n)
+      return err(Fmt("Initial primal solution has size %lld which differs from problem primal size %lld", (long long)initial_solution->primal.size(), (long long)n));
+    P.UploadPrimal(X(), initial_solution->primal.data());
+    if (std::isnan(std::sqrt(D.SumSq(X(), n)))) return err("Initial primal solution has a NAN.");
+    if (const double v = D.LInf(X(), n); v > kBig) return err("Initial primal solution has an entry with absolute value " + G(v) + " which exceeds limit of " + G(kBig));
+    if (static_cast<int64_t>(initial_solution->dual.size()) != m)
+      return err(Fmt("Initial dual solution has size %lld which differs from problem dual size %lld", (long long)initial_solution->dual.size(), (long long)m));
+    P.UploadDual(Y(), initial_solution->dual.data());
+    if (std::isnan(std::sqrt(D.SumSq(Y(), m)))) return err("Initial dual solution has a NAN.");
+    if (const double v = D.LInf(Y(), m); v > kBig) return err("Initial dual solution has an entry with absolute value " + G(v) + " which exceeds limit of " + G(kBig));
+  } else {
+    D.Fill(X(), 0.0, n);
+    D.Fill(Y(), 0.0, m);
+  }
+  original_bound_norms_ = BoundNormsFromProblemStats(solve_log.original_stats);
+  if (params_.verbosity_level >= 1) { logger_.Log("Problem stats before rescaling:"); LogQuadraticProgramStats(solve_log.original_stats); }
+
+  D.ClampPrimal(X(), P.lv(), P.uv(), false, n);  // ProjectToPrimalVariableBounds, pdhg.cc:1164
+  D.ClampDual(Y(), P.lc(), P.uc(), m);
+
+  // ComputeAndApplyRescaling, pdhg.cc:1325-1339
+  P.ApplyRescaling(params_.l_inf_ruiz_iterations, params_.l2_norm_rescaling != 0, &dr_, &dc_);
+  D.Div(X(), dc_, n);
+  D.Div(Y(), dr_, m);
+  solve_log.preprocessed_stats = P.ComputeStats();
+  solve_log.has_preprocessed_stats = true;
+  if (params_.verbosity_level >= 1) { logger_.Log("Problem stats after rescaling:"); LogQuadraticProgramStats(solve_log.preprocessed_stats); }
+
+  double step_size;
+  if (params_.linesearch_rule == PDLP_CONSTANT_STEP_SIZE_RULE) {
+    // EstimateMaximumSingularValueOfConstraintMatrix (sou.cc:559-699): power
+    // iteration on K^T K with a counter-based Gaussian start vector.
+    double* v = P.tmp_n(0);
+    double* w = P.tmp_m(0);
+    double* nv = P.tmp_n(1);
+    std::vector<double> start(n);
+    {
+      // deterministic N(0,1) start (the reference seeds std::mt19937(1); its
+      // stream is unpinned by its tests beyond the 0.2 relative error target)
+      uint64_t s = 0x9E3779B97F4A7C15ull;
+      for (int64_t i = 0; i < n; ++i) {
+        auto next = [&] { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (s >> 11) * (1.0 / 9007199254740992.0); };
+        const double u1 = std::max(next(), 1e-300), u2 = next();
+        start[i] = std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+      }
+    }
+    D.Upload(v, start.data(), n);
+    auto normalize = [&](double* vec) { const double nrm = std::sqrt(D.SumSq(vec, n)); if (nrm != 0.0) { D.Fill(P.tmp_n(2), 1.0 / nrm, n); D.Mul(vec, P.tmp_n(2), n); } };
+    normalize(v);
+    const double desired_relative_error = 0.2, failure_probability = 0.0005;
+    const double epsilon = 1.0 - Sq(1.0 - desired_relative_error);
+    auto failure = [&](int k) {
+      if (k < 2 || epsilon <= 0.0) return 1.0;
+      return std::min(0.824, 0.354 / std::sqrt(epsilon * (k - 1))) * std::sqrt(static_cast<double>(n)) * std::pow(1.0 - epsilon, k - 0.5);
+    };
+    double eigenvalue = 0.0;
+    int iters = 0;
+    while (failure(iters) > failure_probability) {
+      P.Kx(v, w);
+      P.KTy(w, nv);
+      eigenvalue = D.Dot(v, nv, n);
+      D.CopyD2D(v, nv, n);
+      ++iters;
+      normalize(v);
+    }
+    const double upper = std::sqrt(eigenvalue) / (1.0 - desired_relative_error);
+    step_size = upper > 0.0 ? 1.0 / upper : 1.0;
+  } else {
+    step_size = 1.0 / std::max(1.0e-20, solve_log.preprocessed_stats.constraint_matrix_abs_max);  // pdhg.cc:1203-1207
+  }
+  step_size *= params_.initial_step_size_scaling;
+  double primal_weight = 1.0;  // InitialPrimalWeight, pdhg.cc:1401-1419
+  if (params_.has_initial_primal_weight) primal_weight = params_.initial_primal_weight;
+  else if (solve_log.preprocessed_stats.objective_vector_l2_norm > 0.0 && solve_log.preprocessed_stats.combined_bounds_l2_norm > 0.0)
+    primal_weight = solve_log.preprocessed_stats.objective_vector_l2_norm / solve_log.preprocessed_stats.combined_bounds_l2_norm;
+  hs_.step_size = step_size;
+  hs_.primal_weight = primal_weight;
+  hs_.rule = params_.linesearch_rule;
+  hs_.reduction_exponent = params_.adaptive_step_size_reduction_exponent;
+  hs_.growth_exponent = params_.adaptive_step_size_growth_exponent;
+  ClearAverages();
+  solve_log.preprocessing_time_sec = timer.Get();
+  SolverResultCpp result = Solve(interrupt_solve, std::move(solve_log));
+  return ConstructOriginalSolverResult(std::move(result));
+}
+
+}  // namespace
+
+SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
+                                         const volatile int32_t* interrupt_solve, const Logger& logger, StatsCallback callback, int cuda_device) {
+  // pdhg.cc:3120-3147
+  const std::string perr = ValidateParams(params);
+  if (!perr.empty()) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "INVALID_ARGUMENT: " + perr, logger);
+  const std::string derr = ValidateDimensions(view);
+  if (!derr.empty()) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "INVALID_ARGUMENT: " + derr, logger);
+  if (view.objective_scaling_factor == 0) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "The objective scaling factor cannot be zero.", logger);
+  if (params.use_feasibility_polishing && view.objective_matrix_diagonal != nullptr)
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "use_feasibility_polishing is only implemented for linear programs.", logger);
+  if (params.use_feasibility_polishing || params.presolve_use_glop)
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER,
+                             "presolve_options.use_glop and use_feasibility_polishing are host-side features outside this library's scope.", logger);
+  if (params.num_random_projection_seeds > PDLP_MAX_RANDOM_PROJECTION_SEEDS)
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "at most 8 random_projection_seeds are supported.", logger);
+  DeviceProblem problem(view, cuda_device);
+  DeviceSolve solve(problem, params, logger, std::move(callback));
+  const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
+  return solve.PreprocessAndSolve(std::move(initial_solution), interrupt_solve, view.problem_name != nullptr ? &name : nullptr);
+}
+
+}  // namespace pdlp_b200

@@ -1,0 +1,62 @@
+// solver.h -- host C++ driver of the device PDHG solve.
+#ifndef PDLP_B200_SOLVER_H_
+#define PDLP_B200_SOLVER_H_
+
+#include <functional>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../../include/pdlp_b200.h"
+
+namespace pdlp_b200 {
+
+struct SolveLogCpp {
+  std::optional<std::string> instance_name;
+  int termination_reason = PDLP_TERMINATION_REASON_UNSPECIFIED;
+  std::optional<std::string> termination_string;
+  int iteration_count = 0;
+  double solve_time_sec = 0, preprocessing_time_sec = 0;
+  int solution_type = PDLP_POINT_TYPE_UNSPECIFIED;
+  bool has_solution_stats = false;
+  PdlpIterationStats solution_stats{};
+  bool has_original_stats = false, has_preprocessed_stats = false;
+  PdlpQuadraticProgramStats original_stats{}, preprocessed_stats{};
+  std::vector<PdlpIterationStats> iteration_stats;
+  PdlpParams params{};
+  int64_t gpu_kernel_launches = 0;
+  double device_iteration_time_sec = 0;
+};
+
+struct SolverResultCpp {
+  std::vector<double> primal_solution, dual_solution, reduced_costs;
+  SolveLogCpp solve_log;
+};
+
+struct InitialSolution {
+  std::vector<double> primal, dual;
+};
+
+struct Logger {
+  PdlpMessageCallback cb = nullptr;
+  void* user = nullptr;
+  void Log(const std::string& s) const;
+};
+
+using StatsCallback = std::function<void(const PdlpIterationCallbackInfo&)>;
+
+// params.cc
+void SetDefaultParams(PdlpParams* p);
+std::string ValidateParams(const PdlpParams& p);  // "" if valid, else the reference's message
+
+// PrimalDualHybridGradient (pdhg.cc:3107-3152) on the CUDA device. Throws
+// std::runtime_error only for CUDA / device failures; every solver-level
+// outcome (including invalid input) is reported through the returned log.
+SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params,
+                                         std::optional<InitialSolution> initial_solution,
+                                         const volatile int32_t* interrupt_solve, const Logger& logger,
+                                         StatsCallback callback, int cuda_device);
+
+}  // namespace pdlp_b200
+
+#endif  // PDLP_B200_SOLVER_H_
