@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- PDHG iteration throughput of the B200 PDLP hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config c2|c3|c4|c5] [--scale S]
+
+One "step" is ONE PDHG iteration (SpMV pair + projections + step-size rule +
+averaging, plus its share of the restart / termination work of the solver
+loop) on the synthetic LP of BASELINE.json configs[1] ("c2": 1M x 2M, 20M nnz,
+fp64). The timed region is iterations W .. W+K of a real solve whose problem
+and iterates are resident in HBM (session API of the C ABI), timed with CUDA
+events on the launching stream; `e2e` is a full solve to eps_optimal 1e-4
+through the reference-facing C-ABI call with HOST buffers (upload, device
+build, preprocessing, solve, download all inside the timed region).
+
+`--impl reference` times the CPU restatement of reference PDLP (oracle/, the
+one place besides tests/smoke where oracle/ may run) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 3 + k and s[3 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()), default=None),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def make_params(pdlp, eps, iteration_limit=None, num_threads=1):
+    p = pdlp.PrimalDualHybridGradientParams()
+    p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = eps
+    p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = eps
+    if iteration_limit is not None:
+        p.termination_criteria.iteration_limit = int(iteration_limit)
+    p.num_threads = num_threads
+    return p
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def workload_name(args):
+    return args.config + ("" if args.scale == 1.0 else "@scale=%g" % args.scale)
+
+
+def problem_bytes(qp):
+    k = qp.constraint_matrix
+    return int(k.nnz * 16 + (k.shape[1] + 1) * 8 + 8 * (4 * k.shape[1] + 2 * k.shape[0]) + (0 if qp.objective_matrix is None else 8 * k.shape[1]))
+
+
+def cpu_reference_run(qp, pdlp, warmup, steps, budget_s):
+    """Times the CPU restatement of reference PDLP (all host cores) on a bounded
+    number of PDHG iterations of the same problem. Returns (its_per_s, info)."""
+    from oracle import pdlp_oracle
+    ob = pdlp_oracle.backend()
+    cores = host_cores()
+    # pilot: a few iterations to size the sample
+    t0 = time.time()
+    r = ob.primal_dual_hybrid_gradient(qp, make_params(pdlp, 0.0, max(3, warmup), cores))
+    pilot_wall = time.time() - t0
+    it_time = max(1e-9, (r.solve_log.solve_time_sec - r.solve_log.preprocessing_time_sec) / max(1, r.solve_log.iteration_count))
+    pre = r.solve_log.preprocessing_time_sec
+    iters = int(max(8, min(steps, (budget_s - pre) / it_time)))
+    r = ob.primal_dual_hybrid_gradient(qp, make_params(pdlp, 0.0, iters, cores))
+    loop_s = r.solve_log.solve_time_sec - r.solve_log.preprocessing_time_sec
+    value = r.solve_log.iteration_count / loop_s
+    info = {"iterations": r.solve_log.iteration_count, "loop_s": loop_s, "preprocessing_s": r.solve_log.preprocessing_time_sec,
+            "pilot_wall_s": pilot_wall, "cores": cores}
+    return value, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from ortools_b200 import pdlp, synthetic
+    from oracle import pdlp_oracle
+    pdlp_oracle.build()
+    qp, _ = synthetic.CONFIGS[args.config](scale=args.scale)
+    k = qp.constraint_matrix
+    t0 = time.time()
+    value, info = cpu_reference_run(qp, pdlp, args.warmup, args.steps, args.cpu_budget)
+    sample = "%d PDHG iterations of the full %s problem after %d warm-up iterations (eps=0, default params), its/s = iterations / (solve_time - preprocessing_time)" % (
+        info["iterations"], workload_name(args), max(3, args.warmup))
+    line = {
+        "impl": "reference", "metric": "pdhg_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows": int(k.shape[0]), "cols": int(k.shape[1]), "nnz": int(k.nnz),
+                   "step": "one PDHG iteration", "params": "reference defaults"},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": info["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    from ortools_b200 import pdlp, synthetic
+
+    be = pdlp.backend()
+    if be.device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device; libpdlp_b200.so has no CPU fallback")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    be.set_default_device(local_rank)
+
+    t0 = time.time()
+    qp, info = synthetic.CONFIGS[args.config](scale=args.scale)
+    k = qp.constraint_matrix
+    m, n, nnz = int(k.shape[0]), int(k.shape[1]), int(k.nnz)
+    log("[bench] generated %s: %d x %d, nnz %d in %.1fs" % (workload_name(args), m, n, nnz, time.time() - t0))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident leg: iterations W .. W+K of a real solve --------------------------
+    t0 = time.time()
+    if world > 1:
+        from ortools_b200 import distributed
+        sess = distributed.session(qp, make_params(pdlp, 0.0), rank=rank, world_size=world, cuda_device=local_rank)
+    else:
+        sess = be.session(qp, make_params(pdlp, 0.0), cuda_device=local_rank)
+    setup_s = time.time() - t0
+    log("[bench] session create (upload + device build + rescaling): %.2fs" % setup_s)
+    st0 = sess.advance(args.warmup)
+    sess.enable_timing(True, 4)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        w0 = time.time()
+        st1 = sess.advance(args.warmup + args.steps)
+        barrier()
+        wall_ms = (time.time() - w0) * 1000.0
+    if st1.terminated:
+        log("[bench] WARNING: solve terminated inside the timed region (reason %d)" % st1.termination_reason)
+    iters = st1.iterations_completed - st0.iterations_completed
+    dev_ms = st1.device_total_ms - st0.device_total_ms
+    step_ms = st1.device_step_ms - st0.device_step_ms
+    if world > 1:
+        t = torch.tensor([dev_ms, step_ms, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, step_ms, wall_ms = (float(v) for v in t.tolist())
+    launches = st1.gpu_kernel_launches - st0.gpu_kernel_launches
+    value = iters / (dev_ms / 1000.0)
+    clk = clocks.summary()
+
+    # ---- roofline of the dominant kernel (live CUDA-event samples) -------------------
+    peak, peak_src = measured_peak_gbs()
+    names = ["k_primal_step", "k_sell<dot>+DualEpi (K x~, dual update)", "k_sell<dot>+KtyEpi (K^T y', nonlinearity)", "k_step_decide"]
+    kern = []
+    for i in range(4):
+        cnt = st1.kernel_samples[i]
+        avg_ms = st1.kernel_ms[i] / cnt if cnt else None
+        kern.append({"kernel": names[i], "avg_ms": avg_ms, "samples": int(cnt), "algorithmic_bytes": st1.kernel_algorithmic_bytes[i],
+                     "gbs": (st1.kernel_algorithmic_bytes[i] / (avg_ms * 1e-3) / 1e9) if avg_ms else None})
+    dom = max(range(3), key=lambda i: kern[i]["avg_ms"] or 0.0)
+    roofline = {"bound": "hbm", "kernel": kern[dom]["kernel"], "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": (kern[dom]["gbs"] / peak) if kern[dom]["gbs"] else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kern[dom]["algorithmic_bytes"], "avg_launch_ms": kern[dom]["avg_ms"],
+                "kernel_share_of_step": (kern[dom]["avg_ms"] / sum(x["avg_ms"] or 0 for x in kern)) if kern[dom]["avg_ms"] else None}
+    q_bytes = 0 if qp.objective_matrix is None else 8 * n
+    iter_bytes = 2 * nnz * 12 + 4 * (m + 1) + 4 * (n + 1) + 8 * (14 * n + 7 * m) + q_bytes
+    iteration_roofline = {"algorithmic_bytes_per_iteration": iter_bytes, "achieved_gbs": iter_bytes * value / 1e9,
+                          "frac_of_peak": iter_bytes * value / 1e9 / peak,
+                          "step_loop_only_frac": (iter_bytes * (iters / (step_ms / 1000.0)) / 1e9 / peak) if step_ms > 0 else None}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get(args.config, {}).get(str(dom))
+        except Exception:
+            pass
+    sess.close()
+
+    line = {
+        "metric": "pdhg_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / max(1, iters), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows": m, "cols": n, "nnz": nnz, "step": "one PDHG iteration (restart/termination work included)",
+                   "params": "reference defaults, eps_optimal=0 in the resident leg", "l2": "inputs larger than L2 (matrix copies %.0f MB)" % (2 * nnz * 12 / 1e6),
+                   "parallelism": "1 gpu" if world == 1 else "row-sharded x%d" % world},
+        "iterations_timed": iters, "wall_ms_timed": wall_ms, "device_step_loop_ms": step_ms, "setup_s": setup_s,
+        "rejected_steps": st1.num_rejected_steps - st0.num_rejected_steps,
+        "roofline": roofline, "iteration_roofline": iteration_roofline, "kernels": kern,
+        "gpu_launches": int(launches), "clocks": clk,
+    }
+
+    if rank == 0 and not args.no_e2e:
+        # ---- e2e: full solve to 1e-4 through the C-ABI call with host buffers ---------
+        params = make_params(pdlp, args.eps, iteration_limit=args.e2e_iteration_limit)
+        barrier() if world == 1 else None
+        t0 = time.time()
+        if world == 1:
+            res = be.primal_dual_hybrid_gradient(qp, params)
+        else:
+            res = None
+        if res is not None:
+            e2e_s = time.time() - t0
+            lg = res.solve_log
+            line["e2e"] = {"value": lg.iteration_count / e2e_s, "unit": "iterations/s",
+                           "h2d_bytes_per_step": problem_bytes(qp) / max(1, lg.iteration_count),
+                           "d2h_bytes_per_step": 8 * (2 * n + m) / max(1, lg.iteration_count),
+                           "h2d_bytes_per_solve": problem_bytes(qp), "d2h_bytes_per_solve": 8 * (2 * n + m),
+                           "iterations": lg.iteration_count, "wall_s": e2e_s, "termination_reason": pdlp.TerminationReason.Name(lg.termination_reason),
+                           "eps_optimal": args.eps, "preprocessing_s": lg.preprocessing_time_sec, "time_to_tolerance_s": e2e_s,
+                           "gpu_launches": int(lg.gpu_kernel_launches)}
+            ci = [c for c in lg.solution_stats.convergence_information if c.candidate_type == lg.solution_type]
+            if ci:
+                line["e2e"]["primal_objective"] = ci[0].primal_objective
+                line["e2e"]["dual_objective"] = ci[0].dual_objective
+            if "objective" in info:
+                line["e2e"]["planted_objective"] = info["objective"]
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import pdlp_oracle
+        pdlp_oracle.build()
+        v, ci = cpu_reference_run(qp, pdlp, 3, 64, args.cpu_budget)
+        line["cpu_baseline"] = {"value": v, "unit": "iterations/s", "cores": ci["cores"], "kind": "port",
+                                "sample": "%d PDHG iterations of the full %s problem (eps=0, default params; %.1fs loop, %.1fs preprocessing)" % (
+                                    ci["iterations"], workload_name(args), ci["loop_s"], ci["preprocessing_s"])}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--eps", type=float, default=1e-4)
+    ap.add_argument("--e2e-iteration-limit", type=int, default=200000)
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU PDHG loop for the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        if args.cpu_budget == 25.0:
+            args.cpu_budget = 90.0
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

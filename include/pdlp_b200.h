@@ -307,6 +307,53 @@ int32_t pdlp_b200_primal_dual_hybrid_gradient(
     PdlpResult* result);
 void pdlp_b200_result_free(PdlpResult* result);
 
+/* ---- resident solve sessions ---------------------------------------------- *
+ * The same solve, split so that the problem and the iterates stay resident in
+ * HBM between calls: create = PreprocessSolver::PreprocessAndSolve up to the
+ * first iteration (pdhg.cc:1039-1221: upload, validation, stats, Ruiz + L2
+ * rescaling, step-size / primal-weight initialisation); advance = the loop of
+ * Solver::Solve (pdhg.cc:3042-3091) until `target_iterations` iterations are
+ * completed or a termination criterion fires; finish = result construction
+ * (pdhg.cc:1728-1818). Stopping and resuming does not change the iterates.
+ * Used by callers that re-solve / warm-start and by bench.py to time PDHG
+ * iterations with all inputs already on the device.                         */
+typedef struct PdlpSolveSession PdlpSolveSession;
+typedef struct PdlpSessionStatus {
+  int32_t terminated;                  /* 1 once a termination criterion fired */
+  int32_t termination_reason;
+  int32_t iterations_completed;
+  int32_t num_rejected_steps;
+  double step_size, primal_weight;
+  int64_t gpu_kernel_launches;         /* cumulative, this session             */
+  double device_step_ms;               /* CUDA-event time inside the PDHG step loop (cumulative) */
+  double device_total_ms;              /* CUDA-event time of all advance calls (steps + restart /
+                                          termination work, host gaps included) */
+  /* Sampled per-kernel CUDA-event times (pdlp_b200_session_enable_timing):
+   * 0 primal step, 1 K x~ + dual epilogue, 2 K^T y' + epilogue, 3 step decision */
+  double kernel_ms[4];
+  int64_t kernel_samples[4];
+  double kernel_algorithmic_bytes[4];  /* per launch, DESIGN.md accounting      */
+} PdlpSessionStatus;
+int32_t pdlp_b200_session_create(const PdlpProblemView* qp, const PdlpParams* params,
+                                 const double* initial_primal, int64_t initial_primal_size,
+                                 const double* initial_dual, int64_t initial_dual_size,
+                                 PdlpMessageCallback message_callback,
+                                 PdlpIterationStatsCallback iteration_stats_callback,
+                                 void* user_data, int32_t cuda_device,
+                                 PdlpSolveSession** out_session);
+int32_t pdlp_b200_session_advance(PdlpSolveSession* session, int32_t target_iterations,
+                                  const volatile int32_t* interrupt_solve,
+                                  PdlpSessionStatus* out_status);
+int32_t pdlp_b200_session_enable_timing(PdlpSolveSession* session, int32_t enable,
+                                        int32_t sample_stride);
+int32_t pdlp_b200_session_status(PdlpSolveSession* session, PdlpSessionStatus* out_status);
+int32_t pdlp_b200_session_finish(PdlpSolveSession* session, PdlpResult* result);
+void pdlp_b200_session_destroy(PdlpSolveSession* session);
+
+/* CUDA device used by pdlp_b200_primal_dual_hybrid_gradient (default 0; one
+ * process per GPU sets it to its local rank).                                */
+int32_t pdlp_b200_set_default_device(int32_t cuda_device);
+
 /* ---- multi-GPU ------------------------------------ *
  * One process per GPU. Every rank passes the SAME full problem; the library
  * keeps only its contiguous block of constraint rows on its device

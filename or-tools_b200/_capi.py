@@ -221,6 +221,18 @@ class PdlpResult(C.Structure):
     ]
 
 
+class PdlpSessionStatus(C.Structure):
+    _fields_ = [
+        ("terminated", C.c_int32), ("termination_reason", C.c_int32),
+        ("iterations_completed", C.c_int32), ("num_rejected_steps", C.c_int32),
+        ("step_size", C.c_double), ("primal_weight", C.c_double),
+        ("gpu_kernel_launches", C.c_int64),
+        ("device_step_ms", C.c_double), ("device_total_ms", C.c_double),
+        ("kernel_ms", C.c_double * 4), ("kernel_samples", C.c_int64 * 4),
+        ("kernel_algorithmic_bytes", C.c_double * 4),
+    ]
+
+
 MESSAGE_CALLBACK = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
 STATS_CALLBACK = C.CFUNCTYPE(None, C.POINTER(PdlpIterationCallbackInfo), C.c_void_p)
 

@@ -18,6 +18,13 @@ struct PdlpDeviceProblem {
   std::unique_ptr<DeviceProblem> p;
   PdlpParams default_params;
 };
+struct PdlpSolveSession {
+  std::unique_ptr<SolveSession> s;
+  PdlpMessageCallback msg_cb = nullptr;
+  PdlpIterationStatsCallback stats_cb = nullptr;
+  void* user = nullptr;
+};
+static int g_default_device = 0;
 struct PdlpDistributedContext {
   int rank = 0, world = 1, device = 0;
 };
@@ -131,7 +138,7 @@ int32_t pdlp_b200_primal_dual_hybrid_gradient(const PdlpProblemView* qp, const P
   StatsCallback cb;
   if (stats_callback != nullptr) cb = [=](const PdlpIterationCallbackInfo& info) { stats_callback(&info, user_data); };
   try {
-    FillResult(PrimalDualHybridGradient(*qp, *params, std::move(init), interrupt_solve, logger, std::move(cb), 0), result);
+    FillResult(PrimalDualHybridGradient(*qp, *params, std::move(init), interrupt_solve, logger, std::move(cb), g_default_device), result);
     return PDLP_B200_STATUS_OK;
   } catch (const std::exception& e) {
     SolverResultCpp r;
@@ -148,6 +155,58 @@ void pdlp_b200_result_free(PdlpResult* r) {
   std::free(r->instance_name); std::free(r->termination_string); std::free(r->iteration_stats);
   std::memset(r, 0, sizeof(*r));
 }
+
+int32_t pdlp_b200_set_default_device(int32_t cuda_device) {
+  if (cuda_device < 0 || cuda_device >= Device::DeviceCount()) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  g_default_device = cuda_device;
+  return PDLP_B200_STATUS_OK;
+}
+
+// ---- sessions -----------------------------------------------------------------
+int32_t pdlp_b200_session_create(const PdlpProblemView* qp, const PdlpParams* params, const double* initial_primal, int64_t initial_primal_size,
+                                 const double* initial_dual, int64_t initial_dual_size, PdlpMessageCallback message_callback,
+                                 PdlpIterationStatsCallback stats_callback, void* user_data, int32_t cuda_device, PdlpSolveSession** out) {
+  if (qp == nullptr || params == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  *out = nullptr;
+  return Guard([&] {
+    auto h = std::make_unique<PdlpSolveSession>();
+    h->msg_cb = message_callback;
+    h->stats_cb = stats_callback;
+    h->user = user_data;
+    Logger logger{message_callback, user_data};
+    std::optional<InitialSolution> init;
+    if (initial_primal != nullptr || initial_dual != nullptr) {
+      init.emplace();
+      if (initial_primal != nullptr) init->primal.assign(initial_primal, initial_primal + initial_primal_size);
+      if (initial_dual != nullptr) init->dual.assign(initial_dual, initial_dual + initial_dual_size);
+    }
+    StatsCallback cb;
+    if (stats_callback != nullptr) cb = [=](const PdlpIterationCallbackInfo& info) { stats_callback(&info, user_data); };
+    h->s = SolveSession::Create(*qp, *params, std::move(init), logger, std::move(cb), cuda_device);
+    *out = h.release();
+  });
+}
+int32_t pdlp_b200_session_advance(PdlpSolveSession* h, int32_t target_iterations, const volatile int32_t* interrupt_solve, PdlpSessionStatus* out) {
+  if (h == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  return Guard([&] {
+    h->s->Advance(target_iterations, interrupt_solve);
+    if (out != nullptr) h->s->Status(out);
+  });
+}
+int32_t pdlp_b200_session_enable_timing(PdlpSolveSession* h, int32_t enable, int32_t stride) {
+  if (h == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  return Guard([&] { h->s->EnableTiming(enable != 0, stride); });
+}
+int32_t pdlp_b200_session_status(PdlpSolveSession* h, PdlpSessionStatus* out) {
+  if (h == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  return Guard([&] { h->s->Status(out); });
+}
+int32_t pdlp_b200_session_finish(PdlpSolveSession* h, PdlpResult* result) {
+  if (h == nullptr || result == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  std::memset(result, 0, sizeof(*result));
+  return Guard([&] { FillResult(h->s->Finish(), result); });
+}
+void pdlp_b200_session_destroy(PdlpSolveSession* h) { delete h; }
 
 // ---- multi-GPU (implemented in distributed.cc when NCCL is wired in) -------
 int32_t pdlp_b200_nccl_unique_id(const char*, uint8_t*) { return PDLP_B200_STATUS_BAD_ARGUMENT; }

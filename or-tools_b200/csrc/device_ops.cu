@@ -610,6 +610,8 @@ Device::~Device() {
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
   cudaFree(step_partials_);
+  for (void* e : timing_events_) cudaEventDestroy(static_cast<cudaEvent_t>(e));
+  for (auto& pr : timeline_ev_) for (void* e : pr) if (e != nullptr) cudaEventDestroy(static_cast<cudaEvent_t>(e));
   if (stream_ != nullptr) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
 }
 
@@ -1229,19 +1231,67 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   double* pd = pp + np;
   double* pt = pd + nd_main + nd_fix;
   const int32_t* halt = &b.state->halt;
+  constexpr int kMaxSamples = 64;
+  timing_attempt_idx_.clear();
+  auto ev = [&](int slot, int k) { CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timing_events_[slot * 5 + k]), STREAM)); };
   for (int it = 0; it < count; ++it) {
+    int slot = -1;
+    if (step_timing_ && it % step_timing_stride_ == 0 && static_cast<int>(timing_attempt_idx_.size()) < kMaxSamples) {
+      slot = static_cast<int>(timing_attempt_idx_.size());
+      while (static_cast<int>(timing_events_.size()) < (slot + 1) * 5) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreate(&e));
+        timing_events_.push_back(e);
+      }
+      timing_attempt_idx_.push_back(it);
+      ev(slot, 0);
+    }
     k_primal_step<<<np, kThreads, 0, STREAM>>>(p, pp);
     ++launches_;
+    if (slot >= 0) ev(slot, 1);
     if (b.m > 0) {
       launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr);
     }
+    if (slot >= 0) ev(slot, 2);
     if (b.n > 0) {
       launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr);
     }
+    if (slot >= 0) ev(slot, 3);
     k_step_decide<<<1, kThreads, 0, STREAM>>>(b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
     ++launches_;
+    if (slot >= 0) ev(slot, 4);
   }
   CUDA_OK(cudaGetLastError());
+}
+
+void Device::EnableStepTiming(bool on, int stride) {
+  step_timing_ = on;
+  step_timing_stride_ = std::max(1, stride);
+  timing_attempt_idx_.clear();
+}
+void Device::CollectStepTimings(int64_t executed_attempts) {
+  for (size_t s = 0; s < timing_attempt_idx_.size(); ++s) {
+    if (timing_attempt_idx_[s] >= executed_attempts) continue;
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(timing_events_[s * 5 + k]), static_cast<cudaEvent_t>(timing_events_[s * 5 + k + 1])));
+      step_timings_.ms[k] += ms;
+      step_timings_.samples[k] += 1;
+    }
+  }
+  timing_attempt_idx_.clear();
+}
+void Device::TimelineStart(int id) {
+  for (int k = 0; k < 2; ++k)
+    if (timeline_ev_[id][k] == nullptr) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); timeline_ev_[id][k] = e; }
+  CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timeline_ev_[id][0]), STREAM));
+}
+double Device::TimelineStopMs(int id) {
+  CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timeline_ev_[id][1]), STREAM));
+  CUDA_OK(cudaEventSynchronize(static_cast<cudaEvent_t>(timeline_ev_[id][1])));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(timeline_ev_[id][0]), static_cast<cudaEvent_t>(timeline_ev_[id][1])));
+  return ms;
 }
 
 void Device::FlushAverages(const StepBuffers& b) {

@@ -218,6 +218,20 @@ class Device {
   // Enqueues `count` attempts of the fused 3-kernel step; attempts after the
   // device sets `halt` are no-ops. Does not synchronise.
   void EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count);
+  // Per-kernel CUDA-event sampling of the step loop (bench / profiling only).
+  // While enabled, every `stride`-th attempt of an EnqueueSteps batch is
+  // bracketed by events on the launching stream; CollectStepTimings (call it
+  // after the batch has been synchronised) adds the samples whose attempt
+  // index is < `executed_attempts` (later ones were halted no-ops).
+  // Kernel classes: 0 primal step, 1 K x~ + dual epilogue (+fix-up),
+  // 2 K^T y' + nonlinearity epilogue (+fix-up), 3 step decision.
+  struct StepTimings { double ms[4] = {0, 0, 0, 0}; int64_t samples[4] = {0, 0, 0, 0}; };
+  void EnableStepTiming(bool on, int stride = 8);
+  void CollectStepTimings(int64_t executed_attempts);
+  const StepTimings& step_timings() const { return step_timings_; }
+  // Device-timeline stopwatch on the launching stream (CUDA events).
+  void TimelineStart(int id);        // id in {0, 1}
+  double TimelineStopMs(int id);     // synchronises
   // Applies the deferred average update (if any) for both averages.
   void FlushAverages(const StepBuffers& b);
 
@@ -242,6 +256,13 @@ class Device {
   double* step_partials_ = nullptr;
   int64_t step_partials_size_ = 0;
   double* TrScratch(int64_t doubles);
+  // step timing
+  bool step_timing_ = false;
+  int step_timing_stride_ = 8;
+  std::vector<void*> timing_events_;     // 5 per sample slot
+  std::vector<int> timing_attempt_idx_;  // attempt index of each used slot in the last batch
+  StepTimings step_timings_;
+  void* timeline_ev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 };
 
 }  // namespace pdlp_b200

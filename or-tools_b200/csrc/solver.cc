@@ -240,6 +240,15 @@ class DeviceSolve {
   }
 
   SolverResultCpp PreprocessAndSolve(std::optional<InitialSolution> initial_solution, const volatile int32_t* interrupt_solve, const std::string* name);
+  // Resumable form (sessions): Prepare = PreprocessSolver work up to the first
+  // iteration; Advance = the loop of Solver::Solve (pdhg.cc:3042-3091) until
+  // `target_iterations` are completed or a termination criterion fires.
+  std::optional<SolverResultCpp> Prepare(std::optional<InitialSolution> initial_solution, const std::string* name);
+  std::optional<SolverResultCpp> Advance(int target_iterations, const volatile int32_t* interrupt_solve);
+  SolverResultCpp ConstructOriginalSolverResult(SolverResultCpp result);
+  void FillStatus(PdlpSessionStatus* out) const;
+  void EnableTiming(bool on, int stride) { D.EnableStepTiming(on, stride); }
+  void ForceRecheck() { check_done_ = false; }
 
  private:
   enum class Outcome { kSuccessful, kForceNumericalTermination };
@@ -319,12 +328,10 @@ class DeviceSolve {
   void AddPointMetadata(const double* x, const double* y, int type, PdlpIterationStats& stats);
   SolverResultCpp PickSolutionAndConstructSolverResult(const double* avg_x, const double* avg_y, const PdlpIterationStats& stats, int reason,
                                                        int output_type, SolveLogCpp log);
-  SolverResultCpp ConstructOriginalSolverResult(SolverResultCpp result);
   void MaterializeDeltas();
   int NextCheckpoint(int k) const;
   Outcome RunDeviceSteps(int k, const volatile int32_t* interrupt);
   Outcome TakeMalitskyPockStep();
-  SolverResultCpp Solve(const volatile int32_t* interrupt_solve, SolveLogCpp solve_log);
   void LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) const;
 
   DeviceProblem& P;
@@ -353,6 +360,12 @@ class DeviceSolve {
   int iterations_completed_ = 0;
   int num_rejected_steps_ = 0;
   double device_time_sec_ = 0;
+  // session state
+  SolveLogCpp solve_log_;
+  bool check_done_ = false;
+  bool force_numerical_ = false;
+  int target_stop_ = std::numeric_limits<int>::max();
+  double device_step_ms_ = 0, device_total_ms_ = 0;
 };
 
 int DeviceSolve::DetermineDistanceBasedRestartChoice() {  // pdhg.cc:2074-2107
@@ -650,6 +663,7 @@ int DeviceSolve::NextCheckpoint(int k) const {
     if (next_cyc < major) consider(static_cast<int64_t>(k) - cyc + next_cyc);
   }
   consider(tc.iteration_limit);
+  consider(target_stop_);
   if (params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
     // artificial restart (pdhg.cc:2120-2130): first k' with terms + (k'-k) >= k'/2
     const int terms = avg_x_terms_;
@@ -677,14 +691,18 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
   hs_.pending_ratio = 0.0;
   PushState();
   WallTimer t;
+  D.TimelineStart(1);
   for (;;) {
     const int remaining = std::max(1, hs_.k_stop - hs_.iterations_completed);
+    const int64_t attempts_before = hs_.attempts;
     D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining + 1, 4096));
     D.DownloadState(hs_, buf_.state);
+    D.CollectStepTimings(hs_.attempts - attempts_before);
     if (hs_.halt != kHaltNone) break;
   }
   D.FlushAverages(buf_);
   D.DownloadState(hs_, buf_.state);
+  device_step_ms_ += D.TimelineStopMs(1);
   device_time_sec_ += t.Get();
   if (hs_.iterations_completed > k) MaterializeDeltas();
   avg_x_weight_ = avg_y_weight_ = hs_.avg_weight_sum;
@@ -764,28 +782,54 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
   return outcome;
 }
 
-// pdhg.cc:3017-3092
-SolverResultCpp DeviceSolve::Solve(const volatile int32_t* interrupt_solve, SolveLogCpp solve_log) {
-  preprocessing_time_sec_ = solve_log.preprocessing_time_sec;
-  timer_.Start();
-  D.CopyD2D(x0_, X(), P.n());
-  D.CopyD2D(y0_, Y(), P.m());
-  ratio_last_two_step_sizes_ = 1;
-  SetCurrentPrimalAndDualProducts();
-  bool force_numerical = false;
-  num_rejected_steps_ = 0;
-  iterations_completed_ = 0;
+// pdhg.cc:3017-3092 (loop part; the start-up part is at the end of Prepare)
+std::optional<SolverResultCpp> DeviceSolve::Advance(int target_iterations, const volatile int32_t* interrupt_solve) {
+  target_stop_ = target_iterations;
   const bool device_loop = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE;
+  D.TimelineStart(0);
+  std::optional<SolverResultCpp> done;
   for (;;) {
-    auto maybe = MajorIterationAndTerminationCheck(force_numerical, interrupt_solve, solve_log);
-    if (maybe.has_value()) {
-      maybe->solve_log.gpu_kernel_launches = D.launches();
-      maybe->solve_log.device_iteration_time_sec = device_time_sec_;
-      return std::move(*maybe);
+    if (!check_done_) {
+      auto maybe = MajorIterationAndTerminationCheck(force_numerical_, interrupt_solve, solve_log_);
+      check_done_ = true;
+      if (maybe.has_value()) {
+        maybe->solve_log.gpu_kernel_launches = D.launches();
+        maybe->solve_log.device_iteration_time_sec = device_time_sec_;
+        done = std::move(maybe);
+        break;
+      }
     }
+    if (iterations_completed_ >= target_iterations) break;
     const Outcome outcome = device_loop ? RunDeviceSteps(iterations_completed_, interrupt_solve) : TakeMalitskyPockStep();
-    if (outcome == Outcome::kForceNumericalTermination) force_numerical = true;
+    check_done_ = false;
+    if (outcome == Outcome::kForceNumericalTermination) force_numerical_ = true;
   }
+  device_total_ms_ += D.TimelineStopMs(0);
+  return done;
+}
+
+void DeviceSolve::FillStatus(PdlpSessionStatus* out) const {
+  std::memset(out, 0, sizeof(*out));
+  out->iterations_completed = iterations_completed_;
+  out->num_rejected_steps = num_rejected_steps_;
+  out->step_size = hs_.step_size;
+  out->primal_weight = hs_.primal_weight;
+  out->gpu_kernel_launches = D.launches();
+  out->device_step_ms = device_step_ms_;
+  out->device_total_ms = device_total_ms_;
+  const Device::StepTimings& t = D.step_timings();
+  const double n = static_cast<double>(P.n()), m = static_cast<double>(P.m());
+  const double qn = P.is_lp() ? 0.0 : 1.0;
+  for (int k = 0; k < 4; ++k) { out->kernel_ms[k] = t.ms[k]; out->kernel_samples[k] = t.samples[k]; }
+  // Algorithmic bytes per launch (DESIGN.md "Roofline accounting"):
+  //  primal step: reads x, c, K^T y, l_v, u_v (+Q), writes x', x~; deferred average R/W.
+  out->kernel_algorithmic_bytes[0] = 8.0 * (9.0 + qn) * n;
+  //  K x~ + dual epilogue: K-by-rows (8 B value + 4 B index per nonzero, 4 B row offset),
+  //  gathers x~ once, reads y, l_c, u_c, writes y'; deferred dual average R/W.
+  out->kernel_algorithmic_bytes[1] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (m + 1) + 8.0 * n + 8.0 * 6.0 * m;
+  //  K^T y' + nonlinearity epilogue: K-by-columns, gathers y' once, writes K^T y', reads x', x, K^T y.
+  out->kernel_algorithmic_bytes[2] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (n + 1) + 8.0 * m + 8.0 * 4.0 * n;
+  out->kernel_algorithmic_bytes[3] = 0.0;
 }
 
 void DeviceSolve::LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) const {  // pdhg.cc:1341-1399
@@ -811,9 +855,15 @@ void DeviceSolve::LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) c
                   s.variable_bound_gaps_avg));
 }
 
-// pdhg.cc:1039-1221
 SolverResultCpp DeviceSolve::PreprocessAndSolve(std::optional<InitialSolution> initial_solution, const volatile int32_t* interrupt_solve,
                                                 const std::string* name) {
+  if (auto err = Prepare(std::move(initial_solution), name); err.has_value()) return std::move(*err);
+  auto result = Advance(std::numeric_limits<int>::max(), interrupt_solve);
+  return ConstructOriginalSolverResult(std::move(*result));
+}
+
+// pdhg.cc:1039-1221
+std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolution> initial_solution, const std::string* name) {
   WallTimer timer;
   SolveLogCpp solve_log;
   if (params_.verbosity_level >= 1) logger_.Log("Solving with PDLP parameters: (PdlpParams POD)");
@@ -934,15 +984,26 @@ SolverResultCpp DeviceSolve::PreprocessAndSolve(std::optional<InitialSolution> i
   hs_.growth_exponent = params_.adaptive_step_size_growth_exponent;
   ClearAverages();
   solve_log.preprocessing_time_sec = timer.Get();
-  SolverResultCpp result = Solve(interrupt_solve, std::move(solve_log));
-  return ConstructOriginalSolverResult(std::move(result));
+  // start of Solver::Solve, pdhg.cc:3017-3041
+  solve_log_ = std::move(solve_log);
+  preprocessing_time_sec_ = solve_log_.preprocessing_time_sec;
+  timer_.Start();
+  D.CopyD2D(x0_, X(), P.n());
+  D.CopyD2D(y0_, Y(), P.m());
+  ratio_last_two_step_sizes_ = 1;
+  SetCurrentPrimalAndDualProducts();
+  force_numerical_ = false;
+  check_done_ = false;
+  num_rejected_steps_ = 0;
+  iterations_completed_ = 0;
+  return std::nullopt;
 }
 
 }  // namespace
 
-SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
-                                         const volatile int32_t* interrupt_solve, const Logger& logger, StatsCallback callback, int cuda_device) {
-  // pdhg.cc:3120-3147
+namespace {
+// pdhg.cc:3120-3147
+std::optional<SolverResultCpp> ValidateInputs(const PdlpProblemView& view, const PdlpParams& params, const Logger& logger) {
   const std::string perr = ValidateParams(params);
   if (!perr.empty()) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "INVALID_ARGUMENT: " + perr, logger);
   const std::string derr = ValidateDimensions(view);
@@ -955,10 +1016,82 @@ SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const Pdlp
                              "presolve_options.use_glop and use_feasibility_polishing are host-side features outside this library's scope.", logger);
   if (params.num_random_projection_seeds > PDLP_MAX_RANDOM_PROJECTION_SEEDS)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "at most 8 random_projection_seeds are supported.", logger);
+  return std::nullopt;
+}
+}  // namespace
+
+SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
+                                         const volatile int32_t* interrupt_solve, const Logger& logger, StatsCallback callback, int cuda_device) {
+  if (auto err = ValidateInputs(view, params, logger); err.has_value()) return std::move(*err);
   DeviceProblem problem(view, cuda_device);
   DeviceSolve solve(problem, params, logger, std::move(callback));
   const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
   return solve.PreprocessAndSolve(std::move(initial_solution), interrupt_solve, view.problem_name != nullptr ? &name : nullptr);
+}
+
+// ---- sessions ---------------------------------------------------------------
+struct SolveSession::Impl {
+  Logger logger;
+  std::unique_ptr<DeviceProblem> problem;
+  std::unique_ptr<DeviceSolve> solve;
+  std::optional<SolverResultCpp> finished;  // scaled-point result or input error
+  bool input_error = false;
+};
+
+SolveSession::SolveSession() : impl_(new Impl) {}
+SolveSession::~SolveSession() = default;
+
+std::unique_ptr<SolveSession> SolveSession::Create(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
+                                                   const Logger& logger, StatsCallback callback, int cuda_device) {
+  std::unique_ptr<SolveSession> s(new SolveSession);
+  Impl& im = *s->impl_;
+  im.logger = logger;
+  if (auto err = ValidateInputs(view, params, im.logger); err.has_value()) {
+    im.finished = std::move(*err);
+    im.input_error = true;
+    return s;
+  }
+  im.problem.reset(new DeviceProblem(view, cuda_device));
+  im.solve.reset(new DeviceSolve(*im.problem, params, im.logger, std::move(callback)));
+  const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
+  if (auto err = im.solve->Prepare(std::move(initial_solution), view.problem_name != nullptr ? &name : nullptr); err.has_value()) {
+    im.finished = std::move(*err);
+    im.input_error = true;
+  }
+  return s;
+}
+
+bool SolveSession::Advance(int target_iterations, const volatile int32_t* interrupt_solve) {
+  Impl& im = *impl_;
+  if (im.finished.has_value()) return true;
+  auto r = im.solve->Advance(target_iterations, interrupt_solve);
+  if (r.has_value()) im.finished = std::move(*r);
+  return im.finished.has_value();
+}
+
+void SolveSession::EnableTiming(bool on, int stride) {
+  if (impl_->solve) impl_->solve->EnableTiming(on, stride);
+}
+
+void SolveSession::Status(PdlpSessionStatus* out) const {
+  std::memset(out, 0, sizeof(*out));
+  if (impl_->solve) impl_->solve->FillStatus(out);
+  out->terminated = impl_->finished.has_value() ? 1 : 0;
+  out->termination_reason = impl_->finished.has_value() ? impl_->finished->solve_log.termination_reason : PDLP_TERMINATION_REASON_UNSPECIFIED;
+}
+
+SolverResultCpp SolveSession::Finish() {
+  Impl& im = *impl_;
+  if (!im.finished.has_value()) {
+    // Stop like an interrupted solve (pdhg.cc:364-368): the next termination
+    // check sees the flag and returns the average iterate.
+    const int32_t stop = 1;
+    im.solve->ForceRecheck();
+    Advance(std::numeric_limits<int>::max(), &stop);
+  }
+  if (im.input_error) return *im.finished;
+  SolverResultCpp r = im.solve->ConstructOriginalSolverResult(*im.finished);
+  return r;
 }
 
 }  // namespace pdlp_b200

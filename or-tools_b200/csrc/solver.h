@@ -3,6 +3,7 @@
 #define PDLP_B200_SOLVER_H_
 
 #include <functional>
+#include <memory>
 #include <optional>
 #include <string>
 #include <vector>
@@ -56,6 +57,30 @@ SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const Pdlp
                                          std::optional<InitialSolution> initial_solution,
                                          const volatile int32_t* interrupt_solve, const Logger& logger,
                                          StatsCallback callback, int cuda_device);
+
+// A resumable solve whose problem and iterates stay resident in HBM between
+// calls (C ABI: pdlp_b200_session_*). Advance() runs the same loop as
+// PrimalDualHybridGradient; stopping and resuming does not change the iterates.
+class SolveSession {
+ public:
+  static std::unique_ptr<SolveSession> Create(const PdlpProblemView& view, const PdlpParams& params,
+                                              std::optional<InitialSolution> initial_solution, const Logger& logger,
+                                              StatsCallback callback, int cuda_device);
+  ~SolveSession();
+  // Runs until `target_iterations` iterations are completed or the solve
+  // terminates; returns true once terminated.
+  bool Advance(int target_iterations, const volatile int32_t* interrupt_solve);
+  void EnableTiming(bool on, int stride);
+  void Status(PdlpSessionStatus* out) const;
+  // The SolverResult; if the solve has not terminated it is stopped as if
+  // interrupted by the user.
+  SolverResultCpp Finish();
+
+ private:
+  SolveSession();
+  struct Impl;
+  std::unique_ptr<Impl> impl_;
+};
 
 }  // namespace pdlp_b200
 

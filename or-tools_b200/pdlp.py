@@ -721,6 +721,12 @@ class _ProductBackend(Backend):
     def device_count(self):
         return int(self.fn("device_count")())
 
+    def set_default_device(self, cuda_device):
+        self._check(self.fn("set_default_device")(C.c_int32(cuda_device)), "set_default_device")
+
+    def session(self, qp, params, initial_solution=None, cuda_device=0):
+        return SolveSession(self, qp, params, initial_solution, cuda_device)
+
     def solve_trust_region(self, objective_vector, variable_lower_bounds, variable_upper_bounds, center_point,
                            norm_weights, target_radius, cuda_device=0):
         arrs = [capi.as_f64(a) for a in (objective_vector, variable_lower_bounds, variable_upper_bounds, center_point, norm_weights)]
@@ -753,6 +759,60 @@ class _ProductBackend(Backend):
         a = capi.as_f64(a); bb = None if b is None else capi.as_f64(b); out = C.c_double()
         self._check(self.fn("vector_reduce")(C.c_int32(cuda_device), C.c_int32(op), C.c_int64(a.size), capi.ptr_f64(a), capi.ptr_f64(bb), C.byref(out)), "vector_reduce")
         return out.value
+
+
+class SolveSession:
+    """A solve whose problem and iterates stay resident in HBM between calls
+    (C ABI ``pdlp_b200_session_*``): create = preprocessing, ``advance`` = the
+    PDHG loop up to a target iteration count, ``finish`` = the SolverResult."""
+
+    def __init__(self, backend, qp, params, initial_solution=None, cuda_device=0):
+        self.b = backend
+        view, keep = qp._to_view()
+        pod = params.to_pod() if hasattr(params, "to_pod") else params
+        x0 = y0 = None
+        if initial_solution is not None:
+            x0 = capi.as_f64(initial_solution.primal_solution)
+            y0 = capi.as_f64(initial_solution.dual_solution)
+        self.h = C.c_void_p()
+        rc = backend.fn("session_create")(C.byref(view), C.byref(pod), capi.ptr_f64(x0), C.c_int64(0 if x0 is None else x0.size),
+                                          capi.ptr_f64(y0), C.c_int64(0 if y0 is None else y0.size), capi.MESSAGE_CALLBACK(),
+                                          capi.STATS_CALLBACK(), None, C.c_int32(cuda_device), C.byref(self.h))
+        del keep
+        backend._check(rc, "session_create")
+
+    def enable_timing(self, enable=True, sample_stride=8):
+        self.b._check(self.b.fn("session_enable_timing")(self.h, C.c_int32(int(enable)), C.c_int32(sample_stride)), "session_enable_timing")
+
+    def advance(self, target_iterations, interrupt_solve=None):
+        st = capi.PdlpSessionStatus()
+        flag = None if interrupt_solve is None else C.byref(interrupt_solve)
+        self.b._check(self.b.fn("session_advance")(self.h, C.c_int32(int(target_iterations)), flag, C.byref(st)), "session_advance")
+        return _ns(capi.struct_to_dict(st))
+
+    def status(self):
+        st = capi.PdlpSessionStatus()
+        self.b._check(self.b.fn("session_status")(self.h, C.byref(st)), "session_status")
+        return _ns(capi.struct_to_dict(st))
+
+    def finish(self):
+        res = capi.PdlpResult()
+        self.b._check(self.b.fn("session_finish")(self.h, C.byref(res)), "session_finish")
+        try:
+            return self.b._result_from_pod(res)
+        finally:
+            self.b.fn("result_free", None)(C.byref(res))
+
+    def close(self):
+        if self.h:
+            self.b.fn("session_destroy", None)(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def backend():
