@@ -496,6 +496,12 @@ int32_t pdlp_b200_vector_reduce(int32_t cuda_device, int32_t op, int64_t size, c
 /* Number of usable CUDA devices (0 if none); never fails. */
 int32_t pdlp_b200_device_count(void);
 const char* pdlp_b200_version(void);
+/* sizeof() of the boundary structs, for binding self-checks. index: 0
+ * TerminationCriteria, 1 Params, 2 ProblemView, 3 QuadraticProgramStats,
+ * 4 ConvergenceInformation, 5 InfeasibilityInformation, 6 PointMetadata,
+ * 7 IterationStats, 8 BoundNorms, 9 IterationCallbackInfo, 10 Result,
+ * 11 SessionStatus; -1 for an unknown index. */
+int64_t pdlp_b200_sizeof(int32_t index);
 
 #ifdef __cplusplus
 } /* extern "C" */

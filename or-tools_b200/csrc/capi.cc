@@ -120,6 +120,23 @@ int32_t pdlp_b200_params_validate(const PdlpParams* params, char* message, int64
 
 int32_t pdlp_b200_device_count(void) { return Device::DeviceCount(); }
 const char* pdlp_b200_version(void) { return "pdlp_b200 0.1.0 (sm_100a)"; }
+int64_t pdlp_b200_sizeof(int32_t index) {
+  switch (index) {
+    case 0: return sizeof(PdlpTerminationCriteria);
+    case 1: return sizeof(PdlpParams);
+    case 2: return sizeof(PdlpProblemView);
+    case 3: return sizeof(PdlpQuadraticProgramStats);
+    case 4: return sizeof(PdlpConvergenceInformation);
+    case 5: return sizeof(PdlpInfeasibilityInformation);
+    case 6: return sizeof(PdlpPointMetadata);
+    case 7: return sizeof(PdlpIterationStats);
+    case 8: return sizeof(PdlpBoundNorms);
+    case 9: return sizeof(PdlpIterationCallbackInfo);
+    case 10: return sizeof(PdlpResult);
+    case 11: return sizeof(PdlpSessionStatus);
+    default: return -1;
+  }
+}
 
 int32_t pdlp_b200_primal_dual_hybrid_gradient(const PdlpProblemView* qp, const PdlpParams* params, const double* initial_primal,
                                               int64_t initial_primal_size, const double* initial_dual, int64_t initial_dual_size,

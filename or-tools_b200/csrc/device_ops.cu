@@ -177,7 +177,9 @@ struct GatherSrc {
   const StepState* st;
 };
 
-// Epi: __device__ void operator()(int64_t pos, double acc, double* red) const
+// Epi: struct Pre; __device__ Pre prefetch(int64_t pos) const  -- issues the epilogue's
+//      own loads before the gather loop so that they overlap it;
+//      __device__ void operator()(int64_t pos, double acc, double* red, const Pre&) const
 template <int MODE, int NS, class Epi>
 __global__ void __launch_bounds__(kThreads) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt) {
   if (halt != nullptr && *halt != 0) return;
@@ -187,12 +189,15 @@ __global__ void __launch_bounds__(kThreads) k_sell(SellDev a, GatherSrc gs, Epi 
   for (int k = 0; k < NS; ++k) red[k] = 0.0;
   const int64_t slot = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (slot < a.num_slots) {
+    const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
+    const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
+    typename Epi::Pre pre;
+    if (own_row) pre = epi.prefetch(pos);
     const double acc = sell_row<MODE>(a, slot, x);
     if (slot < a.num_virtual_padded) {
       a.virt_partial[slot] = acc;
-    } else {
-      const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
-      if (pos < a.num_rows) epi(pos, acc, red);
+    } else if (own_row) {
+      epi(pos, acc, red, pre);
     }
   }
   if (NS > 0) block_reduce_store<NS, 0>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, dou
     double acc = 0.0;
     for (int k = b + lane; k < e; k += 32) acc = (MODE == kMaxAbs) ? fmax(acc, a.virt_partial[k]) : acc + a.virt_partial[k];
     acc = (MODE == kMaxAbs) ? warp_max(acc) : warp_sum(acc);
-    if (lane == 0) epi(row, acc, red);
+    if (lane == 0) epi(row, acc, red, epi.prefetch(row));
   }
   if (NS > 0) block_reduce_store<NS, 0>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
 }
@@ -287,49 +292,67 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* pa
 
 struct DualEpi {  // pdhg.cc:1912-1930 with theta = 1
   StepPtrs b;
-  __device__ __forceinline__ void operator()(int64_t pos, double kx, double* red) const {
+  struct Pre { double yc, lc, uc, avg; };
+  __device__ __forceinline__ Pre prefetch(int64_t pos) const {
+    const StepState* st = b.state;
+    Pre p;
+    p.yc = b.y[st->cur][pos];
+    p.lc = __ldg(b.lc + pos);
+    p.uc = __ldg(b.uc + pos);
+    p.avg = st->pending_ratio > 0.0 ? b.avg_y[pos] : 0.0;
+    return p;
+  }
+  __device__ __forceinline__ void operator()(int64_t pos, double kx, double* red, const Pre& p) const {
     const StepState* st = b.state;
     const double sigma = st->step_size * st->primal_weight;
     const double ratio = st->pending_ratio;
-    const double yc = b.y[st->cur][pos];
-    if (ratio > 0.0) b.avg_y[pos] += ratio * (yc - b.avg_y[pos]);
-    const double t = yc - sigma * kx;
-    const double yn = fmax(fmin(0.0, t + sigma * b.uc[pos]), t + sigma * b.lc[pos]);
+    if (ratio > 0.0) b.avg_y[pos] = p.avg + ratio * (p.yc - p.avg);
+    const double t = p.yc - sigma * kx;
+    const double yn = fmax(fmin(0.0, t + sigma * p.uc), t + sigma * p.lc);
     b.y[st->cand][pos] = yn;
-    const double d = yn - yc;
+    const double d = yn - p.yc;
     red[0] += d * d;
   }
 };
 
 struct KtyEpi {  // pdhg.cc:2588-2592, 1949-1959
   StepPtrs b;
-  __device__ __forceinline__ void operator()(int64_t pos, double kty_next, double* red) const {
+  struct Pre { double dx, kty; };
+  __device__ __forceinline__ Pre prefetch(int64_t pos) const {
     const StepState* st = b.state;
-    b.kty[st->cand][pos] = kty_next;
-    const double dx = b.x[st->cand][pos] - b.x[st->cur][pos];
-    red[0] += dx * (kty_next - b.kty[st->cur][pos]);
+    Pre p;
+    p.dx = b.x[st->cand][pos] - b.x[st->cur][pos];
+    p.kty = b.kty[st->cur][pos];
+    return p;
+  }
+  __device__ __forceinline__ void operator()(int64_t pos, double kty_next, double* red, const Pre& p) const {
+    b.kty[b.state->cand][pos] = kty_next;
+    red[0] += p.dx * (kty_next - p.kty);
   }
 };
 
-__device__ __forceinline__ double block_sum_range(const double* p, int count) {
-  // fixed order: thread t adds p[t], p[t+256], ...; then a shuffle tree.
-  __shared__ double sh[kThreads / 32];
+constexpr int kDecideThreads = 1024;
+// Fixed-order sum of p[0..count): thread t adds p[t], p[t+1024], ... (independent
+// loads, unrolled so they are all in flight together), then a shuffle tree.
+__device__ __forceinline__ double block_sum_range(const double* __restrict__ p, int count) {
+  __shared__ double sh[kDecideThreads / 32];
   double s = 0.0;
-  for (int i = threadIdx.x; i < count; i += kThreads) s += p[i];
+#pragma unroll 8
+  for (int i = threadIdx.x; i < count; i += kDecideThreads) s += p[i];
   s = warp_sum(s);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
   double t = 0.0;
   if (threadIdx.x < 32) {
-    t = threadIdx.x < kThreads / 32 ? sh[threadIdx.x] : 0.0;
+    t = threadIdx.x < kDecideThreads / 32 ? sh[threadIdx.x] : 0.0;
     t = warp_sum(t);
   }
   return t;  // valid in warp 0
 }
 
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
-__global__ void __launch_bounds__(kThreads) k_step_decide(StepState* st, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
+__global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
   if (st->halt != 0) return;
   const double dx2 = block_sum_range(pp, np);
   const double dy2 = block_sum_range(pd, nd);
@@ -494,25 +517,40 @@ __global__ void __launch_bounds__(kThreads) k_tr_prepare(int64_t total, Elem el,
 
 // One radix-16 pass: per candidate threshold c_j = lo + j * 2^shift (j = 0..15)
 // accumulate A_j = sum_{key <= c_j} a and B_j = sum_{key > c_j} b via 17 bins.
+// Four elements per thread and trip are loaded up front (12 independent loads in
+// flight) because the 34 accumulators keep the occupancy low.
+constexpr int kTrUnroll = 4;
 __global__ void __launch_bounds__(kThreads) k_tr_pass(int64_t total, const unsigned long long* __restrict__ keys, const double* __restrict__ a,
                                                       const double* __restrict__ bcoef, const TrSearchState* st, int shift, double* partials) {
   const unsigned long long lo = st->lo;
   double ba[17], bb[17];
 #pragma unroll
   for (int j = 0; j < 17; ++j) { ba[j] = 0.0; bb[j] = 0.0; }
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * kThreads) {
-    const unsigned long long key = keys[i];
-    int j0 = 0;
-    if (key > lo) {
-      const unsigned long long d = (key - lo - 1ull) >> shift;
-      j0 = d >= 15ull ? 16 : static_cast<int>(d) + 1;
-    }
-    const double av = a[i], bv = bcoef[i];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * kThreads * kTrUnroll;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * kThreads * kTrUnroll + threadIdx.x; base < total; base += stride) {
+    unsigned long long key[kTrUnroll];
+    double av[kTrUnroll], bv[kTrUnroll];
 #pragma unroll
-    for (int j = 0; j < 17; ++j) {
-      const bool p = (j0 == j);
-      ba[j] += p ? av : 0.0;
-      bb[j] += p ? bv : 0.0;
+    for (int u = 0; u < kTrUnroll; ++u) {
+      const int64_t i = base + static_cast<int64_t>(u) * kThreads;
+      const bool ok = i < total;
+      key[u] = ok ? __ldcs(keys + i) : 0ull;
+      av[u] = ok ? __ldcs(a + i) : 0.0;
+      bv[u] = ok ? __ldcs(bcoef + i) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kTrUnroll; ++u) {
+      int j0 = 0;
+      if (key[u] > lo) {
+        const unsigned long long d = (key[u] - lo - 1ull) >> shift;
+        j0 = d >= 15ull ? 16 : static_cast<int>(d) + 1;
+      }
+#pragma unroll
+      for (int j = 0; j < 17; ++j) {
+        const bool p = (j0 == j);
+        ba[j] += p ? av[u] : 0.0;
+        bb[j] += p ? bv[u] : 0.0;
+      }
     }
   }
   double s[34];
@@ -521,12 +559,19 @@ __global__ void __launch_bounds__(kThreads) k_tr_pass(int64_t total, const unsig
   block_reduce_store<34, 0>(s, nullptr, partials + static_cast<int64_t>(blockIdx.x) * 34);
 }
 
-__global__ void __launch_bounds__(64) k_tr_decide(int nblocks, const double* partials, TrSearchState* st, int shift) {
+// 34 warps-worth of columns summed by 17 warps (two columns each), blocks in a
+// fixed lane-strided order; then thread 0 picks the bracket.
+__global__ void __launch_bounds__(17 * 32) k_tr_decide(int nblocks, const double* __restrict__ partials, TrSearchState* st, int shift) {
   __shared__ double tot[34];
-  if (threadIdx.x < 34) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int colx = warp + 17 * h;
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[static_cast<int64_t>(b) * 34 + threadIdx.x];
-    tot[threadIdx.x] = s;
+#pragma unroll 4
+    for (int b = lane; b < nblocks; b += 32) s += partials[static_cast<int64_t>(b) * 34 + colx];
+    s = warp_sum(s);
+    if (lane == 0) tot[colx] = s;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -555,7 +600,9 @@ __global__ void __launch_bounds__(64) k_tr_decide(int nblocks, const double* par
 
 __global__ void k_tr_init(TrSearchState* st, double radius, const double* maxabs_partials, int nblocks) {
   double mx = 0.0;
-  for (int b = 0; b < nblocks; ++b) mx = fmax(mx, maxabs_partials[b]);
+  for (int b = threadIdx.x; b < nblocks; b += 32) mx = fmax(mx, maxabs_partials[b]);
+  mx = warp_max(mx);
+  if (threadIdx.x != 0) return;
   st->lo = 0ull;
   st->fixed_radius_sq = 0.0;
   st->variable_coef = 0.0;
@@ -712,13 +759,17 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
 }
 struct StoreEpi {
   double* out;
-  __device__ __forceinline__ void operator()(int64_t pos, double acc, double*) const { out[pos] = acc; }
+  struct Pre {};
+  __device__ __forceinline__ Pre prefetch(int64_t) const { return Pre(); }
+  __device__ __forceinline__ void operator()(int64_t pos, double acc, double*, const Pre&) const { out[pos] = acc; }
 };
 struct NormEpi {
   double* out;
   const double* own;
   int l2;
-  __device__ __forceinline__ void operator()(int64_t pos, double acc, double*) const { out[pos] = (l2 ? sqrt(acc) : acc) * fabs(own[pos]); }
+  struct Pre { double own; };
+  __device__ __forceinline__ Pre prefetch(int64_t pos) const { return Pre{own[pos]}; }
+  __device__ __forceinline__ void operator()(int64_t pos, double acc, double*, const Pre& p) const { out[pos] = (l2 ? sqrt(acc) : acc) * fabs(p.own); }
 };
 }  // namespace kernels
 
@@ -1031,13 +1082,14 @@ void tr_search(cudaStream_t stream, int64_t total, Elem el, double radius, doubl
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch);
   double* a = scratch + total;
   double* b = scratch + 2 * total;
-  const int nb = static_cast<int>(std::min<int64_t>(148 * 4, std::max<int64_t>(1, (total + kThreads * 4 - 1) / (kThreads * 4))));
-  k_tr_prepare<Elem><<<nb, kThreads, 0, stream>>>(total, el, keys, a, b, partials);
-  k_tr_init<<<1, 1, 0, stream>>>(st, radius, partials, nb);
+  const int nb = static_cast<int>(std::min<int64_t>(148 * 2, std::max<int64_t>(1, (total + kThreads * kTrUnroll - 1) / (kThreads * kTrUnroll))));
+  const int nb_prep = static_cast<int>(std::min<int64_t>(kMaxReduceBlocks, std::max<int64_t>(1, (total + kThreads * 2 - 1) / (kThreads * 2))));
+  k_tr_prepare<Elem><<<nb_prep, kThreads, 0, stream>>>(total, el, keys, a, b, partials);
+  k_tr_init<<<1, 32, 0, stream>>>(st, radius, partials, nb_prep);
   *launches += 2;
   for (int shift = 60; shift >= 0; shift -= 4) {
     k_tr_pass<<<nb, kThreads, 0, stream>>>(total, keys, a, b, st, shift, partials);
-    k_tr_decide<<<1, 64, 0, stream>>>(nb, partials, st, shift);
+    k_tr_decide<<<1, 17 * 32, 0, stream>>>(nb, partials, st, shift);
     *launches += 2;
   }
   k_tr_finish<<<1, 1, 0, stream>>>(st, radius);
@@ -1257,7 +1309,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr);
     }
     if (slot >= 0) ev(slot, 3);
-    k_step_decide<<<1, kThreads, 0, STREAM>>>(b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
+    k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
     ++launches_;
     if (slot >= 0) ev(slot, 4);
   }
