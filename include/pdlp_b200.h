@@ -368,6 +368,12 @@ int32_t pdlp_b200_distributed_init(const char* nccl_library_path, int32_t rank,
                                    const uint8_t nccl_unique_id[128],
                                    PdlpDistributedContext** out_context);
 void pdlp_b200_distributed_destroy(PdlpDistributedContext* context);
+/* The contiguous block [row_begin, row_end) of constraint rows that rank
+ * `rank` of `world_size` keeps (host-only; no device needed): boundaries are
+ * where the running (nnz + rows) count reaches rank / world_size of the total,
+ * the equal-mass rule of Sharder (sharder.cc:51-70) applied to the rows of K. */
+int32_t pdlp_b200_row_block(const PdlpProblemView* qp, int32_t rank, int32_t world_size,
+                            int64_t* row_begin, int64_t* row_end);
 int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(
     PdlpDistributedContext* context, const PdlpProblemView* qp, const PdlpParams* params,
     const double* initial_primal, int64_t initial_primal_size,
@@ -375,6 +381,13 @@ int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(
     const volatile int32_t* interrupt_solve, PdlpMessageCallback message_callback,
     PdlpIterationStatsCallback iteration_stats_callback, void* user_data,
     PdlpResult* result);
+
+/* Row-sharded resident session (see "resident solve sessions" above); advance /
+ * status / finish / destroy are the pdlp_b200_session_* calls, made by every
+ * rank with the same arguments.                                             */
+int32_t pdlp_b200_session_create_distributed(PdlpDistributedContext* context,
+                                             const PdlpProblemView* qp, const PdlpParams* params,
+                                             PdlpSolveSession** out_session);
 
 /* ---- device-resident problem: kernel-level entry points ------------------ *
  * These expose the individual hot-path operators of the reference so that each

@@ -9,6 +9,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "comm.h"
 #include "device_problem.h"
 #include "solver.h"
 
@@ -26,7 +27,7 @@ struct PdlpSolveSession {
 };
 static int g_default_device = 0;
 struct PdlpDistributedContext {
-  int rank = 0, world = 1, device = 0;
+  std::unique_ptr<Comm> comm;
 };
 
 namespace {
@@ -225,14 +226,77 @@ int32_t pdlp_b200_session_finish(PdlpSolveSession* h, PdlpResult* result) {
 }
 void pdlp_b200_session_destroy(PdlpSolveSession* h) { delete h; }
 
-// ---- multi-GPU (implemented in distributed.cc when NCCL is wired in) -------
-int32_t pdlp_b200_nccl_unique_id(const char*, uint8_t*) { return PDLP_B200_STATUS_BAD_ARGUMENT; }
-int32_t pdlp_b200_distributed_init(const char*, int32_t, int32_t, int32_t, const uint8_t*, PdlpDistributedContext**) { return PDLP_B200_STATUS_BAD_ARGUMENT; }
+// ---- multi-GPU: row-sharded solve over NCCL ---------------------
+int32_t pdlp_b200_nccl_unique_id(const char* nccl_library_path, uint8_t out_id[128]) {
+  if (out_id == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  try {
+    Comm::UniqueId(nccl_library_path, out_id);
+    return PDLP_B200_STATUS_OK;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "pdlp_b200: %s\n", e.what());
+    return PDLP_B200_STATUS_CUDA_ERROR;
+  }
+}
+int32_t pdlp_b200_distributed_init(const char* nccl_library_path, int32_t rank, int32_t world_size, int32_t cuda_device,
+                                   const uint8_t nccl_unique_id[128], PdlpDistributedContext** out) {
+  if (out == nullptr || nccl_unique_id == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  *out = nullptr;
+  return Guard([&] {
+    auto h = std::make_unique<PdlpDistributedContext>();
+    h->comm.reset(new Comm(nccl_library_path, rank, world_size, cuda_device, nccl_unique_id));
+    *out = h.release();
+  });
+}
 void pdlp_b200_distributed_destroy(PdlpDistributedContext* c) { delete c; }
-int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(PdlpDistributedContext*, const PdlpProblemView*, const PdlpParams*, const double*, int64_t,
-                                                          const double*, int64_t, const volatile int32_t*, PdlpMessageCallback,
-                                                          PdlpIterationStatsCallback, void*, PdlpResult*) {
-  return PDLP_B200_STATUS_BAD_ARGUMENT;
+int32_t pdlp_b200_row_block(const PdlpProblemView* qp, int32_t rank, int32_t world_size, int64_t* row_begin, int64_t* row_end) {
+  if (qp == nullptr || row_begin == nullptr || row_end == nullptr || world_size < 1 || rank < 0 || rank >= world_size) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  try {
+    ComputeRowBlock(*qp, rank, world_size, row_begin, row_end);
+    return PDLP_B200_STATUS_OK;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "pdlp_b200: %s\n", e.what());
+    return PDLP_B200_STATUS_BAD_ARGUMENT;
+  }
+}
+int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(PdlpDistributedContext* ctx, const PdlpProblemView* qp, const PdlpParams* params,
+                                                          const double* initial_primal, int64_t initial_primal_size, const double* initial_dual,
+                                                          int64_t initial_dual_size, const volatile int32_t* interrupt_solve,
+                                                          PdlpMessageCallback message_callback, PdlpIterationStatsCallback stats_callback,
+                                                          void* user_data, PdlpResult* result) {
+  if (ctx == nullptr || qp == nullptr || params == nullptr || result == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  std::memset(result, 0, sizeof(*result));
+  if (Device::DeviceCount() <= 0) return PDLP_B200_STATUS_NO_DEVICE;
+  Logger logger{message_callback, user_data};
+  std::optional<InitialSolution> init;
+  if (initial_primal != nullptr || initial_dual != nullptr) {
+    init.emplace();
+    if (initial_primal != nullptr) init->primal.assign(initial_primal, initial_primal + initial_primal_size);
+    if (initial_dual != nullptr) init->dual.assign(initial_dual, initial_dual + initial_dual_size);
+  }
+  StatsCallback cb;
+  if (stats_callback != nullptr) cb = [=](const PdlpIterationCallbackInfo& info) { stats_callback(&info, user_data); };
+  try {
+    FillResult(PrimalDualHybridGradient(*qp, *params, std::move(init), interrupt_solve, logger, std::move(cb), ctx->comm->cuda_device(), ctx->comm.get()),
+               result);
+    return PDLP_B200_STATUS_OK;
+  } catch (const std::exception& e) {
+    SolverResultCpp r;
+    r.solve_log.termination_reason = PDLP_TERMINATION_REASON_OTHER;
+    r.solve_log.termination_string = std::string("device failure: ") + e.what();
+    FillResult(std::move(r), result);
+    return PDLP_B200_STATUS_CUDA_ERROR;
+  }
+}
+int32_t pdlp_b200_session_create_distributed(PdlpDistributedContext* ctx, const PdlpProblemView* qp, const PdlpParams* params,
+                                             PdlpSolveSession** out) {
+  if (ctx == nullptr || qp == nullptr || params == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  *out = nullptr;
+  return Guard([&] {
+    auto h = std::make_unique<PdlpSolveSession>();
+    Logger logger{nullptr, nullptr};
+    h->s = SolveSession::Create(*qp, *params, std::nullopt, logger, StatsCallback(), ctx->comm->cuda_device(), ctx->comm.get());
+    *out = h.release();
+  });
 }
 
 // ---- device-resident problem -----------------------------------------------

@@ -28,9 +28,11 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstddef>
 #include <cstring>
 #include <stdexcept>
 
+#include "comm.h"
 #include "device_ops.h"
 
 namespace pdlp_b200 {
@@ -355,7 +357,8 @@ __device__ __forceinline__ double block_sum_range(const double* __restrict__ p, 
 __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
   if (st->halt != 0) return;
   const double dx2 = block_sum_range(pp, np);
-  const double dy2 = block_sum_range(pd, nd);
+  // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
+  const double dy2 = nd < 0 ? *pd : block_sum_range(pd, nd);
   const double dot = block_sum_range(pt, nt);
   if (threadIdx.x != 0) return;
   const double eta = st->step_size, omega = st->primal_weight;
@@ -415,6 +418,29 @@ __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st, c
       st->inner_iterations = 0;
     }
   }
+}
+
+// ---- row-sharded variant of the step ---------------------------
+// The primal side is replicated, the dual side is this rank's row block. After
+// the local K^T y' partial (scattered to column order) one all-reduce of
+// [n + 1] doubles completes both K^T y' and ||dy||^2; then k_kty_finish does
+// what KtyEpi does on one GPU.
+__global__ void __launch_bounds__(kDecideThreads) k_sum_to_slot(const StepState* st, const double* pd, int nd, double* slot) {
+  if (st->halt != 0) return;
+  const double v = block_sum_range(pd, nd);
+  if (threadIdx.x == 0) *slot = v;
+}
+__global__ void __launch_bounds__(kThreads) k_kty_finish(StepPtrs b, const double* __restrict__ reduced, double* partials) {
+  const StepState* st = b.state;
+  if (st->halt != 0) return;
+  double s = 0.0;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i < b.n) {
+    const double v = reduced[i];
+    b.kty[st->cand][i] = v;
+    s = (b.x[st->cand][i] - b.x[st->cur][i]) * (v - b.kty[st->cur][i]);
+  }
+  block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t total) {
@@ -495,9 +521,15 @@ struct VectorElem {
 
 // crit (as key), a = w dist^2 (radius^2 if fixed at its bound), b = obj^2 / w.
 template <class Elem>
-__global__ void __launch_bounds__(kThreads) k_tr_prepare(int64_t total, Elem el, unsigned long long* keys, double* a, double* bcoef, double* partials) {
+__global__ void __launch_bounds__(kThreads) k_tr_prepare(int64_t total, int64_t first, Elem el, unsigned long long* keys, double* a, double* bcoef, double* partials) {
   double m[1] = {-kInfD};
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * kThreads) {
+    if (i < first) {  // replicated (primal) element, counted on rank 0 only
+      keys[i] = 0ull;
+      a[i] = 0.0;
+      bcoef[i] = 0.0;
+      continue;
+    }
     double obj, lb, ub, center, w, qd;
     el.get(i, obj, lb, ub, center, w, qd);
     double crit, dist = 0.0;
@@ -559,10 +591,10 @@ __global__ void __launch_bounds__(kThreads) k_tr_pass(int64_t total, const unsig
   block_reduce_store<34, 0>(s, nullptr, partials + static_cast<int64_t>(blockIdx.x) * 34);
 }
 
-// 34 warps-worth of columns summed by 17 warps (two columns each), blocks in a
-// fixed lane-strided order; then thread 0 picks the bracket.
-__global__ void __launch_bounds__(17 * 32) k_tr_decide(int nblocks, const double* __restrict__ partials, TrSearchState* st, int shift) {
-  __shared__ double tot[34];
+// The 34 bin totals: 17 warps sum two columns each over the blocks in a fixed
+// lane-strided order (k_tr_totals); row-sharded solves all-reduce the totals;
+// one thread then picks the bracket (k_tr_pick).
+__global__ void __launch_bounds__(17 * 32) k_tr_totals(int nblocks, const double* __restrict__ partials, double* __restrict__ tot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -573,8 +605,8 @@ __global__ void __launch_bounds__(17 * 32) k_tr_decide(int nblocks, const double
     s = warp_sum(s);
     if (lane == 0) tot[colx] = s;
   }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+}
+__global__ void k_tr_pick(const double* __restrict__ tot, TrSearchState* st, int shift) {
   const unsigned long long lo = st->lo;
   // A_j = sum of bins 0..j of a; B_j = sum of bins j+1..16 of b.
   double A = 0.0;
@@ -713,6 +745,12 @@ void Device::DownloadPermuted(double* dst_host, const double* src, const int32_t
   Free(tmp);
 }
 
+void Device::ScatterInto(double* dst, const double* src, const int32_t* row_of_pos, int64_t n) {
+  if (n <= 0) return;
+  k_for<<<Blocks(n), kThreads, 0, STREAM>>>(n, [=] __device__(int64_t p) { dst[row_of_pos[p]] = src[p]; });
+  LAUNCHED();
+}
+
 SellDev Device::UploadSell(const SellHost& h) {
   SellDev d;
   d.num_rows = h.num_rows; d.num_cols = h.num_cols; d.num_split = h.num_split;
@@ -763,6 +801,13 @@ struct StoreEpi {
   __device__ __forceinline__ Pre prefetch(int64_t) const { return Pre(); }
   __device__ __forceinline__ void operator()(int64_t pos, double acc, double*, const Pre&) const { out[pos] = acc; }
 };
+struct ScatterEpi {  // out[perm[pos]] = acc
+  double* out;
+  const int32_t* perm;
+  struct Pre { int32_t dst; };
+  __device__ __forceinline__ Pre prefetch(int64_t pos) const { return Pre{__ldg(perm + pos)}; }
+  __device__ __forceinline__ void operator()(int64_t, double acc, double*, const Pre& p) const { out[p.dst] = acc; }
+};
 struct NormEpi {
   double* out;
   const double* own;
@@ -778,20 +823,58 @@ void Device::SpMV(const SellDev& a, const double* x, double* out) {
   launch_sell<kDot, 0>(STREAM, a, GatherSrc{{x, nullptr, nullptr}, nullptr}, StoreEpi{out}, nullptr, nullptr, &launches_, nullptr, nullptr);
   CUDA_OK(cudaGetLastError());
 }
+void Device::SpMVScatter(const SellDev& a, const double* x, const int32_t* perm, double* out) {
+  if (a.num_rows <= 0) return;
+  launch_sell<kDot, 0>(STREAM, a, GatherSrc{{x, nullptr, nullptr}, nullptr}, ScatterEpi{out, perm}, nullptr, nullptr, &launches_, nullptr, nullptr);
+  CUDA_OK(cudaGetLastError());
+}
+void Device::RowNormRawScatter(const SellDev& a, int norm, const double* other_scale, const int32_t* perm, double* out) {
+  if (a.num_rows <= 0) return;
+  if (norm == 0) launch_sell<kMaxAbs, 0>(STREAM, a, GatherSrc{{other_scale, nullptr, nullptr}, nullptr}, ScatterEpi{out, perm}, nullptr, nullptr, &launches_, nullptr, nullptr);
+  else launch_sell<kSumSq, 0>(STREAM, a, GatherSrc{{other_scale, nullptr, nullptr}, nullptr}, ScatterEpi{out, perm}, nullptr, nullptr, &launches_, nullptr, nullptr);
+  CUDA_OK(cudaGetLastError());
+}
+void Device::FinishRowNorm(double* out, int norm, const double* own_scale, int64_t n) {
+  if (n <= 0) return;
+  k_for<<<Blocks(n), kThreads, 0, STREAM>>>(n, [=] __device__(int64_t i) { out[i] = (norm ? sqrt(out[i]) : out[i]) * fabs(own_scale[i]); });
+  LAUNCHED();
+}
+bool Device::count_primal() const { return comm_ == nullptr || comm_->rank() == 0; }
+double Device::RootValue(double v) {
+  if (comm_ == nullptr) return v;
+  host_results_[0] = comm_->rank() == 0 ? v : 0.0;
+  CUDA_OK(cudaMemcpyAsync(results_, host_results_, sizeof(double), cudaMemcpyHostToDevice, STREAM));
+  comm_->AllReduceSum(results_, results_, 1, stream_);
+  CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double), cudaMemcpyDeviceToHost, STREAM));
+  Sync();
+  return host_results_[0];
+}
+double Device::MaxOverRanks(double v) {
+  if (comm_ == nullptr) return v;
+  host_results_[0] = v;
+  CUDA_OK(cudaMemcpyAsync(results_, host_results_, sizeof(double), cudaMemcpyHostToDevice, STREAM));
+  comm_->AllReduceMax(results_, results_, 1, stream_);
+  CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double), cudaMemcpyDeviceToHost, STREAM));
+  Sync();
+  return host_results_[0];
+}
+void Device::AllReduceSumVec(double* buf, int64_t n) { if (comm_ != nullptr) comm_->AllReduceSum(buf, buf, n, stream_); }
+void Device::AllReduceMaxVec(double* buf, int64_t n) { if (comm_ != nullptr) comm_->AllReduceMax(buf, buf, n, stream_); }
+
 void Device::ScaledRowNorm(const SellDev& a, int norm, const double* other_scale, const double* own_scale, double* out) {
   if (a.num_rows <= 0) return;
   if (norm == 0) launch_sell<kMaxAbs, 0>(STREAM, a, GatherSrc{{other_scale, nullptr, nullptr}, nullptr}, NormEpi{out, own_scale, 0}, nullptr, nullptr, &launches_, nullptr, nullptr);
   else launch_sell<kSumSq, 0>(STREAM, a, GatherSrc{{other_scale, nullptr, nullptr}, nullptr}, NormEpi{out, own_scale, 1}, nullptr, nullptr, &launches_, nullptr, nullptr);
   CUDA_OK(cudaGetLastError());
 }
-void Device::ScaleMatrix(SellDev& a, const double* own_scale, const double* other_scale) {
+void Device::ScaleMatrix(SellDev& a, const double* own_scale, const double* other_scale, const int32_t* own_perm) {
   if (a.num_slots <= 0) return;
   const SellDev s = a;
   k_for<<<Blocks(s.num_slots), kThreads, 0, STREAM>>>(s.num_slots, [=] __device__(int64_t slot) {
     const int n = s.slot_len[slot];
     if (n == 0) return;
     const int64_t pos = slot < s.num_virtual_padded ? s.virt_pos[slot] : s.num_split + (slot - s.num_virtual_padded);
-    const double r = own_scale[pos];
+    const double r = own_scale[own_perm != nullptr ? own_perm[pos] : pos];
     const int64_t base = s.slice_ptr[slot >> 5] + (slot & 31);
     for (int j = 0; j < n; ++j) {
       const int64_t k = base + static_cast<int64_t>(j) * 32;
@@ -857,28 +940,38 @@ void Device::DualStepFromProducts(const double* y, const double* kx_cur, const d
 }
 
 // ---- reductions -------------------------------------------------------------
-#define REDUCE(NS, NM, n, ...)                                                                                                    \
+// `sharded`: the reduced elements are row-sharded across ranks (dual side), so
+// the sums / maxes are completed by an all-reduce; replicated (primal side)
+// reductions are identical on every rank and need none. Joint reductions count
+// their primal part on rank 0 only (count_primal()) and are sharded.
+#define REDUCE_S(sharded, NS, NM, n, ...)                                                                                         \
   do {                                                                                                                            \
     const int nb__ = ReduceBlocks(n);                                                                                             \
     k_reduce<NS, NM><<<nb__, kThreads, 0, STREAM>>>((n), [=] __device__(int64_t i, double* s, double* m) __VA_ARGS__, partials_); \
     LAUNCHED();                                                                                                            \
     k_reduce_final<NS, NM><<<1, kThreads, 0, STREAM>>>(nb__, partials_, results_);                                         \
     LAUNCHED();                                                                                                            \
+    if ((sharded) && comm_ != nullptr) {                                                                                   \
+      if ((NS) > 0) comm_->AllReduceSum(results_, results_, (NS), stream_);                                                \
+      if ((NM) > 0) comm_->AllReduceMax(results_ + (NS), results_ + (NS), (NM), stream_);                                  \
+    }                                                                                                                      \
     CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * ((NS) + (NM)), cudaMemcpyDeviceToHost, STREAM));     \
     Sync();                                                                                                                \
   } while (0)
+#define REDUCE(NS, NM, n, ...) REDUCE_S(false, NS, NM, n, __VA_ARGS__)
 
-double Device::Dot(const double* a, const double* b, int64_t n) { REDUCE(1, 0, n, { s[0] += a[i] * b[i]; }); return host_results_[0]; }
-double Device::SumSq(const double* a, int64_t n) { REDUCE(1, 0, n, { s[0] += a[i] * a[i]; }); return host_results_[0]; }
-double Device::SumSqDiff(const double* a, const double* b, int64_t n) { REDUCE(1, 0, n, { const double d = a[i] - b[i]; s[0] += d * d; }); return host_results_[0]; }
-double Device::LInf(const double* a, int64_t n) { REDUCE(0, 1, n, { m[0] = fmax(m[0], fabs(a[i])); }); return std::max(0.0, host_results_[0]); }
-double Device::L1(const double* a, int64_t n) { REDUCE(1, 0, n, { s[0] += fabs(a[i]); }); return host_results_[0]; }
-double Device::ScaledLInf(const double* a, const double* sc, int64_t n) { REDUCE(0, 1, n, { m[0] = fmax(m[0], fabs(a[i] * sc[i])); }); return std::max(0.0, host_results_[0]); }
-double Device::ScaledSumSq(const double* a, const double* sc, int64_t n) { REDUCE(1, 0, n, { const double t = a[i] * sc[i]; s[0] += t * t; }); return host_results_[0]; }
+double Device::Dot(const double* a, const double* b, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { s[0] += a[i] * b[i]; }); return host_results_[0]; }
+double Device::SumSq(const double* a, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { s[0] += a[i] * a[i]; }); return host_results_[0]; }
+double Device::SumSqDiff(const double* a, const double* b, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { const double d = a[i] - b[i]; s[0] += d * d; }); return host_results_[0]; }
+double Device::LInf(const double* a, int64_t n, bool sharded) { REDUCE_S(sharded, 0, 1, n, { m[0] = fmax(m[0], fabs(a[i])); }); return std::max(0.0, host_results_[0]); }
+double Device::L1(const double* a, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { s[0] += fabs(a[i]); }); return host_results_[0]; }
+double Device::ScaledLInf(const double* a, const double* sc, int64_t n, bool sharded) { REDUCE_S(sharded, 0, 1, n, { m[0] = fmax(m[0], fabs(a[i] * sc[i])); }); return std::max(0.0, host_results_[0]); }
+double Device::ScaledSumSq(const double* a, const double* sc, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { const double t = a[i] * sc[i]; s[0] += t * t; }); return host_results_[0]; }
 void Device::DistancesSq(const double* x, const double* x0, int64_t n, const double* y, const double* y0, int64_t mm, double out[2]) {
   const int64_t total = n + mm;
-  REDUCE(2, 0, total, {
-    if (i < n) { const double d = x[i] - x0[i]; s[0] += d * d; }
+  const bool cp = count_primal();
+  REDUCE_S(true, 2, 0, total, {
+    if (i < n) { if (cp) { const double d = x[i] - x0[i]; s[0] += d * d; } }
     else { const int64_t j = i - n; const double d = y[j] - y0[j]; s[1] += d * d; }
   });
   out[0] = host_results_[0];
@@ -909,20 +1002,20 @@ static VectorInfoDev InfoFromHost(const double* r) {
   v.largest = r[5]; v.smallest = -r[6];
   return v;
 }
-VectorInfoDev Device::VectorInfo(const double* v, int64_t n) { REDUCE(5, 2, n, { info_add(v[i], s, m); }); return InfoFromHost(host_results_); }
-VectorInfoDev Device::CombinedBoundsInfo(const double* a, const double* b, int64_t n) { REDUCE(5, 2, n, { info_add(combine_bounds(a[i], b[i]), s, m); }); return InfoFromHost(host_results_); }
+VectorInfoDev Device::VectorInfo(const double* v, int64_t n, bool sharded) { REDUCE_S(sharded, 5, 2, n, { info_add(v[i], s, m); }); return InfoFromHost(host_results_); }
+VectorInfoDev Device::CombinedBoundsInfo(const double* a, const double* b, int64_t n, bool sharded) { REDUCE_S(sharded, 5, 2, n, { info_add(combine_bounds(a[i], b[i]), s, m); }); return InfoFromHost(host_results_); }
 VectorInfoDev Device::GapInfo(const double* lb, const double* ub, int64_t n) { REDUCE(5, 2, n, { info_add(ub[i] - lb[i], s, m); }); return InfoFromHost(host_results_); }
 VectorInfoDev Device::MatrixInfo(const SellDev& a) {
   const SellDev sd = a;
-  REDUCE(5, 2, sd.num_slots, {
+  REDUCE_S(true, 5, 2, sd.num_slots, {
     const int n = sd.slot_len[i];
     const int64_t base = sd.slice_ptr[i >> 5] + (i & 31);
     for (int j = 0; j < n; ++j) info_add(sd.val[base + static_cast<int64_t>(j) * 32], s, m);
   });
   return InfoFromHost(host_results_);
 }
-bool Device::BoundsValid(const double* lb, const double* ub, int64_t n) {  // sou.cc:701-723
-  REDUCE(1, 0, n, { if (!(lb[i] <= ub[i] && lb[i] < kInfD && ub[i] > -kInfD)) s[0] += 1.0; });
+bool Device::BoundsValid(const double* lb, const double* ub, int64_t n, bool sharded) {  // sou.cc:701-723
+  REDUCE_S(sharded, 1, 0, n, { if (!(lb[i] <= ub[i] && lb[i] < kInfD && ub[i] > -kInfD)) s[0] += 1.0; });
   return host_results_[0] == 0.0;
 }
 bool Device::AllNonNegative(const double* v, int64_t n) {
@@ -932,7 +1025,7 @@ bool Device::AllNonNegative(const double* v, int64_t n) {
 
 MSideStats Device::DualSideStats(const double* y, const double* kx, const double* lc, const double* uc, const double* dr, double cw_offset,
                                  bool homogeneous, int64_t mm) {
-  REDUCE(3, 3, mm, {  // iteration_stats.cc:66-134, 328-350
+  REDUCE_S(true, 3, 3, mm, {  // iteration_stats.cc:66-134, 328-350
     const double rs = dr != nullptr ? dr[i] : 1.0;
     const double ub = (homogeneous && isfinite(uc[i])) ? 0.0 : uc[i];
     const double lb = (homogeneous && isfinite(lc[i])) ? 0.0 : lc[i];
@@ -1013,7 +1106,7 @@ double Device::LagrangianPrimalGradient(const double* x, const double* kty, cons
 }
 double Device::LagrangianDualGradient(const double* y, const double* kx, const double* lc, const double* uc, double* grad, int64_t mm) {
   JointElem el{nullptr, y, kx, nullptr, nullptr, nullptr, nullptr, nullptr, lc, uc, 1.0, 0, mm};
-  REDUCE(1, 0, mm, {  // sou.cc:502-527
+  REDUCE_S(true, 1, 0, mm, {  // sou.cc:502-527
     const double coef = el.subgradient_coefficient(i);
     s[0] += coef * y[i];
     grad[i] = coef - kx[i];
@@ -1031,7 +1124,7 @@ void Device::ActiveSetPrimal(const double* x, const double* x0, const double* lv
   out[1] = static_cast<int64_t>(host_results_[1]);
 }
 void Device::ActiveSetDual(const double* y, const double* y0, const double* lc, const double* uc, int64_t mm, int64_t out[2]) {
-  REDUCE(2, 0, mm, {
+  REDUCE_S(true, 2, 0, mm, {
     const bool free_row = lc[i] == -kInfD && uc[i] == kInfD;
     const bool a = y[i] != 0.0 || free_row;
     const bool b = y0[i] != 0.0 || free_row;
@@ -1059,8 +1152,8 @@ __device__ __forceinline__ double gaussian(uint32_t seed, uint32_t stream_id, in
   return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 }  // namespace kernels
-double Device::RandomProjection(const double* v, int64_t n, uint32_t seed, uint32_t stream_id) {
-  REDUCE(2, 0, n, { const double z = gaussian(seed, stream_id, i); s[0] += z * v[i]; s[1] += z * z; });
+double Device::RandomProjection(const double* v, int64_t n, uint32_t seed, uint32_t stream_id, bool sharded, int64_t index_offset) {
+  REDUCE_S(sharded, 2, 0, n, { const double z = gaussian(seed, stream_id, i + index_offset); s[0] += z * v[i]; s[1] += z * z; });
   return host_results_[0] / std::sqrt(host_results_[1]);
 }
 
@@ -1077,20 +1170,28 @@ double* Device::TrScratch(int64_t doubles) {
 
 namespace kernels {
 // Runs the threshold search; leaves the step size in st->step_size (device).
+// Elements below `first` are skipped (replicated primal part on ranks > 0).
 template <class Elem>
-void tr_search(cudaStream_t stream, int64_t total, Elem el, double radius, double* scratch, double* partials, TrSearchState* st, int64_t* launches) {
+void tr_search(cudaStream_t stream, Comm* comm, int64_t total, int64_t first, Elem el, double radius, double* scratch, double* partials,
+               TrSearchState* st, double* totals, int64_t* launches) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch);
   double* a = scratch + total;
   double* b = scratch + 2 * total;
   const int nb = static_cast<int>(std::min<int64_t>(148 * 2, std::max<int64_t>(1, (total + kThreads * kTrUnroll - 1) / (kThreads * kTrUnroll))));
   const int nb_prep = static_cast<int>(std::min<int64_t>(kMaxReduceBlocks, std::max<int64_t>(1, (total + kThreads * 2 - 1) / (kThreads * 2))));
-  k_tr_prepare<Elem><<<nb_prep, kThreads, 0, stream>>>(total, el, keys, a, b, partials);
+  k_tr_prepare<Elem><<<nb_prep, kThreads, 0, stream>>>(total, first, el, keys, a, b, partials);
   k_tr_init<<<1, 32, 0, stream>>>(st, radius, partials, nb_prep);
   *launches += 2;
+  if (comm != nullptr) {
+    double* mx = reinterpret_cast<double*>(st) + offsetof(TrSearchState, max_abs_objective) / sizeof(double);
+    comm->AllReduceMax(mx, mx, 1, stream);
+  }
   for (int shift = 60; shift >= 0; shift -= 4) {
     k_tr_pass<<<nb, kThreads, 0, stream>>>(total, keys, a, b, st, shift, partials);
-    k_tr_decide<<<1, 17 * 32, 0, stream>>>(nb, partials, st, shift);
-    *launches += 2;
+    k_tr_totals<<<1, 17 * 32, 0, stream>>>(nb, partials, totals);
+    if (comm != nullptr) comm->AllReduceSum(totals, totals, 34, stream);
+    k_tr_pick<<<1, 1, 0, stream>>>(totals, st, shift);
+    *launches += 3;
   }
   k_tr_finish<<<1, 1, 0, stream>>>(st, radius);
   *launches += 1;
@@ -1102,8 +1203,10 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
                                        bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t mm, double out[3]) {
   const int64_t total = n + mm;
   const JointElem el{x, y, kx, kty, c, q, lv, uv, lc, uc, primal_weight, n, mm};
+  const int64_t first = count_primal() ? 0 : n;  // the primal part is replicated: rank 0 counts it
   // Lagrangian value = primal part + dual part (sou.cc:446-527).
-  REDUCE(2, 0, total, {
+  REDUCE_S(true, 2, 0, total, {
+    if (i < first) return;
     if (i < n) {
       const double g = el.primal_gradient(i);
       const double op = q != nullptr ? q[i] * x[i] : 0.0;
@@ -1114,15 +1217,16 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
     }
   });
   const double lagrangian = host_results_[0] + host_results_[1];
-  double* scratch = TrScratch(3 * total + 16);
+  double* scratch = TrScratch(3 * total + 64);
   TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * total);
 
   if (!use_diagonal_solver) {
-    tr_search(STREAM, total, el, radius, scratch, partials_, st, &launches_);
+    tr_search(STREAM, comm_, total, first, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
     CUDA_OK(cudaGetLastError());
     // objective deltas at the solution (trust_region.cc:929-967)
     const TrSearchState* cst = st;
-    REDUCE(2, 0, total, {
+    REDUCE_S(true, 2, 0, total, {
+      if (i < first) return;
       double obj, lb, ub, center, w, qd;
       el.get(i, obj, lb, ub, center, w, qd);
       const double sol = projected_value(center, obj, w, lb, ub, cst->step_size);
@@ -1144,7 +1248,8 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
     for (;;) {
       const double sf = bracketing ? hi : (lo + hi) / 2.0;
       if (!bracketing && !((hi - lo) >= diagonal_tol * std::max(1.0, lo))) break;
-      REDUCE(1, 0, total, {
+      REDUCE_S(true, 1, 0, total, {
+        if (i < first) return;
         double obj, lb, ub, center, w, qd;
         el.get(i, obj, lb, ub, center, w, qd);
         const double sw = sqrt(w);
@@ -1161,7 +1266,8 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
     scaling = (hi + lo) / 2.0;
   }
   const bool zero_radius = radius == 0.0;
-  REDUCE(2, 0, total, {
+  REDUCE_S(true, 2, 0, total, {
+    if (i < first) return;
     double obj, lb, ub, center, w, qd;
     el.get(i, obj, lb, ub, center, w, qd);
     double diff = 0.0;
@@ -1182,9 +1288,9 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
 void Device::SolveTrustRegion(const double* obj, const double* lb, const double* ub, const double* center, const double* w, double radius,
                               int64_t n, double* solution, double* step_size, double* objective_value) {
   const VectorElem el{obj, lb, ub, center, w, nullptr};
-  double* scratch = TrScratch(3 * n + 16);
+  double* scratch = TrScratch(3 * n + 64);
   TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * n);
-  tr_search(STREAM, n, el, radius, scratch, partials_, st, &launches_);
+  tr_search(STREAM, nullptr, n, 0, el, radius, scratch, partials_, st, scratch + 3 * n + 16, &launches_);
   CUDA_OK(cudaGetLastError());
   const TrSearchState* cst = st;
   REDUCE(1, 0, n, {
@@ -1271,7 +1377,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int nt_main = static_cast<int>(std::max<int64_t>(1, (cols.num_slots + kThreads - 1) / kThreads));
   const int nt_fix = cols.num_split > 0 ? static_cast<int>((cols.num_split * 32 + kThreads - 1) / kThreads) : 0;
-  const int64_t need = static_cast<int64_t>(np) + nd_main + nd_fix + nt_main + nt_fix + 8;
+  const int64_t need = static_cast<int64_t>(np) + nd_main + nd_fix + std::max<int64_t>(nt_main + nt_fix, Blocks(b.n)) + 8;
   if (need > step_partials_size_) {
     cudaFree(step_partials_);
     step_partials_ = nullptr;
@@ -1305,12 +1411,26 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr);
     }
     if (slot >= 0) ev(slot, 2);
-    if (b.n > 0) {
-      launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr);
+    if (comm_ != nullptr) {
+      // local ||dy||^2 -> exchange[n]; local K^T y' partial -> exchange[0..n) in column order
+      k_sum_to_slot<<<1, kDecideThreads, 0, STREAM>>>(b.state, pd, b.m > 0 ? nd_main + nd_fix : 0, b.exchange + b.n);
+      ++launches_;
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{b.exchange, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr);
+      comm_->AllReduceSum(b.exchange, b.exchange, b.n + 1, stream_);
+      const int nk = Blocks(b.n);
+      k_kty_finish<<<nk, kThreads, 0, STREAM>>>(p, b.exchange, pt);
+      ++launches_;
+      if (slot >= 0) ev(slot, 3);
+      k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, np, b.exchange + b.n, -1, pt, nk);
+      ++launches_;
+    } else {
+      if (b.n > 0) {
+        launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr);
+      }
+      if (slot >= 0) ev(slot, 3);
+      k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
+      ++launches_;
     }
-    if (slot >= 0) ev(slot, 3);
-    k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
-    ++launches_;
     if (slot >= 0) ev(slot, 4);
   }
   CUDA_OK(cudaGetLastError());

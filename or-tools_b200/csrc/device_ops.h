@@ -24,6 +24,8 @@
 
 namespace pdlp_b200 {
 
+class Comm;  // comm.h
+
 // ---------------------------------------------------------------------------
 // Host-side image of one SELL-32 orientation (built by sell_builder.cc).
 // ---------------------------------------------------------------------------
@@ -57,7 +59,7 @@ struct QpHost {  // device-ready problem image
 // image to a contiguous block of constraint rows (multi-GPU row sharding);
 // pass 0 / m for the whole problem. Throws std::runtime_error on bad input.
 QpHost BuildQpHost(const PdlpProblemView& view, int64_t row_begin, int64_t row_end,
-                   int sigma = 4096);
+                   int sigma = 4096, bool natural_primal_order = false);
 
 // ---------------------------------------------------------------------------
 // Device objects
@@ -119,6 +121,18 @@ class Device {
   static int DeviceCount();  // 0 if no driver / device
 
   int64_t launches() const { return launches_; }
+  // Row-sharded solves (one process per GPU): reductions over dual-side
+  // (row-sharded) data are completed by an all-reduce on this communicator;
+  // primal-side data is replicated. Not owned.
+  void SetComm(Comm* comm) { comm_ = comm; }
+  Comm* comm() const { return comm_; }
+  bool count_primal() const;  // true on rank 0 / single GPU
+  // Rank 0's value on every rank (time limits / interrupt flags must lead to
+  // the same control flow everywhere); identity without a communicator.
+  double RootValue(double v);
+  double MaxOverRanks(double v);
+  void AllReduceSumVec(double* buf, int64_t n);
+  void AllReduceMaxVec(double* buf, int64_t n);
   void* stream() const { return stream_; }
   void Sync();
 
@@ -133,6 +147,7 @@ class Device {
   void UploadPermuted(double* dst, const double* src_host, const int32_t* row_of_pos_dev, int64_t n);
   void DownloadPermuted(double* dst_host, const double* src, const int32_t* row_of_pos_dev, int64_t n);
   int32_t* UploadI32(const std::vector<int32_t>& v);
+  void ScatterInto(double* dst, const double* src, const int32_t* row_of_pos_dev, int64_t n);  // dst[row_of_pos[p]] = src[p]
 
   SellDev UploadSell(const SellHost& h);
   void FreeSell(SellDev& s);
@@ -140,10 +155,18 @@ class Device {
 
   // ---- SpMV + generic vector kernels (positions order) -------------------
   void SpMV(const SellDev& a, const double* x, double* out);           // out = A x
+  // out[perm[pos]] = (A x)[pos]: the product scattered into another order
+  // (row-sharded K^T y partials go to the caller's column order before the all-reduce).
+  void SpMVScatter(const SellDev& a, const double* x, const int32_t* perm, double* out);
+  // Raw row-wise max|a_ij s_j| (norm 0) or sum (a_ij s_j)^2 (norm 1) scattered through perm,
+  // and the finishing step out = (norm ? sqrt(out) : out) * |own| after the all-reduce.
+  void RowNormRawScatter(const SellDev& a, int norm, const double* other_scale, const int32_t* perm, double* out);
+  void FinishRowNorm(double* out, int norm, const double* own_scale, int64_t n);
   // out[pos] = norm over the row of |a_ij * other_scale[col]| * |own_scale[pos]|; norm 0 LInf, 1 L2
   // (ScaledColLInfNorm / ScaledColL2Norm, sharder.cc:288-332).
   void ScaledRowNorm(const SellDev& a, int norm, const double* other_scale, const double* own_scale, double* out);
-  void ScaleMatrix(SellDev& a, const double* own_scale, const double* other_scale);  // a_ij *= own[i]*other[j]
+  // a_ij *= own[i]*other[j]; own is indexed by position, or by own_perm[position] when given
+  void ScaleMatrix(SellDev& a, const double* own_scale, const double* other_scale, const int32_t* own_perm = nullptr);
   void DivideBySqrt(double* vec, const double* divisor, int64_t n);                   // skip zeros (sou.cc:354-365)
   void Mul(double* dst, const double* a, int64_t n);                                  // dst *= a
   void Div(double* dst, const double* a, int64_t n);                                  // dst /= a
@@ -156,19 +179,20 @@ class Device {
   void WeightedAverageAdd(double* avg, const double* v, double ratio, int64_t n);     // avg += ratio*(v-avg)
 
   // reductions (deterministic: fixed grid + fixed-order final pass); host result
-  double Dot(const double* a, const double* b, int64_t n);
-  double SumSq(const double* a, int64_t n);
-  double SumSqDiff(const double* a, const double* b, int64_t n);
-  double LInf(const double* a, int64_t n);
-  double L1(const double* a, int64_t n);
-  double ScaledLInf(const double* a, const double* s, int64_t n);
-  double ScaledSumSq(const double* a, const double* s, int64_t n);
+  // `sharded`: the vector is row-sharded across ranks (all-reduced result)
+  double Dot(const double* a, const double* b, int64_t n, bool sharded = false);
+  double SumSq(const double* a, int64_t n, bool sharded = false);
+  double SumSqDiff(const double* a, const double* b, int64_t n, bool sharded = false);
+  double LInf(const double* a, int64_t n, bool sharded = false);
+  double L1(const double* a, int64_t n, bool sharded = false);
+  double ScaledLInf(const double* a, const double* s, int64_t n, bool sharded = false);
+  double ScaledSumSq(const double* a, const double* s, int64_t n, bool sharded = false);
   void DistancesSq(const double* x, const double* x0, int64_t n, const double* y, const double* y0, int64_t m, double out[2]);
-  VectorInfoDev VectorInfo(const double* v, int64_t n);                       // ComputeVectorInfo (sou.cc:179-191)
-  VectorInfoDev CombinedBoundsInfo(const double* a, const double* b, int64_t n);  // sou.cc:223-238
+  VectorInfoDev VectorInfo(const double* v, int64_t n, bool sharded = false);                       // ComputeVectorInfo (sou.cc:179-191)
+  VectorInfoDev CombinedBoundsInfo(const double* a, const double* b, int64_t n, bool sharded = false);  // sou.cc:223-238
   VectorInfoDev GapInfo(const double* lb, const double* ub, int64_t n);       // sou.cc:193-205
   VectorInfoDev MatrixInfo(const SellDev& a);                                 // sou.cc:207-221
-  bool BoundsValid(const double* lb, const double* ub, int64_t n);           // HasValidBounds
+  bool BoundsValid(const double* lb, const double* ub, int64_t n, bool sharded = false);           // HasValidBounds
   bool AllNonNegative(const double* v, int64_t n);
 
   // KKT reductions (iteration_stats.cc:66-350). dr/dc may be null (= ones).
@@ -185,7 +209,7 @@ class Device {
   // SetActiveSetInformation (pdhg.cc:1476-1545): out = {count, change}
   void ActiveSetPrimal(const double* x, const double* x0, const double* lv, const double* uv, int64_t n, int64_t out[2]);
   void ActiveSetDual(const double* y, const double* y0, const double* lc, const double* uc, int64_t m, int64_t out[2]);
-  double RandomProjection(const double* v, int64_t n, uint32_t seed, uint32_t stream_id);
+  double RandomProjection(const double* v, int64_t n, uint32_t seed, uint32_t stream_id, bool sharded = false, int64_t index_offset = 0);
 
   // ---- trust region (trust_region.cc) ------------------------------------
   // Joint problem (trust_region.cc:115-162) over (x, y): returns lagrangian
@@ -211,6 +235,10 @@ class Device {
     double* avg_y = nullptr;
     const double *c = nullptr, *q = nullptr, *lv = nullptr, *uv = nullptr, *lc = nullptr, *uc = nullptr;
     StepState* state = nullptr;  // device
+    // row-sharded solve only: [n + 1] exchange buffer for the K^T y' partial
+    // (+ this rank's ||dy||^2 in the last slot) and the scatter permutation
+    double* exchange = nullptr;
+    const int32_t* primal_scatter = nullptr;
   };
   StepState* AllocState();
   void UploadState(StepState* dev, const StepState& host);
@@ -244,6 +272,7 @@ class Device {
  private:
   friend struct DeviceImpl;
   int device_ = 0;
+  Comm* comm_ = nullptr;
   void* stream_ = nullptr;
   double* partials_ = nullptr;   // reduction scratch
   double* results_ = nullptr;    // small device result vector

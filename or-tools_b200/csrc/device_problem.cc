@@ -1,6 +1,8 @@
 // device_problem.cc -- see device_problem.h.
 #include "device_problem.h"
 
+#include "comm.h"
+
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -12,11 +14,46 @@ namespace {
 constexpr double kInf = std::numeric_limits<double>::infinity();
 }
 
-DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device) : dev_(new Device(cuda_device)) {
-  QpHost h = BuildQpHost(view, 0, view.num_constraints);
+// Contiguous row blocks of (roughly) equal nnz, the mass rule of sharder.cc:51-70
+// applied to the rows of K: block g ends at the first row where the running nnz
+// reaches (g + 1) / G of the total.
+void ComputeRowBlock(const PdlpProblemView& v, int rank, int world, int64_t* begin, int64_t* end) {
+  const int64_t m = v.num_constraints, nnz = v.col_starts[v.num_variables];
+  std::vector<int64_t> cum(m + 1, 0);
+  for (int64_t k = 0; k < nnz; ++k) {
+    const int64_t r = v.row_indices[k];
+    if (r < 0 || r >= m) throw std::runtime_error("row index out of range");
+    ++cum[r + 1];
+  }
+  for (int64_t r = 0; r < m; ++r) cum[r + 1] += cum[r];
+  auto boundary = [&](int g) -> int64_t {
+    if (g <= 0) return 0;
+    if (g >= world) return m;
+    // balance nnz + rows so that empty / very sparse tails are still spread
+    const double target = (static_cast<double>(nnz) + static_cast<double>(m)) * g / world;
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (static_cast<double>(cum[mid]) + static_cast<double>(mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  *begin = boundary(rank);
+  *end = boundary(rank + 1);
+}
+
+DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm* comm) : dev_(new Device(cuda_device)), comm_(comm) {
+  m_global_ = view.num_constraints;
+  int64_t row_end = m_global_;
+  if (comm_ != nullptr) {
+    ComputeRowBlock(view, comm_->rank(), comm_->world_size(), &row_begin_, &row_end);
+    dev_->SetComm(comm_);
+  }
+  QpHost h = BuildQpHost(view, row_begin_, row_end, 4096, /*natural_primal_order=*/comm_ != nullptr);
   n_ = h.n;
   m_ = h.m;
   nnz_ = h.nnz;
+  if (comm_ != nullptr) exchange_ = dev_->AllocF64(n_ + 1);
   objective_offset_ = view.objective_offset;
   objective_scaling_factor_ = view.objective_scaling_factor;
   rows_ = dev_->UploadSell(h.rows);
@@ -47,7 +84,7 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device) : dev
 }
 
 DeviceProblem::~DeviceProblem() {
-  for (double* p : {c_, q_, lv_, uv_, lc_, uc_, ones_n_, ones_m_}) dev_->Free(p);
+  for (double* p : {c_, q_, lv_, uv_, lc_, uc_, ones_n_, ones_m_, exchange_}) dev_->Free(p);
   for (int k = 0; k < 4; ++k) { dev_->Free(tmp_n_[k]); dev_->Free(tmp_m_[k]); }
   dev_->Free(primal_perm_);
   dev_->Free(dual_perm_);
@@ -64,7 +101,38 @@ void DeviceProblem::RescaleQuadraticProgram(const double* col_scaling, const dou
   d.Mul(lc_, row_scaling, m_);
   d.Mul(uc_, row_scaling, m_);
   d.ScaleMatrix(rows_, row_scaling, col_scaling);
-  d.ScaleMatrix(cols_, col_scaling, row_scaling);
+  d.ScaleMatrix(cols_, col_scaling, row_scaling, sharded() ? primal_perm_ : nullptr);
+}
+
+void DeviceProblem::KTy(const double* y, double* out) {
+  if (!sharded()) { dev_->SpMV(cols_, y, out); return; }
+  // local partial in column order, then the exchange step
+  dev_->SpMVScatter(cols_, y, primal_perm_, exchange_);
+  dev_->AllReduceSumVec(exchange_, n_);
+  dev_->CopyD2D(out, exchange_, n_);
+}
+
+void DeviceProblem::DownloadDual(double* host, const double* src) {
+  if (!sharded()) { dev_->DownloadPermuted(host, src, dual_perm_, m_); return; }
+  // every rank receives the whole dual vector: blocks are written into a
+  // zeroed full-length buffer and summed across ranks
+  double* full = dev_->AllocF64(m_global_);
+  dev_->Fill(full, 0.0, m_global_);
+  dev_->ScatterInto(full + row_begin_, src, dual_perm_, m_);
+  dev_->AllReduceSumVec(full, m_global_);
+  dev_->Download(host, full, m_global_);
+  dev_->Free(full);
+}
+
+// Column norms of D_r K D_c (ScaledColLInfNorm / ScaledColL2Norm of the
+// reference applied to K): on a row block they are partial and are completed
+// by an all-reduce (max for LInf, sum of squares for L2).
+void DeviceProblem::ColumnNorms(int norm, const double* row_scaling, const double* col_scaling, double* out) {
+  Device& d = *dev_;
+  if (!sharded()) { d.ScaledRowNorm(cols_, norm, row_scaling, col_scaling, out); return; }
+  d.RowNormRawScatter(cols_, norm, row_scaling, primal_perm_, out);
+  if (norm == 0) d.AllReduceMaxVec(out, n_); else d.AllReduceSumVec(out, n_);
+  d.FinishRowNorm(out, norm, col_scaling, n_);
 }
 
 void DeviceProblem::ReplaceLargeConstraintBoundsWithInfinity(double threshold) {
@@ -72,7 +140,7 @@ void DeviceProblem::ReplaceLargeConstraintBoundsWithInfinity(double threshold) {
   dev_->ReplaceLargeWithInf(uc_, threshold, m_);
 }
 
-bool DeviceProblem::HasValidBounds() { return dev_->BoundsValid(lc_, uc_, m_) && dev_->BoundsValid(lv_, uv_, n_); }
+bool DeviceProblem::HasValidBounds() { return dev_->BoundsValid(lc_, uc_, m_, sharded()) && dev_->BoundsValid(lv_, uv_, n_); }
 bool DeviceProblem::ObjectiveMatrixIsNonNegative() { return q_ == nullptr || dev_->AllNonNegative(q_, n_); }
 
 namespace {
@@ -93,18 +161,18 @@ PdlpQuadraticProgramStats DeviceProblem::ComputeStats() {
   Device& d = *dev_;
   // row / column LInf norms with unit scaling (sou.cc:240-266)
   d.ScaledRowNorm(rows_, 0, ones_n_, ones_m_, tmp_m_[0]);
-  d.ScaledRowNorm(cols_, 0, ones_m_, ones_n_, tmp_n_[0]);
-  const Info row_info = Finish(d.VectorInfo(tmp_m_[0], m_));
+  ColumnNorms(0, ones_m_, ones_n_, tmp_n_[0]);
+  const Info row_info = Finish(d.VectorInfo(tmp_m_[0], m_, sharded()));
   const Info col_info = Finish(d.VectorInfo(tmp_n_[0], n_));
   const Info mat = Finish(d.MatrixInfo(cols_));
-  const Info bounds = Finish(d.CombinedBoundsInfo(uc_, lc_, m_));
+  const Info bounds = Finish(d.CombinedBoundsInfo(uc_, lc_, m_, sharded()));
   const Info var_bounds = Finish(d.CombinedBoundsInfo(uv_, lv_, n_));
   const Info obj = Finish(d.VectorInfo(c_, n_));
   const Info gaps = Finish(d.GapInfo(lv_, uv_, n_));
   PdlpQuadraticProgramStats s;
   std::memset(&s, 0, sizeof(s));
   s.num_variables = n_;
-  s.num_constraints = m_;
+  s.num_constraints = m_global_;
   s.constraint_matrix_col_min_l_inf_norm = col_info.smallest;
   s.constraint_matrix_row_min_l_inf_norm = row_info.smallest;
   s.constraint_matrix_num_nonzeros = mat.nfn;
@@ -134,7 +202,7 @@ PdlpQuadraticProgramStats DeviceProblem::ComputeStats() {
 void DeviceProblem::ApplyScalingIterationsForNorm(int num_iterations, int norm, double* row_scaling, double* col_scaling) {
   Device& d = *dev_;
   for (int it = 0; it < num_iterations; ++it) {
-    d.ScaledRowNorm(cols_, norm, row_scaling, col_scaling, tmp_n_[0]);  // column norms of D_r K D_c
+    ColumnNorms(norm, row_scaling, col_scaling, tmp_n_[0]);             // column norms of D_r K D_c
     d.ScaledRowNorm(rows_, norm, col_scaling, row_scaling, tmp_m_[0]);  // row norms
     d.DivideBySqrt(col_scaling, tmp_n_[0], n_);
     d.DivideBySqrt(row_scaling, tmp_m_[0], m_);
@@ -231,6 +299,7 @@ void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const doub
 }
 
 void DeviceProblem::DownloadValuesCsc(double* values) {
+  if (sharded()) throw std::runtime_error("DownloadValuesCsc is not available on a row-sharded problem");
   std::vector<double> sell;
   dev_->DownloadSellValues(cols_, sell);
   const SellHost& s = cols_meta_;

@@ -13,18 +13,30 @@
 
 namespace pdlp_b200 {
 
+// The block of constraint rows rank `rank` of `world` keeps (host-only helper).
+void ComputeRowBlock(const PdlpProblemView& view, int rank, int world, int64_t* begin, int64_t* end);
+
 class DeviceProblem {
  public:
   // Uploads the QP and builds both sparse orientations. Throws
   // std::runtime_error on CUDA failure / no device.
-  DeviceProblem(const PdlpProblemView& view, int cuda_device);
+  // With a communicator (one process per GPU) this rank keeps
+  // the contiguous block of constraint rows [row_begin, row_end) chosen by the
+  // nnz-balanced rule of sharder.cc:51-70; dual-length vectors are that block,
+  // primal-length vectors are replicated in the caller's column order.
+  DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm* comm = nullptr);
   ~DeviceProblem();
   DeviceProblem(const DeviceProblem&) = delete;
   DeviceProblem& operator=(const DeviceProblem&) = delete;
 
   Device& dev() { return *dev_; }
   int64_t n() const { return n_; }
-  int64_t m() const { return m_; }
+  int64_t m() const { return m_; }                 // rows held by this rank
+  int64_t m_global() const { return m_global_; }   // rows of the whole problem
+  int64_t row_begin() const { return row_begin_; }
+  bool sharded() const { return comm_ != nullptr; }
+  const int32_t* primal_scatter() const { return primal_perm_; }
+  double* exchange() const { return exchange_; }
   int64_t nnz() const { return nnz_; }
   bool is_lp() const { return q_ == nullptr; }
 
@@ -44,13 +56,18 @@ class DeviceProblem {
   // vectors
   double* NewPrimal() { return dev_->AllocF64(n_); }
   double* NewDual() { return dev_->AllocF64(m_); }
-  void UploadPrimal(double* dst, const double* host) { dev_->UploadPermuted(dst, host, primal_perm_, n_); }
-  void UploadDual(double* dst, const double* host) { dev_->UploadPermuted(dst, host, dual_perm_, m_); }
-  void DownloadPrimal(double* host, const double* src) { dev_->DownloadPermuted(host, src, primal_perm_, n_); }
-  void DownloadDual(double* host, const double* src) { dev_->DownloadPermuted(host, src, dual_perm_, m_); }
+  // host vectors are always full length in the caller's order
+  void UploadPrimal(double* dst, const double* host) {
+    if (sharded()) dev_->Upload(dst, host, n_); else dev_->UploadPermuted(dst, host, primal_perm_, n_);
+  }
+  void UploadDual(double* dst, const double* host) { dev_->UploadPermuted(dst, host + row_begin_, dual_perm_, m_); }
+  void DownloadPrimal(double* host, const double* src) {
+    if (sharded()) dev_->Download(host, src, n_); else dev_->DownloadPermuted(host, src, primal_perm_, n_);
+  }
+  void DownloadDual(double* host, const double* src);
 
   void Kx(const double* x, double* out) { dev_->SpMV(rows_, x, out); }    // K x    (pdhg.cc:1912-1916)
-  void KTy(const double* y, double* out) { dev_->SpMV(cols_, y, out); }   // K^T y  (sharder.cc:160-173)
+  void KTy(const double* y, double* out);                                  // K^T y  (sharder.cc:160-173)
 
   // sharded_quadratic_program.cc:148-189
   void RescaleQuadraticProgram(const double* col_scaling, const double* row_scaling);
@@ -86,8 +103,12 @@ class DeviceProblem {
   double* tmp_m(int k) { return tmp_m_[k]; }
 
  private:
+  void ColumnNorms(int norm, const double* row_scaling, const double* col_scaling, double* out);
   std::unique_ptr<Device> dev_;
+  Comm* comm_ = nullptr;
   int64_t n_ = 0, m_ = 0, nnz_ = 0;
+  int64_t m_global_ = 0, row_begin_ = 0;
+  double* exchange_ = nullptr;  // [n + 1], row-sharded solves only
   double objective_offset_ = 0, objective_scaling_factor_ = 1;
   double *c_ = nullptr, *q_ = nullptr, *lv_ = nullptr, *uv_ = nullptr, *lc_ = nullptr, *uc_ = nullptr;
   SellDev rows_, cols_;

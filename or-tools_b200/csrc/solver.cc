@@ -93,11 +93,11 @@ bool OptimalityCriteriaMet(const DetailedCriteria& oc, const PdlpConvergenceInfo
 }
 struct ReasonAndType { int reason, type; };
 std::optional<ReasonAndType> CheckSimpleTerminationCriteria(const PdlpTerminationCriteria& c, const PdlpIterationStats& st,
-                                                            const volatile int32_t* interrupt) {  // termination.cc:161-184
+                                                            bool interrupted) {  // termination.cc:161-184
   if (st.iteration_number >= c.iteration_limit) return ReasonAndType{PDLP_TERMINATION_REASON_ITERATION_LIMIT, PDLP_POINT_TYPE_NONE};
   if (st.cumulative_kkt_matrix_passes >= c.kkt_matrix_pass_limit) return ReasonAndType{PDLP_TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT, PDLP_POINT_TYPE_NONE};
   if (st.cumulative_time_sec >= c.time_sec_limit) return ReasonAndType{PDLP_TERMINATION_REASON_TIME_LIMIT, PDLP_POINT_TYPE_NONE};
-  if (interrupt != nullptr && *interrupt != 0) return ReasonAndType{PDLP_TERMINATION_REASON_INTERRUPTED_BY_USER, PDLP_POINT_TYPE_NONE};
+  if (interrupted) return ReasonAndType{PDLP_TERMINATION_REASON_INTERRUPTED_BY_USER, PDLP_POINT_TYPE_NONE};
   return std::nullopt;
 }
 std::optional<ReasonAndType> CheckIterateTerminationCriteria(const PdlpTerminationCriteria& c, const PdlpIterationStats& st,
@@ -321,8 +321,14 @@ class DeviceSolve {
   void ApplyRestartChoice(int restart);
   PdlpIterationStats CreateSimpleIterationStats(int restart_used) const;
   std::optional<SolverResultCpp> MajorIterationAndTerminationCheck(bool force_numerical, const volatile int32_t* interrupt, SolveLogCpp& log);
-  std::optional<ReasonAndType> UpdateIterationStatsAndCheckTermination(bool force_numerical, const volatile int32_t* interrupt,
+  std::optional<ReasonAndType> UpdateIterationStatsAndCheckTermination(bool force_numerical, bool interrupted,
                                                                        const PdlpIterationStats& full_stats, PdlpIterationStats& stats);
+  // The interrupt flag as every rank must see it (rank 0 decides on a row-sharded solve).
+  bool Interrupted(const volatile int32_t* interrupt) {
+    const bool local = interrupt != nullptr && *interrupt != 0;
+    if (!P.sharded()) return local;
+    return D.RootValue(local ? 1.0 : 0.0) != 0.0;
+  }
   void ConvergenceAndInfeasibility(const double* x, const double* y, const double* kty_or_null, int type, PdlpConvergenceInformation* conv,
                                    PdlpInfeasibilityInformation* infeas);
   void AddPointMetadata(const double* x, const double* y, int type, PdlpIterationStats& stats);
@@ -366,6 +372,7 @@ class DeviceSolve {
   bool force_numerical_ = false;
   int target_stop_ = std::numeric_limits<int>::max();
   double device_step_ms_ = 0, device_total_ms_ = 0;
+  bool interrupt_polled_ = false;  // some rank was given an interrupt flag
 };
 
 int DeviceSolve::DetermineDistanceBasedRestartChoice() {  // pdhg.cc:2074-2107
@@ -500,7 +507,7 @@ void DeviceSolve::AddPointMetadata(const double* x, const double* y, int type, P
   for (int k = 0; k < md.num_random_projections; ++k) {
     const uint32_t seed = static_cast<uint32_t>(params_.random_projection_seeds[k]);
     md.random_primal_projections[k] = D.RandomProjection(x, P.n(), seed, 0);
-    md.random_dual_projections[k] = D.RandomProjection(y, P.m(), seed, 1);
+    md.random_dual_projections[k] = D.RandomProjection(y, P.m(), seed, 1, P.sharded(), P.row_begin());
   }
   if (type != PDLP_POINT_TYPE_ITERATE_DIFFERENCE) {  // SetActiveSetInformation, pdhg.cc:1476-1545
     int64_t pc[2], dcnt[2];
@@ -527,7 +534,7 @@ void DeviceSolve::MaterializeDeltas() {
 }
 
 // pdhg.cc:1567-1653
-std::optional<ReasonAndType> DeviceSolve::UpdateIterationStatsAndCheckTermination(bool force_numerical, const volatile int32_t* interrupt,
+std::optional<ReasonAndType> DeviceSolve::UpdateIterationStatsAndCheckTermination(bool force_numerical, bool interrupted,
                                                                                   const PdlpIterationStats& full_stats, PdlpIterationStats& stats) {
   ConvergenceAndInfeasibility(X(), Y(), Kty(), PDLP_POINT_TYPE_CURRENT_ITERATE, &stats.convergence_information[stats.num_convergence_information],
                               &stats.infeasibility_information[stats.num_infeasibility_information]);
@@ -563,7 +570,7 @@ std::optional<ReasonAndType> DeviceSolve::UpdateIterationStatsAndCheckTerminatio
     callback_(info);
   }
   if (const auto t = CheckIterateTerminationCriteria(params_.termination_criteria, stats, original_bound_norms_, force_numerical); t.has_value()) return t;
-  return CheckSimpleTerminationCriteria(params_.termination_criteria, full_stats, interrupt);
+  return CheckSimpleTerminationCriteria(params_.termination_criteria, full_stats, interrupted);
 }
 
 // pdhg.cc:2216-2244 + 329-342. Downloads the chosen point (still scaled).
@@ -605,7 +612,7 @@ SolverResultCpp DeviceSolve::ConstructOriginalSolverResult(SolverResultCpp resul
   D.Mul(y, dr_, P.m());
   D.Div(rc, dc_, P.n());
   result.primal_solution.resize(P.n());
-  result.dual_solution.resize(P.m());
+  result.dual_solution.resize(P.m_global());
   result.reduced_costs.resize(P.n());
   P.DownloadPrimal(result.primal_solution.data(), x);
   P.DownloadDual(result.dual_solution.data(), y);
@@ -633,13 +640,15 @@ std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bo
   const bool is_major = cycle == 0 && iterations_completed_ > 0;
   const int restart = force_numerical ? PDLP_RESTART_CHOICE_NO_RESTART : ChooseRestartToApply(is_major);
   PdlpIterationStats stats = CreateSimpleIterationStats(restart);
+  if (P.sharded()) stats.cumulative_time_sec = D.RootValue(stats.cumulative_time_sec);  // one clock decides the time limit
   const PdlpIterationStats full_work_stats = stats;
-  const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_work_stats, interrupt);
+  const bool interrupted = Interrupted(interrupt);
+  const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_work_stats, interrupted);
   const bool check_termination = cycle % params_.termination_check_frequency == 0 || simple.has_value() || force_numerical;
   if (check_termination) {
     const double* avg_x = PrimalAverage();
     const double* avg_y = DualAverage();
-    const auto maybe = UpdateIterationStatsAndCheckTermination(force_numerical, interrupt, full_work_stats, stats);
+    const auto maybe = UpdateIterationStatsAndCheckTermination(force_numerical, interrupted, full_work_stats, stats);
     if (params_.record_iteration_stats) log.iteration_stats.push_back(stats);
     if (maybe.has_value()) return PickSolutionAndConstructSolverResult(avg_x, avg_y, stats, maybe->reason, maybe->type, std::move(log));
   } else if (params_.record_iteration_stats) {
@@ -683,7 +692,7 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
   hs_.inner_iterations = 0;
   hs_.halt = kHaltNone;
   int k_stop = NextCheckpoint(k);
-  if (interrupt != nullptr) k_stop = std::min(k_stop, k + 32);
+  if (interrupt_polled_) k_stop = std::min(k_stop, k + 32);
   hs_.k_stop = k_stop;
   hs_.kkt_pass_limit = params_.termination_criteria.kkt_matrix_pass_limit;
   hs_.avg_weight_sum = avg_x_weight_;
@@ -748,7 +757,7 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
     const double new_ratio = new_primal_step_size / primal_step_size;
     D.DualStepFromProducts(Y(), kx_cur_, kx_next_, P.lc(), P.uc(), dual_weight * new_primal_step_size, new_ratio, y_next, m);
     P.KTy(y_next, kty_next);
-    const double delta_dual_norm = std::sqrt(D.SumSqDiff(y_next, Y(), m));
+    const double delta_dual_norm = std::sqrt(D.SumSqDiff(y_next, Y(), m, P.sharded()));
     const double delta_dual_prod_norm = std::sqrt(D.SumSqDiff(Kty(), kty_next, n));
     if (omega * new_primal_step_size * delta_dual_prod_norm <= contraction * delta_dual_norm) {
       hs_.step_size = new_primal_step_size * omega;
@@ -785,6 +794,7 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
 // pdhg.cc:3017-3092 (loop part; the start-up part is at the end of Prepare)
 std::optional<SolverResultCpp> DeviceSolve::Advance(int target_iterations, const volatile int32_t* interrupt_solve) {
   target_stop_ = target_iterations;
+  interrupt_polled_ = D.MaxOverRanks(interrupt_solve != nullptr ? 1.0 : 0.0) != 0.0;
   const bool device_loop = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE;
   D.TimelineStart(0);
   std::optional<SolverResultCpp> done;
@@ -896,6 +906,8 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   if (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE) { kx_cur_ = P.NewDual(); kx_next_ = P.NewDual(); }
   buf_.c = P.c(); buf_.q = P.q(); buf_.lv = P.lv(); buf_.uv = P.uv(); buf_.lc = P.lc(); buf_.uc = P.uc();
   buf_.state = D.AllocState();
+  buf_.exchange = P.exchange();
+  buf_.primal_scatter = P.sharded() ? P.primal_scatter() : nullptr;
   std::memset(&hs_, 0, sizeof(hs_));
   hs_.cur = 0; hs_.prev = 1; hs_.cand = 2;
 
@@ -907,11 +919,11 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
     P.UploadPrimal(X(), initial_solution->primal.data());
     if (std::isnan(std::sqrt(D.SumSq(X(), n)))) return err("Initial primal solution has a NAN.");
     if (const double v = D.LInf(X(), n); v > kBig) return err("Initial primal solution has an entry with absolute value " + G(v) + " which exceeds limit of " + G(kBig));
-    if (static_cast<int64_t>(initial_solution->dual.size()) != m)
-      return err(Fmt("Initial dual solution has size %lld which differs from problem dual size %lld", (long long)initial_solution->dual.size(), (long long)m));
+    if (static_cast<int64_t>(initial_solution->dual.size()) != P.m_global())
+      return err(Fmt("Initial dual solution has size %lld which differs from problem dual size %lld", (long long)initial_solution->dual.size(), (long long)P.m_global()));
     P.UploadDual(Y(), initial_solution->dual.data());
-    if (std::isnan(std::sqrt(D.SumSq(Y(), m)))) return err("Initial dual solution has a NAN.");
-    if (const double v = D.LInf(Y(), m); v > kBig) return err("Initial dual solution has an entry with absolute value " + G(v) + " which exceeds limit of " + G(kBig));
+    if (std::isnan(std::sqrt(D.SumSq(Y(), m, P.sharded())))) return err("Initial dual solution has a NAN.");
+    if (const double v = D.LInf(Y(), m, P.sharded()); v > kBig) return err("Initial dual solution has an entry with absolute value " + G(v) + " which exceeds limit of " + G(kBig));
   } else {
     D.Fill(X(), 0.0, n);
     D.Fill(Y(), 0.0, m);
@@ -1021,9 +1033,10 @@ std::optional<SolverResultCpp> ValidateInputs(const PdlpProblemView& view, const
 }  // namespace
 
 SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
-                                         const volatile int32_t* interrupt_solve, const Logger& logger, StatsCallback callback, int cuda_device) {
+                                         const volatile int32_t* interrupt_solve, const Logger& logger, StatsCallback callback, int cuda_device,
+                                         Comm* comm) {
   if (auto err = ValidateInputs(view, params, logger); err.has_value()) return std::move(*err);
-  DeviceProblem problem(view, cuda_device);
+  DeviceProblem problem(view, cuda_device, comm);
   DeviceSolve solve(problem, params, logger, std::move(callback));
   const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
   return solve.PreprocessAndSolve(std::move(initial_solution), interrupt_solve, view.problem_name != nullptr ? &name : nullptr);
@@ -1042,7 +1055,7 @@ SolveSession::SolveSession() : impl_(new Impl) {}
 SolveSession::~SolveSession() = default;
 
 std::unique_ptr<SolveSession> SolveSession::Create(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
-                                                   const Logger& logger, StatsCallback callback, int cuda_device) {
+                                                   const Logger& logger, StatsCallback callback, int cuda_device, Comm* comm) {
   std::unique_ptr<SolveSession> s(new SolveSession);
   Impl& im = *s->impl_;
   im.logger = logger;
@@ -1051,7 +1064,7 @@ std::unique_ptr<SolveSession> SolveSession::Create(const PdlpProblemView& view, 
     im.input_error = true;
     return s;
   }
-  im.problem.reset(new DeviceProblem(view, cuda_device));
+  im.problem.reset(new DeviceProblem(view, cuda_device, comm));
   im.solve.reset(new DeviceSolve(*im.problem, params, im.logger, std::move(callback)));
   const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
   if (auto err = im.solve->Prepare(std::move(initial_solution), view.problem_name != nullptr ? &name : nullptr); err.has_value()) {

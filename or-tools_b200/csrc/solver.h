@@ -12,6 +12,8 @@
 
 namespace pdlp_b200 {
 
+class Comm;  // comm.h
+
 struct SolveLogCpp {
   std::optional<std::string> instance_name;
   int termination_reason = PDLP_TERMINATION_REASON_UNSPECIFIED;
@@ -56,7 +58,7 @@ std::string ValidateParams(const PdlpParams& p);  // "" if valid, else the refer
 SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params,
                                          std::optional<InitialSolution> initial_solution,
                                          const volatile int32_t* interrupt_solve, const Logger& logger,
-                                         StatsCallback callback, int cuda_device);
+                                         StatsCallback callback, int cuda_device, Comm* comm = nullptr);
 
 // A resumable solve whose problem and iterates stay resident in HBM between
 // calls (C ABI: pdlp_b200_session_*). Advance() runs the same loop as
@@ -65,7 +67,7 @@ class SolveSession {
  public:
   static std::unique_ptr<SolveSession> Create(const PdlpProblemView& view, const PdlpParams& params,
                                               std::optional<InitialSolution> initial_solution, const Logger& logger,
-                                              StatsCallback callback, int cuda_device);
+                                              StatsCallback callback, int cuda_device, Comm* comm = nullptr);
   ~SolveSession();
   // Runs until `target_iterations` iterations are completed or the solve
   // terminates; returns true once terminated.

@@ -1,0 +1,223 @@
+"""Row-sharded multi-GPU path.
+
+CPU (not gpu): the row partition exported by the C ABI, and a world_size-2
+``gloo`` run of the exchange protocol the CUDA path uses (replicated primal
+side, row-local dual side, ONE all-reduce of [n + 1] doubles per PDHG step
+carrying the K^T y' partial and ||dy||^2), restated in numpy and compared with
+the unsharded iteration.
+
+GPU (needs >= 2 devices): the real thing over NCCL against the 1-GPU solve.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from ortools_b200 import distributed, pdlp, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TR = pdlp.TerminationReason
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+# ------------------------------------------------------------------ row partition
+@pytest.mark.parametrize("name,scale", [("c2", 0.002), ("c3", 0.002), ("c4", 0.0005)])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_row_blocks_are_a_balanced_contiguous_partition(name, scale, world):
+    qp, _ = synthetic.CONFIGS[name](scale=scale)
+    k = qp.constraint_matrix.tocsr()
+    m = k.shape[0]
+    blocks = [distributed.row_block(qp, r, world) for r in range(world)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == m
+    for (b0, e0), (b1, e1) in zip(blocks, blocks[1:]):
+        assert e0 == b1 and b0 <= e0
+    mass = np.diff(k.indptr) + 1  # nnz + 1 per row, the balanced quantity
+    per = [mass[b:e].sum() for b, e in blocks]
+    assert max(per) <= mass.sum() / world + mass.max() + 1
+
+
+# ------------------------------------------------------------------ exchange protocol on gloo
+def pdhg_reference(k, c, lc, uc, lv, uv, iters, step, weight):
+    """Unsharded adaptive PDHG iteration (pdhg.cc:1834-1959, 2558-2640), numpy."""
+    n, m = k.shape[1], k.shape[0]
+    x, y = np.zeros(n), np.zeros(m)
+    kty = k.T @ y
+    rejected, done, trace = 0, 0, []
+    while done < iters:
+        inner = 0
+        while True:
+            tau, sigma = step / weight, step * weight
+            xn = np.clip(x - tau * (c - kty), lv, uv)
+            xt = 2 * xn - x
+            t = y - sigma * (k @ xt)
+            yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
+            ktyn = k.T @ yn
+            dx, dy = xn - x, yn - y
+            movement = 0.5 * weight * (dx @ dx) + 0.5 / weight * (dy @ dy)
+            nonlin = -(dx @ (ktyn - kty))
+            limit = movement / nonlin if nonlin > 0 else np.inf
+            total = rejected + inner + done + 1
+            first = limit if np.isinf(limit) else (1 - (total + 1) ** -0.3) * limit
+            second = (1 + (total + 1) ** -0.6) * step
+            accepted = step <= limit
+            step = min(first, second)
+            trace.append(accepted)
+            if accepted:
+                x, y, kty = xn, yn, ktyn
+                rejected += inner
+                done += 1
+                break
+            inner += 1
+    return x, y, trace
+
+
+def _protocol_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    qp, _ = synthetic.c2(scale=0.0005)
+    k = qp.constraint_matrix.tocsr()
+    n = k.shape[1]
+    b, e = distributed.row_block(qp, rank, world)
+    kg = k[b:e]
+    c, lv, uv = qp.objective_vector, qp.variable_lower_bounds, qp.variable_upper_bounds
+    lc, uc = qp.constraint_lower_bounds[b:e], qp.constraint_upper_bounds[b:e]
+    x, y = np.zeros(n), np.zeros(e - b)
+    kty = np.zeros(n)
+    step, weight = 0.1, 1.0
+    rejected, done, trace = 0, 0, []
+    while done < 25:
+        inner = 0
+        while True:
+            tau, sigma = step / weight, step * weight
+            xn = np.clip(x - tau * (c - kty), lv, uv)             # replicated primal half step
+            xt = 2 * xn - x
+            t = y - sigma * (kg @ xt)                              # row-local dual half step
+            yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
+            exchange = np.concatenate([kg.T @ yn, [(yn - y) @ (yn - y)]])   # [n + 1]
+            buf = torch.from_numpy(exchange)
+            dist.all_reduce(buf)                                   # the one exchange of the step
+            ktyn, dy2 = exchange[:n], exchange[n]
+            dx = xn - x
+            movement = 0.5 * weight * (dx @ dx) + 0.5 / weight * dy2
+            nonlin = -(dx @ (ktyn - kty))
+            limit = movement / nonlin if nonlin > 0 else np.inf
+            total = rejected + inner + done + 1
+            first = limit if np.isinf(limit) else (1 - (total + 1) ** -0.3) * limit
+            second = (1 + (total + 1) ** -0.6) * step
+            accepted = step <= limit
+            step = min(first, second)
+            trace.append(accepted)
+            if accepted:
+                x, y, kty = xn, yn, ktyn.copy()
+                rejected += inner
+                done += 1
+                break
+            inner += 1
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), x=x, y=y, b=b, e=e, trace=np.array(trace))
+    dist.destroy_process_group()
+
+
+def test_exchange_protocol_matches_unsharded_iteration_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_protocol_worker, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
+    qp, _ = synthetic.c2(scale=0.0005)
+    k = qp.constraint_matrix.tocsr()
+    x, y, trace = pdhg_reference(k, qp.objective_vector, qp.constraint_lower_bounds, qp.constraint_upper_bounds,
+                                 qp.variable_lower_bounds, qp.variable_upper_bounds, 25, 0.1, 1.0)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    for p in parts:
+        assert list(p["trace"]) == trace                      # identical accept / reject decisions on every rank
+        np.testing.assert_allclose(p["x"], x, rtol=1e-12, atol=1e-13)
+    np.testing.assert_array_equal(parts[0]["x"], parts[1]["x"])  # replicated primal side is bitwise identical
+    ysh = np.concatenate([p["y"] for p in parts])
+    np.testing.assert_allclose(ysh, y, rtol=1e-12, atol=1e-13)
+
+
+# ------------------------------------------------------------------ the CUDA path over NCCL
+def _nccl_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    os.environ["LOCAL_RANK"] = str(rank)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    ctx = distributed.Context(rank, world, rank)
+    out = {}
+    for name, scale in (("c2", 0.004), ("c3", 0.002), ("c5", 0.003)):
+        qp, _ = synthetic.CONFIGS[name](scale=scale)
+        p = pdlp.PrimalDualHybridGradientParams()
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = 1e-6
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = 1e-6
+        p.termination_criteria.iteration_limit = 100000
+        res = ctx.primal_dual_hybrid_gradient(qp, p)
+        ci = [c for c in res.solve_log.solution_stats.convergence_information if c.candidate_type == res.solve_log.solution_type][0]
+        out[name + "_x"] = res.primal_solution
+        out[name + "_y"] = res.dual_solution
+        out[name + "_meta"] = np.array([res.solve_log.termination_reason, res.solve_log.iteration_count, ci.primal_objective, ci.dual_objective])
+        # fixed iteration count, restarts disabled: iterates vs the 1-GPU run
+        p = pdlp.PrimalDualHybridGradientParams()
+        p.restart_strategy = p.NO_RESTARTS
+        p.primal_weight_update_smoothing = 0.0
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = 0.0
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = 0.0
+        p.termination_criteria.iteration_limit = 48
+        res = ctx.primal_dual_hybrid_gradient(qp, p)
+        out[name + "_x48"] = res.primal_solution
+        out[name + "_y48"] = res.dual_solution
+    np.savez(os.path.join(out_dir, "nccl_rank%d.npz" % rank), **out)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_nccl_worker, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "nccl_rank%d.npz" % r)) for r in range(world)]
+    for name, scale in (("c2", 0.004), ("c3", 0.002), ("c5", 0.003)):
+        qp, _ = synthetic.CONFIGS[name](scale=scale)
+        p = pdlp.PrimalDualHybridGradientParams()
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = 1e-6
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = 1e-6
+        p.termination_criteria.iteration_limit = 100000
+        one = b200_backend.primal_dual_hybrid_gradient(qp, p)
+        ci = [c for c in one.solve_log.solution_stats.convergence_information if c.candidate_type == one.solve_log.solution_type][0]
+        for part in parts:
+            reason, iters, pobj, dobj = part[name + "_meta"]
+            assert int(reason) == one.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+            assert pobj == pytest.approx(ci.primal_objective, rel=1e-5, abs=1e-5)
+            assert dobj == pytest.approx(ci.dual_objective, rel=1e-5, abs=1e-5)
+        # every rank returns the same full-length vectors
+        np.testing.assert_array_equal(parts[0][name + "_x"], parts[1][name + "_x"])
+        np.testing.assert_array_equal(parts[0][name + "_y"], parts[1][name + "_y"])
+        p = pdlp.PrimalDualHybridGradientParams()
+        p.restart_strategy = p.NO_RESTARTS
+        p.primal_weight_update_smoothing = 0.0
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = 0.0
+        p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = 0.0
+        p.termination_criteria.iteration_limit = 48
+        one = b200_backend.primal_dual_hybrid_gradient(qp, p)
+        for key, ref in (("_x48", one.primal_solution), ("_y48", one.dual_solution)):
+            got = parts[0][name + key]
+            assert np.linalg.norm(got - ref) <= 1e-9 * max(1.0, np.linalg.norm(ref)), (name, key)
