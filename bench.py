@@ -304,6 +304,20 @@ def run_ours(args):
 
 
 def main():
+    # Keep stdout for the ONE JSON line: libraries (NCCL's version banner, torchrun
+    # notices) write to fd 1, so fd 1 is pointed at stderr and the line goes to a
+    # private duplicate of the original stdout.
+    global print
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):  # noqa: A001
+        if "file" not in k:
+            k["file"] = real_stdout
+        _print(*a, **k)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -354,13 +354,18 @@ __device__ __forceinline__ double block_sum_range(const double* __restrict__ p, 
 }
 
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
-__global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
-  if (st->halt != 0) return;
+__global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
+  if (st_dev->halt != 0) return;
   const double dx2 = block_sum_range(pp, np);
   // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
   const double dy2 = nd < 0 ? *pd : block_sum_range(pd, nd);
   const double dot = block_sum_range(pt, nt);
   if (threadIdx.x != 0) return;
+  // One load of the whole state into registers, one store at the end: the
+  // decision is a chain of dependent scalar updates and must not pay an L2
+  // round trip per field.
+  StepState s = *st_dev;
+  StepState* st = &s;
   const double eta = st->step_size, omega = st->primal_weight;
   const double movement = (0.5 * omega * dx2) + (0.5 / omega) * dy2;
   const double nonlinearity = -dot;
@@ -377,6 +382,7 @@ __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st, c
     st->pending_ratio = 0.0;
     if (adaptive) st->num_rejected_steps += st->inner_iterations - 1;
     st->inner_iterations = 0;
+    *st_dev = s;
     return;
   }
   bool accepted = true;
@@ -418,6 +424,7 @@ __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st, c
       st->inner_iterations = 0;
     }
   }
+  *st_dev = s;
 }
 
 // ---- row-sharded variant of the step ---------------------------
@@ -467,6 +474,7 @@ constexpr unsigned long long kMaxKey = 0x7FEFFFFFFFFFFFFFull;  // DBL_MAX
 
 struct TrSearchState {
   unsigned long long lo;
+  int done, pad;   // no key with a nonzero contribution is left inside the bracket
   double fixed_radius_sq, variable_coef;
   double radius_sq;
   double max_abs_objective;
@@ -554,6 +562,7 @@ __global__ void __launch_bounds__(kThreads) k_tr_prepare(int64_t total, int64_t 
 constexpr int kTrUnroll = 4;
 __global__ void __launch_bounds__(kThreads) k_tr_pass(int64_t total, const unsigned long long* __restrict__ keys, const double* __restrict__ a,
                                                       const double* __restrict__ bcoef, const TrSearchState* st, int shift, double* partials) {
+  if (st->done != 0) return;
   const unsigned long long lo = st->lo;
   double ba[17], bb[17];
 #pragma unroll
@@ -594,7 +603,12 @@ __global__ void __launch_bounds__(kThreads) k_tr_pass(int64_t total, const unsig
 // The 34 bin totals: 17 warps sum two columns each over the blocks in a fixed
 // lane-strided order (k_tr_totals); row-sharded solves all-reduce the totals;
 // one thread then picks the bracket (k_tr_pick).
-__global__ void __launch_bounds__(17 * 32) k_tr_totals(int nblocks, const double* __restrict__ partials, double* __restrict__ tot) {
+__device__ __forceinline__ void tr_pick(const double* tot, TrSearchState* st_dev, int shift);
+// pick_here: single-GPU launches finish the pass in the same kernel.
+__global__ void __launch_bounds__(17 * 32) k_tr_totals(int nblocks, const double* __restrict__ partials, double* __restrict__ tot, TrSearchState* st,
+                                                       int shift, int pick_here) {
+  if (st->done != 0) return;
+  __shared__ double sh_tot[34];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -603,10 +617,17 @@ __global__ void __launch_bounds__(17 * 32) k_tr_totals(int nblocks, const double
 #pragma unroll 4
     for (int b = lane; b < nblocks; b += 32) s += partials[static_cast<int64_t>(b) * 34 + colx];
     s = warp_sum(s);
-    if (lane == 0) tot[colx] = s;
+    if (lane == 0) { tot[colx] = s; sh_tot[colx] = s; }
   }
+  if (!pick_here) return;
+  __syncthreads();
+  if (threadIdx.x == 0) tr_pick(sh_tot, st, shift);
 }
 __global__ void k_tr_pick(const double* __restrict__ tot, TrSearchState* st, int shift) {
+  if (st->done != 0) return;
+  tr_pick(tot, st, shift);
+}
+__device__ __forceinline__ void tr_pick(const double* tot, TrSearchState* st, int shift) {
   const unsigned long long lo = st->lo;
   // A_j = sum of bins 0..j of a; B_j = sum of bins j+1..16 of b.
   double A = 0.0;
@@ -628,6 +649,9 @@ __global__ void k_tr_pick(const double* __restrict__ tot, TrSearchState* st, int
   st->lo = lo + (static_cast<unsigned long long>(best) << shift);
   st->fixed_radius_sq = bestA;
   st->variable_coef = bestB;
+  // The next bracket is bin best+1. If nothing in it contributes to either sum,
+  // A and B can no longer change and the closed form of k_tr_finish is exact.
+  if (tot[best + 1] == 0.0 && tot[17 + best + 1] == 0.0) st->done = 1;
 }
 
 __global__ void k_tr_init(TrSearchState* st, double radius, const double* maxabs_partials, int nblocks) {
@@ -636,6 +660,8 @@ __global__ void k_tr_init(TrSearchState* st, double radius, const double* maxabs
   mx = warp_max(mx);
   if (threadIdx.x != 0) return;
   st->lo = 0ull;
+  st->done = 0;
+  st->pad = 0;
   st->fixed_radius_sq = 0.0;
   st->variable_coef = 0.0;
   st->radius_sq = radius * radius;
@@ -1188,10 +1214,13 @@ void tr_search(cudaStream_t stream, Comm* comm, int64_t total, int64_t first, El
   }
   for (int shift = 60; shift >= 0; shift -= 4) {
     k_tr_pass<<<nb, kThreads, 0, stream>>>(total, keys, a, b, st, shift, partials);
-    k_tr_totals<<<1, 17 * 32, 0, stream>>>(nb, partials, totals);
-    if (comm != nullptr) comm->AllReduceSum(totals, totals, 34, stream);
-    k_tr_pick<<<1, 1, 0, stream>>>(totals, st, shift);
-    *launches += 3;
+    k_tr_totals<<<1, 17 * 32, 0, stream>>>(nb, partials, totals, st, shift, comm == nullptr ? 1 : 0);
+    *launches += 2;
+    if (comm != nullptr) {
+      comm->AllReduceSum(totals, totals, 34, stream);
+      k_tr_pick<<<1, 1, 0, stream>>>(totals, st, shift);
+      *launches += 1;
+    }
   }
   k_tr_finish<<<1, 1, 0, stream>>>(st, radius);
   *launches += 1;
