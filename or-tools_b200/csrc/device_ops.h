@@ -99,6 +99,14 @@ struct StepState {
 };
 enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent = 3, kHaltInnerLimit = 4 };
 
+// What the device builder keeps besides the two SELL images (device pointers).
+struct DeviceBuildInfo {
+  int64_t n = 0, m = 0, nnz = 0;
+  int32_t* col_slot_row = nullptr;  // [cols.num_slots] original column of a slot (-1 = padding)
+  int64_t* col_slot_off = nullptr;  // [cols.num_slots] offset of the slot inside its column
+  int64_t* col_start = nullptr;     // [n + 1] starts of the (row-block) columns in CSC order
+};
+
 struct MSideStats {  // reductions over the dual (row) side
   double linf_residual, sumsq_residual, cw_residual;  // PrimalResidualNorms
   double bounds_term;                                 // DualObjectiveBoundsTerm
@@ -149,6 +157,13 @@ class Device {
   int32_t* UploadI32(const std::vector<int32_t>& v);
   void ScatterInto(double* dst, const double* src, const int32_t* row_of_pos_dev, int64_t n);  // dst[row_of_pos[p]] = src[p]
 
+  // Builds both SELL-32 images on the device from the caller's CSC arrays
+  // (device_build.cu); *dual_perm / *primal_perm are the row_of_pos maps of the
+  // row / column copy (device, owned by the caller).
+  void BuildSellPair(const PdlpProblemView& view, int64_t row_begin, int64_t row_end, int sigma, bool natural_primal_order,
+                     SellDev* rows, SellDev* cols, int32_t** dual_perm, int32_t** primal_perm, DeviceBuildInfo* info);
+  void FreeBuildInfo(DeviceBuildInfo& info);
+  void DownloadValuesCscFromSell(const SellDev& cols, const DeviceBuildInfo& info, double* values_host);
   SellDev UploadSell(const SellHost& h);
   void FreeSell(SellDev& s);
   void DownloadSellValues(const SellDev& s, std::vector<double>& out);

@@ -4,6 +4,7 @@
 #include "comm.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -49,21 +50,36 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
     ComputeRowBlock(view, comm_->rank(), comm_->world_size(), &row_begin_, &row_end);
     dev_->SetComm(comm_);
   }
-  QpHost h = BuildQpHost(view, row_begin_, row_end, 4096, /*natural_primal_order=*/comm_ != nullptr);
-  n_ = h.n;
-  m_ = h.m;
-  nnz_ = h.nnz;
+  // cheap host-side sanity of the column starts (everything else is validated on the device)
+  for (int64_t c = 0; c < view.num_variables; ++c)
+    if (view.col_starts[c + 1] < view.col_starts[c] || view.col_starts[c] < 0) throw std::runtime_error("col_starts is not monotone");
+  const char* host_build = std::getenv("PDLP_B200_HOST_BUILD");
+  device_built_ = !(host_build != nullptr && host_build[0] == '1');
+  QpHost h;
+  if (device_built_) {
+    dev_->BuildSellPair(view, row_begin_, row_end, 4096, /*natural_primal_order=*/comm_ != nullptr, &rows_, &cols_, &dual_perm_, &primal_perm_, &build_info_);
+    n_ = build_info_.n;
+    m_ = build_info_.m;
+    nnz_ = build_info_.nnz;
+  } else {
+    h = BuildQpHost(view, row_begin_, row_end, 4096, /*natural_primal_order=*/comm_ != nullptr);
+    n_ = h.n;
+    m_ = h.m;
+    nnz_ = h.nnz;
+  }
   if (comm_ != nullptr) exchange_ = dev_->AllocF64(n_ + 1);
   objective_offset_ = view.objective_offset;
   objective_scaling_factor_ = view.objective_scaling_factor;
-  rows_ = dev_->UploadSell(h.rows);
-  cols_ = dev_->UploadSell(h.cols);
-  primal_perm_ = dev_->UploadI32(h.cols.row_of_pos);
-  dual_perm_ = dev_->UploadI32(h.rows.row_of_pos);
-  col_starts_.assign(view.col_starts, view.col_starts + n_ + 1);
-  cols_meta_ = std::move(h.cols);
-  std::vector<int32_t>().swap(cols_meta_.col);
-  std::vector<double>().swap(cols_meta_.val);
+  if (!device_built_) {
+    rows_ = dev_->UploadSell(h.rows);
+    cols_ = dev_->UploadSell(h.cols);
+    primal_perm_ = dev_->UploadI32(h.cols.row_of_pos);
+    dual_perm_ = dev_->UploadI32(h.rows.row_of_pos);
+    col_starts_.assign(view.col_starts, view.col_starts + n_ + 1);
+    cols_meta_ = std::move(h.cols);
+    std::vector<int32_t>().swap(cols_meta_.col);
+    std::vector<double>().swap(cols_meta_.val);
+  }
   auto up_primal = [&](const double* src) { double* d = NewPrimal(); UploadPrimal(d, src); return d; };
   auto up_dual = [&](const double* src) { double* d = NewDual(); UploadDual(d, src); return d; };
   c_ = up_primal(view.objective_vector);
@@ -90,6 +106,7 @@ DeviceProblem::~DeviceProblem() {
   dev_->Free(dual_perm_);
   dev_->FreeSell(rows_);
   dev_->FreeSell(cols_);
+  dev_->FreeBuildInfo(build_info_);
 }
 
 void DeviceProblem::RescaleQuadraticProgram(const double* col_scaling, const double* row_scaling) {
@@ -300,6 +317,7 @@ void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const doub
 
 void DeviceProblem::DownloadValuesCsc(double* values) {
   if (sharded()) throw std::runtime_error("DownloadValuesCsc is not available on a row-sharded problem");
+  if (device_built_) { dev_->DownloadValuesCscFromSell(cols_, build_info_, values); return; }
   std::vector<double> sell;
   dev_->DownloadSellValues(cols_, sell);
   const SellHost& s = cols_meta_;

@@ -112,7 +112,9 @@ class DeviceProblem {
   double objective_offset_ = 0, objective_scaling_factor_ = 1;
   double *c_ = nullptr, *q_ = nullptr, *lv_ = nullptr, *uv_ = nullptr, *lc_ = nullptr, *uc_ = nullptr;
   SellDev rows_, cols_;
-  SellHost cols_meta_;                 // structure only (col/val released)
+  bool device_built_ = false;
+  DeviceBuildInfo build_info_;         // device builder: what the value download needs
+  SellHost cols_meta_;                 // host builder: structure only (col/val released)
   std::vector<int64_t> col_starts_;    // caller's CSC column starts
   int32_t *primal_perm_ = nullptr, *dual_perm_ = nullptr;
   double* tmp_n_[4] = {nullptr, nullptr, nullptr, nullptr};
