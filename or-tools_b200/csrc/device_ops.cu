@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -189,8 +190,10 @@ __global__ void __launch_bounds__(kThreads) k_sell(SellDev a, GatherSrc gs, Epi 
   double red[NS > 0 ? NS : 1];
 #pragma unroll
   for (int k = 0; k < NS; ++k) red[k] = 0.0;
-  const int64_t slot = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  if (slot < a.num_slots) {
+  // Grid-stride over slots: with a grid of (SMs x resident blocks) every block
+  // is co-resident (no wave quantisation / tail) and the slot -> thread map is
+  // fixed, so the per-block partial sums stay deterministic.
+  for (int64_t slot = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; slot < a.num_slots; slot += static_cast<int64_t>(gridDim.x) * kThreads) {
     const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
     const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
     typename Epi::Pre pre;
@@ -806,10 +809,27 @@ void Device::DownloadSellValues(const SellDev& s, std::vector<double>& out) {
 
 // ---- generic SELL launch --------------------------------------------------
 namespace kernels {
+// Blocks of a k_sell launch: one block per 256 slots, capped at a persistent
+// grid of SMs x blocks-per-SM (PDLP_B200_SELL_BLOCKS_PER_SM, default 6 = what
+// 40 registers/thread allow; 0 = uncapped).
+int SellGrid(const SellDev& a) {
+  static const int per_sm = [] {
+    const char* v = std::getenv("PDLP_B200_SELL_BLOCKS_PER_SM");
+    return (v != nullptr && *v != 0) ? std::atoi(v) : 6;
+  }();
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  const int64_t need = std::max<int64_t>(1, (a.num_slots + kThreads - 1) / kThreads);
+  if (per_sm <= 0) return static_cast<int>(need);
+  return static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(sms) * per_sm));
+}
 template <int MODE, int NS, class Epi>
 void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, double* partials, const int32_t* halt, int64_t* launches,
                  int* main_blocks, int* fix_blocks) {
-  const int nb = static_cast<int>(std::max<int64_t>(1, a.num_slots / kThreads + (a.num_slots % kThreads != 0)));
+  const int nb = SellGrid(a);
   k_sell<MODE, NS, Epi><<<nb, kThreads, 0, stream>>>(a, x, epi, partials, halt);
   ++*launches;
   int nf = 0;
@@ -1402,9 +1422,9 @@ static StepPtrs MakePtrs(const Device::StepBuffers& b) {
 void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count) {
   const StepPtrs p = MakePtrs(b);
   const int np = static_cast<int>(std::max<int64_t>(1, ((b.n + 1) / 2 + kThreads - 1) / kThreads));
-  const int nd_main = static_cast<int>(std::max<int64_t>(1, (rows.num_slots + kThreads - 1) / kThreads));
+  const int nd_main = SellGrid(rows);
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
-  const int nt_main = static_cast<int>(std::max<int64_t>(1, (cols.num_slots + kThreads - 1) / kThreads));
+  const int nt_main = SellGrid(cols);
   const int nt_fix = cols.num_split > 0 ? static_cast<int>((cols.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int64_t need = static_cast<int64_t>(np) + nd_main + nd_fix + std::max<int64_t>(nt_main + nt_fix, Blocks(b.n)) + 8;
   if (need > step_partials_size_) {
