@@ -67,9 +67,9 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // Block reduction of NS sums followed by NM maxes; thread 0 stores them to out.
-template <int NS, int NM>
+template <int NS, int NM, int BT = kThreads>
 __device__ __forceinline__ void block_reduce_store(const double* s, const double* m, double* out) {
-  __shared__ double sh[(NS + NM > 0 ? NS + NM : 1)][kThreads / 32];
+  __shared__ double sh[(NS + NM > 0 ? NS + NM : 1)][BT / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NS; ++k) {
@@ -85,13 +85,13 @@ __device__ __forceinline__ void block_reduce_store(const double* s, const double
   if (warp == 0) {
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-      double v = lane < kThreads / 32 ? sh[k][lane] : 0.0;
+      double v = lane < BT / 32 ? sh[k][lane] : 0.0;
       v = warp_sum(v);
       if (lane == 0) out[k] = v;
     }
 #pragma unroll
     for (int k = 0; k < NM; ++k) {
-      double v = lane < kThreads / 32 ? sh[NS + k][lane] : -kInfD;
+      double v = lane < BT / 32 ? sh[NS + k][lane] : -kInfD;
       v = warp_max(v);
       if (lane == 0) out[NS + k] = v;
     }
@@ -147,7 +147,7 @@ __device__ __forceinline__ double combine(double acc, double v, double xv) {
 // One thread per slot; lanes of a warp read consecutive addresses of the
 // slice (coalesced 256 B value / 128 B index requests, streamed with
 // evict-first); x is gathered through L2.
-template <int MODE>
+template <int MODE, int V>
 __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const double* __restrict__ x) {
   const int64_t base = a.slice_ptr[slot >> 5] + (slot & 31);
   const int n = a.slot_len[slot];
@@ -155,23 +155,69 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
   const int32_t* __restrict__ col = a.col + base;
   double acc = 0.0;
   int j = 0;
-  for (; j + 4 <= n; j += 4) {
-    double v[4];
-    int c[4];
-    double xv[4];
+  if (V == 0) {
+    for (; j + 4 <= n; j += 4) {
+      double v[4];
+      int c[4];
+      double xv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      v[u] = __ldcs(val + static_cast<int64_t>(j + u) * 32);
-      c[u] = __ldcs(col + static_cast<int64_t>(j + u) * 32);
+      for (int u = 0; u < 4; ++u) {
+        v[u] = __ldcs(val + static_cast<int64_t>(j + u) * 32);
+        c[u] = __ldcs(col + static_cast<int64_t>(j + u) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = combine<MODE>(acc, v[u], xv[u]);
     }
+  } else {
+    // Software-pipelined: the value / index loads of chunk k+1 are issued
+    // right after the gathers of chunk k, so the DRAM latency of the streams
+    // overlaps the L2 latency of the gathers and the gather queue never drains
+    // while a warp waits for its next indices.
+    constexpr int U = V == 1 ? 4 : 8;
+    if (n >= U) {
+      double v[U];
+      int c[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) xv[u] = __ldg(x + c[u]);
+      for (int u = 0; u < U; ++u) {
+        c[u] = __ldcs(col + static_cast<int64_t>(u) * 32);
+        v[u] = __ldcs(val + static_cast<int64_t>(u) * 32);
+      }
+      for (;;) {
+        double xv[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc = combine<MODE>(acc, v[u], xv[u]);
+        for (int u = 0; u < U; ++u) xv[u] = __ldg(x + c[u]);
+        j += U;
+        const bool more = j + U <= n;
+        double vn[U];
+        int cn[U];
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            cn[u] = __ldcs(col + static_cast<int64_t>(j + u) * 32);
+            vn[u] = __ldcs(val + static_cast<int64_t>(j + u) * 32);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc = combine<MODE>(acc, v[u], xv[u]);
+        if (!more) break;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          v[u] = vn[u];
+          c[u] = cn[u];
+        }
+      }
+    }
   }
   for (; j < n; ++j) acc = combine<MODE>(acc, __ldcs(val + static_cast<int64_t>(j) * 32), __ldg(x + __ldcs(col + static_cast<int64_t>(j) * 32)));
   return acc;
 }
+
+// Selects one of three kernel-parameter pointers without dynamic indexing of
+// the parameter array (which would force a copy of it to local memory).
+template <class T>
+__device__ __forceinline__ T* pick3(T* const (&p)[3], int i) { return i == 0 ? p[0] : (i == 1 ? p[1] : p[2]); }
 
 // The gathered vector is either fixed at launch or, inside the device-resident
 // step loop, one of three buffers selected by the state's candidate index.
@@ -180,32 +226,35 @@ struct GatherSrc {
   const StepState* st;
 };
 
-// Epi: struct Pre; __device__ Pre prefetch(int64_t pos) const  -- issues the epilogue's
-//      own loads before the gather loop so that they overlap it;
-//      __device__ void operator()(int64_t pos, double acc, double* red, const Pre&) const
-template <int MODE, int NS, class Epi>
-__global__ void __launch_bounds__(kThreads) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt) {
+// Epi: struct Ctx; __device__ Ctx begin() const -- once per thread: resolves the rotating
+//      buffers and step scalars from the device state;
+//      struct Pre; __device__ Pre prefetch(const Ctx&, int64_t pos) const  -- issues the
+//      epilogue's own loads before the gather loop so that they overlap it;
+//      __device__ void operator()(const Ctx&, int64_t pos, double acc, double* red, const Pre&) const
+template <int MODE, int NS, class Epi, int BT, int V>
+__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt) {
   if (halt != nullptr && *halt != 0) return;
-  const double* __restrict__ x = gs.st != nullptr ? gs.p[gs.st->cand] : gs.p[0];
+  const double* __restrict__ x = gs.st != nullptr ? pick3(gs.p, gs.st->cand) : gs.p[0];
   double red[NS > 0 ? NS : 1];
 #pragma unroll
   for (int k = 0; k < NS; ++k) red[k] = 0.0;
+  const typename Epi::Ctx ctx = epi.begin();
   // Grid-stride over slots: with a grid of (SMs x resident blocks) every block
   // is co-resident (no wave quantisation / tail) and the slot -> thread map is
   // fixed, so the per-block partial sums stay deterministic.
-  for (int64_t slot = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x; slot < a.num_slots; slot += static_cast<int64_t>(gridDim.x) * kThreads) {
+  for (int64_t slot = static_cast<int64_t>(blockIdx.x) * BT + threadIdx.x; slot < a.num_slots; slot += static_cast<int64_t>(gridDim.x) * BT) {
     const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
     const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
     typename Epi::Pre pre;
-    if (own_row) pre = epi.prefetch(pos);
-    const double acc = sell_row<MODE>(a, slot, x);
+    if (own_row) pre = epi.prefetch(ctx, pos);
+    const double acc = sell_row<MODE, V>(a, slot, x);
     if (slot < a.num_virtual_padded) {
       a.virt_partial[slot] = acc;
     } else if (own_row) {
-      epi(pos, acc, red, pre);
+      epi(ctx, pos, acc, red, pre);
     }
   }
-  if (NS > 0) block_reduce_store<NS, 0>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
+  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
 }
 
 // Split rows: one warp per row combines the partials of its virtual slots in
@@ -223,7 +272,10 @@ __global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, dou
     double acc = 0.0;
     for (int k = b + lane; k < e; k += 32) acc = (MODE == kMaxAbs) ? fmax(acc, a.virt_partial[k]) : acc + a.virt_partial[k];
     acc = (MODE == kMaxAbs) ? warp_max(acc) : warp_sum(acc);
-    if (lane == 0) epi(row, acc, red, epi.prefetch(row));
+    if (lane == 0) {
+      const typename Epi::Ctx ctx = epi.begin();
+      epi(ctx, row, acc, red, epi.prefetch(ctx, row));
+    }
   }
   if (NS > 0) block_reduce_store<NS, 0>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
 }
@@ -245,9 +297,9 @@ struct StepPtrs {
 __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* partials) {
   const StepState* st = b.state;
   if (st->halt != 0) return;
-  const double* __restrict__ xc = b.x[st->cur];
-  double* __restrict__ xn = b.x[st->cand];
-  const double* __restrict__ kty = b.kty[st->cur];
+  const double* __restrict__ xc = pick3(b.x, st->cur);
+  double* __restrict__ xn = pick3(b.x, st->cand);
+  const double* __restrict__ kty = pick3(b.kty, st->cur);
   const double tau = st->step_size / st->primal_weight;
   const double ratio = st->pending_ratio;
   const bool has_q = b.q != nullptr;
@@ -297,24 +349,30 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* pa
 
 struct DualEpi {  // pdhg.cc:1912-1930 with theta = 1
   StepPtrs b;
+  struct Ctx { const double* yc; double* yn; double sigma, ratio; };
   struct Pre { double yc, lc, uc, avg; };
-  __device__ __forceinline__ Pre prefetch(int64_t pos) const {
+  __device__ __forceinline__ Ctx begin() const {
     const StepState* st = b.state;
+    Ctx c;
+    c.yc = pick3(b.y, st->cur);
+    c.yn = pick3(b.y, st->cand);
+    c.sigma = st->step_size * st->primal_weight;
+    c.ratio = st->pending_ratio;
+    return c;
+  }
+  __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const {
     Pre p;
-    p.yc = b.y[st->cur][pos];
+    p.yc = c.yc[pos];
     p.lc = __ldg(b.lc + pos);
     p.uc = __ldg(b.uc + pos);
-    p.avg = st->pending_ratio > 0.0 ? b.avg_y[pos] : 0.0;
+    p.avg = c.ratio > 0.0 ? b.avg_y[pos] : 0.0;
     return p;
   }
-  __device__ __forceinline__ void operator()(int64_t pos, double kx, double* red, const Pre& p) const {
-    const StepState* st = b.state;
-    const double sigma = st->step_size * st->primal_weight;
-    const double ratio = st->pending_ratio;
-    if (ratio > 0.0) b.avg_y[pos] = p.avg + ratio * (p.yc - p.avg);
-    const double t = p.yc - sigma * kx;
-    const double yn = fmax(fmin(0.0, t + sigma * p.uc), t + sigma * p.lc);
-    b.y[st->cand][pos] = yn;
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kx, double* red, const Pre& p) const {
+    if (c.ratio > 0.0) b.avg_y[pos] = p.avg + c.ratio * (p.yc - p.avg);
+    const double t = p.yc - c.sigma * kx;
+    const double yn = fmax(fmin(0.0, t + c.sigma * p.uc), t + c.sigma * p.lc);
+    c.yn[pos] = yn;
     const double d = yn - p.yc;
     red[0] += d * d;
   }
@@ -322,16 +380,25 @@ struct DualEpi {  // pdhg.cc:1912-1930 with theta = 1
 
 struct KtyEpi {  // pdhg.cc:2588-2592, 1949-1959
   StepPtrs b;
+  struct Ctx { const double *x_cand, *x_cur, *kty_cur; double* kty_cand; };
   struct Pre { double dx, kty; };
-  __device__ __forceinline__ Pre prefetch(int64_t pos) const {
+  __device__ __forceinline__ Ctx begin() const {
     const StepState* st = b.state;
+    Ctx c;
+    c.x_cand = pick3(b.x, st->cand);
+    c.x_cur = pick3(b.x, st->cur);
+    c.kty_cur = pick3(b.kty, st->cur);
+    c.kty_cand = pick3(b.kty, st->cand);
+    return c;
+  }
+  __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const {
     Pre p;
-    p.dx = b.x[st->cand][pos] - b.x[st->cur][pos];
-    p.kty = b.kty[st->cur][pos];
+    p.dx = c.x_cand[pos] - c.x_cur[pos];
+    p.kty = c.kty_cur[pos];
     return p;
   }
-  __device__ __forceinline__ void operator()(int64_t pos, double kty_next, double* red, const Pre& p) const {
-    b.kty[b.state->cand][pos] = kty_next;
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kty_next, double* red, const Pre& p) const {
+    c.kty_cand[pos] = kty_next;
     red[0] += p.dx * (kty_next - p.kty);
   }
 };
@@ -357,13 +424,47 @@ __device__ __forceinline__ double block_sum_range(const double* __restrict__ p, 
 }
 
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
+// Three fixed-order sums at once: all loads of the three partial arrays are in
+// flight together and one shuffle tree + one shared-memory exchange serves all
+// of them (the decision kernel is pure latency on the critical path of a step).
+__device__ __forceinline__ void block_sum3(const double* __restrict__ p0, int n0, const double* __restrict__ p1, int n1,
+                                           const double* __restrict__ p2, int n2, double out[3]) {
+  __shared__ double sh3[3][kDecideThreads / 32];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n0; i += kDecideThreads) s0 += p0[i];
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n1; i += kDecideThreads) s1 += p1[i];
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n2; i += kDecideThreads) s2 += p2[i];
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    sh3[0][threadIdx.x >> 5] = s0;
+    sh3[1][threadIdx.x >> 5] = s1;
+    sh3[2][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double t = threadIdx.x < kDecideThreads / 32 ? sh3[k][threadIdx.x] : 0.0;
+      out[k] = warp_sum(t);
+    }
+  }
+}
+
+// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
 __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
   if (st_dev->halt != 0) return;
-  const double dx2 = block_sum_range(pp, np);
+  double sums[3];
   // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
-  const double dy2 = nd < 0 ? *pd : block_sum_range(pd, nd);
-  const double dot = block_sum_range(pt, nt);
+  block_sum3(pp, np, pd, nd < 0 ? 0 : nd, pt, nt, sums);
   if (threadIdx.x != 0) return;
+  const double dx2 = sums[0];
+  const double dy2 = nd < 0 ? *pd : sums[1];
+  const double dot = sums[2];
   // One load of the whole state into registers, one store at the end: the
   // decision is a chain of dependent scalar updates and must not pay an L2
   // round trip per field.
@@ -447,8 +548,8 @@ __global__ void __launch_bounds__(kThreads) k_kty_finish(StepPtrs b, const doubl
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (i < b.n) {
     const double v = reduced[i];
-    b.kty[st->cand][i] = v;
-    s = (b.x[st->cand][i] - b.x[st->cur][i]) * (v - b.kty[st->cur][i]);
+    pick3(b.kty, st->cand)[i] = v;
+    s = (pick3(b.x, st->cand)[i] - pick3(b.x, st->cur)[i]) * (v - pick3(b.kty, st->cur)[i]);
   }
   block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
 }
@@ -459,10 +560,10 @@ __global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t 
   if (ratio <= 0.0) return;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (i < b.n) {
-    b.avg_x[i] += ratio * (b.x[st->cur][i] - b.avg_x[i]);
+    b.avg_x[i] += ratio * (pick3(b.x, st->cur)[i] - b.avg_x[i]);
   } else if (i < total) {
     const int64_t j = i - b.n;
-    b.avg_y[j] += ratio * (b.y[st->cur][j] - b.avg_y[j]);
+    b.avg_y[j] += ratio * (pick3(b.y, st->cur)[j] - b.avg_y[j]);
   }
 }
 __global__ void k_clear_pending(StepState* st) { st->pending_ratio = 0.0; }
@@ -812,11 +913,27 @@ namespace kernels {
 // Blocks of a k_sell launch: one block per 256 slots, capped at a persistent
 // grid of SMs x blocks-per-SM (PDLP_B200_SELL_BLOCKS_PER_SM, default 6 = what
 // 40 registers/thread allow; 0 = uncapped).
+int SellThreads() {
+  static const int bt = [] {
+    const char* v = std::getenv("PDLP_B200_SELL_THREADS");
+    const int t = (v != nullptr && *v != 0) ? std::atoi(v) : 128;
+    return (t == 256 || t == 512) ? t : 128;
+  }();
+  return bt;
+}
+int SellVariant() {
+  static const int v = [] {
+    const char* e = std::getenv("PDLP_B200_SELL_VARIANT");
+    return (e != nullptr && *e != 0) ? std::atoi(e) : 1;
+  }();
+  return v;
+}
 int SellGrid(const SellDev& a) {
   static const int per_sm = [] {
     const char* v = std::getenv("PDLP_B200_SELL_BLOCKS_PER_SM");
-    return (v != nullptr && *v != 0) ? std::atoi(v) : 6;
+    return (v != nullptr && *v != 0) ? std::atoi(v) : 0;
   }();
+  const int kThreads = SellThreads();
   static const int sms = [] {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -830,7 +947,16 @@ template <int MODE, int NS, class Epi>
 void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, double* partials, const int32_t* halt, int64_t* launches,
                  int* main_blocks, int* fix_blocks) {
   const int nb = SellGrid(a);
-  k_sell<MODE, NS, Epi><<<nb, kThreads, 0, stream>>>(a, x, epi, partials, halt);
+  const int variant = SellVariant();
+#define PDLP_SELL_LAUNCH(BT, V) k_sell<MODE, NS, Epi, BT, V><<<nb, BT, 0, stream>>>(a, x, epi, partials, halt)
+#define PDLP_SELL_LAUNCH_V(BT) (variant == 1 ? PDLP_SELL_LAUNCH(BT, 1) : variant == 2 ? PDLP_SELL_LAUNCH(BT, 2) : PDLP_SELL_LAUNCH(BT, 0))
+  switch (SellThreads()) {
+    case 256: PDLP_SELL_LAUNCH_V(256); break;
+    case 512: PDLP_SELL_LAUNCH_V(512); break;
+    default: PDLP_SELL_LAUNCH_V(128); break;
+  }
+#undef PDLP_SELL_LAUNCH_V
+#undef PDLP_SELL_LAUNCH
   ++*launches;
   int nf = 0;
   if (a.num_split > 0) {
@@ -841,26 +967,33 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
   if (main_blocks != nullptr) *main_blocks = nb;
   if (fix_blocks != nullptr) *fix_blocks = nf;
 }
+struct NoCtx {};
 struct StoreEpi {
   double* out;
+  typedef NoCtx Ctx;
   struct Pre {};
-  __device__ __forceinline__ Pre prefetch(int64_t) const { return Pre(); }
-  __device__ __forceinline__ void operator()(int64_t pos, double acc, double*, const Pre&) const { out[pos] = acc; }
+  __device__ __forceinline__ Ctx begin() const { return Ctx(); }
+  __device__ __forceinline__ Pre prefetch(const Ctx&, int64_t) const { return Pre(); }
+  __device__ __forceinline__ void operator()(const Ctx&, int64_t pos, double acc, double*, const Pre&) const { out[pos] = acc; }
 };
 struct ScatterEpi {  // out[perm[pos]] = acc
   double* out;
   const int32_t* perm;
+  typedef NoCtx Ctx;
   struct Pre { int32_t dst; };
-  __device__ __forceinline__ Pre prefetch(int64_t pos) const { return Pre{__ldg(perm + pos)}; }
-  __device__ __forceinline__ void operator()(int64_t, double acc, double*, const Pre& p) const { out[p.dst] = acc; }
+  __device__ __forceinline__ Ctx begin() const { return Ctx(); }
+  __device__ __forceinline__ Pre prefetch(const Ctx&, int64_t pos) const { return Pre{__ldg(perm + pos)}; }
+  __device__ __forceinline__ void operator()(const Ctx&, int64_t, double acc, double*, const Pre& p) const { out[p.dst] = acc; }
 };
 struct NormEpi {
   double* out;
   const double* own;
   int l2;
+  typedef NoCtx Ctx;
   struct Pre { double own; };
-  __device__ __forceinline__ Pre prefetch(int64_t pos) const { return Pre{own[pos]}; }
-  __device__ __forceinline__ void operator()(int64_t pos, double acc, double*, const Pre& p) const { out[pos] = (l2 ? sqrt(acc) : acc) * fabs(p.own); }
+  __device__ __forceinline__ Ctx begin() const { return Ctx(); }
+  __device__ __forceinline__ Pre prefetch(const Ctx&, int64_t pos) const { return Pre{own[pos]}; }
+  __device__ __forceinline__ void operator()(const Ctx&, int64_t pos, double acc, double*, const Pre& p) const { out[pos] = (l2 ? sqrt(acc) : acc) * fabs(p.own); }
 };
 }  // namespace kernels
 
