@@ -55,6 +55,15 @@ constexpr int kThreads = 256;
 constexpr int kMaxReduceBlocks = 148 * 8;
 constexpr double kInfD = __builtin_huge_val();
 
+// Programmatic dependent launch (sm_90+): the kernels of the step loop are
+// launched with programmaticStreamSerialization, so the blocks of kernel k+1
+// are scheduled while the last wave of kernel k drains. Every such kernel first
+// lets its own dependents go (pdl_trigger) and then waits until the preceding
+// grid has completed and its writes are visible (pdl_wait) before it touches
+// global memory. Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -232,17 +241,22 @@ struct GatherSrc {
 //      epilogue's own loads before the gather loop so that they overlap it;
 //      __device__ void operator()(const Ctx&, int64_t pos, double acc, double* red, const Pre&) const
 template <int MODE, int NS, class Epi, int BT, int V>
-__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt) {
+__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks) {
+  pdl_trigger();
+  pdl_wait();
   if (halt != nullptr && *halt != 0) return;
   const double* __restrict__ x = gs.st != nullptr ? pick3(gs.p, gs.st->cand) : gs.p[0];
   double red[NS > 0 ? NS : 1];
 #pragma unroll
   for (int k = 0; k < NS; ++k) red[k] = 0.0;
   const typename Epi::Ctx ctx = epi.begin();
-  // Grid-stride over slots: with a grid of (SMs x resident blocks) every block
-  // is co-resident (no wave quantisation / tail) and the slot -> thread map is
-  // fixed, so the per-block partial sums stay deterministic.
-  for (int64_t slot = static_cast<int64_t>(blockIdx.x) * BT + threadIdx.x; slot < a.num_slots; slot += static_cast<int64_t>(gridDim.x) * BT) {
+  // `chunks` consecutive groups of BT slots per block: fewer per-block partial
+  // sums for the decision kernel to add while the hardware block scheduler
+  // still balances the (window-sorted, hence uneven) rows; the slot -> thread
+  // map is fixed, so the partial sums stay deterministic.
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t slot = (static_cast<int64_t>(blockIdx.x) * chunks + c) * BT + threadIdx.x;
+    if (slot >= a.num_slots) break;
     const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
     const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
     typename Epi::Pre pre;
@@ -261,6 +275,8 @@ __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / B
 // slot order and then runs the same epilogue.
 template <int MODE, int NS, class Epi>
 __global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, double* partials, const int32_t* halt) {
+  pdl_trigger();
+  pdl_wait();
   if (halt != nullptr && *halt != 0) return;
   double red[NS > 0 ? NS : 1];
 #pragma unroll
@@ -293,8 +309,69 @@ struct StepPtrs {
   StepState* state;
 };
 
-// Primal half step, two elements per thread (128-bit loads/stores).
-__global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* partials) {
+// Peer-memory exchange of the row-sharded step loop: every rank's
+// arena (comm.h PeerArena, mapped everywhere over NVLink) holds, in doubles,
+//   [xt_off, +n)       x~ in the caller's column order; slice C_h is stored by rank h
+//   [partial_off, +n)  this rank's (K[R_g,:])^T y' partial; peers pull their slice
+//   [scal_off, +4 G)   {||dx||^2, ||dy||^2, dx.(K^T y' - K^T y)} partials of rank h at 4 h
+//   [flags_off, +8 k)  barrier k: epoch last signalled by rank h at 8 k + h (u64)
+//   [epoch_off, +4)    this rank's own epoch counters (u64)
+//   [tr_off, +2*34*G)  trust-region bin totals of rank h for pass parity p at 34 (G p + h)
+struct PeerPtrs {
+  int world, rank;
+  double* base[kMaxPeers];
+  int64_t xt_off, partial_off, scal_off, flags_off, epoch_off, tr_off;
+  int64_t begin, end;  // this rank's slice of the primal vector (begin is even)
+};
+__device__ __forceinline__ double* peer_base(const PeerPtrs& pp, int h) {
+  double* r = pp.base[0];
+#pragma unroll
+  for (int k = 1; k < kMaxPeers; ++k) r = h == k ? pp.base[k] : r;
+  return r;
+}
+
+// Cross-GPU barrier `which` for the threads of ONE warp (lanes < world take
+// part): lane h raises this rank's flag in rank h's arena, then waits for
+// rank h's flag in the local arena. Epochs only grow and every rank runs the
+// same kernel sequence, so a rank is never more than one epoch ahead. A peer
+// that does not arrive within ~4 s of GPU clocks halts the loop with
+// kHaltPeerTimeout instead of hanging the device.
+__device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int which, int32_t* halt_flag) {
+  const int lane = threadIdx.x & 31;
+  double* local = peer_base(pp, pp.rank);
+  unsigned long long* epoch = reinterpret_cast<unsigned long long*>(local + pp.epoch_off) + which;
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(epoch) + 1ull;
+  __threadfence_system();
+  if (lane < pp.world) {
+    volatile unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer_base(pp, lane) + pp.flags_off) + which * 8 + pp.rank;
+    *dst = e;
+    volatile unsigned long long* src = reinterpret_cast<unsigned long long*>(local + pp.flags_off) + which * 8 + lane;
+    const long long t0 = clock64();
+    while (*src < e) {
+      if (clock64() - t0 > 8000000000ll) {
+        *halt_flag = kHaltPeerTimeout;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+  if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(epoch) = e;
+}
+__global__ void k_peer_barrier(PeerPtrs pp, int which, StepState* st) {
+  pdl_trigger();
+  pdl_wait();
+  if (st->halt != 0) return;
+  peer_barrier(pp, which, &st->halt);
+}
+
+// Primal half step, two elements per thread (128-bit loads/stores). PEER: this
+// rank updates only its slice [begin, end) and stores x~ straight into every
+// rank's arena (the all-gather of x~ fused into the producing kernel).
+template <bool PEER>
+__global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs peer, double* partials) {
+  pdl_trigger();
+  pdl_wait();
   const StepState* st = b.state;
   if (st->halt != 0) return;
   const double* __restrict__ xc = pick3(b.x, st->cur);
@@ -304,8 +381,9 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* pa
   const double ratio = st->pending_ratio;
   const bool has_q = b.q != nullptr;
   double s = 0.0;
-  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 2;
-  if (i0 + 1 < b.n) {
+  const int64_t i0 = (PEER ? peer.begin : 0) + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 2;
+  const int64_t iend = PEER ? peer.end : b.n;
+  if (i0 + 1 < iend) {
     const double2 x2 = *reinterpret_cast<const double2*>(xc + i0);
     const double2 k2 = *reinterpret_cast<const double2*>(kty + i0);
     const double2 c2 = *reinterpret_cast<const double2*>(b.c + i0);
@@ -325,7 +403,13 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* pa
     double2 xt;
     xt.x = nx.x + d0;
     xt.y = nx.y + d1;
-    *reinterpret_cast<double2*>(b.x_tilde + i0) = xt;
+    if (PEER) {
+#pragma unroll
+      for (int h = 0; h < kMaxPeers; ++h)
+        if (h < peer.world) *reinterpret_cast<double2*>(peer.base[h] + peer.xt_off + i0) = xt;
+    } else {
+      *reinterpret_cast<double2*>(b.x_tilde + i0) = xt;
+    }
     s = d0 * d0 + d1 * d1;
     if (ratio > 0.0) {
       double2 av = *reinterpret_cast<const double2*>(b.avg_x + i0);
@@ -333,14 +417,20 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, double* pa
       av.y += ratio * (x2.y - av.y);
       *reinterpret_cast<double2*>(b.avg_x + i0) = av;
     }
-  } else if (i0 < b.n) {
+  } else if (i0 < iend) {
     const double x = xc[i0];
     double t = x - tau * (b.c[i0] - kty[i0]);
     if (has_q) t = t / (tau * b.q[i0] + 1.0);
     const double nx = fmax(fmin(t, b.uv[i0]), b.lv[i0]);
     const double d = nx - x;
     xn[i0] = nx;
-    b.x_tilde[i0] = nx + d;
+    if (PEER) {
+#pragma unroll
+      for (int h = 0; h < kMaxPeers; ++h)
+        if (h < peer.world) peer.base[h][peer.xt_off + i0] = nx + d;
+    } else {
+      b.x_tilde[i0] = nx + d;
+    }
     s = d * d;
     if (ratio > 0.0) b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
   }
@@ -424,47 +514,9 @@ __device__ __forceinline__ double block_sum_range(const double* __restrict__ p, 
 }
 
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
-// Three fixed-order sums at once: all loads of the three partial arrays are in
-// flight together and one shuffle tree + one shared-memory exchange serves all
-// of them (the decision kernel is pure latency on the critical path of a step).
-__device__ __forceinline__ void block_sum3(const double* __restrict__ p0, int n0, const double* __restrict__ p1, int n1,
-                                           const double* __restrict__ p2, int n2, double out[3]) {
-  __shared__ double sh3[3][kDecideThreads / 32];
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < n0; i += kDecideThreads) s0 += p0[i];
-#pragma unroll 4
-  for (int i = threadIdx.x; i < n1; i += kDecideThreads) s1 += p1[i];
-#pragma unroll 4
-  for (int i = threadIdx.x; i < n2; i += kDecideThreads) s2 += p2[i];
-  s0 = warp_sum(s0);
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) {
-    sh3[0][threadIdx.x >> 5] = s0;
-    sh3[1][threadIdx.x >> 5] = s1;
-    sh3[2][threadIdx.x >> 5] = s2;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double t = threadIdx.x < kDecideThreads / 32 ? sh3[k][threadIdx.x] : 0.0;
-      out[k] = warp_sum(t);
-    }
-  }
-}
-
-// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
-__global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
-  if (st_dev->halt != 0) return;
-  double sums[3];
-  // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
-  block_sum3(pp, np, pd, nd < 0 ? 0 : nd, pt, nt, sums);
-  if (threadIdx.x != 0) return;
-  const double dx2 = sums[0];
-  const double dy2 = nd < 0 ? *pd : sums[1];
-  const double dot = sums[2];
+// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674) from the three
+// reduced scalars; one thread.
+__device__ void decide_update(StepState* st_dev, double dx2, double dy2, double dot) {
   // One load of the whole state into registers, one store at the end: the
   // decision is a chain of dependent scalar updates and must not pay an L2
   // round trip per field.
@@ -531,17 +583,64 @@ __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_de
   *st_dev = s;
 }
 
+// Three fixed-order sums at once: all loads of the three partial arrays are in
+// flight together and one shuffle tree + one shared-memory exchange serves all
+// of them (the decision kernel is pure latency on the critical path of a step).
+__device__ __forceinline__ void block_sum3(const double* __restrict__ p0, int n0, const double* __restrict__ p1, int n1,
+                                           const double* __restrict__ p2, int n2, double out[3]) {
+  __shared__ double sh3[3][kDecideThreads / 32];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < n0; i += kDecideThreads) s0 += p0[i];
+#pragma unroll 8
+  for (int i = threadIdx.x; i < n1; i += kDecideThreads) s1 += p1[i];
+#pragma unroll 16
+  for (int i = threadIdx.x; i < n2; i += kDecideThreads) s2 += p2[i];
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    sh3[0][threadIdx.x >> 5] = s0;
+    sh3[1][threadIdx.x >> 5] = s1;
+    sh3[2][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double t = threadIdx.x < kDecideThreads / 32 ? sh3[k][threadIdx.x] : 0.0;
+      out[k] = warp_sum(t);
+    }
+  }
+}
+
+// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
+__global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
+  pdl_trigger();
+  pdl_wait();
+  if (st_dev->halt != 0) return;
+  double sums[3];
+  // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
+  block_sum3(pp, np, pd, nd < 0 ? 0 : nd, pt, nt, sums);
+  if (threadIdx.x != 0) return;
+  decide_update(st_dev, sums[0], nd < 0 ? *pd : sums[1], sums[2]);
+}
+
 // ---- row-sharded variant of the step ---------------------------
 // The primal side is replicated, the dual side is this rank's row block. After
 // the local K^T y' partial (scattered to column order) one all-reduce of
 // [n + 1] doubles completes both K^T y' and ||dy||^2; then k_kty_finish does
 // what KtyEpi does on one GPU.
 __global__ void __launch_bounds__(kDecideThreads) k_sum_to_slot(const StepState* st, const double* pd, int nd, double* slot) {
+  pdl_trigger();
+  pdl_wait();
   if (st->halt != 0) return;
   const double v = block_sum_range(pd, nd);
   if (threadIdx.x == 0) *slot = v;
 }
 __global__ void __launch_bounds__(kThreads) k_kty_finish(StepPtrs b, const double* __restrict__ reduced, double* partials) {
+  pdl_trigger();
+  pdl_wait();
   const StepState* st = b.state;
   if (st->halt != 0) return;
   double s = 0.0;
@@ -554,13 +653,87 @@ __global__ void __launch_bounds__(kThreads) k_kty_finish(StepPtrs b, const doubl
   block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
 }
 
-__global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t total) {
+// Peer exchange: the reduce-scatter of the K^T y' partials fused into the
+// consumer. This rank pulls its slice of every rank's partial out of the peer
+// arenas (128-bit loads over NVLink), adds them in rank order (the same order
+// on every rank), stores K^T y' and accumulates the nonlinearity partials.
+__global__ void __launch_bounds__(kThreads) k_kty_finish_peer(StepPtrs b, PeerPtrs peer, double* partials) {
+  pdl_trigger();
+  pdl_wait();
+  const StepState* st = b.state;
+  if (st->halt != 0) return;
+  double s = 0.0;
+  const int64_t i0 = peer.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 2;
+  double* __restrict__ kc = pick3(b.kty, st->cand);
+  const double* __restrict__ xc = pick3(b.x, st->cand);
+  const double* __restrict__ xo = pick3(b.x, st->cur);
+  const double* __restrict__ ko = pick3(b.kty, st->cur);
+  if (i0 + 1 < peer.end) {
+    double2 v = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int h = 0; h < kMaxPeers; ++h) {
+      if (h < peer.world) {
+        const double2 t = *reinterpret_cast<const double2*>(peer.base[h] + peer.partial_off + i0);
+        v.x += t.x;
+        v.y += t.y;
+      }
+    }
+    const double2 a = *reinterpret_cast<const double2*>(xc + i0);
+    const double2 o = *reinterpret_cast<const double2*>(xo + i0);
+    const double2 k = *reinterpret_cast<const double2*>(ko + i0);
+    *reinterpret_cast<double2*>(kc + i0) = v;
+    s = (a.x - o.x) * (v.x - k.x) + (a.y - o.y) * (v.y - k.y);
+  } else if (i0 < peer.end) {
+    double v = 0.0;
+#pragma unroll
+    for (int h = 0; h < kMaxPeers; ++h)
+      if (h < peer.world) v += peer.base[h][peer.partial_off + i0];
+    kc[i0] = v;
+    s = (xc[i0] - xo[i0]) * (v - ko[i0]);
+  }
+  block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
+}
+
+// Step decision of the peer exchange: local fixed-order sums, the three
+// partials stored into every rank's arena, the cross-GPU barrier, then every
+// rank adds the G x 3 partials in rank order and takes the same decision.
+__global__ void __launch_bounds__(kDecideThreads) k_step_decide_peer(StepState* st_dev, PeerPtrs peer, const double* pp, int np, const double* pd, int nd,
+                                                                     const double* pt, int nt) {
+  pdl_trigger();
+  pdl_wait();
+  if (st_dev->halt != 0) return;
+  double sums[3];
+  block_sum3(pp, np, pd, nd, pt, nt, sums);
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  if (lane < peer.world) {
+    volatile double* dst = peer_base(peer, lane) + peer.scal_off + 4 * peer.rank;
+    dst[0] = sums[0];
+    dst[1] = sums[1];
+    dst[2] = sums[2];
+  }
+  peer_barrier(peer, 2, &st_dev->halt);
+  if (lane != 0) return;
+  if (*reinterpret_cast<volatile int32_t*>(&st_dev->halt) != 0) return;  // a peer never arrived
+  const volatile double* sc = peer_base(peer, peer.rank) + peer.scal_off;
+  double t[3] = {0.0, 0.0, 0.0};
+  for (int h = 0; h < peer.world; ++h) {
+    t[0] += sc[4 * h + 0];
+    t[1] += sc[4 * h + 1];
+    t[2] += sc[4 * h + 2];
+  }
+  decide_update(st_dev, t[0], t[1], t[2]);
+}
+
+// [pbegin, pend): the part of the primal average this rank maintains (all of
+// it unless the peer exchange slices the primal update).
+__global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t total, int64_t pbegin, int64_t pend) {
   StepState* st = b.state;
   const double ratio = st->pending_ratio;
   if (ratio <= 0.0) return;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (i < b.n) {
-    b.avg_x[i] += ratio * (pick3(b.x, st->cur)[i] - b.avg_x[i]);
+    if (i >= pbegin && i < pend) b.avg_x[i] += ratio * (pick3(b.x, st->cur)[i] - b.avg_x[i]);
   } else if (i < total) {
     const int64_t j = i - b.n;
     b.avg_y[j] += ratio * (pick3(b.y, st->cur)[j] - b.avg_y[j]);
@@ -590,7 +763,8 @@ struct TrSearchState {
 struct JointElem {
   const double *x, *y, *kx, *kty, *c, *q, *lv, *uv, *lc, *uc;
   double primal_weight;
-  int64_t n, m;
+  int64_t n, m;   // joint index i < n is primal element pbeg + i; i >= n is dual element i - n
+  int64_t pbeg;   // first primal element this rank counts (a slice of the replicated primal side on a row-sharded solve)
   __device__ __forceinline__ double primal_gradient(int64_t i) const {
     return q != nullptr ? (c[i] + q[i] * x[i] - kty[i]) : (c[i] - kty[i]);
   }
@@ -606,12 +780,13 @@ struct JointElem {
   }
   __device__ __forceinline__ void get(int64_t i, double& obj, double& lb, double& ub, double& center, double& w, double& qd) const {
     if (i < n) {
-      obj = primal_gradient(i);
-      lb = lv[i];
-      ub = uv[i];
-      center = x[i];
+      const int64_t ip = pbeg + i;
+      obj = primal_gradient(ip);
+      lb = lv[ip];
+      ub = uv[ip];
+      center = x[ip];
       w = 0.5 * primal_weight;
-      qd = q != nullptr ? q[i] : 0.0;
+      qd = q != nullptr ? q[ip] : 0.0;
     } else {
       const int64_t j = i - n;
       obj = -(subgradient_coefficient(j) - kx[j]);
@@ -758,6 +933,129 @@ __device__ __forceinline__ void tr_pick(const double* tot, TrSearchState* st, in
   if (tot[best + 1] == 0.0 && tot[17 + best + 1] == 0.0) st->done = 1;
 }
 
+// ---- the whole threshold search in ONE persistent launch -----------------------
+// All radix-16 passes of the search run inside one cooperative launch: per pass
+// every thread bins its elements into 34 shared-memory accumulators of its own
+// (column tid: conflict-free, two read-modify-writes per element instead of 34
+// predicated adds), the block reduces them in a fixed order, a grid barrier
+// publishes the per-block partials, and EVERY block then adds the partials of
+// all blocks in the same order and takes the same bracket decision -- so no
+// second kernel, no host round trip, and the loop stops at the first pass that
+// leaves nothing inside the bracket. On a row-sharded solve block 0 also stores
+// the 34 totals into every rank's arena and the ranks meet at a peer barrier;
+// every block then adds the G x 34 totals in rank order.
+constexpr int kTrBlocksPerSm = 2;
+constexpr int kTrMaxBlocks = 320;  // grid cap of k_tr_search (multiple of 32)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+template <bool PEER>
+__global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_search(int64_t total, const unsigned long long* __restrict__ keys, const double* __restrict__ a,
+                                                                        const double* __restrict__ bcoef, TrSearchState* st_dev, double* partials,
+                                                                        unsigned int* sync_counter, PeerPtrs peer, int32_t* peer_error, double radius) {
+  extern __shared__ double bins[];  // [34][kThreads]
+  __shared__ double tot[34];
+  __shared__ TrSearchState s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = gridDim.x;
+  if (tid == 0) s = *st_dev;
+  __syncthreads();
+  unsigned int syncs = 0;
+  const int64_t stride = static_cast<int64_t>(nb) * kThreads * kTrUnroll;
+  int pass = 0;
+  for (int shift = 60; shift >= 0 && s.done == 0; shift -= 4, ++pass) {
+    const unsigned long long lo = s.lo;
+#pragma unroll
+    for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x) * kThreads * kTrUnroll + tid; base < total; base += stride) {
+      unsigned long long key[kTrUnroll];
+      double av[kTrUnroll], bv[kTrUnroll];
+#pragma unroll
+      for (int u = 0; u < kTrUnroll; ++u) {
+        const int64_t i = base + static_cast<int64_t>(u) * kThreads;
+        const bool ok = i < total;
+        key[u] = ok ? keys[i] : 0ull;
+        av[u] = ok ? a[i] : 0.0;
+        bv[u] = ok ? bcoef[i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kTrUnroll; ++u) {
+        int j0 = 0;
+        if (key[u] > lo) {
+          const unsigned long long d = (key[u] - lo - 1ull) >> shift;
+          j0 = d >= 15ull ? 16 : static_cast<int>(d) + 1;
+        }
+        bins[j0 * kThreads + tid] += av[u];
+        bins[(17 + j0) * kThreads + tid] += bv[u];
+      }
+    }
+    __syncthreads();
+    // block totals: warp w adds columns w, w + 8, ... over the 256 threads (lane-strided, then a shuffle tree)
+    double* mine = partials + (static_cast<int64_t>(pass & 1) * nb + blockIdx.x) * 34;
+    for (int j = warp; j < 34; j += kThreads / 32) {
+      double v = 0.0;
+#pragma unroll
+      for (int t = lane; t < kThreads; t += 32) v += bins[j * kThreads + t];
+      v = warp_sum(v);
+      if (lane == 0) mine[j] = v;
+    }
+    grid_barrier(sync_counter, static_cast<unsigned int>(nb) * (++syncs));
+    // every block: the same fixed-order sum over the blocks
+    const double* all = partials + static_cast<int64_t>(pass & 1) * nb * 34;
+    // (all loads of a column are issued before the first add: the sum is a
+    // dependent chain and must not pay one L2 round trip per term)
+    for (int j = warp; j < 34; j += kThreads / 32) {
+      double term[kTrMaxBlocks / 32];
+#pragma unroll
+      for (int k = 0; k < kTrMaxBlocks / 32; ++k) {
+        const int b = lane + 32 * k;
+        term[k] = b < nb ? __ldcg(all + static_cast<int64_t>(b) * 34 + j) : 0.0;
+      }
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < kTrMaxBlocks / 32; ++k) v += term[k];
+      v = warp_sum(v);
+      if (lane == 0) tot[j] = v;
+    }
+    __syncthreads();
+    if (PEER) {
+      const int64_t slot = peer.tr_off + static_cast<int64_t>(pass & 1) * 34 * peer.world;
+      if (blockIdx.x == 0 && warp == 0) {
+        for (int h = 0; h < peer.world; ++h) {
+          volatile double* dst = peer_base(peer, h) + slot + 34 * peer.rank;
+          dst[lane] = tot[lane];
+          if (lane < 2) dst[32 + lane] = tot[32 + lane];
+        }
+        peer_barrier(peer, 3, peer_error);
+      }
+      grid_barrier(sync_counter, static_cast<unsigned int>(nb) * (++syncs));
+      if (tid < 34) {
+        const volatile double* src = peer_base(peer, peer.rank) + slot;
+        double v = 0.0;
+        for (int h = 0; h < peer.world; ++h) v += src[34 * h + tid];
+        tot[tid] = v;
+      }
+      __syncthreads();
+      if (*reinterpret_cast<volatile int32_t*>(peer_error) != 0) break;  // a peer never arrived
+    }
+    if (tid == 0) tr_pick(tot, &s, shift);
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    // trust_region.cc:345-365, 429-444
+    if (radius == 0.0 || !(s.max_abs_objective > 0.0)) s.step_size = 0.0;
+    else s.step_size = s.variable_coef > 0.0 ? sqrt((s.radius_sq - s.fixed_radius_sq) / s.variable_coef) : DBL_MAX;
+    *st_dev = s;
+  }
+}
+
 __global__ void k_tr_init(TrSearchState* st, double radius, const double* maxabs_partials, int nblocks) {
   double mx = 0.0;
   for (int b = threadIdx.x; b < nblocks; b += 32) mx = fmax(mx, maxabs_partials[b]);
@@ -808,6 +1106,8 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   CUDA_OK(cudaGetDeviceProperties(&prop, cuda_device));
   num_sms_ = prop.multiProcessorCount;
   CUDA_OK(cudaMalloc(&partials_, sizeof(double) * kMaxReduceBlocks * 40));
+  CUDA_OK(cudaMalloc(&tr_peer_error_, 64));
+  CUDA_OK(cudaMemset(tr_peer_error_, 0, 64));
   CUDA_OK(cudaMalloc(&results_, sizeof(double) * 64));
   CUDA_OK(cudaMallocHost(&host_results_, sizeof(double) * 64));
 }
@@ -815,10 +1115,16 @@ Device::Device(int cuda_device) : device_(cuda_device) {
 Device::~Device() {
   cudaSetDevice(device_);
   cudaFree(partials_);
+  cudaFree(tr_peer_error_);
   cudaFree(results_);
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
   cudaFree(step_partials_);
+  if (const char* t = std::getenv("PDLP_B200_TRACE"); t != nullptr && t[0] == '1' && detail_samples_ > 0) {
+    std::fprintf(stderr, "[pdlp_b200 trace] step sub-phases (us, %lld samples):", static_cast<long long>(detail_samples_));
+    for (int k = 0; k < 7; ++k) std::fprintf(stderr, " %.1f", 1000.0 * detail_ms_[k] / detail_samples_);
+    std::fprintf(stderr, "\n");
+  }
   for (void* e : timing_events_) cudaEventDestroy(static_cast<cudaEvent_t>(e));
   for (auto& pr : timeline_ev_) for (void* e : pr) if (e != nullptr) cudaEventDestroy(static_cast<cudaEvent_t>(e));
   if (stream_ != nullptr) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
@@ -910,9 +1216,8 @@ void Device::DownloadSellValues(const SellDev& s, std::vector<double>& out) {
 
 // ---- generic SELL launch --------------------------------------------------
 namespace kernels {
-// Blocks of a k_sell launch: one block per 256 slots, capped at a persistent
-// grid of SMs x blocks-per-SM (PDLP_B200_SELL_BLOCKS_PER_SM, default 6 = what
-// 40 registers/thread allow; 0 = uncapped).
+// Launch shape of k_sell, tunable for A/B runs: block size (PDLP_B200_SELL_THREADS),
+// row-loop variant (PDLP_B200_SELL_VARIANT) and slot groups per block (PDLP_B200_SELL_CHUNKS).
 int SellThreads() {
   static const int bt = [] {
     const char* v = std::getenv("PDLP_B200_SELL_THREADS");
@@ -928,27 +1233,46 @@ int SellVariant() {
   }();
   return v;
 }
-int SellGrid(const SellDev& a) {
-  static const int per_sm = [] {
-    const char* v = std::getenv("PDLP_B200_SELL_BLOCKS_PER_SM");
-    return (v != nullptr && *v != 0) ? std::atoi(v) : 0;
+int SellChunks() {
+  static const int v = [] {
+    const char* e = std::getenv("PDLP_B200_SELL_CHUNKS");
+    const int c = (e != nullptr && *e != 0) ? std::atoi(e) : 2;
+    return std::max(1, std::min(64, c));
   }();
-  const int kThreads = SellThreads();
-  static const int sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  const int64_t need = std::max<int64_t>(1, (a.num_slots + kThreads - 1) / kThreads);
-  if (per_sm <= 0) return static_cast<int>(need);
-  return static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(sms) * per_sm));
+  return v;
 }
+// Blocks of a k_sell launch: one block per SellChunks() groups of SellThreads() slots.
+int SellGrid(const SellDev& a) {
+  const int64_t per_block = static_cast<int64_t>(SellThreads()) * SellChunks();
+  return static_cast<int>(std::max<int64_t>(1, (a.num_slots + per_block - 1) / per_block));
+}
+// Launch with (pdl) or without the programmatic-dependent-launch attribute.
+template <class... KArgs, class... Args>
+void launch_k(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+bool StepPdl() {
+  static const bool v = [] { const char* e = std::getenv("PDLP_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
+  return v;
+}
+
 template <int MODE, int NS, class Epi>
 void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, double* partials, const int32_t* halt, int64_t* launches,
-                 int* main_blocks, int* fix_blocks) {
+                 int* main_blocks, int* fix_blocks, bool pdl = false) {
   const int nb = SellGrid(a);
   const int variant = SellVariant();
-#define PDLP_SELL_LAUNCH(BT, V) k_sell<MODE, NS, Epi, BT, V><<<nb, BT, 0, stream>>>(a, x, epi, partials, halt)
+#define PDLP_SELL_LAUNCH(BT, V) launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, nb, BT, stream, a, x, epi, partials, halt, SellChunks())
 #define PDLP_SELL_LAUNCH_V(BT) (variant == 1 ? PDLP_SELL_LAUNCH(BT, 1) : variant == 2 ? PDLP_SELL_LAUNCH(BT, 2) : PDLP_SELL_LAUNCH(BT, 0))
   switch (SellThreads()) {
     case 256: PDLP_SELL_LAUNCH_V(256); break;
@@ -961,7 +1285,7 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
   int nf = 0;
   if (a.num_split > 0) {
     nf = static_cast<int>((a.num_split * 32 + kThreads - 1) / kThreads);
-    k_sell_fixup<MODE, NS, Epi><<<nf, kThreads, 0, stream>>>(a, epi, partials != nullptr ? partials + static_cast<int64_t>(nb) * NS : nullptr, halt);
+    launch_k(pdl, k_sell_fixup<MODE, NS, Epi>, nf, kThreads, stream, a, epi, partials != nullptr ? partials + static_cast<int64_t>(nb) * NS : nullptr, halt);
     ++*launches;
   }
   if (main_blocks != nullptr) *main_blocks = nb;
@@ -1138,6 +1462,24 @@ void Device::DualStepFromProducts(const double* y, const double* kx_cur, const d
     Sync();                                                                                                                \
   } while (0)
 #define REDUCE(NS, NM, n, ...) REDUCE_S(false, NS, NM, n, __VA_ARGS__)
+// Reduction over replicated primal-length vectors: on a row-sharded solve every
+// rank reduces its slice [PrimalSliceBegin, PrimalSliceEnd) and the results are
+// all-reduced (same value everywhere); otherwise the whole range.
+#define REDUCE_P(NS, NM, n, ...)                                                                                                  \
+  do {                                                                                                                            \
+    const int64_t off__ = PrimalSliceBegin(n), len__ = PrimalSliceEnd(n) - off__;                                                 \
+    const int nb__ = ReduceBlocks(len__);                                                                                         \
+    k_reduce<NS, NM><<<nb__, kThreads, 0, STREAM>>>(len__, [=] __device__(int64_t i__, double* s, double* m) { const int64_t i = i__ + off__; __VA_ARGS__ }, partials_); \
+    LAUNCHED();                                                                                                            \
+    k_reduce_final<NS, NM><<<1, kThreads, 0, STREAM>>>(nb__, partials_, results_);                                         \
+    LAUNCHED();                                                                                                            \
+    if (PrimalSliced(n)) {                                                                                                 \
+      if ((NS) > 0) comm_->AllReduceSum(results_, results_, (NS), stream_);                                                \
+      if ((NM) > 0) comm_->AllReduceMax(results_ + (NS), results_ + (NS), (NM), stream_);                                  \
+    }                                                                                                                      \
+    CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * ((NS) + (NM)), cudaMemcpyDeviceToHost, STREAM));     \
+    Sync();                                                                                                                \
+  } while (0)
 
 double Device::Dot(const double* a, const double* b, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { s[0] += a[i] * b[i]; }); return host_results_[0]; }
 double Device::SumSq(const double* a, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { s[0] += a[i] * a[i]; }); return host_results_[0]; }
@@ -1147,11 +1489,11 @@ double Device::L1(const double* a, int64_t n, bool sharded) { REDUCE_S(sharded, 
 double Device::ScaledLInf(const double* a, const double* sc, int64_t n, bool sharded) { REDUCE_S(sharded, 0, 1, n, { m[0] = fmax(m[0], fabs(a[i] * sc[i])); }); return std::max(0.0, host_results_[0]); }
 double Device::ScaledSumSq(const double* a, const double* sc, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { const double t = a[i] * sc[i]; s[0] += t * t; }); return host_results_[0]; }
 void Device::DistancesSq(const double* x, const double* x0, int64_t n, const double* y, const double* y0, int64_t mm, double out[2]) {
-  const int64_t total = n + mm;
-  const bool cp = count_primal();
+  const int64_t pbeg = PrimalSliceBegin(n), plen = PrimalSliceEnd(n) - pbeg;
+  const int64_t total = plen + mm;
   REDUCE_S(true, 2, 0, total, {
-    if (i < n) { if (cp) { const double d = x[i] - x0[i]; s[0] += d * d; } }
-    else { const int64_t j = i - n; const double d = y[j] - y0[j]; s[1] += d * d; }
+    if (i < plen) { const double d = x[pbeg + i] - x0[pbeg + i]; s[0] += d * d; }
+    else { const int64_t j = i - plen; const double d = y[j] - y0[j]; s[1] += d * d; }
   });
   out[0] = host_results_[0];
   out[1] = host_results_[1];
@@ -1230,7 +1572,7 @@ MSideStats Device::DualSideStats(const double* y, const double* kx, const double
 
 NSideStats Device::PrimalSideStats(const double* x, const double* xb, const double* kty, const double* c, const double* q, const double* lv,
                                    const double* uv, const double* dc, double cw_offset, bool zero_objective, bool handle_as_residuals, int64_t n) {
-  REDUCE(6, 4, n, {  // iteration_stats.cc:189-270, 273-323
+  REDUCE_P(6, 4, n, {  // iteration_stats.cc:189-270, 273-323
     const double cs = dc != nullptr ? dc[i] : 1.0;
     const double xi = x[i];
     const double qx = q != nullptr ? q[i] * xi : 0.0;
@@ -1284,7 +1626,7 @@ double Device::LagrangianPrimalGradient(const double* x, const double* kty, cons
   return host_results_[0];
 }
 double Device::LagrangianDualGradient(const double* y, const double* kx, const double* lc, const double* uc, double* grad, int64_t mm) {
-  JointElem el{nullptr, y, kx, nullptr, nullptr, nullptr, nullptr, nullptr, lc, uc, 1.0, 0, mm};
+  JointElem el{nullptr, y, kx, nullptr, nullptr, nullptr, nullptr, nullptr, lc, uc, 1.0, 0, mm, 0};
   REDUCE_S(true, 1, 0, mm, {  // sou.cc:502-527
     const double coef = el.subgradient_coefficient(i);
     s[0] += coef * y[i];
@@ -1293,7 +1635,7 @@ double Device::LagrangianDualGradient(const double* y, const double* kx, const d
   return host_results_[0];
 }
 void Device::ActiveSetPrimal(const double* x, const double* x0, const double* lv, const double* uv, int64_t n, int64_t out[2]) {
-  REDUCE(2, 0, n, {
+  REDUCE_P(2, 0, n, {
     const bool a = x[i] > lv[i] && x[i] < uv[i];
     const bool b = x0[i] > lv[i] && x0[i] < uv[i];
     s[0] += a ? 1.0 : 0.0;
@@ -1350,9 +1692,22 @@ double* Device::TrScratch(int64_t doubles) {
 namespace kernels {
 // Runs the threshold search; leaves the step size in st->step_size (device).
 // Elements below `first` are skipped (replicated primal part on ranks > 0).
+static bool TrLegacy();
+static int TrSms();
+static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n) {
+  PeerPtrs pp;
+  std::memset(&pp, 0, sizeof(pp));
+  if (arena == nullptr) return pp;
+  pp.world = arena->world;
+  pp.rank = arena->rank;
+  for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(arena->base[h]);
+  const PeerLayout l = PeerLayout::For(n, pp.world);
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  return pp;
+}
 template <class Elem>
-void tr_search(cudaStream_t stream, Comm* comm, int64_t total, int64_t first, Elem el, double radius, double* scratch, double* partials,
-               TrSearchState* st, double* totals, int64_t* launches) {
+void tr_search(cudaStream_t stream, Comm* comm, const PeerPtrs& peer, int32_t* peer_error, int64_t total, int64_t first, Elem el, double radius,
+               double* scratch, double* partials, TrSearchState* st, double* totals, int64_t* launches) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch);
   double* a = scratch + total;
   double* b = scratch + 2 * total;
@@ -1364,6 +1719,35 @@ void tr_search(cudaStream_t stream, Comm* comm, int64_t total, int64_t first, El
   if (comm != nullptr) {
     double* mx = reinterpret_cast<double*>(st) + offsetof(TrSearchState, max_abs_objective) / sizeof(double);
     comm->AllReduceMax(mx, mx, 1, stream);
+  }
+  const bool persistent = !TrLegacy();
+  if (persistent) {
+    // one cooperative launch (all blocks co-resident: SMs x kTrBlocksPerSm)
+    const int nbp = static_cast<int>(std::min<int64_t>(std::min<int64_t>(kTrMaxBlocks, static_cast<int64_t>(TrSms()) * kTrBlocksPerSm), std::max<int64_t>(1, (total + kThreads * kTrUnroll - 1) / (kThreads * kTrUnroll))));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(totals + 40);
+    cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
+    double* part2 = partials;  // [2][nbp][34]
+    const size_t smem = sizeof(double) * 34 * kThreads;
+    const unsigned long long* ckeys = keys;
+    const double* ca = a;
+    const double* cb = b;
+    int64_t tot_arg = total;
+    double rad = radius;
+    void* args[] = {&tot_arg, &ckeys, &ca, &cb, &st, &part2, &counter, const_cast<PeerPtrs*>(&peer), &peer_error, &rad};
+    const bool use_peer = comm != nullptr && peer.world > 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_tr_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      cudaFuncSetAttribute(k_tr_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      attr_set = true;
+    }
+    if (comm == nullptr || use_peer) {
+      cudaError_t e = cudaLaunchCooperativeKernel(use_peer ? reinterpret_cast<const void*>(k_tr_search<true>) : reinterpret_cast<const void*>(k_tr_search<false>),
+                                                  dim3(nbp), dim3(kThreads), args, smem, stream);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("cooperative launch of k_tr_search failed: ") + cudaGetErrorString(e));
+      *launches += 1;
+      return;
+    }
   }
   for (int shift = 60; shift >= 0; shift -= 4) {
     k_tr_pass<<<nb, kThreads, 0, stream>>>(total, keys, a, b, st, shift, partials);
@@ -1378,23 +1762,37 @@ void tr_search(cudaStream_t stream, Comm* comm, int64_t total, int64_t first, El
   k_tr_finish<<<1, 1, 0, stream>>>(st, radius);
   *launches += 1;
 }
+static bool TrLegacy() {
+  static const bool v = [] { const char* e = std::getenv("PDLP_B200_TR_LEGACY"); return e != nullptr && e[0] == '1'; }();
+  return v;
+}
+static int TrSms() {
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  return sms;
+}
 }  // namespace kernels
 
 void Device::LocalizedLagrangianBounds(const double* x, const double* y, const double* kx, const double* kty, const double* c, const double* q,
                                        const double* lv, const double* uv, const double* lc, const double* uc, double primal_weight, double radius,
                                        bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t mm, double out[3]) {
-  const int64_t total = n + mm;
-  const JointElem el{x, y, kx, kty, c, q, lv, uv, lc, uc, primal_weight, n, mm};
-  const int64_t first = count_primal() ? 0 : n;  // the primal part is replicated: rank 0 counts it
+  // The primal side is replicated on a row-sharded solve: every rank counts its own slice of it.
+  const int64_t pbeg = PrimalSliceBegin(n), plen = PrimalSliceEnd(n) - pbeg;
+  const int64_t total = plen + mm;
+  const JointElem el{x, y, kx, kty, c, q, lv, uv, lc, uc, primal_weight, plen, mm, pbeg};
+  const int64_t first = 0;
   // Lagrangian value = primal part + dual part (sou.cc:446-527).
   REDUCE_S(true, 2, 0, total, {
-    if (i < first) return;
-    if (i < n) {
-      const double g = el.primal_gradient(i);
-      const double op = q != nullptr ? q[i] * x[i] : 0.0;
-      s[0] += x[i] * (g - 0.5 * op);
+    if (i < plen) {
+      const int64_t ip = pbeg + i;
+      const double g = el.primal_gradient(ip);
+      const double op = q != nullptr ? q[ip] * x[ip] : 0.0;
+      s[0] += x[ip] * (g - 0.5 * op);
     } else {
-      const int64_t j = i - n;
+      const int64_t j = i - plen;
       s[1] += el.subgradient_coefficient(j) * y[j];
     }
   });
@@ -1403,16 +1801,21 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
   TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * total);
 
   if (!use_diagonal_solver) {
-    tr_search(STREAM, comm_, total, first, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
+    tr_search(STREAM, comm_, MakeTrPeerPtrs(peer_arena_, peer_arena_n_), tr_peer_error_, total, first, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
     CUDA_OK(cudaGetLastError());
+    if (comm_ != nullptr && peer_arena_ != nullptr) {
+      int32_t err = 0;
+      CUDA_OK(cudaMemcpyAsync(&err, tr_peer_error_, sizeof(err), cudaMemcpyDeviceToHost, STREAM));
+      Sync();
+      if (err != 0) throw std::runtime_error("peer-memory exchange timed out in the trust-region search: a rank did not arrive");
+    }
     // objective deltas at the solution (trust_region.cc:929-967)
     const TrSearchState* cst = st;
     REDUCE_S(true, 2, 0, total, {
-      if (i < first) return;
-      double obj, lb, ub, center, w, qd;
+        double obj, lb, ub, center, w, qd;
       el.get(i, obj, lb, ub, center, w, qd);
       const double sol = projected_value(center, obj, w, lb, ub, cst->step_size);
-      if (i < n) s[0] += obj * (sol - center);
+      if (i < plen) s[0] += obj * (sol - center);
       else s[1] += (-obj) * (sol - center);
     });
     out[0] = lagrangian;
@@ -1431,8 +1834,7 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
       const double sf = bracketing ? hi : (lo + hi) / 2.0;
       if (!bracketing && !((hi - lo) >= diagonal_tol * std::max(1.0, lo))) break;
       REDUCE_S(true, 1, 0, total, {
-        if (i < first) return;
-        double obj, lb, ub, center, w, qd;
+            double obj, lb, ub, center, w, qd;
         el.get(i, obj, lb, ub, center, w, qd);
         const double sw = sqrt(w);
         const double v = fmin(fmax((-obj / sw) / (qd / w + sf), sw * (lb - center)), sw * (ub - center));
@@ -1449,7 +1851,6 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
   }
   const bool zero_radius = radius == 0.0;
   REDUCE_S(true, 2, 0, total, {
-    if (i < first) return;
     double obj, lb, ub, center, w, qd;
     el.get(i, obj, lb, ub, center, w, qd);
     double diff = 0.0;
@@ -1459,7 +1860,7 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
       const double sol = center + sqrt(1 / w) * v;
       diff = sol - center;
     }
-    if (i < n) s[0] += obj * diff + 0.5 * qd * diff * diff;
+    if (i < plen) s[0] += obj * diff + 0.5 * qd * diff * diff;
     else s[1] += (-obj) * diff;
   });
   out[0] = lagrangian;
@@ -1472,7 +1873,7 @@ void Device::SolveTrustRegion(const double* obj, const double* lb, const double*
   const VectorElem el{obj, lb, ub, center, w, nullptr};
   double* scratch = TrScratch(3 * n + 64);
   TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * n);
-  tr_search(STREAM, nullptr, n, 0, el, radius, scratch, partials_, st, scratch + 3 * n + 16, &launches_);
+  tr_search(STREAM, nullptr, PeerPtrs{}, nullptr, n, 0, el, radius, scratch, partials_, st, scratch + 3 * n + 16, &launches_);
   CUDA_OK(cudaGetLastError());
   const TrSearchState* cst = st;
   REDUCE(1, 0, n, {
@@ -1552,9 +1953,27 @@ static StepPtrs MakePtrs(const Device::StepBuffers& b) {
   return p;
 }
 
+static PeerPtrs MakePeerPtrs(const Device::StepBuffers& b) {
+  PeerPtrs pp;
+  std::memset(&pp, 0, sizeof(pp));
+  if (b.arena == nullptr) return pp;
+  pp.world = b.arena->world;
+  pp.rank = b.arena->rank;
+  for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(b.arena->base[h]);
+  const PeerLayout l = PeerLayout::For(b.n, pp.world);
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  pp.begin = b.slice_begin;
+  pp.end = b.slice_end;
+  return pp;
+}
+
 void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count) {
   const StepPtrs p = MakePtrs(b);
-  const int np = static_cast<int>(std::max<int64_t>(1, ((b.n + 1) / 2 + kThreads - 1) / kThreads));
+  const bool use_peer = b.arena != nullptr;
+  const bool pdl = StepPdl();
+  const PeerPtrs peer = MakePeerPtrs(b);
+  const int64_t primal_work = use_peer ? b.slice_end - b.slice_begin : b.n;
+  const int np = static_cast<int>(std::max<int64_t>(1, ((primal_work + 1) / 2 + kThreads - 1) / kThreads));
   const int nd_main = SellGrid(rows);
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int nt_main = SellGrid(cols);
@@ -1573,12 +1992,13 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const int32_t* halt = &b.state->halt;
   constexpr int kMaxSamples = 64;
   timing_attempt_idx_.clear();
-  auto ev = [&](int slot, int k) { CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timing_events_[slot * 5 + k]), STREAM)); };
+  timing_peer_ = use_peer;
+  auto ev = [&](int slot, int k) { CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timing_events_[slot * kEvPerSlot + k]), STREAM)); };
   for (int it = 0; it < count; ++it) {
     int slot = -1;
     if (step_timing_ && it % step_timing_stride_ == 0 && static_cast<int>(timing_attempt_idx_.size()) < kMaxSamples) {
       slot = static_cast<int>(timing_attempt_idx_.size());
-      while (static_cast<int>(timing_events_.size()) < (slot + 1) * 5) {
+      while (static_cast<int>(timing_events_.size()) < (slot + 1) * kEvPerSlot) {
         cudaEvent_t e;
         CUDA_OK(cudaEventCreate(&e));
         timing_events_.push_back(e);
@@ -1586,18 +2006,41 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       timing_attempt_idx_.push_back(it);
       ev(slot, 0);
     }
-    k_primal_step<<<np, kThreads, 0, STREAM>>>(p, pp);
+    if (use_peer) {
+      // sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual | K^T y' partial | barrier | slice pull + finish | decision (+ barrier)
+      launch_k(pdl, k_primal_step<true>, np, kThreads, STREAM, p, peer, pp);
+      if (slot >= 0) ev(slot, 1);
+      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 0, b.state);
+      launches_ += 2;
+      if (slot >= 0) ev(slot, 2);
+      if (b.m > 0) {
+        launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr, pdl);
+      }
+      if (slot >= 0) ev(slot, 3);
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{peer.base[peer.rank] + peer.partial_off, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
+      if (slot >= 0) ev(slot, 4);
+      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 1, b.state);
+      if (slot >= 0) ev(slot, 5);
+      launch_k(pdl, k_kty_finish_peer, np, kThreads, STREAM, p, peer, pt);
+      launches_ += 2;
+      if (slot >= 0) ev(slot, 6);
+      launch_k(pdl, k_step_decide_peer, 1, kDecideThreads, STREAM, b.state, peer, pp, np, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, np);
+      ++launches_;
+      if (slot >= 0) ev(slot, 7);
+      continue;
+    }
+    launch_k(pdl, k_primal_step<false>, np, kThreads, STREAM, p, peer, pp);
     ++launches_;
     if (slot >= 0) ev(slot, 1);
     if (b.m > 0) {
-      launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr);
+      launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr, pdl);
     }
     if (slot >= 0) ev(slot, 2);
     if (comm_ != nullptr) {
       // local ||dy||^2 -> exchange[n]; local K^T y' partial -> exchange[0..n) in column order
       k_sum_to_slot<<<1, kDecideThreads, 0, STREAM>>>(b.state, pd, b.m > 0 ? nd_main + nd_fix : 0, b.exchange + b.n);
       ++launches_;
-      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{b.exchange, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr);
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{b.exchange, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
       comm_->AllReduceSum(b.exchange, b.exchange, b.n + 1, stream_);
       const int nk = Blocks(b.n);
       k_kty_finish<<<nk, kThreads, 0, STREAM>>>(p, b.exchange, pt);
@@ -1607,10 +2050,10 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       ++launches_;
     } else {
       if (b.n > 0) {
-        launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr);
+        launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr, pdl);
       }
       if (slot >= 0) ev(slot, 3);
-      k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
+      launch_k(pdl, k_step_decide, 1, kDecideThreads, STREAM, b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
       ++launches_;
     }
     if (slot >= 0) ev(slot, 4);
@@ -1624,14 +2067,20 @@ void Device::EnableStepTiming(bool on, int stride) {
   timing_attempt_idx_.clear();
 }
 void Device::CollectStepTimings(int64_t executed_attempts) {
+  // sub-phase -> public kernel class (device_ops.h): peer exchange has 7 sub-phases, otherwise the 4 classes themselves
+  static const int kPeerClass[7] = {0, 0, 1, 2, 2, 2, 3};
+  const int phases = timing_peer_ ? 7 : 4;
   for (size_t s = 0; s < timing_attempt_idx_.size(); ++s) {
     if (timing_attempt_idx_[s] >= executed_attempts) continue;
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < phases; ++k) {
       float ms = 0.f;
-      CUDA_OK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(timing_events_[s * 5 + k]), static_cast<cudaEvent_t>(timing_events_[s * 5 + k + 1])));
-      step_timings_.ms[k] += ms;
-      step_timings_.samples[k] += 1;
+      CUDA_OK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(timing_events_[s * kEvPerSlot + k]), static_cast<cudaEvent_t>(timing_events_[s * kEvPerSlot + k + 1])));
+      const int cls = timing_peer_ ? kPeerClass[k] : k;
+      step_timings_.ms[cls] += ms;
+      detail_ms_[k] += ms;
     }
+    for (int k = 0; k < 4; ++k) step_timings_.samples[k] += 1;
+    detail_samples_ += 1;
   }
   timing_attempt_idx_.clear();
 }
@@ -1648,11 +2097,16 @@ double Device::TimelineStopMs(int id) {
   return ms;
 }
 
+void Device::GatherPrimalSlices(const StepBuffers& b, int cur, int prev) {
+  if (b.arena == nullptr || comm_ == nullptr) return;
+  for (double* v : {b.x[cur], b.x[prev], b.kty[cur], b.avg_x}) comm_->AllGatherInPlace(v, b.slice_stride, stream_);
+}
+
 void Device::FlushAverages(const StepBuffers& b) {
   const StepPtrs p = MakePtrs(b);
   const int64_t total = b.n + b.m;
   if (total > 0) {
-    k_flush_average<<<Blocks(total), kThreads, 0, STREAM>>>(p, total);
+    k_flush_average<<<Blocks(total), kThreads, 0, STREAM>>>(p, total, b.arena != nullptr ? b.slice_begin : 0, b.arena != nullptr ? b.slice_end : b.n);
     ++launches_;
   }
   k_clear_pending<<<1, 1, 0, STREAM>>>(b.state);

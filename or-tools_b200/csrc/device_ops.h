@@ -24,7 +24,8 @@
 
 namespace pdlp_b200 {
 
-class Comm;  // comm.h
+class Comm;        // comm.h
+struct PeerArena;  // comm.h
 
 // ---------------------------------------------------------------------------
 // Host-side image of one SELL-32 orientation (built by sell_builder.cc).
@@ -97,7 +98,29 @@ struct StepState {
   double last_dx2, last_dy2, last_nonlinearity, last_movement;
   int64_t attempts;                 // attempts actually executed (not no-ops)
 };
-enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent = 3, kHaltInnerLimit = 4 };
+enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent = 3, kHaltInnerLimit = 4, kHaltPeerTimeout = 5 };
+
+// Layout (in doubles) of the peer arena of the row-sharded step loop; see
+// PeerPtrs in device_ops.cu. The primal vector is cut into `world` slices of
+// `stride` (even) columns; n_pad = world * stride is also the allocated length
+// of every primal vector so that slices can be all-gathered in place.
+struct PeerLayout {
+  int64_t stride = 0, n_pad = 0, xt_off = 0, partial_off = 0, scal_off = 0, flags_off = 0, epoch_off = 0, tr_off = 0, doubles = 0;
+  static PeerLayout For(int64_t n, int world) {
+    PeerLayout l;
+    l.stride = 2 * ((n + 2 * world - 1) / (2 * world));
+    if (l.stride == 0) l.stride = 2;
+    l.n_pad = l.stride * world;
+    l.xt_off = 0;
+    l.partial_off = l.n_pad;
+    l.scal_off = 2 * l.n_pad;
+    l.flags_off = l.scal_off + 4 * 8;
+    l.epoch_off = l.flags_off + 8 * 4;
+    l.tr_off = l.epoch_off + 4;
+    l.doubles = l.tr_off + 2 * 34 * 8;
+    return l;
+  }
+};
 
 // What the device builder keeps besides the two SELL images (device pointers).
 struct DeviceBuildInfo {
@@ -135,6 +158,16 @@ class Device {
   void SetComm(Comm* comm) { comm_ = comm; }
   Comm* comm() const { return comm_; }
   bool count_primal() const;  // true on rank 0 / single GPU
+  // Row-sharded solves keep primal-length vectors replicated; reductions over
+  // them are split across ranks: this rank reduces [begin, end) of a vector of
+  // length n and the partial results are all-reduced.
+  // The mapped peer arenas of a row-sharded solve on one NVLink box (not owned);
+  // the trust-region search exchanges its bin totals through them.
+  void SetPeerArena(const PeerArena* arena, int64_t n) { peer_arena_ = arena; peer_arena_n_ = n; }
+  void SetPrimalSlice(int64_t n, int64_t begin, int64_t end) { pslice_n_ = n; pslice_begin_ = begin; pslice_end_ = end; }
+  bool PrimalSliced(int64_t n) const { return comm_ != nullptr && pslice_n_ == n && pslice_n_ >= 0; }
+  int64_t PrimalSliceBegin(int64_t n) const { return PrimalSliced(n) ? pslice_begin_ : 0; }
+  int64_t PrimalSliceEnd(int64_t n) const { return PrimalSliced(n) ? pslice_end_ : n; }
   // Rank 0's value on every rank (time limits / interrupt flags must lead to
   // the same control flow everywhere); identity without a communicator.
   double RootValue(double v);
@@ -254,6 +287,10 @@ class Device {
     // (+ this rank's ||dy||^2 in the last slot) and the scatter permutation
     double* exchange = nullptr;
     const int32_t* primal_scatter = nullptr;
+    // peer-memory exchange (row-sharded solve on one NVLink box): the mapped
+    // arenas and this rank's slice [slice_begin, slice_end) of the primal vector
+    const PeerArena* arena = nullptr;
+    int64_t slice_begin = 0, slice_end = 0, slice_stride = 0;
   };
   StepState* AllocState();
   void UploadState(StepState* dev, const StepState& host);
@@ -277,6 +314,11 @@ class Device {
   double TimelineStopMs(int id);     // synchronises
   // Applies the deferred average update (if any) for both averages.
   void FlushAverages(const StepBuffers& b);
+  // Peer exchange only: inside the step loop every rank advances just its slice
+  // of x, K^T y and the primal average; this all-gathers the slices of
+  // x[cur], x[prev], kty[cur] and avg_x so that the replicated primal side is
+  // whole again before restart / termination work reads it.
+  void GatherPrimalSlices(const StepBuffers& b, int cur, int prev);
 
   // Unfused pieces for the Malitsky-Pock rule (pdhg.cc:2463-2556).
   void PrimalStep(const double* x, const double* kty, const double* c, const double* q, const double* lv, const double* uv,
@@ -293,6 +335,10 @@ class Device {
   double* results_ = nullptr;    // small device result vector
   double* host_results_ = nullptr;  // pinned
   int64_t launches_ = 0;
+  int64_t pslice_n_ = -1, pslice_begin_ = 0, pslice_end_ = 0;
+  const PeerArena* peer_arena_ = nullptr;
+  int64_t peer_arena_n_ = 0;
+  int32_t* tr_peer_error_ = nullptr;  // device flag: a peer did not arrive at a barrier of the trust-region search
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)
   double* tr_scratch_ = nullptr;
@@ -303,7 +349,11 @@ class Device {
   // step timing
   bool step_timing_ = false;
   int step_timing_stride_ = 8;
-  std::vector<void*> timing_events_;     // 5 per sample slot
+  static constexpr int kEvPerSlot = 8;
+  std::vector<void*> timing_events_;     // kEvPerSlot per sample slot
+  bool timing_peer_ = false;
+  double detail_ms_[7] = {0, 0, 0, 0, 0, 0, 0};  // PDLP_B200_TRACE: per sub-phase
+  int64_t detail_samples_ = 0;
   std::vector<int> timing_attempt_idx_;  // attempt index of each used slot in the last batch
   StepTimings step_timings_;
   void* timeline_ev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};

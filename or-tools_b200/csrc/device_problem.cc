@@ -3,7 +3,10 @@
 
 #include "comm.h"
 
+#include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -67,7 +70,23 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
     m_ = h.m;
     nnz_ = h.nnz;
   }
-  if (comm_ != nullptr) exchange_ = dev_->AllocF64(n_ + 1);
+  if (comm_ != nullptr) {
+    exchange_ = dev_->AllocF64(n_ + 1);
+    layout_ = PeerLayout::For(n_, comm_->world_size());
+    slice_begin_ = std::min<int64_t>(n_, layout_.stride * comm_->rank());
+    slice_end_ = std::min<int64_t>(n_, slice_begin_ + layout_.stride);
+    dev_->SetPrimalSlice(n_, slice_begin_, slice_end_);
+    // PDLP_B200_EXCHANGE=nccl keeps the all-reduce exchange (A/B and boxes without peer mapping)
+    const char* ex = std::getenv("PDLP_B200_EXCHANGE");
+    if (!(ex != nullptr && std::strcmp(ex, "nccl") == 0)) {
+      const auto t0 = std::chrono::steady_clock::now();
+      arena_ = comm_->AcquirePeerArena(layout_.doubles * static_cast<int64_t>(sizeof(double)), dev_->stream());
+      dev_->SetPeerArena(arena_, n_);
+      if (const char* t = std::getenv("PDLP_B200_TRACE"); t != nullptr && t[0] == '1')
+        std::fprintf(stderr, "[pdlp_b200 trace] rank %d peer arena %s in %.3f s\n", comm_->rank(), arena_ != nullptr ? "mapped" : "unavailable (NCCL exchange)",
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+  }
   objective_offset_ = view.objective_offset;
   objective_scaling_factor_ = view.objective_scaling_factor;
   if (!device_built_) {
@@ -100,6 +119,7 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
 }
 
 DeviceProblem::~DeviceProblem() {
+  if (arena_ != nullptr) comm_->ReleasePeerArena(arena_, dev_->stream());
   for (double* p : {c_, q_, lv_, uv_, lc_, uc_, ones_n_, ones_m_, exchange_}) dev_->Free(p);
   for (int k = 0; k < 4; ++k) { dev_->Free(tmp_n_[k]); dev_->Free(tmp_m_[k]); }
   dev_->Free(primal_perm_);

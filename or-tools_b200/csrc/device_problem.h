@@ -37,6 +37,11 @@ class DeviceProblem {
   bool sharded() const { return comm_ != nullptr; }
   const int32_t* primal_scatter() const { return primal_perm_; }
   double* exchange() const { return exchange_; }
+  // Peer-memory exchange of the step loop (nullptr: NCCL all-reduce exchange).
+  const PeerArena* arena() const { return arena_; }
+  int64_t slice_stride() const { return layout_.stride; }
+  int64_t slice_begin() const { return slice_begin_; }
+  int64_t slice_end() const { return slice_end_; }
   int64_t nnz() const { return nnz_; }
   bool is_lp() const { return q_ == nullptr; }
 
@@ -54,7 +59,8 @@ class DeviceProblem {
   double ApplyObjectiveScalingAndOffset(double v) const { return objective_scaling_factor_ * (v + objective_offset_); }
 
   // vectors
-  double* NewPrimal() { return dev_->AllocF64(n_); }
+  // (row-sharded: padded to world * slice stride so that slices can be all-gathered in place)
+  double* NewPrimal() { return dev_->AllocF64(sharded() ? layout_.n_pad : n_); }
   double* NewDual() { return dev_->AllocF64(m_); }
   // host vectors are always full length in the caller's order
   void UploadPrimal(double* dst, const double* host) {
@@ -109,6 +115,9 @@ class DeviceProblem {
   int64_t n_ = 0, m_ = 0, nnz_ = 0;
   int64_t m_global_ = 0, row_begin_ = 0;
   double* exchange_ = nullptr;  // [n + 1], row-sharded solves only
+  PeerArena* arena_ = nullptr;  // row-sharded solves on one NVLink box
+  PeerLayout layout_;
+  int64_t slice_begin_ = 0, slice_end_ = 0;
   double objective_offset_ = 0, objective_scaling_factor_ = 1;
   double *c_ = nullptr, *q_ = nullptr, *lv_ = nullptr, *uv_ = nullptr, *lc_ = nullptr, *uc_ = nullptr;
   SellDev rows_, cols_;

@@ -18,9 +18,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <stdexcept>
 
 #include "device_problem.h"
 
@@ -234,6 +236,10 @@ class DeviceSolve {
   DeviceSolve(DeviceProblem& p, const PdlpParams& params, const Logger& logger, StatsCallback cb)
       : P(p), D(p.dev()), params_(params), logger_(logger), callback_(std::move(cb)) {}
   ~DeviceSolve() {
+    if (const char* t = std::getenv("PDLP_B200_TRACE"); t != nullptr && t[0] == '1') {
+      std::fprintf(stderr, "[pdlp_b200 trace] host wall seconds: restart-choice %.4f termination-check %.4f apply-restart %.4f step-loop %.4f flush+gather %.4f deltas %.4f\n",
+                   phase_s_[0], phase_s_[1], phase_s_[2], phase_s_[3], phase_s_[4], phase_s_[5]);
+    }
     for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); }
     for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, dc_, dr_, delta_x_, delta_y_}) D.Free(v);
     D.Free(buf_.state);
@@ -373,6 +379,7 @@ class DeviceSolve {
   int target_stop_ = std::numeric_limits<int>::max();
   double device_step_ms_ = 0, device_total_ms_ = 0;
   bool interrupt_polled_ = false;  // some rank was given an interrupt flag
+  double phase_s_[6] = {0, 0, 0, 0, 0, 0};  // PDLP_B200_TRACE=1: host wall time per phase
 };
 
 int DeviceSolve::DetermineDistanceBasedRestartChoice() {  // pdhg.cc:2074-2107
@@ -638,7 +645,9 @@ SolverResultCpp DeviceSolve::ConstructOriginalSolverResult(SolverResultCpp resul
 std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bool force_numerical, const volatile int32_t* interrupt, SolveLogCpp& log) {
   const int cycle = iterations_completed_ % params_.major_iteration_frequency;
   const bool is_major = cycle == 0 && iterations_completed_ > 0;
+  WallTimer phase;
   const int restart = force_numerical ? PDLP_RESTART_CHOICE_NO_RESTART : ChooseRestartToApply(is_major);
+  phase_s_[0] += phase.Get();
   PdlpIterationStats stats = CreateSimpleIterationStats(restart);
   if (P.sharded()) stats.cumulative_time_sec = D.RootValue(stats.cumulative_time_sec);  // one clock decides the time limit
   const PdlpIterationStats full_work_stats = stats;
@@ -648,13 +657,17 @@ std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bo
   if (check_termination) {
     const double* avg_x = PrimalAverage();
     const double* avg_y = DualAverage();
+    phase.Start();
     const auto maybe = UpdateIterationStatsAndCheckTermination(force_numerical, interrupted, full_work_stats, stats);
+    phase_s_[1] += phase.Get();
     if (params_.record_iteration_stats) log.iteration_stats.push_back(stats);
     if (maybe.has_value()) return PickSolutionAndConstructSolverResult(avg_x, avg_y, stats, maybe->reason, maybe->type, std::move(log));
   } else if (params_.record_iteration_stats) {
     log.iteration_stats.push_back(stats);
   }
+  phase.Start();
   ApplyRestartChoice(restart);
+  phase_s_[2] += phase.Get();
   return std::nullopt;
 }
 
@@ -709,11 +722,18 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
     D.CollectStepTimings(hs_.attempts - attempts_before);
     if (hs_.halt != kHaltNone) break;
   }
+  phase_s_[3] += t.Get();
+  WallTimer phase;
   D.FlushAverages(buf_);
   D.DownloadState(hs_, buf_.state);
+  if (hs_.halt == kHaltPeerTimeout) throw std::runtime_error("peer-memory exchange timed out: a rank of the row-sharded solve did not arrive");
+  D.GatherPrimalSlices(buf_, hs_.cur, hs_.prev);
   device_step_ms_ += D.TimelineStopMs(1);
   device_time_sec_ += t.Get();
+  phase_s_[4] += phase.Get();
+  phase.Start();
   if (hs_.iterations_completed > k) MaterializeDeltas();
+  phase_s_[5] += phase.Get();
   avg_x_weight_ = avg_y_weight_ = hs_.avg_weight_sum;
   avg_x_terms_ = avg_y_terms_ = hs_.avg_num_terms;
   num_rejected_steps_ = hs_.num_rejected_steps;
@@ -908,6 +928,10 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   buf_.state = D.AllocState();
   buf_.exchange = P.exchange();
   buf_.primal_scatter = P.sharded() ? P.primal_scatter() : nullptr;
+  buf_.arena = P.arena();
+  buf_.slice_begin = P.slice_begin();
+  buf_.slice_end = P.slice_end();
+  buf_.slice_stride = P.slice_stride();
   std::memset(&hs_, 0, sizeof(hs_));
   hs_.cur = 0; hs_.prev = 1; hs_.cand = 2;
 
@@ -1035,11 +1059,25 @@ std::optional<SolverResultCpp> ValidateInputs(const PdlpProblemView& view, const
 SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const PdlpParams& params, std::optional<InitialSolution> initial_solution,
                                          const volatile int32_t* interrupt_solve, const Logger& logger, StatsCallback callback, int cuda_device,
                                          Comm* comm) {
+  const char* tr = std::getenv("PDLP_B200_TRACE");
+  const bool trace = tr != nullptr && tr[0] == '1';
+  WallTimer t;
   if (auto err = ValidateInputs(view, params, logger); err.has_value()) return std::move(*err);
-  DeviceProblem problem(view, cuda_device, comm);
-  DeviceSolve solve(problem, params, logger, std::move(callback));
-  const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
-  return solve.PreprocessAndSolve(std::move(initial_solution), interrupt_solve, view.problem_name != nullptr ? &name : nullptr);
+  const double t_validate = t.Get();
+  SolverResultCpp result;
+  double t_problem = 0, t_solve = 0;
+  {
+    DeviceProblem problem(view, cuda_device, comm);
+    t_problem = t.Get();
+    DeviceSolve solve(problem, params, logger, std::move(callback));
+    const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
+    result = solve.PreprocessAndSolve(std::move(initial_solution), interrupt_solve, view.problem_name != nullptr ? &name : nullptr);
+    t_solve = t.Get();
+  }
+  if (trace)
+    std::fprintf(stderr, "[pdlp_b200 trace] entry point wall seconds: validate %.4f, device problem (upload + SELL build) %.4f, preprocess + solve + result %.4f, teardown %.4f\n",
+                 t_validate, t_problem - t_validate, t_solve - t_problem, t.Get() - t_solve);
+  return result;
 }
 
 // ---- sessions ---------------------------------------------------------------

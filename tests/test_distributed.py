@@ -1,10 +1,11 @@
 """Row-sharded multi-GPU path.
 
 CPU (not gpu): the row partition exported by the C ABI, and a world_size-2
-``gloo`` run of the exchange protocol the CUDA path uses (replicated primal
-side, row-local dual side, ONE all-reduce of [n + 1] doubles per PDHG step
-carrying the K^T y' partial and ||dy||^2), restated in numpy and compared with
-the unsharded iteration.
+``gloo`` run of the exchange protocol the CUDA path uses inside the step loop
+(each rank advances a slice of the primal vector and its block of dual rows;
+per PDHG step: all-gather of the x~ slices, reduce-scatter of the K^T y'
+partials added in rank order, three partial sums per rank added in rank order),
+restated in numpy and compared with the unsharded iteration.
 
 GPU (needs >= 2 devices): the real thing over NCCL against the 1-GPU solve.
 """
@@ -80,6 +81,13 @@ def pdhg_reference(k, c, lc, uc, lv, uv, iters, step, weight):
     return x, y, trace
 
 
+def primal_slice(n, rank, world):
+    """Slice of the primal vector rank advances inside the step loop (PeerLayout::For in device_ops.h)."""
+    stride = 2 * ((n + 2 * world - 1) // (2 * world))
+    b = min(n, stride * rank)
+    return b, min(n, b + stride), stride
+
+
 def _protocol_worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
@@ -91,27 +99,46 @@ def _protocol_worker(rank, world, port, out_dir):
     n = k.shape[1]
     b, e = distributed.row_block(qp, rank, world)
     kg = k[b:e]
-    c, lv, uv = qp.objective_vector, qp.variable_lower_bounds, qp.variable_upper_bounds
+    c0, c1, stride = primal_slice(n, rank, world)
+    c, lv, uv = qp.objective_vector[c0:c1], qp.variable_lower_bounds[c0:c1], qp.variable_upper_bounds[c0:c1]
     lc, uc = qp.constraint_lower_bounds[b:e], qp.constraint_upper_bounds[b:e]
-    x, y = np.zeros(n), np.zeros(e - b)
-    kty = np.zeros(n)
+    x, y = np.zeros(c1 - c0), np.zeros(e - b)       # this rank's slice of x, block of y
+    kty = np.zeros(c1 - c0)
     step, weight = 0.1, 1.0
     rejected, done, trace = 0, 0, []
+
+    def all_gather_slices(v):                        # what the x~ stores into every peer arena amount to
+        mine = torch.zeros(stride, dtype=torch.float64)
+        mine[:v.size] = torch.from_numpy(v)
+        parts = [torch.zeros(stride, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return torch.cat(parts).numpy()[:n]
+
     while done < 25:
         inner = 0
         while True:
             tau, sigma = step / weight, step * weight
-            xn = np.clip(x - tau * (c - kty), lv, uv)             # replicated primal half step
-            xt = 2 * xn - x
+            xn = np.clip(x - tau * (c - kty), lv, uv)              # primal half step on the slice
+            xt = all_gather_slices(2 * xn - x)                     # exchange 1: x~ slices -> whole x~ everywhere
             t = y - sigma * (kg @ xt)                              # row-local dual half step
             yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
-            exchange = np.concatenate([kg.T @ yn, [(yn - y) @ (yn - y)]])   # [n + 1]
-            buf = torch.from_numpy(exchange)
-            dist.all_reduce(buf)                                   # the one exchange of the step
-            ktyn, dy2 = exchange[:n], exchange[n]
+            partial = torch.from_numpy(kg.T @ yn)                  # [n] partial of K^T y'
+            # exchange 2: reduce-scatter of the partials (each rank adds its slice of every
+            # rank's partial in rank order); gloo has no reduce_scatter, so gather + fixed-order sum
+            parts = [torch.zeros(n, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(parts, partial)
+            ktyn = np.zeros(c1 - c0)
+            for h in range(world):
+                ktyn = ktyn + parts[h].numpy()[c0:c1]
             dx = xn - x
-            movement = 0.5 * weight * (dx @ dx) + 0.5 / weight * dy2
-            nonlin = -(dx @ (ktyn - kty))
+            scal = torch.tensor([dx @ dx, (yn - y) @ (yn - y), dx @ (ktyn - kty)], dtype=torch.float64)
+            per_rank = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(per_rank, scal)                        # exchange 3: three partial sums per rank,
+            tot = np.zeros(3)                                      # added in rank order on every rank
+            for h in range(world):
+                tot = tot + per_rank[h].numpy()
+            movement = 0.5 * weight * tot[0] + 0.5 / weight * tot[1]
+            nonlin = -tot[2]
             limit = movement / nonlin if nonlin > 0 else np.inf
             total = rejected + inner + done + 1
             first = limit if np.isinf(limit) else (1 - (total + 1) ** -0.3) * limit
@@ -125,7 +152,8 @@ def _protocol_worker(rank, world, port, out_dir):
                 done += 1
                 break
             inner += 1
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), x=x, y=y, b=b, e=e, trace=np.array(trace))
+    x_full = all_gather_slices(x)                                  # leaving the loop: the primal side is made whole again
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), x=x_full, y=y, b=b, e=e, trace=np.array(trace))
     dist.destroy_process_group()
 
 
