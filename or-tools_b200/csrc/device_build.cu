@@ -624,6 +624,69 @@ void Device::BuildSellPair(const PdlpProblemView& v, int64_t row_begin, int64_t 
   info->col_start = kt_start;
 }
 
+// SELL-32 image of (K[:, col_begin:col_end])^T: one logical row per column of the
+// slice, all constraint rows kept. Stored indices are row_pos_global[row]: the
+// position of the row in the box-wide dual order of a row-sharded solve (block
+// offset of the owning rank + position inside its row image), so that the image
+// gathers from the all-gathered dual vector. *row_of_pos_out: column (relative
+// to col_begin) at each position of the image (device, owned by the caller).
+void Device::BuildColumnSliceImage(const PdlpProblemView& v, int64_t col_begin, int64_t col_end, const int32_t* row_pos_global, int sigma,
+                                   SellDev* out, int32_t** row_of_pos_out) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t n_all = v.num_variables, m_full = v.num_constraints;
+  if (col_begin < 0 || col_end > n_all || col_begin > col_end) throw std::runtime_error("bad column range");
+  sigma = std::min(4096, std::max(32, EnvIntB("PDLP_B200_SIGMA", sigma)));
+  const int64_t n = col_end - col_begin;
+  const int64_t first = n_all > 0 ? v.col_starts[col_begin] : 0;
+  const int64_t nnz = n_all > 0 ? v.col_starts[col_end] - first : 0;
+  Temps tmp;
+  Scanner scan(stream);
+  std::vector<int64_t> rel(n + 1, 0);
+  for (int64_t c = 0; c <= n && n_all > 0; ++c) rel[c] = v.col_starts[col_begin + c] - first;
+  int64_t* cs = tmp.get<int64_t>(n + 1);
+  int64_t* ri = tmp.get<int64_t>(nnz);
+  double* va = tmp.get<double>(nnz);
+  CUDA_OK(cudaMemcpyAsync(cs, rel.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, stream));
+  if (nnz > 0) {
+    CUDA_OK(cudaMemcpyAsync(ri, v.row_indices + first, sizeof(int64_t) * nnz, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(va, v.values + first, sizeof(double) * nnz, cudaMemcpyHostToDevice, stream));
+  }
+  int* error = tmp.get<int>(1);
+  CUDA_OK(cudaMemsetAsync(error, 0, sizeof(int), stream));
+  int64_t* col_len = tmp.get<int64_t>(n);
+  int64_t* kt_start = tmp.get<int64_t>(n + 1);
+  int64_t total = 0;
+  if (n > 0) {
+    k_count_columns<<<Blk(n), kT, 0, stream>>>(n, cs, ri, m_full, 0, m_full, col_len, error);
+    launches_ += 1;
+    total = scan.Exclusive(col_len, kt_start, n, &launches_);
+  }
+  CUDA_OK(cudaMemcpyAsync(kt_start + n, &total, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+  int herr = 0;
+  CUDA_OK(cudaMemcpyAsync(&herr, error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  if (herr != 0) throw std::runtime_error("bad CSC input (column slice)");
+  int32_t* key = tmp.get<int32_t>(total);
+  int32_t* ecol = tmp.get<int32_t>(total);
+  double* cval = tmp.get<double>(total);
+  if (n > 0) {
+    k_compact_columns<<<Blk(n), kT, 0, stream>>>(n, cs, ri, va, m_full, 0, m_full, kt_start, key, ecol, cval);
+    launches_ += 1;
+  }
+  Orientation ocol;
+  BuildOrientation(stream, scan, tmp, n, m_full, col_len, ChooseSplitLenDev(total), sigma, out, &ocol, &launches_);
+  if (out->num_slots > 0) {
+    k_fill_sell<<<Blk(out->num_slots), kT, 0, stream>>>(out->num_slots, out->slice_ptr, out->slot_len, ocol.slot_row, ocol.slot_off, kt_start, nullptr, key, cval,
+                                                        row_pos_global, out->col, out->val);
+    launches_ += 1;
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(stream));
+  cudaFree(ocol.slot_row);
+  cudaFree(ocol.slot_off);
+  *row_of_pos_out = ocol.row_of_pos;
+}
+
 void Device::FreeBuildInfo(DeviceBuildInfo& info) {
   cudaFree(info.col_slot_row);
   cudaFree(info.col_slot_off);

@@ -313,6 +313,8 @@ struct StepPtrs {
 // arena (comm.h PeerArena, mapped everywhere over NVLink) holds, in doubles,
 //   [xt_off, +n)       x~ in the caller's column order; slice C_h is stored by rank h
 //   [partial_off, +n)  this rank's (K[R_g,:])^T y' partial; peers pull their slice
+//   [y_off, +m_global) y' in the box-wide dual order (block of rank h at its row_begin); the
+//                      all-gather exchange stores it from the dual epilogue
 //   [scal_off, +4 G)   {||dx||^2, ||dy||^2, dx.(K^T y' - K^T y)} partials of rank h at 4 h
 //   [flags_off, +8 k)  barrier k: epoch last signalled by rank h at 8 k + h (u64)
 //   [epoch_off, +4)    this rank's own epoch counters (u64)
@@ -320,7 +322,8 @@ struct StepPtrs {
 struct PeerPtrs {
   int world, rank;
   double* base[kMaxPeers];
-  int64_t xt_off, partial_off, scal_off, flags_off, epoch_off, tr_off;
+  int64_t xt_off, partial_off, y_off, scal_off, flags_off, epoch_off, tr_off;
+  int64_t row_begin;   // this rank's first position in the box-wide dual order
   int64_t begin, end;  // this rank's slice of the primal vector (begin is even)
 };
 __device__ __forceinline__ double* peer_base(const PeerPtrs& pp, int h) {
@@ -437,8 +440,12 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
   block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
 }
 
-struct DualEpi {  // pdhg.cc:1912-1930 with theta = 1
+// PUSH: the all-gather of y' fused into the producing epilogue -- every new
+// dual value is also stored into every rank's arena at its box-wide position.
+template <bool PUSH>
+struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1
   StepPtrs b;
+  PeerPtrs peer;
   struct Ctx { const double* yc; double* yn; double sigma, ratio; };
   struct Pre { double yc, lc, uc, avg; };
   __device__ __forceinline__ Ctx begin() const {
@@ -463,10 +470,22 @@ struct DualEpi {  // pdhg.cc:1912-1930 with theta = 1
     const double t = p.yc - c.sigma * kx;
     const double yn = fmax(fmin(0.0, t + c.sigma * p.uc), t + c.sigma * p.lc);
     c.yn[pos] = yn;
+    if (PUSH) {
+#pragma unroll
+      for (int h = 0; h < kMaxPeers; ++h)
+        if (h < peer.world) peer.base[h][peer.y_off + peer.row_begin + pos] = yn;
+    }
     const double d = yn - p.yc;
     red[0] += d * d;
   }
 };
+struct DualEpi : DualEpiT<false> {};
+inline DualEpi MakeDualEpi(const StepPtrs& p) {
+  DualEpi e;
+  e.b = p;
+  std::memset(&e.peer, 0, sizeof(e.peer));
+  return e;
+}
 
 struct KtyEpi {  // pdhg.cc:2588-2592, 1949-1959
   StepPtrs b;
@@ -489,6 +508,36 @@ struct KtyEpi {  // pdhg.cc:2588-2592, 1949-1959
   }
   __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kty_next, double* red, const Pre& p) const {
     c.kty_cand[pos] = kty_next;
+    red[0] += p.dx * (kty_next - p.kty);
+  }
+};
+
+// All-gather exchange: K^T y' for this rank's column slice only. Position p of the
+// slice image is column begin + perm[p] of the (replicated, column-ordered) primal side.
+struct KtyEpiSlice {
+  StepPtrs b;
+  const int32_t* perm;
+  int64_t col0;
+  struct Ctx { const double *x_cand, *x_cur, *kty_cur; double* kty_cand; };
+  struct Pre { double dx, kty; int32_t idx; };
+  __device__ __forceinline__ Ctx begin() const {
+    const StepState* st = b.state;
+    Ctx c;
+    c.x_cand = pick3(b.x, st->cand) + col0;
+    c.x_cur = pick3(b.x, st->cur) + col0;
+    c.kty_cur = pick3(b.kty, st->cur) + col0;
+    c.kty_cand = pick3(b.kty, st->cand) + col0;
+    return c;
+  }
+  __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const {
+    Pre p;
+    p.idx = __ldg(perm + pos);
+    p.dx = c.x_cand[p.idx] - c.x_cur[p.idx];
+    p.kty = c.kty_cur[p.idx];
+    return p;
+  }
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t, double kty_next, double* red, const Pre& p) const {
+    c.kty_cand[p.idx] = kty_next;
     red[0] += p.dx * (kty_next - p.kty);
   }
 };
@@ -1395,6 +1444,10 @@ void Device::ScaleMatrix(SellDev& a, const double* own_scale, const double* othe
     }                                                                                         \
   } while (0)
 
+void Device::WriteGlobalRowPositions(double* out_full, const int32_t* row_of_pos, int64_t row_begin, int64_t m) {
+  ELEMENTWISE(m, { out_full[row_begin + row_of_pos[i]] = static_cast<double>(row_begin + i); });
+}
+void Device::DoublesToI32(int32_t* dst, const double* src, int64_t n) { ELEMENTWISE(n, { dst[i] = static_cast<int32_t>(src[i]); }); }
 void Device::DivideBySqrt(double* vec, const double* divisor, int64_t n) { ELEMENTWISE(n, { if (divisor[i] != 0) vec[i] /= sqrt(divisor[i]); }); }
 void Device::Mul(double* dst, const double* a, int64_t n) { ELEMENTWISE(n, { dst[i] = dst[i] * a[i]; }); }
 void Device::Div(double* dst, const double* a, int64_t n) { ELEMENTWISE(n, { dst[i] = dst[i] / a[i]; }); }
@@ -1694,15 +1747,15 @@ namespace kernels {
 // Elements below `first` are skipped (replicated primal part on ranks > 0).
 static bool TrLegacy();
 static int TrSms();
-static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n) {
+static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_global) {
   PeerPtrs pp;
   std::memset(&pp, 0, sizeof(pp));
   if (arena == nullptr) return pp;
   pp.world = arena->world;
   pp.rank = arena->rank;
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(arena->base[h]);
-  const PeerLayout l = PeerLayout::For(n, pp.world);
-  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  const PeerLayout l = PeerLayout::For(n, m_global, pp.world);
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
   return pp;
 }
 template <class Elem>
@@ -1801,7 +1854,7 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
   TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * total);
 
   if (!use_diagonal_solver) {
-    tr_search(STREAM, comm_, MakeTrPeerPtrs(peer_arena_, peer_arena_n_), tr_peer_error_, total, first, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
+    tr_search(STREAM, comm_, MakeTrPeerPtrs(peer_arena_, peer_arena_n_, peer_arena_m_), tr_peer_error_, total, first, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
     CUDA_OK(cudaGetLastError());
     if (comm_ != nullptr && peer_arena_ != nullptr) {
       int32_t err = 0;
@@ -1960,8 +2013,9 @@ static PeerPtrs MakePeerPtrs(const Device::StepBuffers& b) {
   pp.world = b.arena->world;
   pp.rank = b.arena->rank;
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(b.arena->base[h]);
-  const PeerLayout l = PeerLayout::For(b.n, pp.world);
-  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  const PeerLayout l = PeerLayout::For(b.n, b.m_global, pp.world);
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  pp.row_begin = b.row_begin;
   pp.begin = b.slice_begin;
   pp.end = b.slice_end;
   return pp;
@@ -1978,7 +2032,9 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int nt_main = SellGrid(cols);
   const int nt_fix = cols.num_split > 0 ? static_cast<int>((cols.num_split * 32 + kThreads - 1) / kThreads) : 0;
-  const int64_t need = static_cast<int64_t>(np) + nd_main + nd_fix + std::max<int64_t>(nt_main + nt_fix, Blocks(b.n)) + 8;
+  const int ns_main = b.cols_slice != nullptr ? SellGrid(*b.cols_slice) : 0;
+  const int ns_fix = b.cols_slice != nullptr && b.cols_slice->num_split > 0 ? static_cast<int>((b.cols_slice->num_split * 32 + kThreads - 1) / kThreads) : 0;
+  const int64_t need = static_cast<int64_t>(np) + nd_main + nd_fix + std::max<int64_t>(std::max<int64_t>(nt_main + nt_fix, ns_main + ns_fix), Blocks(b.n)) + 8;
   if (need > step_partials_size_) {
     cudaFree(step_partials_);
     step_partials_ = nullptr;
@@ -2006,6 +2062,31 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       timing_attempt_idx_.push_back(it);
       ev(slot, 0);
     }
+    if (use_peer && b.cols_slice != nullptr) {
+      // all-gather exchange; sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual + y' stores | - | barrier | K^T y' slice + nonlinearity | decision (+ barrier)
+      launch_k(pdl, k_primal_step<true>, np, kThreads, STREAM, p, peer, pp);
+      if (slot >= 0) ev(slot, 1);
+      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 0, b.state);
+      launches_ += 2;
+      if (slot >= 0) ev(slot, 2);
+      if (b.m > 0) {
+        DualEpiT<true> de;
+        de.b = p;
+        de.peer = peer;
+        launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, de, pd, halt, &launches_, nullptr, nullptr, pdl);
+      }
+      if (slot >= 0) { ev(slot, 3); ev(slot, 4); }
+      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 1, b.state);
+      ++launches_;
+      if (slot >= 0) ev(slot, 5);
+      launch_sell<kDot, 1>(STREAM, *b.cols_slice, GatherSrc{{peer.base[peer.rank] + peer.y_off, nullptr, nullptr}, nullptr}, KtyEpiSlice{p, b.slice_perm, b.slice_begin}, pt, halt,
+                           &launches_, nullptr, nullptr, pdl);
+      if (slot >= 0) ev(slot, 6);
+      launch_k(pdl, k_step_decide_peer, 1, kDecideThreads, STREAM, b.state, peer, pp, np, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, ns_main + ns_fix);
+      ++launches_;
+      if (slot >= 0) ev(slot, 7);
+      continue;
+    }
     if (use_peer) {
       // sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual | K^T y' partial | barrier | slice pull + finish | decision (+ barrier)
       launch_k(pdl, k_primal_step<true>, np, kThreads, STREAM, p, peer, pp);
@@ -2014,7 +2095,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       launches_ += 2;
       if (slot >= 0) ev(slot, 2);
       if (b.m > 0) {
-        launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr, pdl);
+        launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
       }
       if (slot >= 0) ev(slot, 3);
       launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{peer.base[peer.rank] + peer.partial_off, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
@@ -2033,7 +2114,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
     ++launches_;
     if (slot >= 0) ev(slot, 1);
     if (b.m > 0) {
-      launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, DualEpi{p}, pd, halt, &launches_, nullptr, nullptr, pdl);
+      launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
     }
     if (slot >= 0) ev(slot, 2);
     if (comm_ != nullptr) {

@@ -105,15 +105,16 @@ enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent
 // `stride` (even) columns; n_pad = world * stride is also the allocated length
 // of every primal vector so that slices can be all-gathered in place.
 struct PeerLayout {
-  int64_t stride = 0, n_pad = 0, xt_off = 0, partial_off = 0, scal_off = 0, flags_off = 0, epoch_off = 0, tr_off = 0, doubles = 0;
-  static PeerLayout For(int64_t n, int world) {
+  int64_t stride = 0, n_pad = 0, xt_off = 0, partial_off = 0, y_off = 0, scal_off = 0, flags_off = 0, epoch_off = 0, tr_off = 0, doubles = 0;
+  static PeerLayout For(int64_t n, int64_t m_global, int world) {
     PeerLayout l;
     l.stride = 2 * ((n + 2 * world - 1) / (2 * world));
     if (l.stride == 0) l.stride = 2;
     l.n_pad = l.stride * world;
     l.xt_off = 0;
     l.partial_off = l.n_pad;
-    l.scal_off = 2 * l.n_pad;
+    l.y_off = 2 * l.n_pad;
+    l.scal_off = l.y_off + 2 * ((m_global + 1) / 2) + 2;
     l.flags_off = l.scal_off + 4 * 8;
     l.epoch_off = l.flags_off + 8 * 4;
     l.tr_off = l.epoch_off + 4;
@@ -163,7 +164,7 @@ class Device {
   // length n and the partial results are all-reduced.
   // The mapped peer arenas of a row-sharded solve on one NVLink box (not owned);
   // the trust-region search exchanges its bin totals through them.
-  void SetPeerArena(const PeerArena* arena, int64_t n) { peer_arena_ = arena; peer_arena_n_ = n; }
+  void SetPeerArena(const PeerArena* arena, int64_t n, int64_t m_global) { peer_arena_ = arena; peer_arena_n_ = n; peer_arena_m_ = m_global; }
   void SetPrimalSlice(int64_t n, int64_t begin, int64_t end) { pslice_n_ = n; pslice_begin_ = begin; pslice_end_ = end; }
   bool PrimalSliced(int64_t n) const { return comm_ != nullptr && pslice_n_ == n && pslice_n_ >= 0; }
   int64_t PrimalSliceBegin(int64_t n) const { return PrimalSliced(n) ? pslice_begin_ : 0; }
@@ -195,6 +196,10 @@ class Device {
   // row / column copy (device, owned by the caller).
   void BuildSellPair(const PdlpProblemView& view, int64_t row_begin, int64_t row_end, int sigma, bool natural_primal_order,
                      SellDev* rows, SellDev* cols, int32_t** dual_perm, int32_t** primal_perm, DeviceBuildInfo* info);
+  // Column-slice image for the all-gather exchange of a row-sharded solve:
+  // (K[:, col_begin:col_end])^T with indices into the box-wide dual order (device_build.cu).
+  void BuildColumnSliceImage(const PdlpProblemView& view, int64_t col_begin, int64_t col_end, const int32_t* row_pos_global_dev, int sigma,
+                             SellDev* out, int32_t** row_of_pos_out);
   void FreeBuildInfo(DeviceBuildInfo& info);
   void DownloadValuesCscFromSell(const SellDev& cols, const DeviceBuildInfo& info, double* values_host);
   SellDev UploadSell(const SellHost& h);
@@ -215,6 +220,10 @@ class Device {
   void ScaledRowNorm(const SellDev& a, int norm, const double* other_scale, const double* own_scale, double* out);
   // a_ij *= own[i]*other[j]; own is indexed by position, or by own_perm[position] when given
   void ScaleMatrix(SellDev& a, const double* own_scale, const double* other_scale, const int32_t* own_perm = nullptr);
+  // row-sharded helpers for the all-gather exchange: out_full[row_begin + perm[p]] = row_begin + p
+  // (global position of every row; other blocks zero) and out_full[row_begin + p] = v[p]
+  void WriteGlobalRowPositions(double* out_full, const int32_t* row_of_pos, int64_t row_begin, int64_t m);
+  void DoublesToI32(int32_t* dst, const double* src, int64_t n);
   void DivideBySqrt(double* vec, const double* divisor, int64_t n);                   // skip zeros (sou.cc:354-365)
   void Mul(double* dst, const double* a, int64_t n);                                  // dst *= a
   void Div(double* dst, const double* a, int64_t n);                                  // dst /= a
@@ -291,6 +300,12 @@ class Device {
     // arenas and this rank's slice [slice_begin, slice_end) of the primal vector
     const PeerArena* arena = nullptr;
     int64_t slice_begin = 0, slice_end = 0, slice_stride = 0;
+    int64_t m_global = 0, row_begin = 0;
+    // all-gather exchange (chosen when the dual side is the shorter one): image
+    // of (K[:, slice])^T gathering from the all-gathered y', and the column
+    // (relative to slice_begin) at each of its positions
+    const SellDev* cols_slice = nullptr;
+    const int32_t* slice_perm = nullptr;
   };
   StepState* AllocState();
   void UploadState(StepState* dev, const StepState& host);
@@ -337,7 +352,7 @@ class Device {
   int64_t launches_ = 0;
   int64_t pslice_n_ = -1, pslice_begin_ = 0, pslice_end_ = 0;
   const PeerArena* peer_arena_ = nullptr;
-  int64_t peer_arena_n_ = 0;
+  int64_t peer_arena_n_ = 0, peer_arena_m_ = 0;
   int32_t* tr_peer_error_ = nullptr;  // device flag: a peer did not arrive at a barrier of the trust-region search
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)

@@ -72,7 +72,7 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
   }
   if (comm_ != nullptr) {
     exchange_ = dev_->AllocF64(n_ + 1);
-    layout_ = PeerLayout::For(n_, comm_->world_size());
+    layout_ = PeerLayout::For(n_, m_global_, comm_->world_size());
     slice_begin_ = std::min<int64_t>(n_, layout_.stride * comm_->rank());
     slice_end_ = std::min<int64_t>(n_, slice_begin_ + layout_.stride);
     dev_->SetPrimalSlice(n_, slice_begin_, slice_end_);
@@ -81,7 +81,7 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
     if (!(ex != nullptr && std::strcmp(ex, "nccl") == 0)) {
       const auto t0 = std::chrono::steady_clock::now();
       arena_ = comm_->AcquirePeerArena(layout_.doubles * static_cast<int64_t>(sizeof(double)), dev_->stream());
-      dev_->SetPeerArena(arena_, n_);
+      dev_->SetPeerArena(arena_, n_, m_global_);
       if (const char* t = std::getenv("PDLP_B200_TRACE"); t != nullptr && t[0] == '1')
         std::fprintf(stderr, "[pdlp_b200 trace] rank %d peer arena %s in %.3f s\n", comm_->rank(), arena_ != nullptr ? "mapped" : "unavailable (NCCL exchange)",
                      std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
@@ -115,6 +115,30 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
   ones_m_ = NewDual();
   dev_->Fill(ones_n_, 1.0, n_);
   dev_->Fill(ones_m_, 1.0, m_);
+  if (arena_ != nullptr) {
+    // Which exchange the step loop uses: "peer-d" all-gathers x~ and y' and needs
+    // the image of this rank's column slice over ALL rows (8 (n + m) bytes on the
+    // wire per step); "peer-s" all-gathers x~ and reduce-scatters the K^T y'
+    // partials of the row block (16 n bytes). Default: whichever moves less.
+    const char* ex = std::getenv("PDLP_B200_EXCHANGE");
+    bool all_gather = m_global_ <= n_;
+    if (ex != nullptr && std::strcmp(ex, "peer-s") == 0) all_gather = false;
+    if (ex != nullptr && std::strcmp(ex, "peer-d") == 0) all_gather = true;
+    if (all_gather) {
+      // box-wide dual order: the block of rank g starts at its first row, positions inside as in its row image
+      double* full = dev_->AllocF64(m_global_);
+      dev_->Fill(full, 0.0, m_global_);
+      dev_->WriteGlobalRowPositions(full, dual_perm_, row_begin_, m_);
+      dev_->AllReduceSumVec(full, m_global_);
+      double* gpos_buf = dev_->AllocF64(m_global_ / 2 + 2);
+      int32_t* gpos = reinterpret_cast<int32_t*>(gpos_buf);
+      dev_->DoublesToI32(gpos, full, m_global_);
+      dev_->BuildColumnSliceImage(view, slice_begin_, slice_end_, gpos, 4096, &cols_slice_, &slice_perm_);
+      has_cols_slice_ = true;
+      dev_->Free(full);
+      dev_->Free(gpos_buf);
+    }
+  }
   dev_->Sync();
 }
 
@@ -126,6 +150,8 @@ DeviceProblem::~DeviceProblem() {
   dev_->Free(dual_perm_);
   dev_->FreeSell(rows_);
   dev_->FreeSell(cols_);
+  if (has_cols_slice_) dev_->FreeSell(cols_slice_);
+  dev_->Free(slice_perm_);
   dev_->FreeBuildInfo(build_info_);
 }
 
@@ -139,6 +165,16 @@ void DeviceProblem::RescaleQuadraticProgram(const double* col_scaling, const dou
   d.Mul(uc_, row_scaling, m_);
   d.ScaleMatrix(rows_, row_scaling, col_scaling);
   d.ScaleMatrix(cols_, col_scaling, row_scaling, sharded() ? primal_perm_ : nullptr);
+  if (has_cols_slice_) {
+    // the slice image gathers in the box-wide dual order: it needs every rank's row scaling
+    double* dr_full = d.AllocF64(m_global_);
+    d.Fill(dr_full, 0.0, m_global_);
+    d.CopyD2D(dr_full + row_begin_, row_scaling, m_);
+    d.AllReduceSumVec(dr_full, m_global_);
+    d.ScaleMatrix(cols_slice_, col_scaling + slice_begin_, dr_full, slice_perm_);
+    d.Sync();
+    d.Free(dr_full);
+  }
 }
 
 void DeviceProblem::KTy(const double* y, double* out) {

@@ -42,6 +42,9 @@ class DeviceProblem {
   int64_t slice_stride() const { return layout_.stride; }
   int64_t slice_begin() const { return slice_begin_; }
   int64_t slice_end() const { return slice_end_; }
+  // All-gather exchange (chosen when m_global <= n): image of (K[:, slice])^T; nullptr otherwise.
+  const SellDev* cols_slice() const { return has_cols_slice_ ? &cols_slice_ : nullptr; }
+  const int32_t* slice_perm() const { return slice_perm_; }
   int64_t nnz() const { return nnz_; }
   bool is_lp() const { return q_ == nullptr; }
 
@@ -118,6 +121,9 @@ class DeviceProblem {
   PeerArena* arena_ = nullptr;  // row-sharded solves on one NVLink box
   PeerLayout layout_;
   int64_t slice_begin_ = 0, slice_end_ = 0;
+  SellDev cols_slice_;
+  bool has_cols_slice_ = false;
+  int32_t* slice_perm_ = nullptr;
   double objective_offset_ = 0, objective_scaling_factor_ = 1;
   double *c_ = nullptr, *q_ = nullptr, *lv_ = nullptr, *uv_ = nullptr, *lc_ = nullptr, *uc_ = nullptr;
   SellDev rows_, cols_;

@@ -932,6 +932,10 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   buf_.slice_begin = P.slice_begin();
   buf_.slice_end = P.slice_end();
   buf_.slice_stride = P.slice_stride();
+  buf_.m_global = P.m_global();
+  buf_.row_begin = P.row_begin();
+  buf_.cols_slice = P.cols_slice();
+  buf_.slice_perm = P.slice_perm();
   std::memset(&hs_, 0, sizeof(hs_));
   hs_.cur = 0; hs_.prev = 1; hs_.cand = 2;
 

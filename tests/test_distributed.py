@@ -176,12 +176,13 @@ def test_exchange_protocol_matches_unsharded_iteration_gloo(tmp_path):
 
 
 # ------------------------------------------------------------------ the CUDA path over NCCL
-def _nccl_worker(rank, world, port, out_dir):
+def _nccl_worker(rank, world, port, out_dir, exchange):
     import torch
     import torch.distributed as dist
 
     sys.path.insert(0, ROOT)
     os.environ["LOCAL_RANK"] = str(rank)
+    os.environ["PDLP_B200_EXCHANGE"] = exchange
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
@@ -213,15 +214,18 @@ def _nccl_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+# peer-d: x~ and y' all-gathered through peer memory (column-slice image); peer-s: x~ all-gathered,
+# K^T y' partials reduce-scattered through peer memory; nccl: one NCCL all-reduce per step.
 @pytest.mark.gpu
-def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend):
+@pytest.mark.parametrize("exchange", ["peer-d", "peer-s", "nccl"])
+def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend, exchange):
     import torch
     import torch.multiprocessing as mp
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     world = 2
-    mp.spawn(_nccl_worker, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, free_port(), str(tmp_path), exchange), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "nccl_rank%d.npz" % r)) for r in range(world)]
     for name, scale in (("c2", 0.004), ("c3", 0.002), ("c5", 0.003)):
         qp, _ = synthetic.CONFIGS[name](scale=scale)
