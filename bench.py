@@ -123,7 +123,7 @@ def cpu_reference_run(qp, pdlp, warmup, steps, budget_s):
     pilot_wall = time.time() - t0
     it_time = max(1e-9, (r.solve_log.solve_time_sec - r.solve_log.preprocessing_time_sec) / max(1, r.solve_log.iteration_count))
     pre = r.solve_log.preprocessing_time_sec
-    iters = int(max(8, min(steps, (budget_s - pre) / it_time)))
+    iters = int(max(64, min(steps, (budget_s - pre) / it_time)))  # at least one major iteration
     r = ob.primal_dual_hybrid_gradient(qp, make_params(pdlp, 0.0, iters, cores))
     loop_s = r.solve_log.solve_time_sec - r.solve_log.preprocessing_time_sec
     value = r.solve_log.iteration_count / loop_s

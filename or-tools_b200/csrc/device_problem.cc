@@ -298,14 +298,15 @@ void DeviceProblem::ApplyRescaling(int l_inf_ruiz_iterations, bool l2_norm_resca
 
 PdlpConvergenceInformation DeviceProblem::ComputeConvergenceInformation(bool handle_as_residuals, const double* dc, const double* dr, const double* x,
                                                                         const double* y, const double* kty_or_null, double cw_primal_offset,
-                                                                        double cw_dual_offset, int candidate_type) {
+                                                                        double cw_dual_offset, int candidate_type, const double* kx_or_null) {
   Device& d = *dev_;
   PdlpConvergenceInformation r;
   std::memset(&r, 0, sizeof(r));
-  Kx(x, tmp_m_[0]);
+  const double* kx = kx_or_null;
+  if (kx == nullptr) { Kx(x, tmp_m_[0]); kx = tmp_m_[0]; }
   const double* kty = kty_or_null;
   if (kty == nullptr) { KTy(y, tmp_n_[0]); kty = tmp_n_[0]; }
-  const MSideStats ms = d.DualSideStats(y, tmp_m_[0], lc_, uc_, dr, cw_primal_offset, /*homogeneous=*/false, m_);
+  const MSideStats ms = d.DualSideStats(y, kx, lc_, uc_, dr, cw_primal_offset, /*homogeneous=*/false, m_);
   const NSideStats ns = d.PrimalSideStats(x, x, kty, c_, q_, lv_, uv_, dc, cw_dual_offset, /*zero_objective=*/false, handle_as_residuals, n_);
   r.l_inf_primal_residual = ms.linf_residual;
   r.l2_primal_residual = std::sqrt(ms.sumsq_residual);

@@ -92,7 +92,7 @@ class DeviceProblem {
   // iteration_stats.cc; dc / dr may be null (ones). tmp vectors are owned here.
   PdlpConvergenceInformation ComputeConvergenceInformation(bool handle_as_residuals, const double* dc, const double* dr, const double* x,
                                                            const double* y, const double* kty_or_null, double cw_primal_offset,
-                                                           double cw_dual_offset, int candidate_type);
+                                                           double cw_dual_offset, int candidate_type, const double* kx_or_null = nullptr);
   // primal_ray must already be projected to the feasibility bounds and dual_ray
   // to the dual bounds where required (pdhg.cc:1704-1722).
   PdlpInfeasibilityInformation ComputeInfeasibilityInformation(bool handle_as_residuals, const double* dc, const double* dr,

@@ -241,7 +241,7 @@ class DeviceSolve {
                    phase_s_[0], phase_s_[1], phase_s_[2], phase_s_[3], phase_s_[4], phase_s_[5]);
     }
     for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); }
-    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, dc_, dr_, delta_x_, delta_y_}) D.Free(v);
+    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, dc_, dr_, delta_x_, delta_y_, pc_kx_cur_, pc_kx_avg_, pc_kty_avg_}) D.Free(v);
     D.Free(buf_.state);
   }
 
@@ -269,6 +269,7 @@ class DeviceSolve {
   const double* DualAverage() const { return DualAvgHasWeight() ? buf_.avg_y : Y(); }
   void PushState() { D.UploadState(buf_.state, hs_); }
   void ClearAverages() {
+    InvalidateProducts(false, true);
     D.Fill(buf_.avg_x, 0.0, P.n());
     D.Fill(buf_.avg_y, 0.0, P.m());
     avg_x_weight_ = avg_y_weight_ = 0.0;
@@ -281,6 +282,7 @@ class DeviceSolve {
     double& w = primal ? avg_x_weight_ : avg_y_weight_;
     int& terms = primal ? avg_x_terms_ : avg_y_terms_;
     if (weight > 0.0) {
+      InvalidateProducts(false, true);
       D.WeightedAverageAdd(primal ? buf_.avg_x : buf_.avg_y, v, weight / (w + weight), primal ? P.n() : P.m());
       w += weight;
     }
@@ -310,9 +312,13 @@ class DeviceSolve {
     return {out[0], out[1], out[2], out[3]};
   }
   LocalizedBounds ComputeLocalizedBoundsAtCurrent() {  // pdhg.cc:2009-2021
-    return BoundsAt(X(), Y(), params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE ? kx_cur_ : nullptr, Kty());
+    return BoundsAt(X(), Y(), CachedKx(X()), Kty());
   }
-  LocalizedBounds ComputeLocalizedBoundsAtAverage() { return BoundsAt(PrimalAverage(), DualAverage(), nullptr, nullptr); }  // :2023-2039
+  LocalizedBounds ComputeLocalizedBoundsAtAverage() {  // :2023-2039
+    const double* ax = PrimalAverage();
+    const double* ay = DualAverage();
+    return BoundsAt(ax, ay, CachedKx(ax), CachedKty(ay));
+  }
   static bool AverageHasBetterPotential(const LocalizedBounds& avg, const LocalizedBounds& cur) {  // :2041-2048
     return BoundGap(avg) / Sq(avg.radius) < BoundGap(cur) / Sq(cur.radius);
   }
@@ -357,6 +363,36 @@ class DeviceSolve {
   StepState hs_{};
   double *x0_ = nullptr, *y0_ = nullptr;            // last restart point
   double *kx_cur_ = nullptr, *kx_next_ = nullptr;    // Malitsky-Pock product cache
+  // Products of the points a major iteration looks at more than once (restart
+  // test, termination check, restart): K x of the current iterate and K x / K^T y
+  // of the average. Valid only until the iterates or the averages change.
+  double *pc_kx_cur_ = nullptr, *pc_kx_avg_ = nullptr, *pc_kty_avg_ = nullptr;
+  bool pc_kx_cur_ok_ = false, pc_kx_avg_ok_ = false, pc_kty_avg_ok_ = false;
+  void InvalidateProducts(bool current, bool average) {
+    if (current) pc_kx_cur_ok_ = false;
+    if (average) pc_kx_avg_ok_ = pc_kty_avg_ok_ = false;
+  }
+  const double* CachedKx(const double* x) {  // nullptr: not one of the cached points
+    const bool mp = params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE;
+    if (x == X()) {
+      if (mp) return kx_cur_;
+      if (!pc_kx_cur_ok_) { P.Kx(x, pc_kx_cur_); pc_kx_cur_ok_ = true; }
+      return pc_kx_cur_;
+    }
+    if (x == buf_.avg_x) {
+      if (!pc_kx_avg_ok_) { P.Kx(x, pc_kx_avg_); pc_kx_avg_ok_ = true; }
+      return pc_kx_avg_;
+    }
+    return nullptr;
+  }
+  const double* CachedKty(const double* y) {
+    if (y == Y()) return Kty();
+    if (y == buf_.avg_y) {
+      if (!pc_kty_avg_ok_) { P.KTy(y, pc_kty_avg_); pc_kty_avg_ok_ = true; }
+      return pc_kty_avg_;
+    }
+    return nullptr;
+  }
   double *delta_x_ = nullptr, *delta_y_ = nullptr;   // materialised iterate difference
   bool have_delta_ = false;
   double avg_x_weight_ = 0, avg_y_weight_ = 0;
@@ -448,7 +484,18 @@ void DeviceSolve::ApplyRestartChoice(int restart) {  // pdhg.cc:2246-2296
       if (params_.verbosity_level >= 4) logger_.Log(Fmt("Restarted to average on iteration %d after %d iterations", iterations_completed_, avg_x_terms_));
       D.CopyD2D(X(), buf_.avg_x, P.n());
       D.CopyD2D(Y(), buf_.avg_y, P.m());
-      SetCurrentPrimalAndDualProducts();
+      // the new current iterate is the average: its products are the average's
+      if (pc_kty_avg_ok_ && params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE) {
+        D.CopyD2D(Kty(), pc_kty_avg_, P.n());
+      } else {
+        SetCurrentPrimalAndDualProducts();
+      }
+      if (pc_kx_avg_ok_) {
+        D.CopyD2D(pc_kx_cur_, pc_kx_avg_, P.m());
+        pc_kx_cur_ok_ = true;
+      } else {
+        pc_kx_cur_ok_ = false;
+      }
       break;
   }
   hs_.primal_weight = ComputeNewPrimalWeight();
@@ -485,9 +532,10 @@ void DeviceSolve::ConvergenceAndInfeasibility(const double* x, const double* y, 
                                               PdlpInfeasibilityInformation* infeas) {
   const DetailedCriteria oc = EffectiveOptimalityCriteria(params_.termination_criteria);
   const bool har = params_.handle_some_primal_gradients_on_finite_bounds_as_residuals != 0;
+  if (kty_or_null == nullptr) kty_or_null = CachedKty(y);
   if (conv != nullptr)
     *conv = P.ComputeConvergenceInformation(har, dc_, dr_, x, y, kty_or_null, EpsilonRatio(oc.primal_abs, oc.primal_rel),
-                                            EpsilonRatio(oc.dual_abs, oc.dual_rel), type);
+                                            EpsilonRatio(oc.dual_abs, oc.dual_rel), type, CachedKx(x));
   if (infeas != nullptr) {
     double* primal_copy = P.tmp_n(3);
     D.CopyD2D(primal_copy, x, P.n());
@@ -700,6 +748,7 @@ int DeviceSolve::NextCheckpoint(int k) const {
 }
 
 DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* interrupt) {
+  InvalidateProducts(true, true);
   hs_.iterations_completed = k;
   hs_.num_rejected_steps = num_rejected_steps_;
   hs_.inner_iterations = 0;
@@ -752,6 +801,7 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
 
 // pdhg.cc:2463-2556, host-driven (one sync per inner step).
 DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
+  InvalidateProducts(true, true);
   Outcome outcome = Outcome::kSuccessful;
   const int64_t n = P.n(), m = P.m();
   const double omega = hs_.primal_weight;
@@ -922,6 +972,9 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   x0_ = P.NewPrimal();
   y0_ = P.NewDual();
   delta_x_ = P.NewPrimal();
+  pc_kx_cur_ = P.NewDual();
+  pc_kx_avg_ = P.NewDual();
+  pc_kty_avg_ = P.NewPrimal();
   delta_y_ = P.NewDual();
   if (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE) { kx_cur_ = P.NewDual(); kx_next_ = P.NewDual(); }
   buf_.c = P.c(); buf_.q = P.q(); buf_.lv = P.lv(); buf_.uv = P.uv(); buf_.lc = P.lc(); buf_.uc = P.uc();
