@@ -357,10 +357,16 @@ int32_t pdlp_b200_set_default_device(int32_t cuda_device);
 /* ---- multi-GPU ------------------------------------ *
  * One process per GPU. Every rank passes the SAME full problem; the library
  * keeps only its contiguous block of constraint rows on its device
- * (nnz-balanced, same mass rule as sharder.cc:51-70) and exchanges x~ /
- * K^T y partials over NCCL. nccl_unique_id is the 128-byte ncclUniqueId made
- * by rank 0 (pdlp_b200_nccl_unique_id) and broadcast by the caller (e.g.
- * torch.distributed).                                                       */
+ * (nnz-balanced, same mass rule as sharder.cc:51-70) plus, when the dual side
+ * is the shorter one, its slice of the columns over all rows. Inside the step
+ * loop the ranks exchange x~ and y' (or the K^T y' partials) through
+ * peer-mapped device memory (CUDA IPC over NVLink / NVSwitch, mapped once per
+ * context); NCCL carries the set-up, the small reductions outside the loop and
+ * the whole exchange when peer mapping is unavailable
+ * (PDLP_B200_EXCHANGE=peer-d|peer-s|nccl forces one). nccl_unique_id is the
+ * 128-byte ncclUniqueId made by rank 0 (pdlp_b200_nccl_unique_id) and
+ * broadcast by the caller (e.g. torch.distributed). All ranks of a context
+ * must be processes on the same box.                                        */
 int32_t pdlp_b200_nccl_unique_id(const char* nccl_library_path, uint8_t out_id[128]);
 typedef struct PdlpDistributedContext PdlpDistributedContext;
 int32_t pdlp_b200_distributed_init(const char* nccl_library_path, int32_t rank,
