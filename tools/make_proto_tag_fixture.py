@@ -14,12 +14,14 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 
 def strip_comments(text):
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return re.sub(r"//[^\n]*", "", text)
 
 
 def parse(path):
     text = strip_comments(open(path).read())
-    tokens = re.findall(r"[A-Za-z_][A-Za-z0-9_.]*|-?[0-9][0-9.eE+-]*|[{}=;\[\]]|\"[^\"]*\"", text)
+    text = re.sub(r"map<[^>]*>[^;]*;", "", text)  # map fields are not used on this path
+    tokens = re.findall(r"[A-Za-z_][A-Za-z0-9_.]*|0x[0-9A-Fa-f]+|-?[0-9][0-9.eE+-]*|-inf|[{}=;\[\]]|\"[^\"]*\"", text)
     messages, enums = {}, {}
     stack = []
     i = 0
@@ -40,7 +42,7 @@ def parse(path):
             continue
         if stack and stack[-1][0] == "enum" and i + 2 < len(tokens) and tokens[i + 1] == "=":
             scope = ".".join(n for k, n in stack if k != "oneof")
-            enums[scope][t] = int(tokens[i + 2])
+            enums[scope][t] = int(tokens[i + 2], 0)
             i += 3
             continue
         in_msg = stack and stack[-1][0] in ("message", "oneof")
@@ -75,6 +77,11 @@ def main():
         m, e = parse(os.path.join(REF, f))
         out["messages"].update(m)
         out["enums"].update(e)
+    # the MPSolver-side messages the PDLP proto solver reads / writes (pdlp_proto_solver.cc:36-130)
+    m, e = parse(os.path.join(os.path.dirname(REF), "linear_solver", "linear_solver.proto"))
+    keep = ("MPVariableProto", "MPConstraintProto", "MPQuadraticObjective", "MPModelProto", "MPModelRequest", "MPSolutionResponse")
+    out["linear_solver_messages"] = {k: m[k] for k in keep}
+    out["linear_solver_enums"] = {"MPSolverResponseStatus": e["MPSolverResponseStatus"], "MPModelRequest.SolverType": e["MPModelRequest.SolverType"]}
     json.dump(out, open(OUT, "w"), indent=1, sort_keys=True)
     print("wrote", OUT, len(out["messages"]), "messages", len(out["enums"]), "enums")
 
