@@ -667,10 +667,13 @@ __device__ __forceinline__ void block_sum3(const double* __restrict__ p0, int n0
 __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
   pdl_trigger();
   pdl_wait();
-  if (st_dev->halt != 0) return;
+  // The halt flag is read while the partial sums are already in flight (a halted
+  // attempt only wastes those loads): one L2 round trip less on the critical path.
+  const int32_t halted = *reinterpret_cast<const volatile int32_t*>(&st_dev->halt);
   double sums[3];
   // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
   block_sum3(pp, np, pd, nd < 0 ? 0 : nd, pt, nt, sums);
+  if (halted != 0) return;
   if (threadIdx.x != 0) return;
   decide_update(st_dev, sums[0], nd < 0 ? *pd : sums[1], sums[2]);
 }
