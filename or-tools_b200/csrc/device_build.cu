@@ -377,17 +377,17 @@ struct Temps {
   cudaStream_t stream;
   std::vector<void*> ptrs;
   explicit Temps(cudaStream_t s) : stream(s) {
-    static bool pool_configured = false;
-    if (!pool_configured) {
-      int dev = 0;
+    static bool pool_configured[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && !pool_configured[dev]) {
       cudaMemPool_t pool;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t keep = ~uint64_t{0};
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
       }
-      cudaGetLastError();
-      pool_configured = true;
+      pool_configured[dev] = true;
     }
+    cudaGetLastError();
   }
   template <class T>
   T* get(int64_t count) {

@@ -1791,12 +1791,9 @@ void tr_search(cudaStream_t stream, Comm* comm, const PeerPtrs& peer, int32_t* p
     double rad = radius;
     void* args[] = {&tot_arg, &ckeys, &ca, &cb, &st, &part2, &counter, const_cast<PeerPtrs*>(&peer), &peer_error, &rad};
     const bool use_peer = comm != nullptr && peer.world > 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_tr_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      cudaFuncSetAttribute(k_tr_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      attr_set = true;
-    }
+    // (per device, so set on every launch: a process may drive several devices)
+    cudaFuncSetAttribute(k_tr_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(k_tr_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (comm == nullptr || use_peer) {
       cudaError_t e = cudaLaunchCooperativeKernel(use_peer ? reinterpret_cast<const void*>(k_tr_search<true>) : reinterpret_cast<const void*>(k_tr_search<false>),
                                                   dim3(nbp), dim3(kThreads), args, smem, stream);
@@ -1823,12 +1820,9 @@ static bool TrLegacy() {
   return v;
 }
 static int TrSms() {
-  static const int sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
-  }();
-  return sms;
+  int dev = 0, n = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
 }
 }  // namespace kernels
 

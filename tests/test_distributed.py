@@ -175,6 +175,96 @@ def test_exchange_protocol_matches_unsharded_iteration_gloo(tmp_path):
     np.testing.assert_allclose(ysh, y, rtol=1e-12, atol=1e-13)
 
 
+def _protocol_worker_all_gather(rank, world, port, out_dir):
+    """The all-gather exchange (`peer-d`): rank g keeps K[R_g, :] AND K[:, C_g]; per step the x~
+    slices and the y' blocks are all-gathered, K^T y' of the slice is computed whole (no partial
+    sums), three partial sums per rank are added in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    qp, _ = synthetic.c2(scale=0.0005)
+    k = qp.constraint_matrix.tocsr()
+    m, n = k.shape
+    blocks = [distributed.row_block(qp, r, world) for r in range(world)]
+    b, e = blocks[rank]
+    c0, c1, stride = primal_slice(n, rank, world)
+    k_rows = k[b:e]                       # row block, all columns
+    k_cols_t = k.tocsc()[:, c0:c1].T.tocsr()  # (K[:, C_g])^T: slice columns over ALL rows
+    c, lv, uv = qp.objective_vector[c0:c1], qp.variable_lower_bounds[c0:c1], qp.variable_upper_bounds[c0:c1]
+    lc, uc = qp.constraint_lower_bounds[b:e], qp.constraint_upper_bounds[b:e]
+    x, y, kty = np.zeros(c1 - c0), np.zeros(e - b), np.zeros(c1 - c0)
+    step, weight = 0.1, 1.0
+    rejected, done, trace = 0, 0, []
+    max_rows = max(e1 - b1 for b1, e1 in blocks)
+
+    def all_gather(v, width, total, offsets):
+        mine = torch.zeros(width, dtype=torch.float64)
+        mine[:v.size] = torch.from_numpy(v)
+        parts = [torch.zeros(width, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        out = np.zeros(total)
+        for h in range(world):
+            lo, hi = offsets[h]
+            out[lo:hi] = parts[h].numpy()[:hi - lo]
+        return out
+
+    col_offsets = [primal_slice(n, h, world)[:2] for h in range(world)]
+    while done < 25:
+        inner = 0
+        while True:
+            tau, sigma = step / weight, step * weight
+            xn = np.clip(x - tau * (c - kty), lv, uv)
+            xt = all_gather(2 * xn - x, stride, n, col_offsets)            # exchange 1: x~
+            t = y - sigma * (k_rows @ xt)
+            yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
+            y_full = all_gather(yn, max_rows, m, blocks)                   # exchange 2: y'
+            ktyn = k_cols_t @ y_full                                       # whole products of the slice
+            dx = xn - x
+            scal = torch.tensor([dx @ dx, (yn - y) @ (yn - y), dx @ (ktyn - kty)], dtype=torch.float64)
+            per_rank = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(per_rank, scal)                                # exchange 3
+            tot = np.zeros(3)
+            for h in range(world):
+                tot = tot + per_rank[h].numpy()
+            movement = 0.5 * weight * tot[0] + 0.5 / weight * tot[1]
+            nonlin = -tot[2]
+            limit = movement / nonlin if nonlin > 0 else np.inf
+            total = rejected + inner + done + 1
+            first = limit if np.isinf(limit) else (1 - (total + 1) ** -0.3) * limit
+            second = (1 + (total + 1) ** -0.6) * step
+            accepted = step <= limit
+            step = min(first, second)
+            trace.append(accepted)
+            if accepted:
+                x, y, kty = xn, yn, ktyn.copy()
+                rejected += inner
+                done += 1
+                break
+            inner += 1
+    x_full = all_gather(x, stride, n, col_offsets)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), x=x_full, y=y, b=b, e=e, trace=np.array(trace))
+    dist.destroy_process_group()
+
+
+def test_all_gather_exchange_protocol_matches_unsharded_iteration_gloo(tmp_path):
+    import torch.multiprocessing as mp
+
+    world = 2
+    mp.spawn(_protocol_worker_all_gather, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
+    qp, _ = synthetic.c2(scale=0.0005)
+    k = qp.constraint_matrix.tocsr()
+    x, y, trace = pdhg_reference(k, qp.objective_vector, qp.constraint_lower_bounds, qp.constraint_upper_bounds,
+                                 qp.variable_lower_bounds, qp.variable_upper_bounds, 25, 0.1, 1.0)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    for p in parts:
+        assert list(p["trace"]) == trace
+        np.testing.assert_allclose(p["x"], x, rtol=1e-12, atol=1e-13)
+    np.testing.assert_array_equal(parts[0]["x"], parts[1]["x"])
+    np.testing.assert_allclose(np.concatenate([p["y"] for p in parts]), y, rtol=1e-12, atol=1e-13)
+
+
 # ------------------------------------------------------------------ the CUDA path over NCCL
 def _nccl_worker(rank, world, port, out_dir, exchange):
     import torch
