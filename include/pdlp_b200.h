@@ -253,6 +253,23 @@ typedef struct PdlpIterationCallbackInfo {
 /* SolverResult + SolveLog (primal_dual_hybrid_gradient.h:60-71,
  * solve_log.proto:385-459). Vectors are for the ORIGINAL (unscaled) problem.
  * Buffers are owned by the library: release with pdlp_b200_result_free().   */
+/* FeasibilityPolishingDetails (solve_log.proto:362-383): one entry per primal /
+ * dual feasibility polishing phase, in the order they ran.                   */
+enum { PDLP_POLISHING_PHASE_TYPE_UNSPECIFIED = 0, PDLP_POLISHING_PHASE_TYPE_PRIMAL_FEASIBILITY = 1,
+       PDLP_POLISHING_PHASE_TYPE_DUAL_FEASIBILITY = 2 };
+typedef struct PdlpFeasibilityPolishingDetails {
+  int32_t polishing_phase_type;
+  int32_t main_iteration_count;               /* main iterations done when the phase started */
+  PdlpParams params;                          /* parameters of the phase      */
+  int32_t termination_reason;
+  int32_t iteration_count;
+  double solve_time_sec;
+  PdlpIterationStats solution_stats;
+  int32_t solution_type;
+  int64_t num_iteration_stats;                /* record_iteration_stats       */
+  PdlpIterationStats* iteration_stats;
+} PdlpFeasibilityPolishingDetails;
+
 typedef struct PdlpResult {
   int64_t primal_size, dual_size;             /* 0 for INVALID_* results      */
   double* primal_solution;                    /* [primal_size]                */
@@ -273,6 +290,8 @@ typedef struct PdlpResult {
   int64_t num_iteration_stats;                /* record_iteration_stats       */
   PdlpIterationStats* iteration_stats;
   PdlpParams params;                          /* SolveLog.params              */
+  int64_t num_feasibility_polishing_details;
+  PdlpFeasibilityPolishingDetails* feasibility_polishing_details;
   /* Device-side accounting for this solve (not in the reference log).       */
   int64_t gpu_kernel_launches;
   double device_iteration_time_sec;           /* CUDA-event time in PDHG steps*/

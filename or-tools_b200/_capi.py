@@ -197,6 +197,19 @@ class PdlpIterationCallbackInfo(C.Structure):
     ]
 
 
+class PdlpFeasibilityPolishingDetails(C.Structure):
+    _fields_ = [
+        ("polishing_phase_type", C.c_int32), ("main_iteration_count", C.c_int32),
+        ("params", PdlpParams),
+        ("termination_reason", C.c_int32), ("iteration_count", C.c_int32),
+        ("solve_time_sec", C.c_double),
+        ("solution_stats", PdlpIterationStats),
+        ("solution_type", C.c_int32),
+        ("num_iteration_stats", C.c_int64),
+        ("iteration_stats", C.POINTER(PdlpIterationStats)),
+    ]
+
+
 class PdlpResult(C.Structure):
     _fields_ = [
         ("primal_size", C.c_int64), ("dual_size", C.c_int64),
@@ -216,6 +229,8 @@ class PdlpResult(C.Structure):
         ("num_iteration_stats", C.c_int64),
         ("iteration_stats", C.POINTER(PdlpIterationStats)),
         ("params", PdlpParams),
+        ("num_feasibility_polishing_details", C.c_int64),
+        ("feasibility_polishing_details", C.POINTER(PdlpFeasibilityPolishingDetails)),
         ("gpu_kernel_launches", C.c_int64),
         ("device_iteration_time_sec", C.c_double),
     ]

@@ -70,6 +70,28 @@ void FillResult(SolverResultCpp&& r, PdlpResult* out) {
     std::memcpy(out->iteration_stats, l.iteration_stats.data(), l.iteration_stats.size() * sizeof(PdlpIterationStats));
   }
   out->params = l.params;
+  out->num_feasibility_polishing_details = static_cast<int64_t>(l.feasibility_polishing_details.size());
+  if (!l.feasibility_polishing_details.empty()) {
+    out->feasibility_polishing_details =
+        static_cast<PdlpFeasibilityPolishingDetails*>(std::calloc(l.feasibility_polishing_details.size(), sizeof(PdlpFeasibilityPolishingDetails)));
+    for (size_t k = 0; k < l.feasibility_polishing_details.size(); ++k) {
+      const PolishingDetailsCpp& d = l.feasibility_polishing_details[k];
+      PdlpFeasibilityPolishingDetails& o = out->feasibility_polishing_details[k];
+      o.polishing_phase_type = d.polishing_phase_type;
+      o.main_iteration_count = d.main_iteration_count;
+      o.params = d.params;
+      o.termination_reason = d.termination_reason;
+      o.iteration_count = d.iteration_count;
+      o.solve_time_sec = d.solve_time_sec;
+      o.solution_stats = d.solution_stats;
+      o.solution_type = d.solution_type;
+      o.num_iteration_stats = static_cast<int64_t>(d.iteration_stats.size());
+      if (!d.iteration_stats.empty()) {
+        o.iteration_stats = static_cast<PdlpIterationStats*>(std::malloc(d.iteration_stats.size() * sizeof(PdlpIterationStats)));
+        std::memcpy(o.iteration_stats, d.iteration_stats.data(), d.iteration_stats.size() * sizeof(PdlpIterationStats));
+      }
+    }
+  }
   out->gpu_kernel_launches = l.gpu_kernel_launches;
   out->device_iteration_time_sec = l.device_iteration_time_sec;
 }
@@ -171,6 +193,8 @@ void pdlp_b200_result_free(PdlpResult* r) {
   if (r == nullptr) return;
   std::free(r->primal_solution); std::free(r->dual_solution); std::free(r->reduced_costs);
   std::free(r->instance_name); std::free(r->termination_string); std::free(r->iteration_stats);
+  for (int64_t k = 0; k < r->num_feasibility_polishing_details; ++k) std::free(r->feasibility_polishing_details[k].iteration_stats);
+  std::free(r->feasibility_polishing_details);
   std::memset(r, 0, sizeof(*r));
 }
 

@@ -1460,6 +1460,7 @@ void Device::Sub(double* dst, const double* a, const double* b, int64_t n) { ELE
 void Device::ReplaceLargeWithInf(double* v, double threshold, int64_t n) {
   ELEMENTWISE(n, { if (v[i] <= -threshold) v[i] = -kInfD; if (v[i] >= threshold) v[i] = kInfD; });
 }
+void Device::MapFiniteValuesToZero(double* dst, const double* src, int64_t n) { ELEMENTWISE(n, { dst[i] = isfinite(src[i]) ? 0.0 : src[i]; }); }
 void Device::ClampPrimal(double* x, const double* lb, const double* ub, bool feas, int64_t n) {
   ELEMENTWISE(n, {
     double u = ub[i], l = lb[i];

@@ -231,6 +231,7 @@ class Device {
   void Axpy(double* dst, double s, const double* a, int64_t n);                       // dst += s*a
   void Sub(double* dst, const double* a, const double* b, int64_t n);                 // dst = a - b
   void ReplaceLargeWithInf(double* v, double threshold, int64_t n);
+  void MapFiniteValuesToZero(double* dst, const double* src, int64_t n);             // pdhg.cc:2940-2949
   void ClampPrimal(double* x, const double* lb, const double* ub, bool feasibility_bounds, int64_t n);
   void ClampDual(double* y, const double* lc, const double* uc, int64_t m);
   void WeightedAverageAdd(double* avg, const double* v, double ratio, int64_t n);     // avg += ratio*(v-avg)

@@ -7,6 +7,7 @@
 
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "device_ops.h"
@@ -78,6 +79,11 @@ class DeviceProblem {
   void Kx(const double* x, double* out) { dev_->SpMV(rows_, x, out); }    // K x    (pdhg.cc:1912-1916)
   void KTy(const double* y, double* out);                                  // K^T y  (sharder.cc:160-173)
 
+  // SwapObjectiveVector / SwapVariableBounds / SwapConstraintBounds (sharded_quadratic_program.h:88-109):
+  // exchange the device vectors of the working problem with the caller's (feasibility polishing).
+  void SwapObjectiveVector(double** objective) { std::swap(c_, *objective); }
+  void SwapVariableBounds(double** lower, double** upper) { std::swap(lv_, *lower); std::swap(uv_, *upper); }
+  void SwapConstraintBounds(double** lower, double** upper) { std::swap(lc_, *lower); std::swap(uc_, *upper); }
   // sharded_quadratic_program.cc:148-189
   void RescaleQuadraticProgram(const double* col_scaling, const double* row_scaling);
   void ReplaceLargeConstraintBoundsWithInfinity(double threshold);

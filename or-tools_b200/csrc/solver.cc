@@ -49,9 +49,14 @@ std::string Fmt(const char* fmt, ...) {
 std::string G(double v) { return Fmt("%g", v); }
 
 struct WallTimer {
-  std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
-  void Start() { start = std::chrono::steady_clock::now(); }
-  double Get() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); }
+  using Clock = std::chrono::steady_clock;
+  Clock::time_point start = Clock::now();
+  double accumulated = 0;
+  bool running = true;
+  void Start() { start = Clock::now(); accumulated = 0; running = true; }
+  void Stop() { if (running) { accumulated += std::chrono::duration<double>(Clock::now() - start).count(); running = false; } }
+  void Resume() { if (!running) { start = Clock::now(); running = true; } }
+  double Get() const { return accumulated + (running ? std::chrono::duration<double>(Clock::now() - start).count() : 0.0); }
 };
 
 SolverResultCpp ErrorSolverResult(int reason, const std::string& message, const Logger& logger) {  // pdhg.cc:776-785
@@ -224,6 +229,56 @@ std::string ValidateDimensions(const PdlpProblemView& v) {  // quadratic_program
   return "";
 }
 
+// ---- feasibility polishing helpers (pdhg.cc:2298-2358, 2684-2700, 2867-2886) ------------
+PdlpIterationStats AddWorkStats(PdlpIterationStats stats, const PdlpIterationStats& more) {
+  stats.iteration_number += more.iteration_number;
+  stats.cumulative_kkt_matrix_passes += more.cumulative_kkt_matrix_passes;
+  stats.cumulative_rejected_steps += more.cumulative_rejected_steps;
+  stats.cumulative_time_sec += more.cumulative_time_sec;
+  return stats;
+}
+PdlpIterationStats WorkFromFeasibilityPolishing(const SolveLogCpp& log) {
+  PdlpIterationStats result;
+  std::memset(&result, 0, sizeof(result));
+  for (const PolishingDetailsCpp& d : log.feasibility_polishing_details) result = AddWorkStats(result, d.solution_stats);
+  return result;
+}
+bool TerminationReasonIsInterrupted(int reason) { return reason == PDLP_TERMINATION_REASON_INTERRUPTED_BY_USER; }
+bool TerminationReasonIsWorkLimitNotInterrupted(int reason) {
+  return reason == PDLP_TERMINATION_REASON_ITERATION_LIMIT || reason == PDLP_TERMINATION_REASON_TIME_LIMIT ||
+         reason == PDLP_TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT;
+}
+bool TerminationReasonIsWorkLimit(int reason) { return TerminationReasonIsWorkLimitNotInterrupted(reason) || TerminationReasonIsInterrupted(reason); }
+bool DoFeasibilityPolishingAfterLimitsReached(const PdlpParams& params, int reason) {
+  if (TerminationReasonIsWorkLimitNotInterrupted(reason)) return params.apply_feasibility_polishing_after_limits_reached != 0;
+  if (TerminationReasonIsInterrupted(reason)) return params.apply_feasibility_polishing_if_solver_is_interrupted != 0;
+  return false;
+}
+PdlpTerminationCriteria ReduceWorkLimitsByPreviousWork(PdlpTerminationCriteria criteria, int iteration_limit, const PdlpIterationStats& previous_work,
+                                                       bool apply_after_limits_reached) {
+  if (apply_after_limits_reached) {
+    criteria.iteration_limit = iteration_limit;
+    criteria.kkt_matrix_pass_limit = kInf;
+    criteria.time_sec_limit = kInf;
+  } else {
+    criteria.iteration_limit = std::max(0, std::min(iteration_limit, criteria.iteration_limit - previous_work.iteration_number));
+    criteria.kkt_matrix_pass_limit = std::max(0.0, criteria.kkt_matrix_pass_limit - previous_work.cumulative_kkt_matrix_passes);
+    criteria.time_sec_limit = std::max(0.0, criteria.time_sec_limit - previous_work.cumulative_time_sec);
+  }
+  return criteria;
+}
+void SetDetailedCriteria(PdlpTerminationCriteria& c, const DetailedCriteria& d) {
+  c.optimality_criteria_case = PDLP_DETAILED_OPTIMALITY_CRITERIA;
+  c.eps_optimal_primal_residual_absolute = d.primal_abs;
+  c.eps_optimal_primal_residual_relative = d.primal_rel;
+  c.eps_optimal_dual_residual_absolute = d.dual_abs;
+  c.eps_optimal_dual_residual_relative = d.dual_rel;
+  c.eps_optimal_objective_gap_absolute = d.gap_abs;
+  c.eps_optimal_objective_gap_relative = d.gap_rel;
+  c.has_eps_optimal_absolute = 0;
+  c.has_eps_optimal_relative = 0;
+}
+
 struct LocalizedBounds { double lagrangian_value, lower_bound, upper_bound, radius; };
 inline double BoundGap(const LocalizedBounds& b) { return b.upper_bound - b.lower_bound; }
 
@@ -241,7 +296,8 @@ class DeviceSolve {
                    phase_s_[0], phase_s_[1], phase_s_[2], phase_s_[3], phase_s_[4], phase_s_[5]);
     }
     for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); }
-    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, dc_, dr_, delta_x_, delta_y_, pc_kx_cur_, pc_kx_avg_, pc_kty_avg_}) D.Free(v);
+    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, delta_x_, delta_y_, pc_kx_cur_, pc_kx_avg_, pc_kty_avg_, polish_x_, polish_y_}) D.Free(v);
+    if (!nested_) { D.Free(dc_); D.Free(dr_); }
     D.Free(buf_.state);
   }
 
@@ -415,6 +471,21 @@ class DeviceSolve {
   int target_stop_ = std::numeric_limits<int>::max();
   double device_step_ms_ = 0, device_total_ms_ = 0;
   bool interrupt_polled_ = false;  // some rank was given an interrupt flag
+  // ---- feasibility polishing (pdhg.cc:2676-3015) ----------------------------
+  static constexpr int kFeasibilityIterationFraction = 8;
+  int iteration_type_ = PDLP_ITERATION_TYPE_NORMAL;  // what this object's loop is: the main solve or a polishing phase
+  bool nested_ = false;                               // a polishing phase: shares the parent's scaling vectors
+  int next_feasibility_polishing_iteration_ = 100;
+  PdlpIterationStats work_from_feasibility_polishing_{};
+  double *polish_x_ = nullptr, *polish_y_ = nullptr;  // working-space result of the primal / dual phase
+  void AllocateIterates();
+  void InitNested(const DeviceSolve& parent, int iteration_type, const double* x_start, const double* y_start);
+  PdlpIterationStats TotalWorkSoFar() const {
+    return AddWorkStats(CreateSimpleIterationStats(PDLP_RESTART_CHOICE_NO_RESTART), WorkFromFeasibilityPolishing(solve_log_));
+  }
+  std::optional<SolverResultCpp> TryFeasibilityPolishing(int iteration_limit, const volatile int32_t* interrupt);
+  SolveLogCpp RunPolishingPhase(bool primal_phase, const double* start, int iteration_limit, const volatile int32_t* interrupt);
+  SolverResultCpp ConstructSolverResultFromPolished(const PdlpIterationStats& stats, int reason);
   double phase_s_[6] = {0, 0, 0, 0, 0, 0};  // PDLP_B200_TRACE=1: host wall time per phase
 };
 
@@ -621,7 +692,7 @@ std::optional<ReasonAndType> DeviceSolve::UpdateIterationStatsAndCheckTerminatio
     if (++log_counter_ >= kLogEvery) log_counter_ = 0;
   }
   if (callback_) {
-    PdlpIterationCallbackInfo info{PDLP_ITERATION_TYPE_NORMAL, &params_.termination_criteria, &stats, original_bound_norms_};
+    PdlpIterationCallbackInfo info{iteration_type_, &params_.termination_criteria, &stats, original_bound_norms_};
     callback_(info);
   }
   if (const auto t = CheckIterateTerminationCriteria(params_.termination_criteria, stats, original_bound_norms_, force_numerical); t.has_value()) return t;
@@ -673,7 +744,11 @@ SolverResultCpp DeviceSolve::ConstructOriginalSolverResult(SolverResultCpp resul
   P.DownloadDual(result.dual_solution.data(), y);
   P.DownloadPrimal(result.reduced_costs.data(), rc);
   if (callback_) {
-    PdlpIterationCallbackInfo info{PDLP_ITERATION_TYPE_NORMAL_TERMINATION, &params_.termination_criteria, &result.solve_log.solution_stats, original_bound_norms_};
+    const int termination_type = result.solve_log.solution_type == PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION
+                                     ? PDLP_ITERATION_TYPE_FEASIBILITY_POLISHING_TERMINATION
+                                     : (result.solve_log.solution_type == PDLP_POINT_TYPE_PRESOLVER_SOLUTION ? PDLP_ITERATION_TYPE_PRESOLVE_TERMINATION
+                                                                                                            : PDLP_ITERATION_TYPE_NORMAL_TERMINATION);
+    PdlpIterationCallbackInfo info{termination_type, &params_.termination_criteria, &result.solve_log.solution_stats, original_bound_norms_};
     callback_(info);
   }
   if (params_.verbosity_level >= 1) {
@@ -698,7 +773,7 @@ std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bo
   phase_s_[0] += phase.Get();
   PdlpIterationStats stats = CreateSimpleIterationStats(restart);
   if (P.sharded()) stats.cumulative_time_sec = D.RootValue(stats.cumulative_time_sec);  // one clock decides the time limit
-  const PdlpIterationStats full_work_stats = stats;
+  const PdlpIterationStats full_work_stats = AddWorkStats(stats, work_from_feasibility_polishing_);
   const bool interrupted = Interrupted(interrupt);
   const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_work_stats, interrupted);
   const bool check_termination = cycle % params_.termination_check_frequency == 0 || simple.has_value() || force_numerical;
@@ -709,13 +784,164 @@ std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bo
     const auto maybe = UpdateIterationStatsAndCheckTermination(force_numerical, interrupted, full_work_stats, stats);
     phase_s_[1] += phase.Get();
     if (params_.record_iteration_stats) log.iteration_stats.push_back(stats);
-    if (maybe.has_value()) return PickSolutionAndConstructSolverResult(avg_x, avg_y, stats, maybe->reason, maybe->type, std::move(log));
+    if (maybe.has_value()) {
+      if (iteration_type_ == PDLP_ITERATION_TYPE_NORMAL && DoFeasibilityPolishingAfterLimitsReached(params_, maybe->reason)) {
+        auto feasibility_result = TryFeasibilityPolishing(iterations_completed_ / kFeasibilityIterationFraction, interrupt);
+        if (feasibility_result.has_value()) return feasibility_result;
+      }
+      const PdlpIterationStats terminating_full_stats = AddWorkStats(stats, work_from_feasibility_polishing_);
+      return PickSolutionAndConstructSolverResult(avg_x, avg_y, terminating_full_stats, maybe->reason, maybe->type, std::move(log));
+    }
   } else if (params_.record_iteration_stats) {
     log.iteration_stats.push_back(stats);
   }
   phase.Start();
   ApplyRestartChoice(restart);
   phase_s_[2] += phase.Get();
+  return std::nullopt;
+}
+
+// pdhg.cc:329-342 for the polished pair: leaves it where ConstructOriginalSolverResult reads it.
+SolverResultCpp DeviceSolve::ConstructSolverResultFromPolished(const PdlpIterationStats& stats, int reason) {
+  D.CopyD2D(P.tmp_n(1), polish_x_, P.n());
+  D.CopyD2D(P.tmp_m(1), polish_y_, P.m());
+  SolveLogCpp log = solve_log_;
+  log.iteration_count = stats.iteration_number;
+  log.termination_reason = reason;
+  log.solution_type = PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION;
+  log.solve_time_sec = stats.cumulative_time_sec;
+  log.solution_stats = stats;
+  log.has_solution_stats = true;
+  SolverResultCpp r;
+  r.solve_log = std::move(log);
+  return r;
+}
+
+// TryPrimalPolishing / TryDualPolishing (pdhg.cc:2888-3015). The primal phase solves the
+// working problem with a zero objective from (average primal, 0); the dual phase the
+// problem with homogeneous bounds (finite -> 0) from (0, average dual). Only the pointers
+// of the device problem are exchanged; the result (working space) is kept in polish_x_ /
+// polish_y_. Returns the phase's solve log; appends the details to solve_log_.
+SolveLogCpp DeviceSolve::RunPolishingPhase(bool primal_phase, const double* start, int iteration_limit, const volatile int32_t* interrupt) {
+  PdlpParams phase_params = params_;
+  phase_params.termination_criteria = ReduceWorkLimitsByPreviousWork(params_.termination_criteria, iteration_limit, TotalWorkSoFar(),
+                                                                     params_.apply_feasibility_polishing_after_limits_reached != 0);
+  if (params_.apply_feasibility_polishing_if_solver_is_interrupted) interrupt = nullptr;
+  DetailedCriteria criteria = EffectiveOptimalityCriteria(params_.termination_criteria);
+  if (primal_phase) criteria.dual_abs = criteria.dual_rel = kInf; else criteria.primal_abs = criteria.primal_rel = kInf;
+  criteria.gap_abs = criteria.gap_rel = kInf;
+  SetDetailedCriteria(phase_params.termination_criteria, criteria);
+  const int64_t n = P.n(), m = P.m();
+  if (polish_x_ == nullptr) { polish_x_ = P.NewPrimal(); polish_y_ = P.NewDual(); }
+  double *swap_c = nullptr, *swap_lv = nullptr, *swap_uv = nullptr, *swap_lc = nullptr, *swap_uc = nullptr;
+  if (primal_phase) {
+    swap_c = P.NewPrimal();
+    D.Fill(swap_c, 0.0, n);
+    P.SwapObjectiveVector(&swap_c);
+  } else {
+    swap_lv = P.NewPrimal(); swap_uv = P.NewPrimal(); swap_lc = P.NewDual(); swap_uc = P.NewDual();
+    D.MapFiniteValuesToZero(swap_lv, P.lv(), n);
+    D.MapFiniteValuesToZero(swap_uv, P.uv(), n);
+    D.MapFiniteValuesToZero(swap_lc, P.lc(), m);
+    D.MapFiniteValuesToZero(swap_uc, P.uc(), m);
+    P.SwapVariableBounds(&swap_lv, &swap_uv);
+    P.SwapConstraintBounds(&swap_lc, &swap_uc);
+  }
+  SolveLogCpp phase_log;
+  timer_.Stop();  // the time inside the phase is recorded by its own timer
+  {
+    DeviceSolve phase(P, phase_params, logger_, callback_);
+    phase.InitNested(*this, primal_phase ? PDLP_ITERATION_TYPE_PRIMAL_FEASIBILITY : PDLP_ITERATION_TYPE_DUAL_FEASIBILITY, primal_phase ? start : nullptr,
+                     primal_phase ? nullptr : start);
+    auto result = phase.Advance(std::numeric_limits<int>::max(), interrupt);
+    phase_log = std::move(result->solve_log);
+    // the phase's chosen point is in tmp_n(1) / tmp_m(1) (PickSolutionAndConstructSolverResult)
+    if (primal_phase) D.CopyD2D(polish_x_, P.tmp_n(1), n); else D.CopyD2D(polish_y_, P.tmp_m(1), m);
+    device_time_sec_ += phase.device_time_sec_;
+    device_step_ms_ += phase.device_step_ms_;
+  }
+  timer_.Resume();
+  if (primal_phase) {
+    P.SwapObjectiveVector(&swap_c);
+    D.Free(swap_c);
+  } else {
+    P.SwapVariableBounds(&swap_lv, &swap_uv);
+    P.SwapConstraintBounds(&swap_lc, &swap_uc);
+    for (double* v : {swap_lv, swap_uv, swap_lc, swap_uc}) D.Free(v);
+  }
+  InvalidateProducts(true, true);  // scratch vectors were reused by the phase
+  PolishingDetailsCpp d;  // BuildFeasibilityPolishingDetails, pdhg.cc:2684-2700
+  d.polishing_phase_type = primal_phase ? PDLP_POLISHING_PHASE_TYPE_PRIMAL_FEASIBILITY : PDLP_POLISHING_PHASE_TYPE_DUAL_FEASIBILITY;
+  d.main_iteration_count = iterations_completed_;
+  d.params = phase_params;
+  d.termination_reason = phase_log.termination_reason;
+  d.iteration_count = phase_log.iteration_count;
+  d.solve_time_sec = phase_log.solve_time_sec;
+  d.solution_stats = phase_log.solution_stats;
+  d.solution_type = phase_log.solution_type;
+  d.iteration_stats = phase_log.iteration_stats;
+  solve_log_.feasibility_polishing_details.push_back(std::move(d));
+  return phase_log;
+}
+
+// pdhg.cc:2702-2865
+std::optional<SolverResultCpp> DeviceSolve::TryFeasibilityPolishing(int iteration_limit, const volatile int32_t* interrupt) {
+  const DetailedCriteria optimality_criteria = EffectiveOptimalityCriteria(params_.termination_criteria);
+  // copies: the averages must survive the phases (they reuse nothing of this object, but a
+  // restart-to-average of the main loop later must still see them)
+  const double* average_primal = PrimalAverage();
+  const double* average_dual = DualAverage();
+  PdlpConvergenceInformation first_convergence_info;
+  ConvergenceAndInfeasibility(average_primal, average_dual, nullptr, PDLP_POINT_TYPE_AVERAGE_ITERATE, &first_convergence_info, nullptr);
+  auto simple_now = [&] { return CheckSimpleTerminationCriteria(params_.termination_criteria, TotalWorkSoFar(), Interrupted(interrupt)); };
+  // The objective gap is usually increased by polishing: do not start while it is still too large.
+  if (!ObjectiveGapMet(optimality_criteria, first_convergence_info)) {
+    const auto simple = simple_now();
+    if (!(simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason))) {
+      if (params_.verbosity_level >= 2) logger_.Log("Skipping feasibility polishing because the objective gap is too large.");
+      return std::nullopt;
+    }
+  }
+  if (params_.verbosity_level >= 2) logger_.Log("Starting primal feasibility polishing");
+  const SolveLogCpp primal_log = RunPolishingPhase(true, average_primal, iteration_limit, interrupt);
+  if (params_.verbosity_level >= 2) logger_.Log(Fmt("Primal feasibility polishing termination reason: %d", primal_log.termination_reason));
+  if (TerminationReasonIsWorkLimit(primal_log.termination_reason)) {
+    const auto simple = simple_now();
+    if (!(simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason))) return std::nullopt;
+  } else if (primal_log.termination_reason != PDLP_TERMINATION_REASON_OPTIMAL) {
+    logger_.Log(Fmt("WARNING: Primal feasibility polishing terminated with error %d", primal_log.termination_reason));
+    return std::nullopt;
+  }
+  if (params_.verbosity_level >= 2) logger_.Log("Starting dual feasibility polishing");
+  const SolveLogCpp dual_log = RunPolishingPhase(false, average_dual, iteration_limit, interrupt);
+  if (params_.verbosity_level >= 2) logger_.Log(Fmt("Dual feasibility polishing termination reason: %d", dual_log.termination_reason));
+  PdlpIterationStats full_stats = TotalWorkSoFar();
+  const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_stats, Interrupted(interrupt));
+  auto add_polished_convergence = [&] {
+    ConvergenceAndInfeasibility(polish_x_, polish_y_, nullptr, PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION,
+                                &full_stats.convergence_information[full_stats.num_convergence_information], nullptr);
+    full_stats.num_convergence_information += 1;
+  };
+  if (TerminationReasonIsWorkLimit(dual_log.termination_reason)) {
+    if (simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason)) {
+      add_polished_convergence();
+      return ConstructSolverResultFromPolished(full_stats, simple->reason);
+    }
+    return std::nullopt;
+  } else if (dual_log.termination_reason != PDLP_TERMINATION_REASON_OPTIMAL) {
+    logger_.Log(Fmt("WARNING: Dual feasibility polishing terminated with error %d", dual_log.termination_reason));
+    return std::nullopt;
+  }
+  add_polished_convergence();
+  if (params_.verbosity_level >= 2) {
+    logger_.Log("solution stats for polished solution:");
+    LogIterationStatsHeader(params_.verbosity_level, logger_);
+    LogIterationStats(params_.verbosity_level, full_stats, params_.termination_criteria, original_bound_norms_, PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION,
+                      logger_);
+  }
+  const auto earned = CheckIterateTerminationCriteria(params_.termination_criteria, full_stats, original_bound_norms_, /*force_numerical=*/false);
+  if (earned.has_value() || (simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason)))
+    return ConstructSolverResultFromPolished(full_stats, earned.has_value() ? earned->reason : simple->reason);
   return std::nullopt;
 }
 
@@ -732,8 +958,9 @@ int DeviceSolve::NextCheckpoint(int k) const {
     const int next_cyc = (cyc / check + 1) * check;
     if (next_cyc < major) consider(static_cast<int64_t>(k) - cyc + next_cyc);
   }
-  consider(tc.iteration_limit);
+  consider(static_cast<int64_t>(tc.iteration_limit) - work_from_feasibility_polishing_.iteration_number);
   consider(target_stop_);
+  if (params_.use_feasibility_polishing && iteration_type_ == PDLP_ITERATION_TYPE_NORMAL) consider(next_feasibility_polishing_iteration_);
   if (params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
     // artificial restart (pdhg.cc:2120-2130): first k' with terms + (k'-k) >= k'/2
     const int terms = avg_x_terms_;
@@ -756,7 +983,7 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
   int k_stop = NextCheckpoint(k);
   if (interrupt_polled_) k_stop = std::min(k_stop, k + 32);
   hs_.k_stop = k_stop;
-  hs_.kkt_pass_limit = params_.termination_criteria.kkt_matrix_pass_limit;
+  hs_.kkt_pass_limit = params_.termination_criteria.kkt_matrix_pass_limit - work_from_feasibility_polishing_.cumulative_kkt_matrix_passes;
   hs_.avg_weight_sum = avg_x_weight_;
   hs_.avg_num_terms = avg_x_terms_;
   hs_.pending_ratio = 0.0;
@@ -866,7 +1093,7 @@ std::optional<SolverResultCpp> DeviceSolve::Advance(int target_iterations, const
   target_stop_ = target_iterations;
   interrupt_polled_ = D.MaxOverRanks(interrupt_solve != nullptr ? 1.0 : 0.0) != 0.0;
   const bool device_loop = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE;
-  D.TimelineStart(0);
+  if (!nested_) D.TimelineStart(0);
   std::optional<SolverResultCpp> done;
   for (;;) {
     if (!check_done_) {
@@ -879,12 +1106,25 @@ std::optional<SolverResultCpp> DeviceSolve::Advance(int target_iterations, const
         break;
       }
     }
+    // pdhg.cc:3056-3070: polishing attempts at iterations 100, 200, 400, ... of the main solve
+    if (params_.use_feasibility_polishing && iteration_type_ == PDLP_ITERATION_TYPE_NORMAL &&
+        iterations_completed_ >= next_feasibility_polishing_iteration_) {
+      auto feasibility_result = TryFeasibilityPolishing(iterations_completed_ / kFeasibilityIterationFraction, interrupt_solve);
+      if (feasibility_result.has_value()) {
+        feasibility_result->solve_log.gpu_kernel_launches = D.launches();
+        feasibility_result->solve_log.device_iteration_time_sec = device_time_sec_;
+        done = std::move(feasibility_result);
+        break;
+      }
+      next_feasibility_polishing_iteration_ *= 2;
+      work_from_feasibility_polishing_ = WorkFromFeasibilityPolishing(solve_log_);
+    }
     if (iterations_completed_ >= target_iterations) break;
     const Outcome outcome = device_loop ? RunDeviceSteps(iterations_completed_, interrupt_solve) : TakeMalitskyPockStep();
     check_done_ = false;
     if (outcome == Outcome::kForceNumericalTermination) force_numerical_ = true;
   }
-  device_total_ms_ += D.TimelineStopMs(0);
+  if (!nested_) device_total_ms_ += D.TimelineStopMs(0);
   return done;
 }
 
@@ -943,26 +1183,8 @@ SolverResultCpp DeviceSolve::PreprocessAndSolve(std::optional<InitialSolution> i
 }
 
 // pdhg.cc:1039-1221
-std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolution> initial_solution, const std::string* name) {
-  WallTimer timer;
-  SolveLogCpp solve_log;
-  if (params_.verbosity_level >= 1) logger_.Log("Solving with PDLP parameters: (PdlpParams POD)");
-  if (name != nullptr) solve_log.instance_name = *name;
-  solve_log.params = params_;
+void DeviceSolve::AllocateIterates() {
   const int64_t n = P.n(), m = P.m();
-  P.ReplaceLargeConstraintBoundsWithInfinity(params_.infinite_constraint_bound_threshold);
-  if (!P.HasValidBounds())
-    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
-                             "The input problem has invalid bounds (after replacing large constraint bounds with infinity): some variable or "
-                             "constraint has lower_bound > upper_bound, lower_bound == inf, or upper_bound == -inf.", logger_);
-  if (!P.ObjectiveMatrixIsNonNegative())
-    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
-                             "The objective is not convex (i.e., the objective matrix contains negative or NAN entries).", logger_);
-  solve_log.original_stats = P.ComputeStats();
-  solve_log.has_original_stats = true;
-  if (auto r = CheckProblemStats(solve_log.original_stats, P.objective_offset(), params_.presolve_use_glop != 0, logger_); r.has_value()) return std::move(*r);
-
-  // iterate buffers
   buf_.n = n;
   buf_.m = m;
   for (int k = 0; k < 3; ++k) { buf_.x[k] = P.NewPrimal(); buf_.y[k] = P.NewDual(); buf_.kty[k] = P.NewPrimal(); }
@@ -991,6 +1213,61 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   buf_.slice_perm = P.slice_perm();
   std::memset(&hs_, 0, sizeof(hs_));
   hs_.cur = 0; hs_.prev = 1; hs_.cand = 2;
+
+}
+
+// A polishing phase (the nested `Solver` of pdhg.cc:2913-2921 / 2992-2999): same working
+// problem, scaling vectors and bound norms as the parent, its own iterates; starts from
+// (x_start, y_start) (nullptr = zero) with the parent's step size and primal weight and
+// performs the start of Solver::Solve (pdhg.cc:3017-3041).
+void DeviceSolve::InitNested(const DeviceSolve& parent, int iteration_type, const double* x_start, const double* y_start) {
+  nested_ = true;
+  iteration_type_ = iteration_type;
+  dc_ = parent.dc_;
+  dr_ = parent.dr_;
+  original_bound_norms_ = parent.original_bound_norms_;
+  AllocateIterates();
+  if (x_start != nullptr) D.CopyD2D(X(), x_start, P.n()); else D.Fill(X(), 0.0, P.n());
+  if (y_start != nullptr) D.CopyD2D(Y(), y_start, P.m()); else D.Fill(Y(), 0.0, P.m());
+  hs_.step_size = parent.hs_.step_size;
+  hs_.primal_weight = parent.hs_.primal_weight;
+  hs_.rule = params_.linesearch_rule;
+  hs_.reduction_exponent = params_.adaptive_step_size_reduction_exponent;
+  hs_.growth_exponent = params_.adaptive_step_size_growth_exponent;
+  ClearAverages();
+  solve_log_ = SolveLogCpp();
+  preprocessing_time_sec_ = 0;
+  timer_.Start();
+  D.CopyD2D(x0_, X(), P.n());
+  D.CopyD2D(y0_, Y(), P.m());
+  ratio_last_two_step_sizes_ = 1;
+  SetCurrentPrimalAndDualProducts();
+  force_numerical_ = false;
+  check_done_ = false;
+  num_rejected_steps_ = 0;
+  iterations_completed_ = 0;
+}
+
+std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolution> initial_solution, const std::string* name) {
+  WallTimer timer;
+  SolveLogCpp solve_log;
+  if (params_.verbosity_level >= 1) logger_.Log("Solving with PDLP parameters: (PdlpParams POD)");
+  if (name != nullptr) solve_log.instance_name = *name;
+  solve_log.params = params_;
+  const int64_t n = P.n(), m = P.m();
+  P.ReplaceLargeConstraintBoundsWithInfinity(params_.infinite_constraint_bound_threshold);
+  if (!P.HasValidBounds())
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
+                             "The input problem has invalid bounds (after replacing large constraint bounds with infinity): some variable or "
+                             "constraint has lower_bound > upper_bound, lower_bound == inf, or upper_bound == -inf.", logger_);
+  if (!P.ObjectiveMatrixIsNonNegative())
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
+                             "The objective is not convex (i.e., the objective matrix contains negative or NAN entries).", logger_);
+  solve_log.original_stats = P.ComputeStats();
+  solve_log.has_original_stats = true;
+  if (auto r = CheckProblemStats(solve_log.original_stats, P.objective_offset(), params_.presolve_use_glop != 0, logger_); r.has_value()) return std::move(*r);
+
+  AllocateIterates();
 
   if (initial_solution.has_value()) {  // CheckInitialSolution, pdhg.cc:985-1037
     const double kBig = 1e50;
@@ -1104,9 +1381,9 @@ std::optional<SolverResultCpp> ValidateInputs(const PdlpProblemView& view, const
   if (view.objective_scaling_factor == 0) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "The objective scaling factor cannot be zero.", logger);
   if (params.use_feasibility_polishing && view.objective_matrix_diagonal != nullptr)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "use_feasibility_polishing is only implemented for linear programs.", logger);
-  if (params.use_feasibility_polishing || params.presolve_use_glop)
+  if (params.presolve_use_glop)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER,
-                             "presolve_options.use_glop and use_feasibility_polishing are host-side features outside this library's scope.", logger);
+                             "presolve_options.use_glop (glop presolve) is a host-side feature outside this library's scope.", logger);
   if (params.num_random_projection_seeds > PDLP_MAX_RANDOM_PROJECTION_SEEDS)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "at most 8 random_projection_seeds are supported.", logger);
   return std::nullopt;

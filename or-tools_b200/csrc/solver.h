@@ -14,6 +14,19 @@ namespace pdlp_b200 {
 
 class Comm;  // comm.h
 
+// FeasibilityPolishingDetails (solve_log.proto:371-383)
+struct PolishingDetailsCpp {
+  int polishing_phase_type = 0;
+  int main_iteration_count = 0;
+  PdlpParams params{};
+  int termination_reason = 0;
+  int iteration_count = 0;
+  double solve_time_sec = 0;
+  PdlpIterationStats solution_stats{};
+  int solution_type = 0;
+  std::vector<PdlpIterationStats> iteration_stats;
+};
+
 struct SolveLogCpp {
   std::optional<std::string> instance_name;
   int termination_reason = PDLP_TERMINATION_REASON_UNSPECIFIED;
@@ -27,6 +40,7 @@ struct SolveLogCpp {
   PdlpQuadraticProgramStats original_stats{}, preprocessed_stats{};
   std::vector<PdlpIterationStats> iteration_stats;
   PdlpParams params{};
+  std::vector<PolishingDetailsCpp> feasibility_polishing_details;
   int64_t gpu_kernel_launches = 0;
   double device_iteration_time_sec = 0;
 };

@@ -96,6 +96,12 @@ class TerminationReason(_Enum):  # solve_log.proto:336-360
     TERMINATION_REASON_INVALID_INITIAL_SOLUTION = 13
 
 
+class PolishingPhaseType(_Enum):  # solve_log.proto:362-369
+    POLISHING_PHASE_TYPE_UNSPECIFIED = 0
+    POLISHING_PHASE_TYPE_PRIMAL_FEASIBILITY = 1
+    POLISHING_PHASE_TYPE_DUAL_FEASIBILITY = 2
+
+
 class IterationType(_Enum):  # primal_dual_hybrid_gradient.h:75-88
     NORMAL = 0
     PRIMAL_FEASIBILITY = 1
@@ -537,6 +543,15 @@ class Backend:
         log.preprocessed_problem_stats = _ns(capi.struct_to_dict(res.preprocessed_problem_stats)) if res.has_preprocessed_problem_stats else None
         log.iteration_stats = [_iteration_stats_from_pod(res.iteration_stats[i]) for i in range(res.num_iteration_stats)]
         log.params = _ns(capi.struct_to_dict(res.params))
+        log.feasibility_polishing_details = []
+        for k in range(res.num_feasibility_polishing_details):
+            d = res.feasibility_polishing_details[k]
+            log.feasibility_polishing_details.append(types.SimpleNamespace(
+                polishing_phase_type=d.polishing_phase_type, main_iteration_count=d.main_iteration_count,
+                params=_ns(capi.struct_to_dict(d.params)), termination_reason=d.termination_reason,
+                iteration_count=d.iteration_count, solve_time_sec=d.solve_time_sec,
+                solution_stats=_iteration_stats_from_pod(d.solution_stats), solution_type=d.solution_type,
+                iteration_stats=[_iteration_stats_from_pod(d.iteration_stats[i]) for i in range(d.num_iteration_stats)]))
         log.gpu_kernel_launches = res.gpu_kernel_launches
         log.device_iteration_time_sec = res.device_iteration_time_sec
         out.solve_log = log

@@ -406,6 +406,17 @@ def solve_log_to_proto(solve_log, params=None):
         _stats_to_proto(solve_log.original_problem_stats, out.original_problem_stats)
     if solve_log.preprocessed_problem_stats is not None:
         _stats_to_proto(solve_log.preprocessed_problem_stats, out.preprocessed_problem_stats)
+    for d in getattr(solve_log, "feasibility_polishing_details", []):
+        m = out.feasibility_polishing_details.add()
+        m.polishing_phase_type = int(d.polishing_phase_type)
+        m.main_iteration_count = int(d.main_iteration_count)
+        m.termination_reason = int(d.termination_reason)
+        m.iteration_count = int(d.iteration_count)
+        m.solve_time_sec = d.solve_time_sec
+        _iteration_stats_to_proto(d.solution_stats, m.solution_stats)
+        m.solution_type = int(d.solution_type)
+        for s in d.iteration_stats:
+            _iteration_stats_to_proto(s, m.iteration_stats.add())
     return out
 
 

@@ -23,8 +23,12 @@ namespace {
 using Clock = std::chrono::steady_clock;
 struct WallTimer {
   Clock::time_point start = Clock::now();
-  void Start() { start = Clock::now(); }
-  double Get() const { return std::chrono::duration<double>(Clock::now() - start).count(); }
+  double accumulated = 0;
+  bool running = true;
+  void Start() { start = Clock::now(); accumulated = 0; running = true; }
+  void Stop() { if (running) { accumulated += std::chrono::duration<double>(Clock::now() - start).count(); running = false; } }
+  void Resume() { if (!running) { start = Clock::now(); running = true; } }
+  double Get() const { return accumulated + (running ? std::chrono::duration<double>(Clock::now() - start).count() : 0.0); }
 };
 
 struct Logger {
@@ -36,6 +40,18 @@ struct Logger {
   }
 };
 
+// FeasibilityPolishingDetails (solve_log.proto:371-383)
+struct PolishingDetailsCpp {
+  int polishing_phase_type = 0;
+  int main_iteration_count = 0;
+  PdlpParams params{};
+  int termination_reason = 0;
+  int iteration_count = 0;
+  double solve_time_sec = 0;
+  PdlpIterationStats solution_stats{};
+  int solution_type = 0;
+  std::vector<PdlpIterationStats> iteration_stats;
+};
 struct SolveLogCpp {
   std::optional<std::string> instance_name;
   int termination_reason = PDLP_TERMINATION_REASON_UNSPECIFIED;
@@ -49,6 +65,7 @@ struct SolveLogCpp {
   PdlpQuadraticProgramStats original_stats{}, preprocessed_stats{};
   std::vector<PdlpIterationStats> iteration_stats;
   PdlpParams params{};
+  std::vector<PolishingDetailsCpp> feasibility_polishing_details;
 };
 struct SolverResultCpp {
   Vec primal_solution, dual_solution, reduced_costs;
@@ -220,6 +237,88 @@ double RandomProjection(const Vec& v, const Sharder& sharder, std::mt19937& seed
   return d / std::sqrt(q);
 }
 
+// ---- feasibility polishing helpers (pdhg.cc:2298-2358, 2684-2700, 2867-2886) ------------
+PdlpIterationStats AddWorkStats(PdlpIterationStats stats, const PdlpIterationStats& more) {
+  stats.iteration_number += more.iteration_number;
+  stats.cumulative_kkt_matrix_passes += more.cumulative_kkt_matrix_passes;
+  stats.cumulative_rejected_steps += more.cumulative_rejected_steps;
+  stats.cumulative_time_sec += more.cumulative_time_sec;
+  return stats;
+}
+PdlpIterationStats WorkFromFeasibilityPolishing(const SolveLogCpp& log) {
+  PdlpIterationStats result;
+  std::memset(&result, 0, sizeof(result));
+  for (const PolishingDetailsCpp& d : log.feasibility_polishing_details) result = AddWorkStats(result, d.solution_stats);
+  return result;
+}
+bool TerminationReasonIsInterrupted(int reason) { return reason == PDLP_TERMINATION_REASON_INTERRUPTED_BY_USER; }
+bool TerminationReasonIsWorkLimitNotInterrupted(int reason) {
+  return reason == PDLP_TERMINATION_REASON_ITERATION_LIMIT || reason == PDLP_TERMINATION_REASON_TIME_LIMIT ||
+         reason == PDLP_TERMINATION_REASON_KKT_MATRIX_PASS_LIMIT;
+}
+bool TerminationReasonIsWorkLimit(int reason) { return TerminationReasonIsWorkLimitNotInterrupted(reason) || TerminationReasonIsInterrupted(reason); }
+bool DoFeasibilityPolishingAfterLimitsReached(const PdlpParams& params, int reason) {
+  if (TerminationReasonIsWorkLimitNotInterrupted(reason)) return params.apply_feasibility_polishing_after_limits_reached != 0;
+  if (TerminationReasonIsInterrupted(reason)) return params.apply_feasibility_polishing_if_solver_is_interrupted != 0;
+  return false;
+}
+PolishingDetailsCpp BuildFeasibilityPolishingDetails(int phase_type, int iteration_count, const PdlpParams& params, const SolveLogCpp& log) {
+  PolishingDetailsCpp d;
+  d.polishing_phase_type = phase_type;
+  d.main_iteration_count = iteration_count;
+  d.params = params;
+  d.termination_reason = log.termination_reason;
+  d.iteration_count = log.iteration_count;
+  d.solve_time_sec = log.solve_time_sec;
+  d.solution_stats = log.solution_stats;
+  d.solution_type = log.solution_type;
+  d.iteration_stats = log.iteration_stats;
+  return d;
+}
+PdlpTerminationCriteria ReduceWorkLimitsByPreviousWork(PdlpTerminationCriteria criteria, int iteration_limit, const PdlpIterationStats& previous_work,
+                                                       bool apply_after_limits_reached) {
+  if (apply_after_limits_reached) {
+    criteria.iteration_limit = iteration_limit;
+    criteria.kkt_matrix_pass_limit = kInf;
+    criteria.time_sec_limit = kInf;
+  } else {
+    criteria.iteration_limit = std::max(0, std::min(iteration_limit, criteria.iteration_limit - previous_work.iteration_number));
+    criteria.kkt_matrix_pass_limit = std::max(0.0, criteria.kkt_matrix_pass_limit - previous_work.cumulative_kkt_matrix_passes);
+    criteria.time_sec_limit = std::max(0.0, criteria.time_sec_limit - previous_work.cumulative_time_sec);
+  }
+  return criteria;
+}
+// The detailed criteria of a polishing phase: `base` with the listed tolerances made infinite.
+void SetDetailedCriteria(PdlpTerminationCriteria& c, const DetailedCriteria& d) {
+  c.optimality_criteria_case = PDLP_DETAILED_OPTIMALITY_CRITERIA;
+  c.eps_optimal_primal_residual_absolute = d.primal_abs;
+  c.eps_optimal_primal_residual_relative = d.primal_rel;
+  c.eps_optimal_dual_residual_absolute = d.dual_abs;
+  c.eps_optimal_dual_residual_relative = d.dual_rel;
+  c.eps_optimal_objective_gap_absolute = d.gap_abs;
+  c.eps_optimal_objective_gap_relative = d.gap_rel;
+  c.has_eps_optimal_absolute = 0;
+  c.has_eps_optimal_relative = 0;
+}
+Vec MapFiniteValuesToZero(const Vec& in) {
+  Vec out(in.size());
+  for (size_t i = 0; i < in.size(); ++i) out[i] = std::isfinite(in[i]) ? 0.0 : in[i];
+  return out;
+}
+SolverResultCpp ConstructSolverResult(Vec primal, Vec dual, const PdlpIterationStats& stats, int reason, int output_type, SolveLogCpp log) {  // pdhg.cc:329-342
+  log.iteration_count = stats.iteration_number;
+  log.termination_reason = reason;
+  log.solution_type = output_type;
+  log.solve_time_sec = stats.cumulative_time_sec;
+  log.solution_stats = stats;
+  log.has_solution_stats = true;
+  SolverResultCpp r;
+  r.primal_solution = std::move(primal);
+  r.dual_solution = std::move(dual);
+  r.solve_log = std::move(log);
+  return r;
+}
+
 class Solver;
 
 // ---------------------------------------------------------------------------
@@ -248,6 +347,16 @@ class PreprocessSolver {
   SolverResultCpp ConstructOriginalSolverResult(const PdlpParams& params, SolverResultCpp result) const;
 
   const ShardedQp& ShardedWorkingQp() const { return sharded_qp_; }
+  // pdhg.cc:420-443: exchange bounds / objective with the working problem (feasibility polishing)
+  void SwapVariableBounds(Vec& lower, Vec& upper) {
+    std::swap(sharded_qp_.MutableQp().variable_lower_bounds, lower);
+    std::swap(sharded_qp_.MutableQp().variable_upper_bounds, upper);
+  }
+  void SwapConstraintBounds(Vec& lower, Vec& upper) {
+    std::swap(sharded_qp_.MutableQp().constraint_lower_bounds, lower);
+    std::swap(sharded_qp_.MutableQp().constraint_upper_bounds, upper);
+  }
+  void SwapObjectiveVector(Vec& objective) { std::swap(sharded_qp_.MutableQp().objective_vector, objective); }
   const PdlpBoundNorms& OriginalBoundNorms() const { return original_bound_norms_; }
   const Logger& GetLogger() const { return logger_; }
 
@@ -524,12 +633,13 @@ class Solver {
   }
   // pdhg.cc:2360-2435
   std::optional<SolverResultCpp> MajorIterationAndTerminationCheck(int iteration_type, bool force_numerical_termination,
-                                                                  const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log) {
+                                                                  const volatile int32_t* interrupt_solve,
+                                                                  const PdlpIterationStats& work_from_feasibility_polishing, SolveLogCpp& solve_log) {
     const int cycle = iterations_completed_ % params_.major_iteration_frequency;
     const bool is_major = cycle == 0 && iterations_completed_ > 0;
     const int restart = force_numerical_termination ? PDLP_RESTART_CHOICE_NO_RESTART : ChooseRestartToApply(is_major);
     PdlpIterationStats stats = CreateSimpleIterationStats(restart);
-    const PdlpIterationStats full_work_stats = stats;  // no feasibility polishing work
+    const PdlpIterationStats full_work_stats = AddWorkStats(stats, work_from_feasibility_polishing);
     const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_work_stats, interrupt_solve);
     const bool check_termination = cycle % params_.termination_check_frequency == 0 || simple.has_value() || force_numerical_termination;
     if (check_termination) {
@@ -542,7 +652,13 @@ class Solver {
           last_primal_start_point_, last_dual_start_point_, interrupt_solve, iteration_type, full_work_stats, stats);
       if (params_.record_iteration_stats) solve_log.iteration_stats.push_back(stats);
       if (maybe.has_value()) {
-        return PickSolutionAndConstructSolverResult(std::move(primal_average), std::move(dual_average), stats, maybe->reason, maybe->type, std::move(solve_log));
+        if (iteration_type == PDLP_ITERATION_TYPE_NORMAL && DoFeasibilityPolishingAfterLimitsReached(params_, maybe->reason)) {
+          auto feasibility_result = TryFeasibilityPolishing(iterations_completed_ / kFeasibilityIterationFraction, interrupt_solve, solve_log);
+          if (feasibility_result.has_value()) return feasibility_result;
+        }
+        const PdlpIterationStats terminating_full_stats = AddWorkStats(stats, work_from_feasibility_polishing);
+        return PickSolutionAndConstructSolverResult(std::move(primal_average), std::move(dual_average), terminating_full_stats, maybe->reason, maybe->type,
+                                                    std::move(solve_log));
       }
     } else if (params_.record_iteration_stats) {
       solve_log.iteration_stats.push_back(stats);
@@ -550,6 +666,14 @@ class Solver {
     ApplyRestartChoice(restart);
     return std::nullopt;
   }
+  // ---- feasibility polishing (pdhg.cc:2676-3015) -------------------------------------
+  static constexpr int kFeasibilityIterationFraction = 8;
+  PdlpIterationStats TotalWorkSoFar(const SolveLogCpp& solve_log) const {
+    return AddWorkStats(CreateSimpleIterationStats(PDLP_RESTART_CHOICE_NO_RESTART), WorkFromFeasibilityPolishing(solve_log));
+  }
+  std::optional<SolverResultCpp> TryFeasibilityPolishing(int iteration_limit, const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log);
+  SolverResultCpp TryPrimalPolishing(Vec starting_primal, int iteration_limit, const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log);
+  SolverResultCpp TryDualPolishing(Vec starting_dual, int iteration_limit, const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log);
   // pdhg.cc:2437-2442
   void ResetAverageToCurrent() {
     primal_average_.Clear(); dual_average_.Clear();
@@ -720,10 +844,18 @@ SolverResultCpp Solver::Solve(int iteration_type, const volatile int32_t* interr
   ratio_last_two_step_sizes_ = 1;
   SetCurrentPrimalAndDualProducts();
   bool force_numerical_termination = false;
+  int next_feasibility_polishing_iteration = 100;
   num_rejected_steps_ = 0;
+  PdlpIterationStats work_from_feasibility_polishing = WorkFromFeasibilityPolishing(solve_log);
   for (iterations_completed_ = 0;; ++iterations_completed_) {
-    auto maybe = MajorIterationAndTerminationCheck(iteration_type, force_numerical_termination, interrupt_solve, solve_log);
+    auto maybe = MajorIterationAndTerminationCheck(iteration_type, force_numerical_termination, interrupt_solve, work_from_feasibility_polishing, solve_log);
     if (maybe.has_value()) return std::move(*maybe);
+    if (params_.use_feasibility_polishing && iteration_type == PDLP_ITERATION_TYPE_NORMAL && iterations_completed_ >= next_feasibility_polishing_iteration) {
+      auto feasibility_result = TryFeasibilityPolishing(iterations_completed_ / kFeasibilityIterationFraction, interrupt_solve, solve_log);
+      if (feasibility_result.has_value()) return std::move(*feasibility_result);
+      next_feasibility_polishing_iteration *= 2;
+      work_from_feasibility_polishing = WorkFromFeasibilityPolishing(solve_log);
+    }
     InnerStepOutcome outcome;
     switch (params_.linesearch_rule) {
       case PDLP_MALITSKY_POCK_LINESEARCH_RULE: outcome = TakeMalitskyPockStep(); break;
@@ -732,6 +864,125 @@ SolverResultCpp Solver::Solve(int iteration_type, const volatile int32_t* interr
     }
     if (outcome == InnerStepOutcome::kForceNumericalTermination) force_numerical_termination = true;
   }
+}
+
+// pdhg.cc:2702-2865
+std::optional<SolverResultCpp> Solver::TryFeasibilityPolishing(int iteration_limit, const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log) {
+  const Logger& logger = preprocess_solver_->GetLogger();
+  const DetailedCriteria optimality_criteria = EffectiveOptimalityCriteria(params_.termination_criteria);
+  Vec average_primal = PrimalAverage();
+  Vec average_dual = DualAverage();
+  PdlpConvergenceInformation first_convergence_info;
+  preprocess_solver_->ComputeConvergenceAndInfeasibilityFromWorkingSolution(params_, average_primal, average_dual, PDLP_POINT_TYPE_AVERAGE_ITERATE,
+                                                                            &first_convergence_info, nullptr);
+  // The objective gap is usually increased by polishing: do not start while it is still too large.
+  if (!ObjectiveGapMet(optimality_criteria, first_convergence_info)) {
+    const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, TotalWorkSoFar(solve_log), interrupt_solve);
+    if (!(simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason))) {
+      if (params_.verbosity_level >= 2) logger.Log("Skipping feasibility polishing because the objective gap is too large.");
+      return std::nullopt;
+    }
+  }
+  if (params_.verbosity_level >= 2) logger.Log("Starting primal feasibility polishing");
+  SolverResultCpp primal_result = TryPrimalPolishing(std::move(average_primal), iteration_limit, interrupt_solve, solve_log);
+  if (params_.verbosity_level >= 2) logger.Log(Fmt("Primal feasibility polishing termination reason: %d", primal_result.solve_log.termination_reason));
+  if (TerminationReasonIsWorkLimit(primal_result.solve_log.termination_reason)) {
+    const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, TotalWorkSoFar(solve_log), interrupt_solve);
+    if (!(simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason))) return std::nullopt;
+  } else if (primal_result.solve_log.termination_reason != PDLP_TERMINATION_REASON_OPTIMAL) {
+    logger.Log(Fmt("WARNING: Primal feasibility polishing terminated with error %d", primal_result.solve_log.termination_reason));
+    return std::nullopt;
+  }
+  if (params_.verbosity_level >= 2) logger.Log("Starting dual feasibility polishing");
+  SolverResultCpp dual_result = TryDualPolishing(std::move(average_dual), iteration_limit, interrupt_solve, solve_log);
+  if (params_.verbosity_level >= 2) logger.Log(Fmt("Dual feasibility polishing termination reason: %d", dual_result.solve_log.termination_reason));
+  PdlpIterationStats full_stats = TotalWorkSoFar(solve_log);
+  const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_stats, interrupt_solve);
+  auto add_polished_convergence = [&] {
+    preprocess_solver_->ComputeConvergenceAndInfeasibilityFromWorkingSolution(
+        params_, primal_result.primal_solution, dual_result.dual_solution, PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION,
+        &full_stats.convergence_information[full_stats.num_convergence_information], nullptr);
+    full_stats.num_convergence_information += 1;
+  };
+  if (TerminationReasonIsWorkLimit(dual_result.solve_log.termination_reason)) {
+    if (simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason)) {
+      add_polished_convergence();
+      return ConstructSolverResult(std::move(primal_result.primal_solution), std::move(dual_result.dual_solution), full_stats, simple->reason,
+                                   PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION, solve_log);
+    }
+    return std::nullopt;
+  } else if (dual_result.solve_log.termination_reason != PDLP_TERMINATION_REASON_OPTIMAL) {
+    logger.Log(Fmt("WARNING: Dual feasibility polishing terminated with error %d", dual_result.solve_log.termination_reason));
+    return std::nullopt;
+  }
+  add_polished_convergence();
+  if (params_.verbosity_level >= 2) {
+    logger.Log("solution stats for polished solution:");
+    LogIterationStatsHeader(params_.verbosity_level, logger);
+    LogIterationStats(params_.verbosity_level, full_stats, params_.termination_criteria, preprocess_solver_->OriginalBoundNorms(),
+                      PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION, logger);
+  }
+  const auto earned = CheckIterateTerminationCriteria(params_.termination_criteria, full_stats, preprocess_solver_->OriginalBoundNorms(),
+                                                      /*force_numerical_termination=*/false);
+  if (earned.has_value() || (simple.has_value() && DoFeasibilityPolishingAfterLimitsReached(params_, simple->reason))) {
+    return ConstructSolverResult(std::move(primal_result.primal_solution), std::move(dual_result.dual_solution), full_stats,
+                                 earned.has_value() ? earned->reason : simple->reason, PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION, solve_log);
+  }
+  return std::nullopt;
+}
+
+// pdhg.cc:2888-2938
+SolverResultCpp Solver::TryPrimalPolishing(Vec starting_primal, int iteration_limit, const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log) {
+  PdlpParams phase_params = params_;
+  phase_params.termination_criteria = ReduceWorkLimitsByPreviousWork(params_.termination_criteria, iteration_limit, TotalWorkSoFar(solve_log),
+                                                                     params_.apply_feasibility_polishing_after_limits_reached != 0);
+  if (params_.apply_feasibility_polishing_if_solver_is_interrupted) interrupt_solve = nullptr;
+  Vec objective(ShardedWorkingQp().PrimalSize(), 0.0);  // holds the original objective after the swap
+  preprocess_solver_->SwapObjectiveVector(objective);
+  DetailedCriteria criteria = EffectiveOptimalityCriteria(params_.termination_criteria);
+  criteria.dual_abs = criteria.dual_rel = kInf;
+  criteria.gap_abs = criteria.gap_rel = kInf;
+  SetDetailedCriteria(phase_params.termination_criteria, criteria);
+  Vec starting_dual(ShardedWorkingQp().DualSize(), 0.0);
+  Solver primal_solver(phase_params, std::move(starting_primal), std::move(starting_dual), step_size_, primal_weight_, preprocess_solver_);
+  SolveLogCpp phase_log;
+  timer_.Stop();  // the time inside the phase is recorded by its own timer
+  SolverResultCpp result = primal_solver.Solve(PDLP_ITERATION_TYPE_PRIMAL_FEASIBILITY, interrupt_solve, phase_log);
+  timer_.Resume();
+  preprocess_solver_->SwapObjectiveVector(objective);
+  solve_log.feasibility_polishing_details.push_back(
+      BuildFeasibilityPolishingDetails(PDLP_POLISHING_PHASE_TYPE_PRIMAL_FEASIBILITY, iterations_completed_, phase_params, result.solve_log));
+  return result;
+}
+
+// pdhg.cc:2951-3015
+SolverResultCpp Solver::TryDualPolishing(Vec starting_dual, int iteration_limit, const volatile int32_t* interrupt_solve, SolveLogCpp& solve_log) {
+  PdlpParams phase_params = params_;
+  phase_params.termination_criteria = ReduceWorkLimitsByPreviousWork(params_.termination_criteria, iteration_limit, TotalWorkSoFar(solve_log),
+                                                                     params_.apply_feasibility_polishing_after_limits_reached != 0);
+  if (params_.apply_feasibility_polishing_if_solver_is_interrupted) interrupt_solve = nullptr;
+  // homogeneous bounds now, the original ones after the swap
+  Vec constraint_lower = MapFiniteValuesToZero(WorkingQp().constraint_lower_bounds);
+  Vec constraint_upper = MapFiniteValuesToZero(WorkingQp().constraint_upper_bounds);
+  Vec variable_lower = MapFiniteValuesToZero(WorkingQp().variable_lower_bounds);
+  Vec variable_upper = MapFiniteValuesToZero(WorkingQp().variable_upper_bounds);
+  preprocess_solver_->SwapConstraintBounds(constraint_lower, constraint_upper);
+  preprocess_solver_->SwapVariableBounds(variable_lower, variable_upper);
+  DetailedCriteria criteria = EffectiveOptimalityCriteria(params_.termination_criteria);
+  criteria.primal_abs = criteria.primal_rel = kInf;
+  criteria.gap_abs = criteria.gap_rel = kInf;
+  SetDetailedCriteria(phase_params.termination_criteria, criteria);
+  Vec starting_primal(ShardedWorkingQp().PrimalSize(), 0.0);
+  Solver dual_solver(phase_params, std::move(starting_primal), std::move(starting_dual), step_size_, primal_weight_, preprocess_solver_);
+  SolveLogCpp phase_log;
+  timer_.Stop();
+  SolverResultCpp result = dual_solver.Solve(PDLP_ITERATION_TYPE_DUAL_FEASIBILITY, interrupt_solve, phase_log);
+  timer_.Resume();
+  preprocess_solver_->SwapConstraintBounds(constraint_lower, constraint_upper);
+  preprocess_solver_->SwapVariableBounds(variable_lower, variable_upper);
+  solve_log.feasibility_polishing_details.push_back(
+      BuildFeasibilityPolishingDetails(PDLP_POLISHING_PHASE_TYPE_DUAL_FEASIBILITY, iterations_completed_, phase_params, result.solve_log));
+  return result;
 }
 
 void PreprocessSolver::LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) const {
@@ -910,7 +1161,11 @@ SolverResultCpp PreprocessSolver::ConstructOriginalSolverResult(const PdlpParams
   CoefficientWiseProductInPlace(row_scaling_vec_, sharded_qp_.DualSharder(), result.dual_solution);
   CoefficientWiseQuotientInPlace(col_scaling_vec_, sharded_qp_.PrimalSharder(), result.reduced_costs);
   if (iteration_stats_callback_) {
-    PdlpIterationCallbackInfo info{PDLP_ITERATION_TYPE_NORMAL_TERMINATION, &params.termination_criteria, &result.solve_log.solution_stats, original_bound_norms_};
+    const int termination_type = result.solve_log.solution_type == PDLP_POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION
+                                     ? PDLP_ITERATION_TYPE_FEASIBILITY_POLISHING_TERMINATION
+                                     : (result.solve_log.solution_type == PDLP_POINT_TYPE_PRESOLVER_SOLUTION ? PDLP_ITERATION_TYPE_PRESOLVE_TERMINATION
+                                                                                                            : PDLP_ITERATION_TYPE_NORMAL_TERMINATION);
+    PdlpIterationCallbackInfo info{termination_type, &params.termination_criteria, &result.solve_log.solution_stats, original_bound_norms_};
     iteration_stats_callback_(info);
   }
   if (params.verbosity_level >= 1) {
@@ -970,8 +1225,8 @@ SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const Pdlp
   if (view.objective_scaling_factor == 0) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "The objective scaling factor cannot be zero.", logger);
   if (params.use_feasibility_polishing && view.objective_matrix_diagonal != nullptr)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "use_feasibility_polishing is only implemented for linear programs.", logger);
-  if (params.use_feasibility_polishing || params.presolve_use_glop)
-    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "presolve_options.use_glop and use_feasibility_polishing are host-side features that this build does not provide.", logger);
+  if (params.presolve_use_glop)
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "presolve_options.use_glop is a host-side feature that this build does not provide.", logger);
   if (params.num_random_projection_seeds > PDLP_MAX_RANDOM_PROJECTION_SEEDS)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "at most 8 random_projection_seeds are supported.", logger);
   PreprocessSolver solver(QpFromView(view), params, &logger);
@@ -1016,6 +1271,28 @@ void FillResult(SolverResultCpp&& r, PdlpResult* out) {
     std::memcpy(out->iteration_stats, l.iteration_stats.data(), l.iteration_stats.size() * sizeof(PdlpIterationStats));
   }
   out->params = l.params;
+  out->num_feasibility_polishing_details = static_cast<int64_t>(l.feasibility_polishing_details.size());
+  if (!l.feasibility_polishing_details.empty()) {
+    out->feasibility_polishing_details =
+        static_cast<PdlpFeasibilityPolishingDetails*>(std::calloc(l.feasibility_polishing_details.size(), sizeof(PdlpFeasibilityPolishingDetails)));
+    for (size_t k = 0; k < l.feasibility_polishing_details.size(); ++k) {
+      const PolishingDetailsCpp& d = l.feasibility_polishing_details[k];
+      PdlpFeasibilityPolishingDetails& o = out->feasibility_polishing_details[k];
+      o.polishing_phase_type = d.polishing_phase_type;
+      o.main_iteration_count = d.main_iteration_count;
+      o.params = d.params;
+      o.termination_reason = d.termination_reason;
+      o.iteration_count = d.iteration_count;
+      o.solve_time_sec = d.solve_time_sec;
+      o.solution_stats = d.solution_stats;
+      o.solution_type = d.solution_type;
+      o.num_iteration_stats = static_cast<int64_t>(d.iteration_stats.size());
+      if (!d.iteration_stats.empty()) {
+        o.iteration_stats = static_cast<PdlpIterationStats*>(std::malloc(d.iteration_stats.size() * sizeof(PdlpIterationStats)));
+        std::memcpy(o.iteration_stats, d.iteration_stats.data(), d.iteration_stats.size() * sizeof(PdlpIterationStats));
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -1065,6 +1342,8 @@ void pdlp_oracle_result_free(PdlpResult* r) {
   if (r == nullptr) return;
   std::free(r->primal_solution); std::free(r->dual_solution); std::free(r->reduced_costs);
   std::free(r->instance_name); std::free(r->termination_string); std::free(r->iteration_stats);
+  for (int64_t k = 0; k < r->num_feasibility_polishing_details; ++k) std::free(r->feasibility_polishing_details[k].iteration_stats);
+  std::free(r->feasibility_polishing_details);
   std::memset(r, 0, sizeof(*r));
 }
 
