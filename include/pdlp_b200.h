@@ -137,10 +137,10 @@ typedef struct PdlpParams {
   double diagonal_qp_trust_region_solver_tolerance; /* 1e-8                   */
   int32_t num_random_projection_seeds; /* <= PDLP_MAX_RANDOM_PROJECTION_SEEDS */
   int32_t random_projection_seeds[PDLP_MAX_RANDOM_PROJECTION_SEEDS];
-  /* Host-side features of the reference that this library does not run:
-   * presolve_options.use_glop (tag 16) and feasibility polishing (tags 30,
-   * 33, 34). Setting either yields TERMINATION_REASON_INVALID_PARAMETER with
-   * an explanatory termination_string (never a silent fallback).            */
+  /* presolve_options.use_glop (tag 16) is host-side glop presolve, which this
+   * library does not run: setting it yields TERMINATION_REASON_INVALID_PARAMETER
+   * with an explanatory termination_string (never a silent fallback).
+   * Feasibility polishing (tags 30, 33, 34; LPs only) runs on the device.     */
   int32_t presolve_use_glop;           /* false                               */
   int32_t use_feasibility_polishing;   /* false                               */
   int32_t apply_feasibility_polishing_after_limits_reached;      /* false    */

@@ -9,8 +9,9 @@
 // baseline in bench.py (kind "port"): the reference itself is unbuildable in
 // this image.
 //
-// Not restated (host features outside the hot path): glop presolve
-// and feasibility polishing -> TERMINATION_REASON_INVALID_PARAMETER.
+// Not restated (host feature outside the hot path): glop presolve
+// -> TERMINATION_REASON_INVALID_PARAMETER. Feasibility polishing is restated
+// (pdhg.cc:2676-3015) and pinned by the reference's FeasibilityPolishing tests.
 #include <chrono>
 #include <cstdarg>
 #include <memory>

@@ -266,6 +266,20 @@ def test_all_gather_exchange_protocol_matches_unsharded_iteration_gloo(tmp_path)
 
 
 # ------------------------------------------------------------------ the CUDA path over NCCL
+def _polishing_params():
+    p = pdlp.PrimalDualHybridGradientParams()
+    p.use_feasibility_polishing = True
+    p.handle_some_primal_gradients_on_finite_bounds_as_residuals = False
+    d = p.termination_criteria.detailed_optimality_criteria
+    for f in ("primal_residual", "dual_residual"):
+        setattr(d, "eps_optimal_%s_absolute" % f, 1e-6)
+        setattr(d, "eps_optimal_%s_relative" % f, 1e-6)
+    d.eps_optimal_objective_gap_absolute = 0.2   # loose: the polishing phases start at iteration 400 and finish the solve
+    d.eps_optimal_objective_gap_relative = 0.2
+    p.termination_criteria.iteration_limit = 100000
+    return p
+
+
 def _nccl_worker(rank, world, port, out_dir, exchange):
     import torch
     import torch.distributed as dist
@@ -299,6 +313,11 @@ def _nccl_worker(rank, world, port, out_dir, exchange):
         res = ctx.primal_dual_hybrid_gradient(qp, p)
         out[name + "_x48"] = res.primal_solution
         out[name + "_y48"] = res.dual_solution
+        if name == "c2":  # feasibility polishing phases on the sharded problem
+            res = ctx.primal_dual_hybrid_gradient(qp, _polishing_params())
+            ci = [c for c in res.solve_log.solution_stats.convergence_information if c.candidate_type == res.solve_log.solution_type][0]
+            out["polish_meta"] = np.array([res.solve_log.termination_reason, res.solve_log.solution_type, ci.primal_objective,
+                                           len(res.solve_log.feasibility_polishing_details)])
     np.savez(os.path.join(out_dir, "nccl_rank%d.npz" % rank), **out)
     ctx.close()
     dist.destroy_process_group()
@@ -343,3 +362,14 @@ def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend, exchange):
         for key, ref in (("_x48", one.primal_solution), ("_y48", one.dual_solution)):
             got = parts[0][name + key]
             assert np.linalg.norm(got - ref) <= 1e-9 * max(1.0, np.linalg.norm(ref)), (name, key)
+    # feasibility polishing: same outcome as on one GPU
+    qp, _ = synthetic.CONFIGS["c2"](scale=0.004)
+    one = b200_backend.primal_dual_hybrid_gradient(qp, _polishing_params())
+    ci = [c for c in one.solve_log.solution_stats.convergence_information if c.candidate_type == one.solve_log.solution_type][0]
+    for part in parts:
+        reason, sol_type, pobj, phases = part["polish_meta"]
+        assert int(reason) == one.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+        assert int(sol_type) == one.solve_log.solution_type
+        assert pobj == pytest.approx(ci.primal_objective, rel=2e-3, abs=2e-3)
+        assert int(phases) == len(one.solve_log.feasibility_polishing_details) >= 2
+        assert int(sol_type) == pdlp.PointType.POINT_TYPE_FEASIBILITY_POLISHING_SOLUTION
