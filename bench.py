@@ -219,6 +219,9 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (live CUDA-event samples) -------------------
     peak, peak_src = measured_peak_gbs()
     names = ["k_primal_step", "k_sell<dot>+DualEpi (K x~, dual update)", "k_sell<dot>+KtyEpi (K^T y', nonlinearity)", "k_step_decide"]
+    if world > 1:  # row-sharded: each class includes its part of the fused peer-memory exchange
+        names = ["k_primal_step<PEER> (slice, x~ stores to every arena) + barrier", "k_sell<dot>+DualEpi (row block; y' stores in the all-gather exchange)",
+                 "K^T y' side (barrier + slice product, or partial + barrier + peer pull)", "k_step_decide_peer (scalar slots + barrier)"]
     kern = []
     for i in range(4):
         cnt = st1.kernel_samples[i]
@@ -249,7 +252,8 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args), "rows": m, "cols": n, "nnz": nnz, "step": "one PDHG iteration (restart/termination work included)",
                    "params": "reference defaults, eps_optimal=0 in the resident leg", "l2": "inputs larger than L2 (matrix copies %.0f MB)" % (2 * nnz * 12 / 1e6),
-                   "parallelism": "1 gpu" if world == 1 else "row-sharded x%d" % world},
+                   "parallelism": "1 gpu" if world == 1 else "row-sharded x%d, %s" % (world, {"nccl": "NCCL all-reduce exchange", "peer-s": "peer-memory reduce-scatter exchange", "peer-d": "peer-memory all-gather exchange"}.get(
+                       os.environ.get("PDLP_B200_EXCHANGE", ""), "peer-memory exchange (all-gather if m <= n else reduce-scatter)"))},
         "iterations_timed": iters, "wall_ms_timed": wall_ms, "device_step_loop_ms": step_ms, "setup_s": setup_s,
         "rejected_steps": st1.num_rejected_steps - st0.num_rejected_steps,
         "roofline": roofline, "iteration_roofline": iteration_roofline, "kernels": kern,

@@ -324,6 +324,7 @@ struct PeerPtrs {
   double* base[kMaxPeers];
   int64_t xt_off, partial_off, y_off, scal_off, flags_off, epoch_off, tr_off;
   int64_t row_begin;   // this rank's first position in the box-wide dual order
+  long long timeout_cycles;  // a peer that does not arrive within this many SM clocks halts the loop
   int64_t begin, end;  // this rank's slice of the primal vector (begin is even)
 };
 __device__ __forceinline__ double* peer_base(const PeerPtrs& pp, int h) {
@@ -337,8 +338,8 @@ __device__ __forceinline__ double* peer_base(const PeerPtrs& pp, int h) {
 // part): lane h raises this rank's flag in rank h's arena, then waits for
 // rank h's flag in the local arena. Epochs only grow and every rank runs the
 // same kernel sequence, so a rank is never more than one epoch ahead. A peer
-// that does not arrive within ~4 s of GPU clocks halts the loop with
-// kHaltPeerTimeout instead of hanging the device.
+// that does not arrive within PDLP_B200_PEER_TIMEOUT_S (default 20 s) halts the
+// loop with kHaltPeerTimeout instead of hanging the device.
 __device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int which, int32_t* halt_flag) {
   const int lane = threadIdx.x & 31;
   double* local = peer_base(pp, pp.rank);
@@ -351,7 +352,7 @@ __device__ __forceinline__ void peer_barrier(const PeerPtrs& pp, int which, int3
     volatile unsigned long long* src = reinterpret_cast<unsigned long long*>(local + pp.flags_off) + which * 8 + lane;
     const long long t0 = clock64();
     while (*src < e) {
-      if (clock64() - t0 > 8000000000ll) {
+      if (clock64() - t0 > pp.timeout_cycles) {
         *halt_flag = kHaltPeerTimeout;
         break;
       }
@@ -1751,6 +1752,14 @@ namespace kernels {
 // Elements below `first` are skipped (replicated primal part on ranks > 0).
 static bool TrLegacy();
 static int TrSms();
+static long long PeerTimeoutCycles() {
+  static const long long v = [] {
+    const char* e = std::getenv("PDLP_B200_PEER_TIMEOUT_S");
+    const double seconds = (e != nullptr && *e != 0) ? std::max(0.1, std::atof(e)) : 20.0;
+    return static_cast<long long>(seconds * 1.9e9);  // SM clocks (~1.9 GHz)
+  }();
+  return v;
+}
 static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_global) {
   PeerPtrs pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -1760,6 +1769,7 @@ static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_glob
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(arena->base[h]);
   const PeerLayout l = PeerLayout::For(n, m_global, pp.world);
   pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  pp.timeout_cycles = PeerTimeoutCycles();
   return pp;
 }
 template <class Elem>
@@ -2014,6 +2024,7 @@ static PeerPtrs MakePeerPtrs(const Device::StepBuffers& b) {
   const PeerLayout l = PeerLayout::For(b.n, b.m_global, pp.world);
   pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
   pp.row_begin = b.row_begin;
+  pp.timeout_cycles = PeerTimeoutCycles();
   pp.begin = b.slice_begin;
   pp.end = b.slice_end;
   return pp;
