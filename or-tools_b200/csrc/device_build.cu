@@ -361,10 +361,19 @@ namespace {
 
 inline int Blk(int64_t n, int t = kT) { return static_cast<int>(std::max<int64_t>(1, (n + t - 1) / t)); }
 
+// Persistent arrays of the images: from the stream-ordered pool of the device (see
+// Device::Device) on the stream of the running build; released with cudaFree.
+thread_local cudaStream_t g_build_stream = nullptr;
+struct BuildStreamScope {
+  explicit BuildStreamScope(cudaStream_t s) { g_build_stream = s; }
+  ~BuildStreamScope() { g_build_stream = nullptr; }
+};
 template <class T>
 T* DevAlloc(int64_t count) {
   T* p = nullptr;
-  CUDA_OK(cudaMalloc(&p, sizeof(T) * static_cast<size_t>(std::max<int64_t>(count, 1) + 8)));
+  const size_t bytes = sizeof(T) * static_cast<size_t>(std::max<int64_t>(count, 1) + 8);
+  if (g_build_stream != nullptr) CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&p), bytes, g_build_stream));
+  else CUDA_OK(cudaMalloc(&p, bytes));
   return p;
 }
 
@@ -541,6 +550,7 @@ void Device::BuildSellPair(const PdlpProblemView& v, int64_t row_begin, int64_t 
   const int64_t m = row_end - row_begin;
   const int64_t nnz_full = n > 0 ? v.col_starts[n] : 0;
   const auto t_build_start = std::chrono::steady_clock::now();
+  BuildStreamScope build_scope(stream);
   Temps tmp(stream);
   Scanner scan(stream);
   // ---- upload the raw CSC arrays
@@ -670,6 +680,7 @@ void Device::BuildColumnSliceImage(const PdlpProblemView& v, int64_t col_begin, 
   const int64_t n = col_end - col_begin;
   const int64_t first = n_all > 0 ? v.col_starts[col_begin] : 0;
   const int64_t nnz = n_all > 0 ? v.col_starts[col_end] - first : 0;
+  BuildStreamScope build_scope(stream);
   Temps tmp(stream);
   Scanner scan(stream);
   std::vector<int64_t> rel(n + 1, 0);

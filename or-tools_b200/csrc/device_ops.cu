@@ -1155,6 +1155,17 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   cudaStream_t s;
   CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   stream_ = s;
+  {
+    // Vectors, matrix images and scratch come from the device's stream-ordered pool with a raised
+    // release threshold: after the first solve of a process a new solve maps no fresh device
+    // memory (cudaMalloc / cudaFree of hundreds of MB are the slow driver calls of a solve).
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess) {
+      uint64_t keep = ~uint64_t{0};
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, cuda_device));
   num_sms_ = prop.multiProcessorCount;
@@ -1189,10 +1200,10 @@ Device::~Device() {
 void Device::Sync() { CUDA_OK(cudaStreamSynchronize(STREAM)); }
 double* Device::AllocF64(int64_t n) {
   double* p = nullptr;
-  CUDA_OK(cudaMalloc(&p, sizeof(double) * static_cast<size_t>(std::max<int64_t>(n, 1) + 2)));
+  CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(double) * static_cast<size_t>(std::max<int64_t>(n, 1) + 2), STREAM));
   return p;
 }
-void Device::Free(void* p) { if (p != nullptr) cudaFree(p); }
+void Device::Free(void* p) { if (p != nullptr) cudaFree(p); }  // (cudaFree also returns pool allocations to their pool)
 void Device::Upload(double* dst, const double* src, int64_t n) {
   if (n > 0) { CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, STREAM)); Sync(); }
 }
@@ -1741,7 +1752,7 @@ double* Device::TrScratch(int64_t doubles) {
   if (doubles > tr_scratch_size_) {
     cudaFree(tr_scratch_);
     tr_scratch_ = nullptr;
-    CUDA_OK(cudaMalloc(&tr_scratch_, sizeof(double) * static_cast<size_t>(doubles + 64)));
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&tr_scratch_), sizeof(double) * static_cast<size_t>(doubles + 64), STREAM));
     tr_scratch_size_ = doubles;
   }
   return tr_scratch_;
