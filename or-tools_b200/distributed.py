@@ -1,7 +1,8 @@
 """Row-sharded multi-GPU solve: one process per GPU, launched
 with torchrun; ``torch.distributed`` is only the plumbing that hands the NCCL
-unique id to every rank -- the exchange itself (all-reduce of the K^T y
-partials, scalar reductions) is issued by libpdlp_b200.so on its own stream.
+unique id to every rank -- the exchange itself (peer-memory stores / loads fused
+into the step kernels, or the NCCL all-reduce fallback) is issued
+by libpdlp_b200.so on its own stream.
 """
 import ctypes as C
 import glob
@@ -68,7 +69,7 @@ class Context:
     def primal_dual_hybrid_gradient(self, qp, params, initial_solution=None):
         """Every rank passes the same problem and receives the same SolverResult."""
         view, keep = qp._to_view()
-        pod = params.to_pod() if hasattr(params, "to_pod") else params
+        pod = pdlp.params_to_pod(params)
         x0 = y0 = None
         if initial_solution is not None:
             x0 = capi.as_f64(initial_solution.primal_solution)
@@ -88,7 +89,7 @@ class Context:
         s = pdlp.SolveSession.__new__(pdlp.SolveSession)
         s.b = self.b
         view, keep = qp._to_view()
-        pod = params.to_pod() if hasattr(params, "to_pod") else params
+        pod = pdlp.params_to_pod(params)
         s.h = C.c_void_p()
         rc = self.b.fn("session_create_distributed")(self.h, C.byref(view), C.byref(pod), C.byref(s.h))
         del keep

@@ -308,6 +308,18 @@ class PrimalDualHybridGradientParams(_Message):  # solvers.proto:238-497
         return p
 
 
+def params_to_pod(params):
+    """The C-ABI parameter POD of `params`: a PrimalDualHybridGradientParams of this module, a
+    protobuf PrimalDualHybridGradientParams message (what the reference's wrapper takes,
+    python/pdlp.cc:143-150; see pdlp_proto), or an already built POD."""
+    if hasattr(params, "to_pod"):
+        return params.to_pod()
+    if hasattr(params, "ListFields") and hasattr(params, "DESCRIPTOR"):  # a protobuf message
+        from . import pdlp_proto
+        return pdlp_proto.params_from_proto(params).to_pod()
+    return params
+
+
 # --------------------------------------------------------------------------
 # QuadraticProgram (quadratic_program.h:61-151; python/pdlp.cc:48-85)
 # --------------------------------------------------------------------------
@@ -473,7 +485,7 @@ class Backend:
         return p
 
     def validate_params(self, params):
-        pod = params.to_pod() if hasattr(params, "to_pod") else params
+        pod = params_to_pod(params)
         buf = C.create_string_buffer(1024)
         ok = self.fn("params_validate")(C.byref(pod), buf, C.c_int64(1024))
         return bool(ok), buf.value.decode()
@@ -489,7 +501,7 @@ class Backend:
     def primal_dual_hybrid_gradient(self, qp, params, initial_solution=None, interrupt_solve=None,
                                     message_callback=None, iteration_stats_callback=None):
         view, keep = qp._to_view()
-        pod = params.to_pod() if hasattr(params, "to_pod") else params
+        pod = params_to_pod(params)
         x0 = y0 = None
         if initial_solution is not None:
             x0 = capi.as_f64(initial_solution.primal_solution)
@@ -784,7 +796,7 @@ class SolveSession:
     def __init__(self, backend, qp, params, initial_solution=None, cuda_device=0):
         self.b = backend
         view, keep = qp._to_view()
-        pod = params.to_pod() if hasattr(params, "to_pod") else params
+        pod = params_to_pod(params)
         x0 = y0 = None
         if initial_solution is not None:
             x0 = capi.as_f64(initial_solution.primal_solution)
@@ -847,3 +859,22 @@ def primal_dual_hybrid_gradient(qp, params, initial_solution=None, interrupt_sol
     """
     return backend().primal_dual_hybrid_gradient(qp, params, initial_solution, interrupt_solve,
                                                  message_callback, iteration_stats_callback)
+
+
+# --------------------------------------------------------------------------
+# quadratic_program.h / quadratic_program_io.h functions of the reference's wrapper
+# (python/pdlp.cc:95-126); errors surface as ValueError like std::invalid_argument.
+# --------------------------------------------------------------------------
+def qp_from_mpmodel_proto(proto_str, relax_integer_variables, include_names=False):
+    from . import mp_model
+    return mp_model.qp_from_mp_model_proto(proto_str, relax_integer_variables, include_names)
+
+
+def qp_to_mpmodel_proto(qp):
+    from . import mp_model
+    return mp_model.qp_to_mp_model_proto(qp)
+
+
+def read_quadratic_program_or_die(filename, include_names=False):
+    from . import qp_io
+    return qp_io.read_quadratic_program(filename, include_names)

@@ -1,0 +1,134 @@
+"""The reference's own Python test, ``ortools/pdlp/python/pdlp_test.py:23-250``, against this
+package's module with the same calls (``solvers_pb2`` / ``linear_solver_pb2`` are the runtime
+message classes of ``pdlp_proto`` / ``mp_model``; the solver takes the protobuf parameters
+directly, like the pybind wrapper)."""
+import numpy as np
+import pytest
+import scipy.sparse
+
+from ortools_b200 import mp_model, pdlp, pdlp_proto
+
+TR = pdlp.TerminationReason
+
+
+def small_proto_lp():  # pdlp_test.py:26-49: min -2y s.t. x + y <= 1, x, y >= 0
+    m = mp_model.MPModelProto(maximize=False, objective_offset=0.0)
+    m.variable.add(lower_bound=0, upper_bound=np.inf, objective_coefficient=0, name="x")
+    m.variable.add(lower_bound=0, upper_bound=np.inf, objective_coefficient=-2, name="y")
+    m.constraint.add(var_index=[0, 1], coefficient=[1, 1], lower_bound=-np.inf, upper_bound=1)
+    return m
+
+
+def small_proto_qp():  # pdlp_test.py:52-76: min 2 x*x s.t. x + y <= 1, x, y >= 0
+    m = mp_model.MPModelProto(maximize=False, objective_offset=0.0)
+    m.variable.add(lower_bound=0, upper_bound=np.inf, objective_coefficient=0, name="x")
+    m.variable.add(lower_bound=0, upper_bound=np.inf, objective_coefficient=0, name="y")
+    m.constraint.add(var_index=[0, 1], coefficient=[1, 1], lower_bound=-np.inf, upper_bound=1)
+    m.quadratic_objective.qvar1_index.append(0)
+    m.quadratic_objective.qvar2_index.append(0)
+    m.quadratic_objective.coefficient.append(2)
+    return m
+
+
+def test_validate_quadratic_program_dimensions_for_empty_qp():  # :81-85
+    qp = pdlp.QuadraticProgram()
+    qp.resize_and_initialize(3, 2)
+    pdlp.validate_quadratic_program_dimensions(qp)
+    assert pdlp.is_linear_program(qp)
+
+
+def test_converts_from_tiny_mpmodel_lp_and_qp():  # :86-98
+    qp = pdlp.qp_from_mpmodel_proto(small_proto_lp(), relax_integer_variables=False)
+    pdlp.validate_quadratic_program_dimensions(qp)
+    assert pdlp.is_linear_program(qp)
+    assert sorted(qp.objective_vector) == [-2, 0]
+    qp = pdlp.qp_from_mpmodel_proto(small_proto_qp(), relax_integer_variables=False)
+    pdlp.validate_quadratic_program_dimensions(qp)
+    assert not pdlp.is_linear_program(qp)
+    assert list(qp.objective_vector) == [0, 0]
+
+
+def _build(objective, diagonal=None):
+    qp = pdlp.QuadraticProgram()
+    qp.objective_vector = objective
+    qp.constraint_matrix = scipy.sparse.csr_matrix(np.array([[1.0, 1.0]]))
+    if diagonal is not None:
+        qp.set_objective_matrix_diagonal(diagonal)
+    qp.constraint_lower_bounds = [-np.inf]
+    qp.constraint_upper_bounds = [1.0]
+    qp.variable_lower_bounds = [0.0, 0.0]
+    qp.variable_upper_bounds = [np.inf, np.inf]
+    qp.variable_names = ["x", "y"]
+    return qp
+
+
+def test_build_lp_and_qp():  # :100-127
+    assert pdlp.qp_to_mpmodel_proto(_build([0, -2])) == small_proto_lp()
+    assert pdlp.qp_to_mpmodel_proto(_build([0, 0], [4.0])) == small_proto_qp()
+
+
+def tiny_lp():  # :130-157, optimum x = [1, 0, 6, 2], y = [0.5, 4, 0], reduced costs [0, 1.5, -3.5, 0]
+    qp = pdlp.QuadraticProgram()
+    qp.objective_offset = -14
+    qp.objective_vector = [5, 2, 1, 1]
+    qp.constraint_lower_bounds = [12, 7, 1]
+    qp.constraint_upper_bounds = [12, np.inf, np.inf]
+    qp.variable_lower_bounds = np.zeros(4)
+    qp.variable_upper_bounds = [2, 4, 6, 3]
+    qp.constraint_matrix = scipy.sparse.csr_matrix(np.array([[2, 1, 1, 2], [1, 0, 1, 0], [0, 0, 1, -1]]))
+    return qp
+
+
+def small_lp():  # :160-188, optimum x = [-1, 8, 1, 2.5], y = [-2, 0, 2.375, 2/3]
+    qp = pdlp.QuadraticProgram()
+    qp.objective_offset = -14
+    qp.objective_vector = [5.5, -2, -1, 1]
+    qp.constraint_lower_bounds = [12, -np.inf, -4, -1]
+    qp.constraint_upper_bounds = [12, 7, np.inf, 1]
+    qp.variable_lower_bounds = [-np.inf, -2, -np.inf, 2.5]
+    qp.variable_upper_bounds = [np.inf, np.inf, 6, 3.5]
+    qp.constraint_matrix = scipy.sparse.csr_matrix(np.array([[2, 1, 1, 2], [1, 0, 1, 0], [4, 0, 0, 0], [0, 0, 1.5, -1]]))
+    return qp
+
+
+def _tight_params():
+    params = pdlp_proto.PrimalDualHybridGradientParamsProto()   # solvers_pb2.PrimalDualHybridGradientParams()
+    params.termination_criteria.simple_optimality_criteria.eps_optimal_relative = 0.0
+    params.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = 1.0e-10
+    return params
+
+
+def test_iteration_limit(backend):  # :193-202
+    params = pdlp_proto.PrimalDualHybridGradientParamsProto()
+    params.termination_criteria.iteration_limit = 1
+    params.termination_check_frequency = 1
+    result = backend.primal_dual_hybrid_gradient(tiny_lp(), params)
+    assert result.solve_log.iteration_count <= 1
+    assert result.solve_log.termination_reason == TR.TERMINATION_REASON_ITERATION_LIMIT
+
+
+def test_solution(backend):  # :204-216 (assertSequenceAlmostEqual: 7 places)
+    result = backend.primal_dual_hybrid_gradient(tiny_lp(), _tight_params())
+    assert result.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+    np.testing.assert_allclose(result.primal_solution, [1.0, 0.0, 6.0, 2.0], atol=5e-8)
+    np.testing.assert_allclose(result.dual_solution, [0.5, 4.0, 0.0], atol=5e-8)
+    np.testing.assert_allclose(result.reduced_costs, [0.0, 1.5, -3.5, 0.0], atol=5e-8)
+
+
+def test_solution_2(backend):  # :218-229
+    result = backend.primal_dual_hybrid_gradient(small_lp(), _tight_params())
+    assert result.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+    np.testing.assert_allclose(result.primal_solution, [-1, 8, 1, 2.5], atol=5e-8)
+    np.testing.assert_allclose(result.dual_solution, [-2, 0, 2.375, 2 / 3], atol=5e-8)
+
+
+def test_starting_point(backend):  # :231-250
+    params = _tight_params()
+    params.l_inf_ruiz_iterations = 0
+    params.l2_norm_rescaling = False
+    start = pdlp.PrimalAndDualSolution()
+    start.primal_solution = [1.0, 0.0, 6.0, 2.0]
+    start.dual_solution = [0.5, 4.0, 0.0]
+    result = backend.primal_dual_hybrid_gradient(tiny_lp(), params, initial_solution=start)
+    assert result.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+    assert result.solve_log.iteration_count == 0
