@@ -1,8 +1,9 @@
-// Solves a simple LP with the C++ face of libpdlp_b200 -- the counterpart of
-// ortools/pdlp/samples/simple_pdlp_program.cc (same LP, same parameters, same output):
+// A four-variable LP solved on the GPU through include/pdlp_b200.hpp. It plays the role of the
+// reference's direct-API sample (ortools/pdlp/samples/simple_pdlp_program.cc): same problem and
+// parameter choices, same report, so the two outputs can be compared line by line.
 //
-//   g++ -std=c++17 -Iinclude examples/simple_pdlp_program.cc -Lor-tools_b200/lib -lpdlp_b200
-//       -Wl,-rpath,$PWD/or-tools_b200/lib -o simple_pdlp_program && ./simple_pdlp_program
+//   g++ -std=c++17 -Iinclude examples/solve_simple_lp.cc -Lor-tools_b200/lib -lpdlp_b200
+//       -Wl,-rpath,$PWD/or-tools_b200/lib -o solve_simple_lp && ./solve_simple_lp
 #include <iostream>
 #include <optional>
 #include <vector>
@@ -12,13 +13,13 @@
 namespace pdlp = ::pdlp_b200;
 using pdlp::kInfinity;
 
-// min 5.5 x_0 - 2 x_1 - x_2 +   x_3 - 14 s.t.
-//     2 x_0 +     x_1 +   x_2 + 2 x_3  = 12
-//       x_0 +             x_2          <=  7
-//     4 x_0                            >=  -4
-//    -1 <=            1.5 x_2 -   x_3  <= 1
-//   -infinity <= x_0 <= infinity,  -2 <= x_1 <= infinity,  -infinity <= x_2 <= 6,  2.5 <= x_3 <= 3.5
-pdlp::QuadraticProgram SimpleLp() {
+// minimise c'x - 14 with c = (5.5, -2, -1, 1) subject to l_c <= K x <= u_c, l_v <= x <= u_v where
+//       | 2  1  1    2 |        l_c = (12, -inf, -4, -1)     l_v = (-inf, -2, -inf, 2.5)
+//   K = | 1  0  1    0 |        u_c = (12,    7, inf,  1)     u_v = ( inf, inf,    6, 3.5)
+//       | 4  0  0    0 |
+//       | 0  0  1.5 -1 |
+// (the TestLp of the reference's test_util.cc; optimum x = (-1, 8, 1, 2.5), objective -34).
+pdlp::QuadraticProgram FourVariableLp() {
   pdlp::QuadraticProgram lp(4, 4);
   lp.constraint_lower_bounds = {12, -kInfinity, -4, -1};
   lp.constraint_upper_bounds = {12, 7, kInfinity, 1};
@@ -37,14 +38,14 @@ static void Print(const char* title, const std::vector<double>& v) {
 
 int main() {
   pdlp::PrimalDualHybridGradientParams params;
-  // Some common parameters to modify. Here, we just re-assign the defaults.
+  // The knobs callers usually touch, set to their default values.
   params.SetSimpleOptimalityCriteria(/*eps_optimal_absolute=*/1.0e-6, /*eps_optimal_relative=*/1.0e-6);
   params.termination_criteria.time_sec_limit = kInfinity;
   params.num_threads = 1;
   params.verbosity_level = 0;
   params.presolve_use_glop = 0;
 
-  const pdlp::SolverResult result = pdlp::PrimalDualHybridGradient(SimpleLp(), params);
+  const pdlp::SolverResult result = pdlp::PrimalDualHybridGradient(FourVariableLp(), params);
   const pdlp::SolveLog& solve_log = result.solve_log;
 
   if (solve_log.termination_reason == PDLP_TERMINATION_REASON_OPTIMAL) {
@@ -53,8 +54,8 @@ int main() {
     std::cout << "Solve not successful. Status: " << pdlp::TerminationReason_Name(solve_log.termination_reason) << '\n';
     if (solve_log.termination_string) std::cout << *solve_log.termination_string << '\n';
   }
-  // Solution vectors are always returned; their interpretation depends on termination_reason
-  // (primal_dual_hybrid_gradient.h:36-71).
+  // The three vectors are filled whatever the outcome; what they mean depends on the
+  // termination reason (primal_dual_hybrid_gradient.h:36-71).
   Print("Primal solution:", result.primal_solution);
   Print("Dual solution:", result.dual_solution);
   Print("Reduced costs:", result.reduced_costs);

@@ -7,7 +7,7 @@
 //   ortools/pdlp/primal_dual_hybrid_gradient.h:36-169-> pdlp_b200::SolverResult, PrimalDualHybridGradient(...)
 //   ortools/pdlp/iteration_stats.h (GetConvergenceInformation), *_Name() of the generated enums
 //
-// examples/simple_pdlp_program.cc is ortools/pdlp/samples/simple_pdlp_program.cc written
+// examples/solve_simple_lp.cc is ortools/pdlp/samples/simple_pdlp_program.cc written
 // against this header. Link with -lpdlp_b200 (or-tools_b200/lib). There is no CPU fallback:
 // without a usable GPU the result carries TERMINATION_REASON_OTHER and an explanatory string.
 #ifndef PDLP_B200_HPP_

@@ -16,8 +16,8 @@ def example_binary(tmp_path_factory):
     if not os.path.exists(os.path.join(LIB_DIR, "libpdlp_b200.so")):
         import __graft_entry__
         __graft_entry__.build()
-    out = str(tmp_path_factory.mktemp("cpp") / "simple_pdlp_program")
-    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "simple_pdlp_program.cc"),
+    out = str(tmp_path_factory.mktemp("cpp") / "solve_simple_lp")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "solve_simple_lp.cc"),
                            "-L" + LIB_DIR, "-lpdlp_b200", "-Wl,-rpath," + LIB_DIR, "-o", out])
     return out
 
