@@ -500,6 +500,11 @@ int32_t pdlp_b200_compute_localized_lagrangian_bounds(
     double radius, const double* primal_product, const double* dual_product,
     int32_t use_diagonal_qp_trust_region_solver,
     double diagonal_qp_trust_region_solver_tolerance, double out[4]);
+/* The same with PrimalDualNorm::kMaxNorm (trust_region.cc:855-884): primal and
+ * dual trust-region problems solved separately. Not used by the solver.      */
+int32_t pdlp_b200_compute_localized_lagrangian_bounds_max_norm(
+    PdlpDeviceProblem* problem, const double* primal, const double* dual, double primal_weight,
+    double radius, const double* primal_product, const double* dual_product, double out[4]);
 /* SolveTrustRegion (trust_region.h:58-64): explicit-vector problem of size
  * `size`. Writes solution[size], *step_size, *objective_value.               */
 int32_t pdlp_b200_solve_trust_region(int32_t cuda_device, int64_t size,

@@ -494,6 +494,16 @@ int32_t pdlp_b200_compute_localized_lagrangian_bounds(PdlpDeviceProblem* h, cons
   });
 }
 
+int32_t pdlp_b200_compute_localized_lagrangian_bounds_max_norm(PdlpDeviceProblem* h, const double* primal, const double* dual, double primal_weight,
+                                                               double radius, const double* primal_product, const double* dual_product, double out[4]) {
+  return Guard([&] {
+    DeviceProblem& p = *h->p;
+    PrimalVec x(p, primal), dp(p, dual_product);
+    DualVec y(p, dual), pp(p, primal_product);
+    p.ComputeLocalizedLagrangianBoundsMaxNorm(x.d, y.d, primal_weight, radius, primal_product ? pp.d : nullptr, dual_product ? dp.d : nullptr, out);
+  });
+}
+
 // ---- problem-free vector entry points ---------------------------------------
 int32_t pdlp_b200_solve_trust_region(int32_t cuda_device, int64_t size, const double* objective, const double* lb, const double* ub,
                                      const double* center, const double* weights, double target_radius, double* solution, double* step_size,

@@ -1473,6 +1473,13 @@ void Device::ReplaceLargeWithInf(double* v, double threshold, int64_t n) {
   ELEMENTWISE(n, { if (v[i] <= -threshold) v[i] = -kInfD; if (v[i] >= threshold) v[i] = kInfD; });
 }
 void Device::MapFiniteValuesToZero(double* dst, const double* src, int64_t n) { ELEMENTWISE(n, { dst[i] = isfinite(src[i]) ? 0.0 : src[i]; }); }
+void Device::DualTrustRegionProblem(const double* g, const double* lc, const double* uc, double* objective, double* lb, double* ub, int64_t m) {
+  ELEMENTWISE(m, {
+    objective[i] = -g[i];
+    lb[i] = isfinite(uc[i]) ? -kInfD : 0.0;
+    ub[i] = isfinite(lc[i]) ? kInfD : 0.0;
+  });
+}
 void Device::ClampPrimal(double* x, const double* lb, const double* ub, bool feas, int64_t n) {
   ELEMENTWISE(n, {
     double u = ub[i], l = lb[i];

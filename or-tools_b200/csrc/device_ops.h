@@ -232,6 +232,9 @@ class Device {
   void Sub(double* dst, const double* a, const double* b, int64_t n);                 // dst = a - b
   void ReplaceLargeWithInf(double* v, double threshold, int64_t n);
   void MapFiniteValuesToZero(double* dst, const double* src, int64_t n);             // pdhg.cc:2940-2949
+  // DualTrustRegionProblem (trust_region.h:386-417): objective = -gradient, y_i >= 0 unless the
+  // constraint has a finite upper bound, y_i <= 0 unless it has a finite lower bound.
+  void DualTrustRegionProblem(const double* dual_gradient, const double* lc, const double* uc, double* objective, double* lb, double* ub, int64_t m);
   void ClampPrimal(double* x, const double* lb, const double* ub, bool feasibility_bounds, int64_t n);
   void ClampDual(double* y, const double* lc, const double* uc, int64_t m);
   void WeightedAverageAdd(double* avg, const double* v, double ratio, int64_t n);     // avg += ratio*(v-avg)

@@ -372,6 +372,27 @@ void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const doub
   out[0] = r3[0]; out[1] = r3[1]; out[2] = r3[2]; out[3] = radius;
 }
 
+void DeviceProblem::ComputeLocalizedLagrangianBoundsMaxNorm(const double* x, const double* y, double primal_weight, double radius, const double* kx,
+                                                            const double* kty, double out[4]) {
+  if (sharded()) throw std::runtime_error("max-norm localized Lagrangian bounds are not available on a row-sharded problem");
+  Device& d = *dev_;
+  if (kx == nullptr) { Kx(x, tmp_m_[2]); kx = tmp_m_[2]; }
+  if (kty == nullptr) { KTy(y, tmp_n_[2]); kty = tmp_n_[2]; }
+  double* gx = tmp_n_[0];
+  double* gy = tmp_m_[0];
+  const double primal_value = d.LagrangianPrimalGradient(x, kty, c_, q_, gx, n_);
+  const double dual_value = d.LagrangianDualGradient(y, kx, lc_, uc_, gy, m_);
+  const double lagrangian = primal_value + dual_value;
+  double step = 0.0, primal_objective = 0.0, dual_objective = 0.0;
+  d.SolveTrustRegion(gx, lv_, uv_, x, ones_n_, std::sqrt(2.0) * radius / std::sqrt(primal_weight), n_, tmp_n_[1], &step, &primal_objective);
+  d.DualTrustRegionProblem(gy, lc_, uc_, tmp_m_[1], tmp_m_[2], tmp_m_[3], m_);
+  d.SolveTrustRegion(tmp_m_[1], tmp_m_[2], tmp_m_[3], y, ones_m_, std::sqrt(2.0) * radius * std::sqrt(primal_weight), m_, tmp_m_[0], &step, &dual_objective);
+  out[0] = lagrangian;
+  out[1] = lagrangian + primal_objective;
+  out[2] = lagrangian - dual_objective;
+  out[3] = radius;
+}
+
 void DeviceProblem::DownloadValuesCsc(double* values) {
   if (sharded()) throw std::runtime_error("DownloadValuesCsc is not available on a row-sharded problem");
   if (device_built_) { dev_->DownloadValuesCscFromSell(cols_, build_info_, values); return; }

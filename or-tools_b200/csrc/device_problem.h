@@ -110,6 +110,12 @@ class DeviceProblem {
   void ComputeLocalizedLagrangianBounds(const double* x, const double* y, double primal_weight, double radius, const double* kx,
                                         const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4]);
 
+  // trust_region.cc:855-884 (max norm): the primal and the dual trust-region problems are solved
+  // separately with radii sqrt(2) r / sqrt(w) and sqrt(2) r sqrt(w). Not used by the solver
+  // (pdhg.cc asks for the Euclidean norm); single GPU only.
+  void ComputeLocalizedLagrangianBoundsMaxNorm(const double* x, const double* y, double primal_weight, double radius, const double* kx,
+                                               const double* kty, double out[4]);
+
   // download of the (possibly rescaled) problem in the caller's CSC order
   void DownloadValuesCsc(double* values);
 

@@ -720,8 +720,9 @@ class DeviceProblem:
                 C.c_int32(int(use_diagonal_qp_trust_region_solver)), C.c_double(diagonal_qp_trust_region_solver_tolerance)]
         if self.b.prefix == "pdlp_oracle_":
             args.append(C.c_int32(1 if max_norm else 0))
-        elif max_norm:
-            raise NotImplementedError("the device path implements the Euclidean norm used by the solver")
+        elif max_norm:  # PrimalDualNorm::kMaxNorm has its own entry point on the device library
+            self._call("compute_localized_lagrangian_bounds_max_norm", *args[:6], out)
+            return types.SimpleNamespace(lagrangian_value=out[0], lower_bound=out[1], upper_bound=out[2], radius=out[3])
         self._call("compute_localized_lagrangian_bounds", *args, out)
         return types.SimpleNamespace(lagrangian_value=out[0], lower_bound=out[1], upper_bound=out[2], radius=out[3])
 

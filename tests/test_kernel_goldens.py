@@ -595,3 +595,21 @@ def test_localized_bounds_one_dim_qp_diagonal_solver(backend):
                                               diagonal_qp_trust_region_solver_tolerance=1e-6)
     assert b.lagrangian_value == approx(-1.0)
     assert b.lower_bound == pytest.approx(-1.75, abs=1e-5) and b.upper_bound == pytest.approx(-0.5, abs=1e-5)
+
+
+def test_localized_bounds_max_norm(backend):
+    # PrimalDualNorm::kMaxNorm (trust_region.cc:855-884): trust_region_test.cc:617-636 (zero gap at the
+    # optimum), :675-712 (closed form), :884-963 (one-dimensional LP, primal weights 1 and 100)
+    p = mk(backend, fx.test_lp())
+    b = p.compute_localized_lagrangian_bounds([-1.0, 8.0, 1.0, 2.5], [-2.0, 0.0, 2.375, 2.0 / 3.0], 1.0, 1.0, max_norm=True)
+    assert b.lagrangian_value == approx(-20.0)
+    assert b.lower_bound == pytest.approx(-20.0, abs=1e-9) and b.upper_bound == pytest.approx(-20.0, abs=1e-9)
+    b = p.compute_localized_lagrangian_bounds([0.0, 0.0, 0.0, 3.0], np.zeros(4), 1.0, 0.1, max_norm=True)
+    assert b.lagrangian_value == approx(3.0)
+    assert b.lower_bound == pytest.approx(3.0 - 0.1 * math.sqrt(2) * math.sqrt(36.25), abs=1e-6)
+    assert b.upper_bound == pytest.approx(3.0 + 0.1 * math.sqrt(2) * math.sqrt(40.0), abs=1e-6)
+    q = mk(backend, fx.one_dim_lp())
+    b = q.compute_localized_lagrangian_bounds([0.0], [-1.0], 1.0, 1.0 / math.sqrt(2.0), max_norm=True)
+    assert b.lagrangian_value == approx(-1.0) and b.lower_bound == approx(-3.0) and b.upper_bound == approx(0.0)
+    b = q.compute_localized_lagrangian_bounds([0.0], [-1.0], 100.0, 1.0 / math.sqrt(2.0), max_norm=True)
+    assert b.lower_bound == approx(-1.2) and b.upper_bound == approx(9.0)
