@@ -505,6 +505,33 @@ int32_t pdlp_b200_compute_localized_lagrangian_bounds(
 int32_t pdlp_b200_compute_localized_lagrangian_bounds_max_norm(
     PdlpDeviceProblem* problem, const double* primal, const double* dual, double primal_weight,
     double radius, const double* primal_product, const double* dual_product, double out[4]);
+/* ---- termination.h (host-only scalar logic; no device needed) ------------- *
+ * CheckSimpleTerminationCriteria / CheckIterateTerminationCriteria
+ * (termination.cc:161-219): return 1 and fill *reason / *point_type when a
+ * criterion fires, else 0. OptimalityCriteriaMet / ObjectiveGapMet (:26-97),
+ * EffectiveOptimalityCriteria (:126-159; out = {primal abs, rel, dual abs, rel,
+ * gap abs, rel}), ComputeRelativeResiduals (:239-271; out = {l_inf primal, l2
+ * primal, l_inf dual, l2 dual, optimality gap}), BoundNormsFromProblemStats
+ * (:221-228).                                                                */
+int32_t pdlp_b200_check_simple_termination_criteria(const PdlpTerminationCriteria* criteria,
+                                                    const PdlpIterationStats* stats,
+                                                    const volatile int32_t* interrupt_solve,
+                                                    int32_t* reason, int32_t* point_type);
+int32_t pdlp_b200_check_iterate_termination_criteria(const PdlpTerminationCriteria* criteria,
+                                                     const PdlpIterationStats* stats,
+                                                     const PdlpBoundNorms* bound_norms,
+                                                     int32_t force_numerical_termination,
+                                                     int32_t* reason, int32_t* point_type);
+int32_t pdlp_b200_optimality_criteria_met(const PdlpTerminationCriteria* criteria,
+                                          const PdlpConvergenceInformation* stats,
+                                          const PdlpBoundNorms* bound_norms,
+                                          int32_t* objective_gap_met);
+void pdlp_b200_effective_optimality_criteria(const PdlpTerminationCriteria* criteria, double out[6]);
+void pdlp_b200_compute_relative_residuals(const PdlpTerminationCriteria* criteria,
+                                          const PdlpConvergenceInformation* stats,
+                                          const PdlpBoundNorms* bound_norms, double out[5]);
+void pdlp_b200_bound_norms_from_problem_stats(const PdlpQuadraticProgramStats* stats,
+                                              PdlpBoundNorms* out);
 /* SolveTrustRegion (trust_region.h:58-64): explicit-vector problem of size
  * `size`. Writes solution[size], *step_size, *objective_value.               */
 int32_t pdlp_b200_solve_trust_region(int32_t cuda_device, int64_t size,

@@ -128,6 +128,18 @@ PdlpBoundNorms BoundNormsFromProblemStats(const PdlpQuadraticProgramStats& s) { 
   return {s.objective_vector_l2_norm, s.combined_bounds_l2_norm, s.objective_vector_abs_max, s.combined_bounds_max};
 }
 
+struct RelativeResiduals { double l_inf_primal, l2_primal, l_inf_dual, l2_dual, gap; };
+RelativeResiduals ComputeRelativeResiduals(const DetailedCriteria& oc, const PdlpConvergenceInformation& s, const PdlpBoundNorms& bn) {  // termination.cc:239-271
+  const double rp = EpsilonRatio(oc.primal_abs, oc.primal_rel), rd = EpsilonRatio(oc.dual_abs, oc.dual_rel), rg = EpsilonRatio(oc.gap_abs, oc.gap_rel);
+  RelativeResiduals r;
+  r.l_inf_primal = s.l_inf_primal_residual / (rp + bn.l_inf_norm_constraint_bounds);
+  r.l2_primal = s.l2_primal_residual / (rp + bn.l2_norm_constraint_bounds);
+  r.l_inf_dual = s.l_inf_dual_residual / (rd + bn.l_inf_norm_primal_linear_objective);
+  r.l2_dual = s.l2_dual_residual / (rd + bn.l2_norm_primal_linear_objective);
+  r.gap = (s.primal_objective - s.dual_objective) / (rg + std::abs(s.primal_objective) + std::abs(s.dual_objective));
+  return r;
+}
+
 const PdlpConvergenceInformation* GetConvergenceInformation(const PdlpIterationStats& s, int type) {
   for (int i = 0; i < s.num_convergence_information; ++i)
     if (s.convergence_information[i].candidate_type == type) return &s.convergence_information[i];
@@ -154,19 +166,16 @@ void LogIterationStats(int verbosity, const PdlpIterationStats& st, const PdlpTe
   if (verbosity >= 4)
     tag = ci->candidate_type == PDLP_POINT_TYPE_CURRENT_ITERATE ? "C " : ci->candidate_type == PDLP_POINT_TYPE_AVERAGE_ITERATE ? "A "
         : ci->candidate_type == PDLP_POINT_TYPE_ITERATE_DIFFERENCE ? "D " : "? ";
-  // ComputeRelativeResiduals, termination.cc:239-271
-  const DetailedCriteria oc = EffectiveOptimalityCriteria(tc);
-  const double rp = EpsilonRatio(oc.primal_abs, oc.primal_rel), rd = EpsilonRatio(oc.dual_abs, oc.dual_rel), rg = EpsilonRatio(oc.gap_abs, oc.gap_rel);
-  const double abs_obj = std::abs(ci->primal_objective) + std::abs(ci->dual_objective);
-  const double rel_gap = (ci->primal_objective - ci->dual_objective) / (rg + abs_obj);
+  const RelativeResiduals rr = ComputeRelativeResiduals(EffectiveOptimalityCriteria(tc), *ci, bn);
+  const double rel_gap = rr.gap;
   double relp, reld, absp, absd;
   if (tc.optimality_norm == PDLP_OPTIMALITY_NORM_L_INF) {
-    relp = ci->l_inf_primal_residual / (rp + bn.l_inf_norm_constraint_bounds); reld = ci->l_inf_dual_residual / (rd + bn.l_inf_norm_primal_linear_objective);
+    relp = rr.l_inf_primal; reld = rr.l_inf_dual;
     absp = ci->l_inf_primal_residual; absd = ci->l_inf_dual_residual;
   } else if (tc.optimality_norm == PDLP_OPTIMALITY_NORM_L_INF_COMPONENTWISE) {
     relp = ci->l_inf_componentwise_primal_residual; reld = ci->l_inf_componentwise_dual_residual; absp = ci->l_inf_primal_residual; absd = ci->l_inf_dual_residual;
   } else {
-    relp = ci->l2_primal_residual / (rp + bn.l2_norm_constraint_bounds); reld = ci->l2_dual_residual / (rd + bn.l2_norm_primal_linear_objective);
+    relp = rr.l2_primal; reld = rr.l2_dual;
     absp = ci->l2_primal_residual; absd = ci->l2_dual_residual;
   }
   const std::string conv = verbosity >= 3
@@ -1478,5 +1487,44 @@ SolverResultCpp SolveSession::Finish() {
   SolverResultCpp r = im.solve->ConstructOriginalSolverResult(*im.finished);
   return r;
 }
+
+// ---- termination.h as host-only C entry points (no device needed): the scalar predicates the
+// solve loop uses, exported so that the reference's termination_test known answers run against
+// this library's own code.
+extern "C" {
+int32_t pdlp_b200_check_simple_termination_criteria(const PdlpTerminationCriteria* criteria, const PdlpIterationStats* stats,
+                                                    const volatile int32_t* interrupt_solve, int32_t* reason, int32_t* point_type) {
+  const auto r = CheckSimpleTerminationCriteria(*criteria, *stats, interrupt_solve != nullptr && *interrupt_solve != 0);
+  if (!r.has_value()) return 0;
+  *reason = r->reason;
+  *point_type = r->type;
+  return 1;
+}
+int32_t pdlp_b200_check_iterate_termination_criteria(const PdlpTerminationCriteria* criteria, const PdlpIterationStats* stats,
+                                                     const PdlpBoundNorms* bound_norms, int32_t force_numerical_termination, int32_t* reason,
+                                                     int32_t* point_type) {
+  const auto r = CheckIterateTerminationCriteria(*criteria, *stats, *bound_norms, force_numerical_termination != 0);
+  if (!r.has_value()) return 0;
+  *reason = r->reason;
+  *point_type = r->type;
+  return 1;
+}
+int32_t pdlp_b200_optimality_criteria_met(const PdlpTerminationCriteria* criteria, const PdlpConvergenceInformation* stats,
+                                          const PdlpBoundNorms* bound_norms, int32_t* objective_gap_met) {
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(*criteria);
+  if (objective_gap_met != nullptr) *objective_gap_met = ObjectiveGapMet(oc, *stats) ? 1 : 0;
+  return OptimalityCriteriaMet(oc, *stats, criteria->optimality_norm, *bound_norms) ? 1 : 0;
+}
+void pdlp_b200_effective_optimality_criteria(const PdlpTerminationCriteria* criteria, double out[6]) {
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(*criteria);
+  out[0] = oc.primal_abs; out[1] = oc.primal_rel; out[2] = oc.dual_abs; out[3] = oc.dual_rel; out[4] = oc.gap_abs; out[5] = oc.gap_rel;
+}
+void pdlp_b200_compute_relative_residuals(const PdlpTerminationCriteria* criteria, const PdlpConvergenceInformation* stats,
+                                          const PdlpBoundNorms* bound_norms, double out[5]) {
+  const RelativeResiduals r = ComputeRelativeResiduals(EffectiveOptimalityCriteria(*criteria), *stats, *bound_norms);
+  out[0] = r.l_inf_primal; out[1] = r.l2_primal; out[2] = r.l_inf_dual; out[3] = r.l2_dual; out[4] = r.gap;
+}
+void pdlp_b200_bound_norms_from_problem_stats(const PdlpQuadraticProgramStats* stats, PdlpBoundNorms* out) { *out = BoundNormsFromProblemStats(*stats); }
+}  // extern "C"
 
 }  // namespace pdlp_b200

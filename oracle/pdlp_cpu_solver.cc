@@ -1607,6 +1607,16 @@ int32_t pdlp_oracle_compute_relative_residuals(const PdlpTerminationCriteria* c,
   out[3] = r.relative_l2_dual_residual; out[4] = r.relative_optimality_gap;
   return 0;
 }
+int32_t pdlp_oracle_optimality_criteria_met(const PdlpTerminationCriteria* c, const PdlpConvergenceInformation* s, const PdlpBoundNorms* bn,
+                                            int32_t* objective_gap_met) {
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(*c);
+  if (objective_gap_met != nullptr) *objective_gap_met = ObjectiveGapMet(oc, *s) ? 1 : 0;
+  return OptimalityCriteriaMet(oc, *s, c->optimality_norm, *bn) ? 1 : 0;
+}
+void pdlp_oracle_effective_optimality_criteria(const PdlpTerminationCriteria* c, double out[6]) {
+  const DetailedCriteria oc = EffectiveOptimalityCriteria(*c);
+  out[0] = oc.primal_abs; out[1] = oc.primal_rel; out[2] = oc.dual_abs; out[3] = oc.dual_rel; out[4] = oc.gap_abs; out[5] = oc.gap_rel;
+}
 void pdlp_oracle_bound_norms_from_problem_stats(const PdlpQuadraticProgramStats* s, PdlpBoundNorms* out) { *out = BoundNormsFromProblemStats(*s); }
 
 const char* pdlp_oracle_version(void) { return "pdlp-oracle 0.1 (CPU restatement of or-tools 9.15 ortools/pdlp)"; }
