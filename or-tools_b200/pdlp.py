@@ -499,7 +499,9 @@ class Backend:
         return self.fn("primal_dual_hybrid_gradient"), ()
 
     def primal_dual_hybrid_gradient(self, qp, params, initial_solution=None, interrupt_solve=None,
-                                    message_callback=None, iteration_stats_callback=None):
+                                    message_callback=None, iteration_stats_callback=None, result_pod_consumer=None):
+        """`result_pod_consumer(res)`: called with the raw PdlpResult before it is released
+        (e.g. native_io.solve_log_serialize)."""
         view, keep = qp._to_view()
         pod = params_to_pod(params)
         x0 = y0 = None
@@ -531,6 +533,8 @@ class Backend:
         del keep
         self._check(rc, "primal_dual_hybrid_gradient")
         try:
+            if result_pod_consumer is not None:
+                result_pod_consumer(res)
             return self._result_from_pod(res)
         finally:
             self.fn("result_free", None)(C.byref(res))

@@ -12,20 +12,24 @@ from ortools_b200 import _capi as capi
 from ortools_b200 import pdlp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADER = os.path.join(ROOT, "include", "pdlp_b200.h")
+HEADERS = [os.path.join(ROOT, "include", "pdlp_b200.h"), os.path.join(ROOT, "include", "pdlp_b200_io.h")]
 
 
 def declared_functions():
-    text = open(HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pdlp_b200_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in HEADERS:
+        text = open(header).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(pdlp_b200_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_declares_the_expected_entry_points():
     names = declared_functions()
     assert "pdlp_b200_primal_dual_hybrid_gradient" in names
     assert "pdlp_b200_session_create" in names and "pdlp_b200_session_advance" in names
-    assert len(names) >= 35
+    assert "pdlp_b200_solve_proto" in names and "pdlp_b200_read_quadratic_program" in names   # pdlp_b200_io.h
+    assert len(names) >= 55
 
 
 @pytest.mark.parametrize("name", declared_functions())
