@@ -54,6 +54,8 @@ struct QuadraticProgram {
     variable_lower_bounds.assign(num_variables, -kInfinity);
     variable_upper_bounds.assign(num_variables, kInfinity);
     problem_name.reset();
+    variable_names.reset();
+    constraint_names.reset();
     objective_offset = 0.0;
     objective_scaling_factor = 1.0;
   }
@@ -84,6 +86,7 @@ struct QuadraticProgram {
   std::vector<double> values;
   std::vector<double> constraint_lower_bounds, constraint_upper_bounds, variable_lower_bounds, variable_upper_bounds;
   std::optional<std::string> problem_name;
+  std::optional<std::vector<std::string>> variable_names, constraint_names;  // quadratic_program.h:146-147
   double objective_offset = 0.0, objective_scaling_factor = 1.0;
 
   PdlpProblemView View() const {

@@ -992,6 +992,10 @@ bool JsonOut(const Schema& schema, std::string_view bytes, int indent, std::stri
         return false;
       }
     }
+    if (values.empty() && !def->repeated) {  // e.g. a scalar field that arrived as an empty packed run
+      i = j;
+      continue;
+    }
     if (!first) *out += ",\n";
     first = false;
     *out += pad + JsonString(CamelCase(def->name)) + ": ";

@@ -633,3 +633,22 @@ def test_cli_solves_an_mps_file_on_the_gpu(cli, tmp_path, b200_backend):
     np.testing.assert_allclose(list(got.values()), want.primal_solution, rtol=0, atol=1e-9)   # the same library on the same inputs
     np.testing.assert_allclose(list(got.values()), [1, -1, 6], atol=1e-6)
     assert float(lines[0].split()[1]) == pytest.approx(27.0, abs=1e-6)
+
+
+def test_format_layer_survives_mutation_fuzzing(tmp_path):
+    """tools/fuzz_formats.cc under AddressSanitizer + UBSan: mutated parameter texts, JSON, MPS and
+    serialized messages through every host-only entry point must all come back as status codes."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seeds = []
+    for name, blob in (("lp.pb", mp_model.qp_to_mp_model_proto(fixtures.test_lp()).SerializeToString()),
+                       ("req.pb", _request(True).SerializeToString()),
+                       ("params.pb", text_format.Parse(PARAM_TEXTS[2] + " random_projection_seeds: [1, 2]", pdlp_proto.PrimalDualHybridGradientParamsProto()).SerializeToString())):
+        path = str(tmp_path / name)
+        open(path, "wb").write(blob)
+        seeds.append(path)
+    p = subprocess.run([os.path.join(root, "tools", "fuzz_formats.sh"), "4000", *seeds], capture_output=True, text=True, timeout=600)
+    if p.returncode != 0 and ("cannot find -lasan" in p.stderr or "libasan" in p.stderr and "No such file" in p.stderr):
+        pytest.skip("no sanitizer runtime in this toolchain")
+    assert p.returncode == 0 and "fuzz ok: 4000 inputs" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
