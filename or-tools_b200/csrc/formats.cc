@@ -1329,6 +1329,21 @@ const proto::Schema* SchemaByName(const std::string& name) {
 // ---------------------------------------------------------------------------
 using namespace pdlp_b200;  // NOLINT
 
+namespace {
+// No exception may cross the C boundary: allocation failures and the like
+// become PDLP_B200_STATUS_BAD_ARGUMENT with the message.
+template <class F>
+int32_t HostGuard(char* error, int64_t error_capacity, F body) {
+  try {
+    return body();
+  } catch (const std::exception& e) {
+    return BadArgument(error, error_capacity, e.what());
+  } catch (...) {
+    return BadArgument(error, error_capacity, "unknown failure");
+  }
+}
+}  // namespace
+
 extern "C" {
 
 void pdlp_b200_blob_free(PdlpBlob* blob) {
@@ -1339,102 +1354,122 @@ void pdlp_b200_blob_free(PdlpBlob* blob) {
 }
 
 int32_t pdlp_b200_params_merge_bytes(const uint8_t* data, int64_t size, PdlpParams* params, char* error, int64_t error_capacity) {
-  if (params == nullptr || size < 0 || (data == nullptr && size > 0)) return BadArgument(error, error_capacity, "null argument");
-  std::string err;
-  PdlpParams merged = *params;  // all or nothing
-  if (!MergeParams(std::string_view(reinterpret_cast<const char*>(data), static_cast<size_t>(size)), &merged, &err))
-    return BadArgument(error, error_capacity, err);
-  *params = merged;
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (params == nullptr || size < 0 || (data == nullptr && size > 0)) return BadArgument(error, error_capacity, "null argument");
+    std::string err;
+    PdlpParams merged = *params;  // all or nothing
+    if (!MergeParams(std::string_view(reinterpret_cast<const char*>(data), static_cast<size_t>(size)), &merged, &err))
+      return BadArgument(error, error_capacity, err);
+    *params = merged;
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 int32_t pdlp_b200_params_parse_bytes(const uint8_t* data, int64_t size, PdlpParams* params, char* error, int64_t error_capacity) {
-  if (params == nullptr) return BadArgument(error, error_capacity, "null argument");
-  PdlpParams p;
-  SetDefaultParams(&p);
-  const int32_t rc = pdlp_b200_params_merge_bytes(data, size, &p, error, error_capacity);
-  if (rc == PDLP_B200_STATUS_OK) *params = p;
-  return rc;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (params == nullptr) return BadArgument(error, error_capacity, "null argument");
+    PdlpParams p;
+    SetDefaultParams(&p);
+    const int32_t rc = pdlp_b200_params_merge_bytes(data, size, &p, error, error_capacity);
+    if (rc == PDLP_B200_STATUS_OK) *params = p;
+    return rc;
+  });
 }
 
 int32_t pdlp_b200_params_merge_text(const char* text, PdlpParams* params, char* error, int64_t error_capacity) {
-  if (params == nullptr || text == nullptr) return BadArgument(error, error_capacity, "null argument");
-  std::string wire, err;
-  if (!proto::TextToWire(proto::ParamsSchema(), text, &wire, &err, /*allow_singular_overwrites=*/true)) return BadArgument(error, error_capacity, err);
-  return pdlp_b200_params_merge_bytes(reinterpret_cast<const uint8_t*>(wire.data()), static_cast<int64_t>(wire.size()), params, error, error_capacity);
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (params == nullptr || text == nullptr) return BadArgument(error, error_capacity, "null argument");
+    std::string wire, err;
+    if (!proto::TextToWire(proto::ParamsSchema(), text, &wire, &err, /*allow_singular_overwrites=*/true)) return BadArgument(error, error_capacity, err);
+    return pdlp_b200_params_merge_bytes(reinterpret_cast<const uint8_t*>(wire.data()), static_cast<int64_t>(wire.size()), params, error, error_capacity);
+  });
 }
 
 int32_t pdlp_b200_params_parse_text(const char* text, PdlpParams* params, char* error, int64_t error_capacity) {
-  if (params == nullptr || text == nullptr) return BadArgument(error, error_capacity, "null argument");
-  std::string wire, err;
-  if (!proto::TextToWire(proto::ParamsSchema(), text, &wire, &err, /*allow_singular_overwrites=*/false)) return BadArgument(error, error_capacity, err);
-  return pdlp_b200_params_parse_bytes(reinterpret_cast<const uint8_t*>(wire.data()), static_cast<int64_t>(wire.size()), params, error, error_capacity);
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (params == nullptr || text == nullptr) return BadArgument(error, error_capacity, "null argument");
+    std::string wire, err;
+    if (!proto::TextToWire(proto::ParamsSchema(), text, &wire, &err, /*allow_singular_overwrites=*/false)) return BadArgument(error, error_capacity, err);
+    return pdlp_b200_params_parse_bytes(reinterpret_cast<const uint8_t*>(wire.data()), static_cast<int64_t>(wire.size()), params, error, error_capacity);
+  });
 }
 
 int32_t pdlp_b200_params_serialize(const PdlpParams* params, int32_t format, PdlpBlob* out) {
-  if (params == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
-  Writer w;
-  ParamsToWire(*params, &w);
-  std::string encoded;
-  if (!Encode(proto::ParamsSchema(), w.out(), format, &encoded)) return PDLP_B200_STATUS_BAD_ARGUMENT;
-  return ToBlob(encoded, out);
+  return HostGuard(nullptr, 0, [&]() -> int32_t {
+    if (params == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+    Writer w;
+    ParamsToWire(*params, &w);
+    std::string encoded;
+    if (!Encode(proto::ParamsSchema(), w.out(), format, &encoded)) return PDLP_B200_STATUS_BAD_ARGUMENT;
+    return ToBlob(encoded, out);
+  });
 }
 
 int32_t pdlp_b200_solve_log_serialize(const PdlpResult* result, int32_t format, PdlpBlob* out) {
-  if (result == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
-  Writer w;
-  SolveLogToWire(*result, &w);
-  std::string encoded;
-  if (!Encode(proto::SolveLogSchema(), w.out(), format, &encoded)) return PDLP_B200_STATUS_BAD_ARGUMENT;
-  return ToBlob(encoded, out);
+  return HostGuard(nullptr, 0, [&]() -> int32_t {
+    if (result == nullptr || out == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+    Writer w;
+    SolveLogToWire(*result, &w);
+    std::string encoded;
+    if (!Encode(proto::SolveLogSchema(), w.out(), format, &encoded)) return PDLP_B200_STATUS_BAD_ARGUMENT;
+    return ToBlob(encoded, out);
+  });
 }
 
 int32_t pdlp_b200_write_solve_log(const PdlpResult* result, const char* path, char* error, int64_t error_capacity) {
-  if (result == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
-  const std::string p = path;
-  int32_t format;
-  if (EndsWith(p, ".textproto")) format = PDLP_FORMAT_TEXT;
-  else if (EndsWith(p, ".pb")) format = PDLP_FORMAT_BINARY;
-  else if (EndsWith(p, ".json")) format = PDLP_FORMAT_JSON;
-  else return BadArgument(error, error_capacity, "Unrecognized file extension for --solve_log_file: " + p + ". Expected .textproto, .pb, or .json");
-  Writer w;
-  SolveLogToWire(*result, &w);
-  std::string encoded, err;
-  if (!Encode(proto::SolveLogSchema(), w.out(), format, &encoded)) return BadArgument(error, error_capacity, "cannot encode the solve log");
-  if (!WriteFile(p, encoded, &err)) return BadArgument(error, error_capacity, err);
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (result == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
+    const std::string p = path;
+    int32_t format;
+    if (EndsWith(p, ".textproto")) format = PDLP_FORMAT_TEXT;
+    else if (EndsWith(p, ".pb")) format = PDLP_FORMAT_BINARY;
+    else if (EndsWith(p, ".json")) format = PDLP_FORMAT_JSON;
+    else return BadArgument(error, error_capacity, "Unrecognized file extension for --solve_log_file: " + p + ". Expected .textproto, .pb, or .json");
+    Writer w;
+    SolveLogToWire(*result, &w);
+    std::string encoded, err;
+    if (!Encode(proto::SolveLogSchema(), w.out(), format, &encoded)) return BadArgument(error, error_capacity, "cannot encode the solve log");
+    if (!WriteFile(p, encoded, &err)) return BadArgument(error, error_capacity, err);
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 int32_t pdlp_b200_read_quadratic_program(const char* path, int32_t include_names, PdlpModel** out_model, char* error, int64_t error_capacity) {
-  if (path == nullptr || out_model == nullptr) return BadArgument(error, error_capacity, "null argument");
-  auto model = std::make_unique<PdlpModel>();
-  std::string err;
-  if (!ReadModel(path, include_names != 0, model.get(), &err)) return BadArgument(error, error_capacity, err);
-  *out_model = model.release();
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (path == nullptr || out_model == nullptr) return BadArgument(error, error_capacity, "null argument");
+    auto model = std::make_unique<PdlpModel>();
+    std::string err;
+    if (!ReadModel(path, include_names != 0, model.get(), &err)) return BadArgument(error, error_capacity, err);
+    *out_model = model.release();
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 int32_t pdlp_b200_model_from_mps_text(const char* text, int64_t size, int32_t include_names, PdlpModel** out_model, char* error,
                                       int64_t error_capacity) {
-  if (text == nullptr || size < 0 || out_model == nullptr) return BadArgument(error, error_capacity, "null argument");
-  auto model = std::make_unique<PdlpModel>();
-  std::string err;
-  if (!ModelFromMpsText(std::string_view(text, static_cast<size_t>(size)), include_names != 0, model.get(), &err))
-    return BadArgument(error, error_capacity, err);
-  *out_model = model.release();
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (text == nullptr || size < 0 || out_model == nullptr) return BadArgument(error, error_capacity, "null argument");
+    auto model = std::make_unique<PdlpModel>();
+    std::string err;
+    if (!ModelFromMpsText(std::string_view(text, static_cast<size_t>(size)), include_names != 0, model.get(), &err))
+      return BadArgument(error, error_capacity, err);
+    *out_model = model.release();
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 int32_t pdlp_b200_model_from_mp_model_proto(const uint8_t* data, int64_t size, int32_t relax_integer_variables, int32_t include_names,
                                             PdlpModel** out_model, char* error, int64_t error_capacity) {
-  if (size < 0 || (data == nullptr && size > 0) || out_model == nullptr) return BadArgument(error, error_capacity, "null argument");
-  auto model = std::make_unique<PdlpModel>();
-  std::string err;
-  if (!ModelFromMpModelBytes(std::string_view(reinterpret_cast<const char*>(data), static_cast<size_t>(size)), relax_integer_variables != 0,
-                             include_names != 0, model.get(), &err))
-    return BadArgument(error, error_capacity, err);
-  *out_model = model.release();
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (size < 0 || (data == nullptr && size > 0) || out_model == nullptr) return BadArgument(error, error_capacity, "null argument");
+    auto model = std::make_unique<PdlpModel>();
+    std::string err;
+    if (!ModelFromMpModelBytes(std::string_view(reinterpret_cast<const char*>(data), static_cast<size_t>(size)), relax_integer_variables != 0,
+                               include_names != 0, model.get(), &err))
+      return BadArgument(error, error_capacity, err);
+    *out_model = model.release();
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 const PdlpProblemView* pdlp_b200_model_view(const PdlpModel* model) { return model == nullptr ? nullptr : &model->view; }
@@ -1453,57 +1488,67 @@ void pdlp_b200_model_free(PdlpModel* model) { delete model; }
 
 int32_t pdlp_b200_qp_to_mp_model_proto(const PdlpProblemView* qp, const char* const* variable_names, const char* const* constraint_names,
                                        PdlpBlob* out, char* error, int64_t error_capacity) {
-  if (qp == nullptr || out == nullptr) return BadArgument(error, error_capacity, "null argument");
-  std::string wire, err;
-  if (!QpToMpModelWire(*qp, variable_names, constraint_names, &wire, &err)) return BadArgument(error, error_capacity, err);
-  return ToBlob(wire, out);
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (qp == nullptr || out == nullptr) return BadArgument(error, error_capacity, "null argument");
+    std::string wire, err;
+    if (!QpToMpModelWire(*qp, variable_names, constraint_names, &wire, &err)) return BadArgument(error, error_capacity, err);
+    return ToBlob(wire, out);
+  });
 }
 
 int32_t pdlp_b200_write_linear_program_to_mps(const PdlpProblemView* qp, const char* const* variable_names, const char* const* constraint_names,
                                               const char* path, char* error, int64_t error_capacity) {
-  if (qp == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
-  std::string text, err;
-  if (!LinearProgramToMps(*qp, variable_names, constraint_names, &text, &err) || !WriteFile(path, text, &err))
-    return BadArgument(error, error_capacity, err);
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (qp == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
+    std::string text, err;
+    if (!LinearProgramToMps(*qp, variable_names, constraint_names, &text, &err) || !WriteFile(path, text, &err))
+      return BadArgument(error, error_capacity, err);
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 int32_t pdlp_b200_write_quadratic_program_to_mp_model_proto(const PdlpProblemView* qp, const char* const* variable_names,
                                                             const char* const* constraint_names, const char* path, char* error,
                                                             int64_t error_capacity) {
-  if (qp == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
-  std::string wire, err;
-  if (!QpToMpModelWire(*qp, variable_names, constraint_names, &wire, &err) || !WriteFile(path, wire, &err))
-    return BadArgument(error, error_capacity, err);
-  return PDLP_B200_STATUS_OK;
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (qp == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
+    std::string wire, err;
+    if (!QpToMpModelWire(*qp, variable_names, constraint_names, &wire, &err) || !WriteFile(path, wire, &err))
+      return BadArgument(error, error_capacity, err);
+    return PDLP_B200_STATUS_OK;
+  });
 }
 
 int32_t pdlp_b200_solve_proto(const uint8_t* request, int64_t request_size, int32_t relax_integer_variables,
                               const volatile int32_t* interrupt_solve, PdlpBlob* response) {
-  if (request_size < 0 || (request == nullptr && request_size > 0) || response == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
-  std::string out;
-  const int32_t rc = SolveProto(std::string_view(reinterpret_cast<const char*>(request), static_cast<size_t>(request_size)),
-                                relax_integer_variables != 0, interrupt_solve, &out);
-  if (rc != PDLP_B200_STATUS_OK) return rc;
-  return ToBlob(out, response);
+  return HostGuard(nullptr, 0, [&]() -> int32_t {
+    if (request_size < 0 || (request == nullptr && request_size > 0) || response == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+    std::string out;
+    const int32_t rc = SolveProto(std::string_view(reinterpret_cast<const char*>(request), static_cast<size_t>(request_size)),
+                                  relax_integer_variables != 0, interrupt_solve, &out);
+    if (rc != PDLP_B200_STATUS_OK) return rc;
+    return ToBlob(out, response);
+  });
 }
 
 int32_t pdlp_b200_proto_convert(const char* message, int32_t from_format, const uint8_t* data, int64_t size, int32_t to_format, PdlpBlob* out,
                                 char* error, int64_t error_capacity) {
-  if (message == nullptr || size < 0 || (data == nullptr && size > 0) || out == nullptr) return BadArgument(error, error_capacity, "null argument");
-  const proto::Schema* schema = SchemaByName(message);
-  if (schema == nullptr) return BadArgument(error, error_capacity, std::string("unknown message type ") + message);
-  const std::string_view in(reinterpret_cast<const char*>(data), static_cast<size_t>(size));
-  std::string wire, err;
-  switch (from_format) {
-    case PDLP_FORMAT_BINARY: wire = std::string(in); break;
-    case PDLP_FORMAT_TEXT: if (!proto::TextToWire(*schema, in, &wire, &err)) return BadArgument(error, error_capacity, err); break;
-    case PDLP_FORMAT_JSON: if (!proto::JsonToWire(*schema, in, &wire, &err)) return BadArgument(error, error_capacity, err); break;
-    default: return BadArgument(error, error_capacity, "unknown input format");
-  }
-  std::string encoded;
-  if (!Encode(*schema, wire, to_format, &encoded)) return BadArgument(error, error_capacity, "malformed message bytes or unknown output format");
-  return ToBlob(encoded, out);
+  return HostGuard(error, error_capacity, [&]() -> int32_t {
+    if (message == nullptr || size < 0 || (data == nullptr && size > 0) || out == nullptr) return BadArgument(error, error_capacity, "null argument");
+    const proto::Schema* schema = SchemaByName(message);
+    if (schema == nullptr) return BadArgument(error, error_capacity, std::string("unknown message type ") + message);
+    const std::string_view in(reinterpret_cast<const char*>(data), static_cast<size_t>(size));
+    std::string wire, err;
+    switch (from_format) {
+      case PDLP_FORMAT_BINARY: wire = std::string(in); break;
+      case PDLP_FORMAT_TEXT: if (!proto::TextToWire(*schema, in, &wire, &err)) return BadArgument(error, error_capacity, err); break;
+      case PDLP_FORMAT_JSON: if (!proto::JsonToWire(*schema, in, &wire, &err)) return BadArgument(error, error_capacity, err); break;
+      default: return BadArgument(error, error_capacity, "unknown input format");
+    }
+    std::string encoded;
+    if (!Encode(*schema, wire, to_format, &encoded)) return BadArgument(error, error_capacity, "malformed message bytes or unknown output format");
+    return ToBlob(encoded, out);
+  });
 }
 
 }  // extern "C"
