@@ -6,6 +6,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -792,286 +793,399 @@ bool QpToMpModelWire(const PdlpProblemView& qp, const char* const* variable_name
 // first appearance, integrality dropped, the negated right-hand side of the
 // objective row is the objective offset, maximisation becomes minimisation.
 // ---------------------------------------------------------------------------
-std::vector<std::string> SplitFields(const std::string& line) {
-  std::vector<std::string> out;
+using Fields = std::vector<std::string_view>;
+
+bool IsSpace(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+void SplitFields(std::string_view line, Fields* out) {
+  out->clear();
   size_t i = 0;
-  while (i < line.size()) {
-    while (i < line.size() && std::isspace(static_cast<unsigned char>(line[i]))) ++i;
+  const size_t n = line.size();
+  while (i < n) {
+    while (i < n && IsSpace(line[i])) ++i;
     size_t j = i;
-    while (j < line.size() && !std::isspace(static_cast<unsigned char>(line[j]))) ++j;
-    if (j > i) out.push_back(line.substr(i, j - i));
+    while (j < n && !IsSpace(line[j])) ++j;
+    if (j > i) out->push_back(line.substr(i, j - i));
     i = j;
   }
-  return out;
 }
 
-std::string Strip(const std::string& s) {
+std::string_view Strip(std::string_view s) {
   size_t a = 0, b = s.size();
-  while (a < b && std::isspace(static_cast<unsigned char>(s[a]))) ++a;
-  while (b > a && std::isspace(static_cast<unsigned char>(s[b - 1]))) --b;
+  while (a < b && IsSpace(s[a])) ++a;
+  while (b > a && IsSpace(s[b - 1])) --b;
   return s.substr(a, b - a);
 }
 
 // Fixed-format fields: columns 2-3, 5-12, 15-22, 25-36, 40-47, 50-61 (1-based).
-std::vector<std::string> FixedFields(const std::string& line) {
+void FixedFields(std::string_view line, Fields* out) {
   static const int kCols[6][2] = {{1, 3}, {4, 12}, {14, 22}, {24, 36}, {39, 47}, {49, 61}};
-  std::vector<std::string> out;
+  out->clear();
   for (const auto& c : kCols) {
     if (static_cast<int>(line.size()) <= c[0]) continue;
-    out.push_back(Strip(line.substr(static_cast<size_t>(c[0]), static_cast<size_t>(c[1] - c[0]))));
+    out->push_back(Strip(line.substr(static_cast<size_t>(c[0]), static_cast<size_t>(c[1] - c[0]))));
   }
-  while (!out.empty() && out.back().empty()) out.pop_back();
-  return out;
+  while (!out->empty() && out->back().empty()) out->pop_back();
 }
 
-std::string Upper(std::string s) {
-  for (char& c : s) c = static_cast<char>(std::toupper(static_cast<unsigned char>(c)));
-  return s;
+// Case-insensitive comparison with an upper-case literal.
+bool IsWord(std::string_view s, std::string_view upper) {
+  if (s.size() != upper.size()) return false;
+  for (size_t i = 0; i < s.size(); ++i)
+    if (std::toupper(static_cast<unsigned char>(s[i])) != upper[i]) return false;
+  return true;
 }
+
+// Names -> dense indices in order of first appearance: open addressing over
+// (hash, index) pairs, so a lookup touches one slot run and one name (the
+// chained std::unordered_map cost ~400 ns per entry of a large COLUMNS section).
+class NameIndex {
+ public:
+  int64_t Find(std::string_view s) const {
+    if (slots_.empty()) return -1;
+    const uint64_t h = Hash(s);
+    for (size_t at = h & mask_;; at = (at + 1) & mask_) {
+      const Slot& slot = slots_[at];
+      if (slot.hash == 0) return -1;
+      if (slot.hash == h && names_[static_cast<size_t>(slot.index)] == s) return slot.index;
+    }
+  }
+  // Appends a name that is not present yet; returns its index.
+  int64_t Insert(std::string_view s) {
+    if ((names_.size() + 1) * 2 > slots_.size()) Grow();
+    const int64_t index = static_cast<int64_t>(names_.size());
+    names_.emplace_back(s);
+    Place(Hash(s), index);
+    return index;
+  }
+  size_t size() const { return names_.size(); }
+  std::vector<std::string>& names() { return names_; }
+
+ private:
+  struct Slot {
+    uint64_t hash = 0;  // 0 = empty
+    int64_t index = 0;
+  };
+  static uint64_t Hash(std::string_view s) {  // FNV-1a, never 0
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) h = (h ^ c) * 1099511628211ull;
+    return h | 1ull;
+  }
+  void Place(uint64_t h, int64_t index) {
+    size_t at = h & mask_;
+    while (slots_[at].hash != 0) at = (at + 1) & mask_;
+    slots_[at].hash = h;
+    slots_[at].index = index;
+  }
+  void Grow() {
+    const size_t size = slots_.empty() ? 1024 : slots_.size() * 2;
+    slots_.assign(size, Slot{});
+    mask_ = size - 1;
+    for (size_t i = 0; i < names_.size(); ++i) Place(Hash(names_[i]), static_cast<int64_t>(i));
+  }
+  std::vector<std::string> names_;
+  std::vector<Slot> slots_;
+  size_t mask_ = 0;
+};
 
 struct MpsParser {
+  enum Section { kNone, kName, kObjsense, kRows, kColumns, kRhs, kRanges, kBounds, kOther };
+
   bool include_names;
   PdlpModel* model;
   std::string error;
 
-  std::string section;
+  Section section = kNone;
   bool maximize = false;
-  std::unordered_map<std::string, int64_t> row_index, col_index;
+  NameIndex rows, cols;  // constraint rows / columns in order of first appearance
   bool has_objective_row = false;
   std::string objective_row;
   std::unordered_set<std::string> ignored_rows;  // extra N rows
-  std::vector<std::string> row_names, col_names;
   std::vector<char> binary_by_default;
   std::vector<Triplet> entries;
   double offset = 0.0;
   bool in_integer_block = false;
   int lineno = 0;
+  // scratch reused from line to line
+  Fields f, g;
+  std::string key;
+  std::string last_col_name;
+  int64_t last_col = -1;
 
   bool Fail(const std::string& what) {
     if (error.empty()) error = "line " + std::to_string(lineno) + ": " + what;
     return false;
   }
-  bool Number(const std::string& tok, double* out) {
-    std::string t = tok;
-    const std::string low = [&] { std::string l; for (char c : tok) l.push_back(static_cast<char>(std::tolower(static_cast<unsigned char>(c)))); return l; }();
+  static std::string Quoted(std::string_view s) { return "'" + std::string(s) + "'"; }
+
+  bool Number(std::string_view tok, double* out) {
+    // fast path: plain decimal / scientific notation
+    if (!tok.empty()) {
+      const char* b = tok.data();
+      const char* e = b + tok.size();
+      auto r = std::from_chars(*b == '+' && tok.size() > 1 && tok[1] != '-' && tok[1] != '+' ? b + 1 : b, e, *out);
+      if (r.ec == std::errc() && r.ptr == e && !std::isnan(*out) && !std::isinf(*out)) return true;
+    }
+    // slow path: Fortran exponents (1.5D0), inf / infinity, out-of-range values
+    std::string t(tok), low;
+    for (char c : t) low.push_back(static_cast<char>(std::tolower(static_cast<unsigned char>(c))));
     if (low.find("inf") == std::string::npos)
       for (char& c : t)
-        if (c == 'D' || c == 'd') c = 'e';  // Fortran exponents
+        if (c == 'D' || c == 'd') c = 'e';
     char* end = nullptr;
     const double v = std::strtod(t.c_str(), &end);
-    if (t.empty() || end == nullptr || *end != '\0' || end == t.c_str()) return Fail("cannot parse number '" + tok + "'");
+    if (t.empty() || end == nullptr || *end != '\0' || end == t.c_str()) return Fail("cannot parse number " + Quoted(tok));
     if (std::isnan(v)) return Fail("NaN value");
-    if (low.find('x') != std::string::npos) return Fail("cannot parse number '" + tok + "'");  // strtod accepts hex floats; the reader does not
+    if (low.find('x') != std::string::npos) return Fail("cannot parse number " + Quoted(tok));  // strtod accepts hex floats; the reader does not
     *out = v;
     return true;
   }
-  int64_t FindCol(const std::string& name) {
-    auto it = col_index.find(name);
-    if (it != col_index.end()) return it->second;
-    const int64_t j = static_cast<int64_t>(col_names.size());
-    col_index.emplace(name, j);
-    col_names.push_back(name);
-    model->objective.push_back(0.0);
-    model->lv.push_back(0.0);
-    model->uv.push_back(kInf);
-    binary_by_default.push_back(0);
+  bool IsObjectiveRow(std::string_view row) const { return has_objective_row && row == objective_row; }
+  bool IsIgnoredRow(std::string_view row) {
+    if (ignored_rows.empty()) return false;
+    key.assign(row);
+    return ignored_rows.count(key) != 0;
+  }
+  // Index of a constraint row, -1 if unknown.
+  int64_t FindRow(std::string_view row) const { return rows.Find(row); }
+  int64_t FindCol(std::string_view name, bool* is_new = nullptr) {
+    if (is_new != nullptr) *is_new = false;
+    if (last_col >= 0 && name == last_col_name) return last_col;  // consecutive lines of a column
+    int64_t j = cols.Find(name);
+    if (j < 0) {
+      j = cols.Insert(name);
+      model->objective.push_back(0.0);
+      model->lv.push_back(0.0);
+      model->uv.push_back(kInf);
+      binary_by_default.push_back(0);
+      if (is_new != nullptr) *is_new = true;
+    }
+    last_col = j;
+    last_col_name.assign(name);
     return j;
   }
-  bool SetRhs(const std::string& row, double value) {
-    if (has_objective_row && row == objective_row) {
+  bool SetRhs(std::string_view row, double value) {
+    if (IsObjectiveRow(row)) {
       offset = -value;  // minus the right-hand side of the objective row
       return true;
     }
-    if (ignored_rows.count(row)) return true;
-    auto it = row_index.find(row);
-    if (it == row_index.end()) return Fail("unknown row '" + row + "'");
-    double& lo = model->lc[static_cast<size_t>(it->second)];
-    double& hi = model->uc[static_cast<size_t>(it->second)];
+    if (IsIgnoredRow(row)) return true;
+    const int64_t i = FindRow(row);
+    if (i < 0) return Fail("unknown row " + Quoted(row));
+    double& lo = model->lc[static_cast<size_t>(i)];
+    double& hi = model->uc[static_cast<size_t>(i)];
     if (lo != -kInf) lo = value;
     if (hi != kInf) hi = value;
     return true;
   }
-  bool SetRange(const std::string& row, double value) {
-    if ((has_objective_row && row == objective_row) || ignored_rows.count(row)) return true;
-    auto it = row_index.find(row);
-    if (it == row_index.end()) return Fail("unknown row '" + row + "'");
-    double lo = model->lc[static_cast<size_t>(it->second)], hi = model->uc[static_cast<size_t>(it->second)];
+  bool SetRange(std::string_view row, double value) {
+    if (IsObjectiveRow(row) || IsIgnoredRow(row)) return true;
+    const int64_t i = FindRow(row);
+    if (i < 0) return Fail("unknown row " + Quoted(row));
+    double lo = model->lc[static_cast<size_t>(i)], hi = model->uc[static_cast<size_t>(i)];
     if (lo == hi) {
       if (value < 0.0) lo += value;
       else hi += value;
     }
     if (lo == -kInf) lo = hi - std::fabs(value);
     if (hi == kInf) hi = lo + std::fabs(value);
-    model->lc[static_cast<size_t>(it->second)] = lo;
-    model->uc[static_cast<size_t>(it->second)] = hi;
+    model->lc[static_cast<size_t>(i)] = lo;
+    model->uc[static_cast<size_t>(i)] = hi;
+    return true;
+  }
+  void SetSense(std::string_view word) { maximize = IsWord(word, "MAX") || IsWord(word, "MAXIMIZE"); }
+
+  bool Header(std::string_view line, bool* done) {
+    SplitFields(line, &f);
+    std::string name;
+    for (char c : f[0]) name.push_back(static_cast<char>(std::toupper(static_cast<unsigned char>(c))));
+    if (name == "NAME") {
+      section = kName;
+      model->name.clear();
+      for (size_t k = 1; k < f.size(); ++k) {
+        if (k > 1) model->name += " ";
+        model->name.append(f[k]);
+      }
+    } else if (name == "OBJSENSE" || name == "OBJSENCE") {
+      section = kObjsense;
+      if (f.size() > 1) SetSense(f[1]);
+    } else if (name == "OBJSENSEMAX") {
+      section = kOther;
+      maximize = true;
+    } else if (name == "ROWS" || name == "LAZYCONS" || name == "USERCUTS") {
+      section = kRows;
+    } else if (name == "COLUMNS") {
+      section = kColumns;
+    } else if (name == "RHS") {
+      section = kRhs;
+    } else if (name == "RANGES") {
+      section = kRanges;
+    } else if (name == "BOUNDS") {
+      section = kBounds;
+    } else if (name == "ENDATA") {
+      section = kOther;
+      *done = true;
+    } else if (name == "QUADOBJ" || name == "QMATRIX" || name == "QSECTION") {
+      return Fail("quadratic objective sections are not supported by the linear-program reader");
+    } else if (name == "INDICATORS" || name == "SOS") {
+      return Fail("section " + name + " is not supported");
+    } else {
+      return Fail("unknown section " + Quoted(f[0]));
+    }
     return true;
   }
 
   // Returns false on error; *done is set at ENDATA.
-  bool Line(const std::string& raw, bool* done) {
+  bool Line(std::string_view line, bool* done) {
     ++lineno;
-    std::string line = raw;
-    while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
-    const std::string stripped = Strip(line);
+    while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.remove_suffix(1);
+    const std::string_view stripped = Strip(line);
     if (stripped.empty() || stripped[0] == '*') return true;
-    if (!std::isspace(static_cast<unsigned char>(line[0]))) {  // section header
-      const std::vector<std::string> parts = SplitFields(line);
-      const std::string key = Upper(parts[0]);
-      static const char* kSections[] = {"NAME", "OBJSENSE", "OBJSENCE", "OBJSENSEMAX", "ROWS", "LAZYCONS", "COLUMNS", "RHS", "RANGES", "BOUNDS",
-                                        "INDICATORS", "ENDATA", "QUADOBJ", "QMATRIX", "QSECTION", "SOS", "USERCUTS"};
-      bool known = false;
-      for (const char* s : kSections) known = known || key == s;
-      if (!known) return Fail("unknown section '" + parts[0] + "'");
-      section = key;
-      if (key == "NAME") {
-        model->name.clear();
-        for (size_t k = 1; k < parts.size(); ++k) model->name += (k > 1 ? " " : "") + parts[k];
-      } else if ((key == "OBJSENSE" || key == "OBJSENCE") && parts.size() > 1) {
-        const std::string v = Upper(parts[1]);
-        maximize = v == "MAX" || v == "MAXIMIZE";
-      } else if (key == "OBJSENSEMAX") {
-        maximize = true;
-      } else if (key == "ENDATA") {
-        *done = true;
-      } else if (key == "QUADOBJ" || key == "QMATRIX" || key == "QSECTION") {
-        return Fail("quadratic objective sections are not supported by the linear-program reader");
-      } else if (key == "INDICATORS" || key == "SOS") {
-        return Fail("section " + key + " is not supported");
+    if (!IsSpace(line[0])) return Header(line, done);
+    SplitFields(line, &f);
+    switch (section) {
+      case kObjsense:
+        SetSense(f[0]);
+        return true;
+      case kRows: {
+        if (f.size() != 2) FixedFields(line, &f);
+        if (f.size() != 2) return Fail("expected <type> <row name>");
+        const std::string_view t = f[0], name = f[1];
+        if (IsWord(t, "N")) {
+          if (!has_objective_row) {
+            has_objective_row = true;
+            objective_row.assign(name);
+          } else {
+            ignored_rows.insert(std::string(name));
+          }
+          return true;
+        }
+        const bool e = IsWord(t, "E"), l = IsWord(t, "L"), gq = IsWord(t, "G");
+        if (!e && !l && !gq) return Fail("unknown row type " + Quoted(t));
+        if (rows.Find(name) >= 0) return Fail("duplicate row " + Quoted(name));
+        rows.Insert(name);
+        model->lc.push_back(l ? -kInf : 0.0);
+        model->uc.push_back(gq ? kInf : 0.0);
+        return true;
       }
-      return true;
-    }
-    std::vector<std::string> f = SplitFields(line);
-    if (section == "OBJSENSE" || section == "OBJSENCE") {
-      const std::string v = Upper(f[0]);
-      maximize = v == "MAX" || v == "MAXIMIZE";
-    } else if (section == "ROWS" || section == "LAZYCONS" || section == "USERCUTS") {
-      if (f.size() != 2) f = FixedFields(line);
-      if (f.size() != 2) return Fail("expected <type> <row name>");
-      const std::string t = Upper(f[0]);
-      const std::string& name = f[1];
-      if (t == "N") {
-        if (!has_objective_row) {
-          has_objective_row = true;
-          objective_row = name;
-        } else {
-          ignored_rows.insert(name);
+      case kColumns: {
+        if (f.size() >= 3 && IsWord(f[1], "'MARKER'")) {
+          std::string upper;
+          for (char c : f[2]) upper.push_back(static_cast<char>(std::toupper(static_cast<unsigned char>(c))));
+          in_integer_block = upper.find("INTORG") != std::string::npos;
+          return true;
+        }
+        if (f.size() != 3 && f.size() != 5) {
+          FixedFields(line, &f);
+          if (!f.empty()) f.erase(f.begin());
+        }
+        if (f.size() != 3 && f.size() != 5) return Fail("expected <column> <row> <value> [<row> <value>]");
+        bool is_new;
+        const int64_t j = FindCol(f[0], &is_new);
+        if (is_new && in_integer_block) {  // integer by marker, no bound yet: [0, 1]
+          binary_by_default[static_cast<size_t>(j)] = 1;
+          model->uv[static_cast<size_t>(j)] = 1.0;
+        }
+        for (size_t k = 1; k + 1 < f.size(); k += 2) {
+          double value;
+          if (!Number(f[k + 1], &value)) return false;
+          const std::string_view row = f[k];
+          if (IsObjectiveRow(row)) {
+            model->objective[static_cast<size_t>(j)] = value;
+          } else if (IsIgnoredRow(row)) {
+            continue;
+          } else {
+            const int64_t i = FindRow(row);
+            if (i < 0) return Fail("unknown row " + Quoted(row));
+            entries.push_back({i, j, value});
+          }
         }
         return true;
       }
-      if (t != "E" && t != "L" && t != "G") return Fail("unknown row type '" + f[0] + "'");
-      if (row_index.count(name)) return Fail("duplicate row '" + name + "'");
-      row_index.emplace(name, static_cast<int64_t>(row_names.size()));
-      row_names.push_back(name);
-      model->lc.push_back(t == "L" ? -kInf : 0.0);
-      model->uc.push_back(t == "G" ? kInf : 0.0);
-    } else if (section == "COLUMNS") {
-      if (f.size() >= 3 && Upper(f[1]) == "'MARKER'") {
-        in_integer_block = Upper(f[2]).find("INTORG") != std::string::npos;
+      case kRhs:
+      case kRanges: {
+        g.assign(f.begin(), f.end());
+        if (g.size() % 2 == 0) g.insert(g.begin(), std::string_view());  // the set name may be missing
+        if (g.size() != 3 && g.size() != 5) {
+          FixedFields(line, &g);
+          if (!g.empty()) g.erase(g.begin());
+        }
+        for (size_t k = 1; k + 1 < g.size(); k += 2) {
+          double value;
+          if (!Number(g[k + 1], &value)) return false;
+          if (!(section == kRhs ? SetRhs(g[k], value) : SetRange(g[k], value))) return false;
+        }
         return true;
       }
-      if (f.size() != 3 && f.size() != 5) {
-        f = FixedFields(line);
-        if (!f.empty()) f.erase(f.begin());
-      }
-      if (f.size() != 3 && f.size() != 5) return Fail("expected <column> <row> <value> [<row> <value>]");
-      const bool is_new = col_index.find(f[0]) == col_index.end();
-      const int64_t j = FindCol(f[0]);
-      if (is_new && in_integer_block) {  // integer by marker, no bound yet: [0, 1]
-        binary_by_default[static_cast<size_t>(j)] = 1;
-        model->uv[static_cast<size_t>(j)] = 1.0;
-      }
-      for (size_t k = 1; k + 1 < f.size(); k += 2) {
-        double value;
-        if (!Number(f[k + 1], &value)) return false;
-        const std::string& row = f[k];
-        if (has_objective_row && row == objective_row) {
-          model->objective[static_cast<size_t>(j)] = value;
-        } else if (ignored_rows.count(row)) {
-          continue;
-        } else {
-          auto it = row_index.find(row);
-          if (it == row_index.end()) return Fail("unknown row '" + row + "'");
-          entries.push_back({it->second, j, value});
-        }
-      }
-    } else if (section == "RHS" || section == "RANGES") {
-      std::vector<std::string> g = f;
-      if (g.size() % 2 == 0) g.insert(g.begin(), std::string());  // the set name may be missing
-      if (g.size() != 3 && g.size() != 5) {
-        g = FixedFields(line);
-        if (!g.empty()) g.erase(g.begin());
-      }
-      for (size_t k = 1; k + 1 < g.size(); k += 2) {
-        double value;
-        if (!Number(g[k + 1], &value)) return false;
-        if (!(section == "RHS" ? SetRhs(g[k], value) : SetRange(g[k], value))) return false;
-      }
-    } else if (section == "BOUNDS") {
-      const std::string kind = Upper(f[0]);
-      const bool needs_value = kind == "LO" || kind == "UP" || kind == "FX" || kind == "LI" || kind == "UI" || kind == "SC";
-      std::string column;
-      double value = 0.0;
-      if (needs_value) {  // ' <type> <set name> <column> <value>'; the set name may be missing
-        if (f.size() == 4) {
+      case kBounds: {
+        const std::string_view kind = f[0];
+        const bool lo_k = IsWord(kind, "LO"), li_k = IsWord(kind, "LI"), up_k = IsWord(kind, "UP"), ui_k = IsWord(kind, "UI");
+        const bool fx_k = IsWord(kind, "FX"), sc_k = IsWord(kind, "SC");
+        const bool needs_value = lo_k || up_k || fx_k || li_k || ui_k || sc_k;
+        std::string_view column;
+        double value = 0.0;
+        if (needs_value) {  // ' <type> <set name> <column> <value>'; the set name may be missing
+          if (f.size() == 4) {
+            column = f[2];
+            if (!Number(f[3], &value)) return false;
+          } else if (f.size() == 3) {
+            column = f[1];
+            if (!Number(f[2], &value)) return false;
+          } else {
+            FixedFields(line, &g);
+            if (g.size() < 4) return Fail("malformed bound");
+            column = g[2];
+            if (!Number(g[3], &value)) return false;
+          }
+        } else if (f.size() >= 3) {
           column = f[2];
-          if (!Number(f[3], &value)) return false;
-        } else if (f.size() == 3) {
+        } else if (f.size() == 2) {
           column = f[1];
-          if (!Number(f[2], &value)) return false;
         } else {
-          const std::vector<std::string> g = FixedFields(line);
-          if (g.size() < 4) return Fail("malformed bound");
-          column = g[2];
-          if (!Number(g[3], &value)) return false;
+          return Fail("malformed bound");
         }
-      } else if (f.size() >= 3) {
-        column = f[2];
-      } else if (f.size() == 2) {
-        column = f[1];
-      } else {
-        return Fail("malformed bound");
+        const int64_t j = FindCol(column);
+        double lo = model->lv[static_cast<size_t>(j)], hi = model->uv[static_cast<size_t>(j)];
+        if (binary_by_default[static_cast<size_t>(j)]) {
+          lo = 0.0;
+          hi = kInf;
+        }
+        if (lo_k || li_k) {
+          lo = value;
+          if (li_k && lo == 0.0) hi = kInf;
+        } else if (up_k || ui_k) {
+          hi = value;
+        } else if (fx_k) {
+          lo = hi = value;
+        } else if (IsWord(kind, "FR")) {
+          lo = -kInf;
+          hi = kInf;
+        } else if (IsWord(kind, "MI")) {
+          lo = -kInf;
+        } else if (IsWord(kind, "PL")) {
+          hi = kInf;
+        } else if (IsWord(kind, "BV")) {
+          lo = 0.0;
+          hi = 1.0;
+        } else if (sc_k) {
+          return Fail("semi-continuous variables are not supported");
+        } else {
+          return Fail("unknown bound type " + Quoted(kind));
+        }
+        binary_by_default[static_cast<size_t>(j)] = 0;
+        model->lv[static_cast<size_t>(j)] = lo;
+        model->uv[static_cast<size_t>(j)] = hi;
+        return true;
       }
-      const int64_t j = FindCol(column);
-      double lo = model->lv[static_cast<size_t>(j)], hi = model->uv[static_cast<size_t>(j)];
-      if (binary_by_default[static_cast<size_t>(j)]) {
-        lo = 0.0;
-        hi = kInf;
-      }
-      if (kind == "LO" || kind == "LI") {
-        lo = value;
-        if (kind == "LI" && lo == 0.0) hi = kInf;
-      } else if (kind == "UP" || kind == "UI") {
-        hi = value;
-      } else if (kind == "FX") {
-        lo = hi = value;
-      } else if (kind == "FR") {
-        lo = -kInf;
-        hi = kInf;
-      } else if (kind == "MI") {
-        lo = -kInf;
-      } else if (kind == "PL") {
-        hi = kInf;
-      } else if (kind == "BV") {
-        lo = 0.0;
-        hi = 1.0;
-      } else if (kind == "SC") {
-        return Fail("semi-continuous variables are not supported");
-      } else {
-        return Fail("unknown bound type '" + f[0] + "'");
-      }
-      binary_by_default[static_cast<size_t>(j)] = 0;
-      model->lv[static_cast<size_t>(j)] = lo;
-      model->uv[static_cast<size_t>(j)] = hi;
-    } else if (section == "NAME") {
-      return true;
-    } else {
-      return Fail("data outside of a section");
+      case kName:
+        return true;
+      default:
+        return Fail("data outside of a section");
     }
-    return true;
   }
 
   bool Finish() {
-    const int64_t n = static_cast<int64_t>(col_names.size());
+    const int64_t n = static_cast<int64_t>(cols.size());
     BuildCsc(n, entries, model);
     model->objective_offset = offset;
     if (maximize) {  // quadratic_program_io.cc:259-266
@@ -1081,8 +1195,8 @@ struct MpsParser {
     }
     model->has_names = include_names;
     if (include_names) {
-      model->variable_names = std::move(col_names);
-      model->constraint_names = std::move(row_names);
+      model->variable_names = std::move(cols.names());
+      model->constraint_names = std::move(rows.names());
     } else {
       model->name.clear();
     }
@@ -1096,13 +1210,13 @@ bool ModelFromMpsText(std::string_view text, bool include_names, PdlpModel* mode
   size_t at = 0;
   bool done = false;
   while (at < text.size() && !done) {
-    size_t nl = text.find('\n', at);
-    if (nl == std::string_view::npos) nl = text.size();
-    if (!parser.Line(std::string(text.substr(at, nl - at)), &done)) {
+    const char* nl = static_cast<const char*>(std::memchr(text.data() + at, '\n', text.size() - at));
+    const size_t end = nl == nullptr ? text.size() : static_cast<size_t>(nl - text.data());
+    if (!parser.Line(text.substr(at, end - at), &done)) {
       *error = parser.error;
       return false;
     }
-    at = nl + 1;
+    at = end + 1;
   }
   return parser.Finish();
 }
@@ -1110,11 +1224,6 @@ bool ModelFromMpsText(std::string_view text, bool include_names, PdlpModel* mode
 // ---------------------------------------------------------------------------
 // WriteLinearProgramToMps (quadratic_program_io.cc:80-93), free format
 // ---------------------------------------------------------------------------
-std::string MpsNumber(double v) {
-  if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-  return proto::RoundTripDouble(v);
-}
-
 bool LinearProgramToMps(const PdlpProblemView& qp, const char* const* variable_names, const char* const* constraint_names, std::string* out,
                         std::string* error) {
   if (qp.objective_matrix_diagonal != nullptr) {
@@ -1126,10 +1235,35 @@ bool LinearProgramToMps(const PdlpProblemView& qp, const char* const* variable_n
   }
   const int64_t n = qp.num_variables, m = qp.num_constraints;
   const double s = qp.objective_scaling_factor;
-  auto row_name = [&](int64_t i) { return constraint_names != nullptr && constraint_names[i] != nullptr && constraint_names[i][0] ? std::string(constraint_names[i]) : "R" + std::to_string(i); };
+  std::vector<std::string> row_names(static_cast<size_t>(m));
+  for (int64_t i = 0; i < m; ++i)
+    row_names[static_cast<size_t>(i)] =
+        constraint_names != nullptr && constraint_names[i] != nullptr && constraint_names[i][0] ? std::string(constraint_names[i]) : "R" + std::to_string(i);
   auto col_name = [&](int64_t j) { return variable_names != nullptr && variable_names[j] != nullptr && variable_names[j][0] ? std::string(variable_names[j]) : "C" + std::to_string(j); };
   std::string& o = *out;
-  o += "NAME " + std::string(qp.problem_name != nullptr ? qp.problem_name : "") + "\n";
+  o.reserve(static_cast<size_t>(64 + 24 * (m + n) + 48 * (n > 0 ? qp.col_starts[n] : 0)));
+  auto number = [&](double v) {
+    if (std::isinf(v)) {
+      o += v > 0 ? "inf" : "-inf";
+      return;
+    }
+    char buf[40];
+    const std::to_chars_result r = std::to_chars(buf, buf + sizeof buf, v);
+    o.append(buf, r.ptr);
+  };
+  auto entry = [&](const char* lead, const std::string& a, const std::string& b, double v) {  // "<lead><a> <b> <v>\n"
+    o += lead;
+    o += a;
+    o += ' ';
+    o += b;
+    o += ' ';
+    number(v);
+    o += '\n';
+  };
+  static const std::string kCost = "COST", kRhs = "RHS", kRng = "RNG", kBnd = "BND";
+  o += "NAME ";
+  o += qp.problem_name != nullptr ? qp.problem_name : "";
+  o += '\n';
   if (s < 0) o += "OBJSENSE\n    MAX\n";
   o += "ROWS\n N COST\n";
   std::vector<char> kinds(static_cast<size_t>(m));
@@ -1142,34 +1276,38 @@ bool LinearProgramToMps(const PdlpProblemView& qp, const char* const* variable_n
     else if (lc[i] == -kInf) t = 'L';
     else t = 'G';  // ranged rows: G with a RANGES entry
     kinds[static_cast<size_t>(i)] = t;
-    o += std::string(" ") + t + " " + row_name(i) + "\n";
+    o += ' ';
+    o += t;
+    o += ' ';
+    o += row_names[static_cast<size_t>(i)];
+    o += '\n';
   }
   o += "COLUMNS\n";
   for (int64_t j = 0; j < n; ++j) {
     bool wrote = false;
     const std::string cn = col_name(j);
     if (qp.objective_vector[j] != 0.0) {
-      o += "    " + cn + " COST " + MpsNumber(s * qp.objective_vector[j]) + "\n";
+      entry("    ", cn, kCost, s * qp.objective_vector[j]);
       wrote = true;
     }
     for (int64_t p = qp.col_starts[j]; p < qp.col_starts[j + 1]; ++p) {
-      o += "    " + cn + " " + row_name(qp.row_indices[p]) + " " + MpsNumber(qp.values[p]) + "\n";
+      entry("    ", cn, row_names[static_cast<size_t>(qp.row_indices[p])], qp.values[p]);
       wrote = true;
     }
-    if (!wrote) o += "    " + cn + " COST 0\n";
+    if (!wrote) entry("    ", cn, kCost, 0.0);
   }
   o += "RHS\n";
-  if (qp.objective_offset != 0.0) o += "    RHS COST " + MpsNumber(-s * qp.objective_offset) + "\n";
+  if (qp.objective_offset != 0.0) entry("    ", kRhs, kCost, -s * qp.objective_offset);
   for (int64_t i = 0; i < m; ++i) {
     const double rhs = kinds[static_cast<size_t>(i)] == 'L' ? uc[i] : lc[i];
-    if (rhs != 0.0) o += "    RHS " + row_name(i) + " " + MpsNumber(rhs) + "\n";
+    if (rhs != 0.0) entry("    ", kRhs, row_names[static_cast<size_t>(i)], rhs);
   }
   bool any_range = false;
   for (int64_t i = 0; i < m; ++i)
     if (kinds[static_cast<size_t>(i)] == 'G' && uc[i] != kInf) {
       if (!any_range) o += "RANGES\n";
       any_range = true;
-      o += "    RNG " + row_name(i) + " " + MpsNumber(uc[i] - lc[i]) + "\n";
+      entry("    ", kRng, row_names[static_cast<size_t>(i)], uc[i] - lc[i]);
     }
   o += "BOUNDS\n";
   const double* lv = qp.variable_lower_bounds;
@@ -1179,11 +1317,11 @@ bool LinearProgramToMps(const PdlpProblemView& qp, const char* const* variable_n
     if (lv[j] == -kInf && uv[j] == kInf) {
       o += " FR BND " + cn + "\n";
     } else if (lv[j] == uv[j]) {
-      o += " FX BND " + cn + " " + MpsNumber(lv[j]) + "\n";
+      entry(" FX ", kBnd, cn, lv[j]);
     } else {
       if (lv[j] == -kInf) o += " MI BND " + cn + "\n";
-      else if (lv[j] != 0.0) o += " LO BND " + cn + " " + MpsNumber(lv[j]) + "\n";
-      if (uv[j] != kInf) o += " UP BND " + cn + " " + MpsNumber(uv[j]) + "\n";
+      else if (lv[j] != 0.0) entry(" LO ", kBnd, cn, lv[j]);
+      if (uv[j] != kInf) entry(" UP ", kBnd, cn, uv[j]);
     }
   }
   o += "ENDATA\n";
