@@ -132,3 +132,22 @@ def test_starting_point(backend):  # :231-250
     result = backend.primal_dual_hybrid_gradient(tiny_lp(), params, initial_solution=start)
     assert result.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
     assert result.solve_log.iteration_count == 0
+
+
+def test_read_quadratic_program_or_die(tmp_path):  # quadratic_program_io.h:28-40 through the Python surface
+    import fixtures
+    import bz2
+    from ortools_b200 import qp_io
+    lp = fixtures.test_lp()
+    lp.problem_name, lp.variable_names, lp.constraint_names = "lp", ["a", "b", "c", "d"], ["r0", "r1", "r2", "r3"]
+    path = str(tmp_path / "lp.mps")
+    qp_io.write_linear_program_to_mps(lp, path)
+    got = pdlp.read_quadratic_program_or_die(path, include_names=True)          # the library's C++ reader
+    np.testing.assert_array_equal(got.constraint_matrix.toarray(), lp.constraint_matrix.toarray())
+    np.testing.assert_array_equal(got.objective_vector, lp.objective_vector)
+    assert got.variable_names == lp.variable_names and got.constraint_names == lp.constraint_names and got.problem_name == "lp"
+    with bz2.open(path + ".bz2", "wb") as f:                                      # bzip2 goes through the Python reader
+        f.write(open(path, "rb").read())
+    np.testing.assert_array_equal(pdlp.read_quadratic_program_or_die(path + ".bz2").objective_vector, lp.objective_vector)
+    with pytest.raises(ValueError, match="Invalid filename suffix"):
+        pdlp.read_quadratic_program_or_die(str(tmp_path / "lp.txt"))
