@@ -4,6 +4,8 @@
 #include "comm.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -24,11 +26,32 @@ constexpr double kInf = std::numeric_limits<double>::infinity();
 void ComputeRowBlock(const PdlpProblemView& v, int rank, int world, int64_t* begin, int64_t* end) {
   const int64_t m = v.num_constraints, nnz = v.col_starts[v.num_variables];
   std::vector<int64_t> cum(m + 1, 0);
-  for (int64_t k = 0; k < nnz; ++k) {
-    const int64_t r = v.row_indices[k];
-    if (r < 0 || r >= m) throw std::runtime_error("row index out of range");
-    ++cum[r + 1];
+  // Row histogram of K. Every rank of a sharded solve computes it, so the threads
+  // available to one rank are the host's divided by the world size; counts are
+  // integers, so the (relaxed atomic) order of the increments does not matter.
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int threads = nnz < (int64_t{1} << 21) ? 1 : static_cast<int>(std::min<unsigned>(16u, std::max(1u, hw / static_cast<unsigned>(std::max(world, 1)))));
+  std::atomic<bool> bad{false};
+  auto count = [&](int64_t k0, int64_t k1, bool shared) {
+    int64_t* c = cum.data();
+    for (int64_t k = k0; k < k1; ++k) {
+      const int64_t r = v.row_indices[k];
+      if (r < 0 || r >= m) {
+        bad.store(true, std::memory_order_relaxed);
+        return;
+      }
+      if (shared) __atomic_fetch_add(&c[r + 1], int64_t{1}, __ATOMIC_RELAXED);
+      else ++c[r + 1];
+    }
+  };
+  if (threads <= 1) {
+    count(0, nnz, false);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t) pool.emplace_back(count, nnz * t / threads, nnz * (t + 1) / threads, true);
+    for (std::thread& th : pool) th.join();
   }
+  if (bad.load()) throw std::runtime_error("row index out of range");
   for (int64_t r = 0; r < m; ++r) cum[r + 1] += cum[r];
   auto boundary = [&](int g) -> int64_t {
     if (g <= 0) return 0;

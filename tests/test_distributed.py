@@ -46,6 +46,31 @@ def test_row_blocks_are_a_balanced_contiguous_partition(name, scale, world):
     assert max(per) <= mass.sum() / world + mass.max() + 1
 
 
+def test_row_blocks_of_a_large_matrix_follow_the_mass_rule_exactly():
+    """Above 2 M nonzeros the row histogram is threaded (relaxed atomic counts): the boundaries must
+    still be exactly the first rows where nnz + rows reaches g / world of the total, and a bad row
+    index must still be reported."""
+    import ctypes as C
+    import scipy.sparse as sp
+    from ortools_b200 import pdlp
+    rng = np.random.default_rng(3)
+    m, n, nnz = 200_000, 300_000, 2_500_000
+    rows = np.minimum((rng.pareto(1.5, size=nnz) * m / 20).astype(np.int64), m - 1)          # skewed row lengths
+    k = sp.csc_matrix((np.ones(nnz), (rows, rng.integers(0, n, size=nnz))), shape=(m, n))
+    qp = pdlp.QuadraticProgram(n, m)
+    qp.constraint_matrix = k
+    total = float(k.nnz + m)
+    running = np.concatenate([[0], np.cumsum(np.diff(k.tocsr().indptr))]) + np.arange(m + 1)     # nnz + rows before row r
+    for world in (1, 3, 8):
+        want = [0] + [int(np.searchsorted(running, total * g / world, side="left")) for g in range(1, world)] + [m]
+        got = [distributed.row_block(qp, r, world) for r in range(world)]
+        assert got == list(zip(want[:-1], want[1:])), world
+    view, keep = qp._to_view()
+    keep["row_indices"][12345] = m + 7
+    b, e = C.c_int64(), C.c_int64()
+    assert pdlp.backend().fn("row_block")(C.byref(view), C.c_int32(0), C.c_int32(2), C.byref(b), C.byref(e)) != 0
+
+
 # ------------------------------------------------------------------ exchange protocol on gloo
 def pdhg_reference(k, c, lc, uc, lv, uv, iters, step, weight):
     """Unsharded adaptive PDHG iteration (pdhg.cc:1834-1959, 2558-2640), numpy."""
