@@ -184,6 +184,17 @@ inline std::optional<PdlpConvergenceInformation> GetConvergenceInformation(const
     if (stats.convergence_information[i].candidate_type == candidate_type) return stats.convergence_information[i];
   return std::nullopt;
 }
+// iteration_stats.cc:605-625
+inline std::optional<PdlpInfeasibilityInformation> GetInfeasibilityInformation(const PdlpIterationStats& stats, int candidate_type) {
+  for (int i = 0; i < stats.num_infeasibility_information; ++i)
+    if (stats.infeasibility_information[i].candidate_type == candidate_type) return stats.infeasibility_information[i];
+  return std::nullopt;
+}
+inline std::optional<PdlpPointMetadata> GetPointMetadata(const PdlpIterationStats& stats, int point_type) {
+  for (int i = 0; i < stats.num_point_metadata; ++i)
+    if (stats.point_metadata[i].point_type == point_type) return stats.point_metadata[i];
+  return std::nullopt;
+}
 
 // PrimalDualHybridGradient(qp, params, initial_solution, interrupt_solve, message_callback,
 // iteration_stats_callback), primal_dual_hybrid_gradient.h:151-169. Blocking; callbacks run on

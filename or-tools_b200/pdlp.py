@@ -870,6 +870,19 @@ def primal_dual_hybrid_gradient(qp, params, initial_solution=None, interrupt_sol
 # quadratic_program.h / quadratic_program_io.h functions of the reference's wrapper
 # (python/pdlp.cc:95-126); errors surface as ValueError like std::invalid_argument.
 # --------------------------------------------------------------------------
+# iteration_stats.h:94-106: the entry of a repeated field of IterationStats for one point type, or None.
+def get_convergence_information(stats, candidate_type):
+    return next((c for c in (stats.convergence_information if stats is not None else []) if c.candidate_type == candidate_type), None)
+
+
+def get_infeasibility_information(stats, candidate_type):
+    return next((c for c in (stats.infeasibility_information if stats is not None else []) if c.candidate_type == candidate_type), None)
+
+
+def get_point_metadata(stats, point_type):
+    return next((c for c in (stats.point_metadata if stats is not None else []) if c.point_type == point_type), None)
+
+
 def qp_from_mpmodel_proto(proto_str, relax_integer_variables, include_names=False):
     from . import mp_model
     return mp_model.qp_from_mp_model_proto(proto_str, relax_integer_variables, include_names)

@@ -151,3 +151,25 @@ def test_read_quadratic_program_or_die(tmp_path):  # quadratic_program_io.h:28-4
     np.testing.assert_array_equal(pdlp.read_quadratic_program_or_die(path + ".bz2").objective_vector, lp.objective_vector)
     with pytest.raises(ValueError, match="Invalid filename suffix"):
         pdlp.read_quadratic_program_or_die(str(tmp_path / "lp.txt"))
+
+
+def test_get_entries_of_iteration_stats_by_point_type():  # iteration_stats_test.cc:651-732
+    from google.protobuf import text_format
+    stats = text_format.Parse("""
+        convergence_information { candidate_type: POINT_TYPE_CURRENT_ITERATE primal_objective: 1.0 }
+        convergence_information { candidate_type: POINT_TYPE_AVERAGE_ITERATE primal_objective: 2.0 }
+        infeasibility_information { candidate_type: POINT_TYPE_CURRENT_ITERATE primal_ray_linear_objective: 1.0 }
+        infeasibility_information { candidate_type: POINT_TYPE_AVERAGE_ITERATE primal_ray_linear_objective: 2.0 }
+        point_metadata { point_type: POINT_TYPE_CURRENT_ITERATE active_primal_variable_count: 1 }
+        point_metadata { point_type: POINT_TYPE_AVERAGE_ITERATE active_primal_variable_count: 2 }""", pdlp_proto.IterationStatsProto())
+    PT = pdlp.PointType
+    assert pdlp.get_convergence_information(stats, PT.POINT_TYPE_AVERAGE_ITERATE).primal_objective == 2.0
+    assert pdlp.get_convergence_information(stats, PT.POINT_TYPE_CURRENT_ITERATE).primal_objective == 1.0
+    assert pdlp.get_convergence_information(stats, PT.POINT_TYPE_ITERATE_DIFFERENCE) is None
+    assert pdlp.get_infeasibility_information(stats, PT.POINT_TYPE_AVERAGE_ITERATE).primal_ray_linear_objective == 2.0
+    assert pdlp.get_infeasibility_information(stats, PT.POINT_TYPE_CURRENT_ITERATE).primal_ray_linear_objective == 1.0
+    assert pdlp.get_infeasibility_information(stats, PT.POINT_TYPE_ITERATE_DIFFERENCE) is None
+    assert pdlp.get_point_metadata(stats, PT.POINT_TYPE_AVERAGE_ITERATE).active_primal_variable_count == 2
+    assert pdlp.get_point_metadata(stats, PT.POINT_TYPE_CURRENT_ITERATE).active_primal_variable_count == 1
+    assert pdlp.get_point_metadata(stats, PT.POINT_TYPE_ITERATE_DIFFERENCE) is None
+    assert pdlp.get_convergence_information(None, PT.POINT_TYPE_CURRENT_ITERATE) is None
