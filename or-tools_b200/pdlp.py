@@ -870,6 +870,72 @@ def primal_dual_hybrid_gradient(qp, params, initial_solution=None, interrupt_sol
 # quadratic_program.h / quadratic_program_io.h functions of the reference's wrapper
 # (python/pdlp.cc:95-126); errors surface as ValueError like std::invalid_argument.
 # --------------------------------------------------------------------------
+def to_string(qp, max_size=1_000_000):
+    """A readable rendering of `qp` cut to at most `max_size` characters (ToString,
+    quadratic_program.h:188-192; for debugging, not LP format). Numbers print with six
+    significant digits like absl::StrCat."""
+    try:
+        validate_quadratic_program_dimensions(qp)
+    except ValueError as e:
+        return "Quadratic program with inconsistent dimensions: %s" % e
+    import scipy.sparse as sp
+    n, m = len(qp.variable_lower_bounds), len(qp.constraint_lower_bounds)
+    vname = (lambda j: qp.variable_names[j]) if qp.variable_names is not None else (lambda j: "x%d" % j)
+    cname = (lambda i: qp.constraint_names[i]) if qp.constraint_names is not None else (lambda i: "c%d" % i)
+    num = lambda v: "%g" % v
+    pieces, size = [], 0
+
+    def emit(text):
+        nonlocal size
+        pieces.append(text)
+        size += len(text)
+        return size < max_size
+
+    def render():
+        if qp.problem_name is not None:
+            emit("%s:\n" % qp.problem_name)
+        scale = qp.objective_scaling_factor
+        emit("%s %s * (%s" % ("maximize" if scale < 0.0 else "minimize", num(scale), num(qp.objective_offset)))
+        for j in np.flatnonzero(np.asarray(qp.objective_vector) != 0.0):
+            if not emit(" + %s %s" % (num(qp.objective_vector[j]), vname(j))):
+                break
+        if qp.objective_matrix is not None:
+            emit(" + 1/2 * (")
+            for j in np.flatnonzero(np.asarray(qp.objective_matrix) != 0.0):
+                if not emit(" + %s %s^2" % (num(qp.objective_matrix[j]), vname(j))):
+                    break
+            emit(")")
+        emit(")\n")
+        rows = sp.csr_matrix(qp.constraint_matrix)
+        rows.sort_indices()
+        for i in range(m):
+            emit("%s:" % cname(i))
+            if qp.constraint_lower_bounds[i] != -math.inf:
+                emit(" %s <=" % num(qp.constraint_lower_bounds[i]))
+            for p in range(rows.indptr[i], rows.indptr[i + 1]):
+                if not emit(" + %s %s" % (num(rows.data[p]), vname(rows.indices[p]))):
+                    break
+            if qp.constraint_upper_bounds[i] != math.inf:
+                emit(" <= %s" % num(qp.constraint_upper_bounds[i]))
+            if not emit("\n"):
+                return
+        emit("Bounds\n")
+        for j in range(n):
+            lo, hi = qp.variable_lower_bounds[j], qp.variable_upper_bounds[j]
+            if lo == -math.inf:
+                line = "%s free\n" % vname(j) if hi == math.inf else "%s <= %s\n" % (vname(j), num(hi))
+            else:
+                line = "%s >= %s\n" % (vname(j), num(lo)) if hi == math.inf else "%s <= %s <= %s\n" % (num(lo), vname(j), num(hi))
+            if not emit(line):
+                return
+
+    render()
+    text = "".join(pieces)
+    if len(text) > max_size:
+        text = text[: max(0, max_size - 4)] + "...\n"
+    return text
+
+
 # iteration_stats.h:94-106: the entry of a repeated field of IterationStats for one point type, or None.
 def get_convergence_information(stats, candidate_type):
     return next((c for c in (stats.convergence_information if stats is not None else []) if c.candidate_type == candidate_type), None)

@@ -173,3 +173,40 @@ def test_get_entries_of_iteration_stats_by_point_type():  # iteration_stats_test
     assert pdlp.get_point_metadata(stats, PT.POINT_TYPE_CURRENT_ITERATE).active_primal_variable_count == 1
     assert pdlp.get_point_metadata(stats, PT.POINT_TYPE_ITERATE_DIFFERENCE) is None
     assert pdlp.get_convergence_information(None, PT.POINT_TYPE_CURRENT_ITERATE) is None
+
+
+def test_quadratic_program_to_string():  # quadratic_program_test.cc:477-556
+    import fixtures
+    lp_body = ("c0: 12 <= + 2 x0 + 1 x1 + 1 x2 + 2 x3 <= 12\n"
+               "c1: + 1 x0 + 1 x2 <= 7\n"
+               "c2: -4 <= + 4 x0\n"
+               "c3: -1 <= + 1.5 x2 + -1 x3 <= 1\n"
+               "Bounds\n"
+               "x0 free\n"
+               "x1 >= -2\n"
+               "x2 <= 6\n"
+               "2.5 <= x3 <= 3.5\n")
+    qp = fixtures.test_lp()
+    assert pdlp.to_string(qp) == "minimize 1 * (-14 + 5.5 x0 + -2 x1 + -1 x2 + 1 x3)\n" + lp_body
+    qp.objective_scaling_factor = -1
+    assert pdlp.to_string(qp) == "maximize -1 * (-14 + 5.5 x0 + -2 x1 + -1 x2 + 1 x3)\n" + lp_body
+    cut = pdlp.to_string(fixtures.test_lp(), 100)
+    assert len(cut) == 100 and cut == ("minimize 1 * (-14 + 5.5 x0 + -2 x1 + -1 x2 + 1 x3)\n"
+                                       "c0: 12 <= + 2 x0 + 1 x1 + 1 x2 + 2 x3 <= 12\n"
+                                       "c...\n")
+    qp = fixtures.test_diagonal_qp1()
+    assert pdlp.to_string(qp) == ("minimize 1 * (5 + -1 x0 + -1 x1 + 1/2 * ( + 4 x0^2 + 1 x1^2))\n"
+                                  "c0: + 1 x0 + 1 x1 <= 1\n"
+                                  "Bounds\n"
+                                  "1 <= x0 <= 2\n"
+                                  "-2 <= x1 <= 4\n")
+    qp.problem_name, qp.variable_names, qp.constraint_names = "test", ["x", "y"], ["total"]
+    assert pdlp.to_string(qp) == ("test:\n"
+                                  "minimize 1 * (5 + -1 x + -1 y + 1/2 * ( + 4 x^2 + 1 y^2))\n"
+                                  "total: + 1 x + 1 y <= 1\n"
+                                  "Bounds\n"
+                                  "1 <= x <= 2\n"
+                                  "-2 <= y <= 4\n")
+    qp = fixtures.test_lp()
+    qp.variable_lower_bounds = qp.variable_lower_bounds[:3]
+    assert pdlp.to_string(qp).startswith("Quadratic program with inconsistent dimensions: ")
