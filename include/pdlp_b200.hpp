@@ -35,6 +35,20 @@ struct Triplet {
   double value;
 };
 
+// Adds up runs of consecutive triplets with the same (row, column) in place, keeping the order
+// (CombineRepeatedTripletsInPlace, quadratic_program.h:200-208).
+inline void CombineRepeatedTripletsInPlace(std::vector<Triplet>& triplets) {
+  size_t kept = 0;
+  for (size_t k = 0; k < triplets.size(); ++k) {
+    if (kept > 0 && triplets[kept - 1].row == triplets[k].row && triplets[kept - 1].col == triplets[k].col) {
+      triplets[kept - 1].value += triplets[k].value;
+    } else {
+      triplets[kept++] = triplets[k];
+    }
+  }
+  triplets.resize(kept);
+}
+
 // min 1/2 x'Qx + c'x  s.t.  l_c <= Kx <= u_c,  l_v <= x <= u_v, Q diagonal (quadratic_program.h:61-151).
 // K is held in compressed column form with int64 indices, like the reference's
 // Eigen::SparseMatrix<double, ColMajor, int64_t>.

@@ -86,3 +86,11 @@ def test_io_header_round_trips_formats_from_cpp(tmp_path):
     assert log["instanceName"] == "tiny" and log["terminationReason"] == "TERMINATION_REASON_OPTIMAL" and log["iterationCount"] == 12
     assert log["params"]["terminationCriteria"]["iterationLimit"] == 100
     assert "response bytes=" in out and "response bytes=0" not in out  # MPSOLVER_MODEL_INVALID, made without a device
+
+
+def test_triplet_helpers_from_cpp(tmp_path):  # quadratic_program_test.cc:558-628
+    exe = str(tmp_path / "triplets")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "triplets.cc"),
+                           "-L" + LIB_DIR, "-lpdlp_b200", "-Wl,-rpath," + LIB_DIR, "-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and "triplets ok" in p.stdout, (p.returncode, p.stdout, p.stderr)
