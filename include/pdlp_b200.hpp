@@ -133,6 +133,37 @@ struct QuadraticProgram {
   int64_t num_variables_ = 0, num_constraints_ = 0;
 };
 
+// quadratic_program.h:153-158
+inline bool IsLinearProgram(const QuadraticProgram& qp) { return !qp.objective_matrix_diagonal.has_value(); }
+
+// ValidateQuadraticProgramDimensions (quadratic_program.cc:38-97): "" if the vector and matrix sizes
+// agree, else the description of the first inconsistency (the reference's InvalidArgumentError text).
+inline std::string ValidateQuadraticProgramDimensions(const QuadraticProgram& qp) {
+  const int64_t var_lb_size = static_cast<int64_t>(qp.variable_lower_bounds.size());
+  const int64_t con_lb_size = static_cast<int64_t>(qp.constraint_lower_bounds.size());
+  auto mismatch = [](const char* a, int64_t a_size, const char* b, int64_t b_size, const char* unit) {
+    return std::string("Inconsistent dimensions: ") + a + " has size " + std::to_string(a_size) + " while " + b + " has " +
+           (unit[0] != '\0' ? std::to_string(b_size) + " " + unit : "size " + std::to_string(b_size));
+  };
+  if (var_lb_size != static_cast<int64_t>(qp.variable_upper_bounds.size()))
+    return mismatch("variable lower bound vector", var_lb_size, "variable upper bound vector", static_cast<int64_t>(qp.variable_upper_bounds.size()), "");
+  if (var_lb_size != static_cast<int64_t>(qp.objective_vector.size()))
+    return mismatch("variable lower bound vector", var_lb_size, "objective vector", static_cast<int64_t>(qp.objective_vector.size()), "");
+  if (var_lb_size != qp.num_variables() || var_lb_size + 1 != static_cast<int64_t>(qp.col_starts.size()))
+    return mismatch("variable lower bound vector", var_lb_size, "constraint matrix", static_cast<int64_t>(qp.col_starts.size()) - 1, "columns");
+  if (qp.objective_matrix_diagonal && var_lb_size != static_cast<int64_t>(qp.objective_matrix_diagonal->size()))
+    return mismatch("variable lower bound vector", var_lb_size, "objective matrix", static_cast<int64_t>(qp.objective_matrix_diagonal->size()), "rows");
+  if (con_lb_size != static_cast<int64_t>(qp.constraint_upper_bounds.size()))
+    return mismatch("constraint lower bound vector", con_lb_size, "constraint upper bound vector", static_cast<int64_t>(qp.constraint_upper_bounds.size()), "");
+  if (con_lb_size != qp.num_constraints())
+    return mismatch("constraint lower bound vector", con_lb_size, "constraint matrix", qp.num_constraints(), "rows");
+  if (qp.variable_names && var_lb_size != static_cast<int64_t>(qp.variable_names->size()))
+    return mismatch("variable lower bound vector", var_lb_size, "variable names", static_cast<int64_t>(qp.variable_names->size()), "");
+  if (qp.constraint_names && con_lb_size != static_cast<int64_t>(qp.constraint_names->size()))
+    return mismatch("constraint lower bound vector", con_lb_size, "constraint names", static_cast<int64_t>(qp.constraint_names->size()), "");
+  return std::string();
+}
+
 // The parameter POD with the proto defaults (solvers.proto:238-497); fields are set directly,
 // e.g. params.termination_criteria.simple_eps_optimal_relative = 1e-6 after choosing
 // params.termination_criteria.optimality_criteria_case = PDLP_SIMPLE_OPTIMALITY_CRITERIA.

@@ -1,6 +1,7 @@
 // triplets.cc -- known answers of quadratic_program_test.cc:558-628 (CombineRepeatedTripletsInPlace,
 // SetEigenMatrixFromTriplets) for the helpers of include/pdlp_b200.hpp. Exit code = first failing check.
 #include <cstdio>
+#include <string>
 #include <vector>
 
 #include "pdlp_b200.hpp"
@@ -34,6 +35,40 @@ int main() {
   if (qp.col_starts != std::vector<int64_t>{0, 2, 3} || qp.row_indices != std::vector<int64_t>{0, 1, 1} ||
       qp.values != std::vector<double>{2.0, -1.0, 1.0})
     return 8;
+  // ValidateQuadraticProgramDimensions, quadratic_program_test.cc:68-162
+  {
+    using pdlp_b200::QuadraticProgram;
+    using pdlp_b200::ValidateQuadraticProgramDimensions;
+    QuadraticProgram ok(2, 1);
+    ok.objective_matrix_diagonal = std::vector<double>{4.0, 1.0};
+    ok.variable_names = std::vector<std::string>{"x0", "x1"};
+    ok.constraint_names = std::vector<std::string>{"c0"};
+    if (!ValidateQuadraticProgramDimensions(ok).empty() || pdlp_b200::IsLinearProgram(ok)) return 9;
+    int code = 10;
+    auto bad = [&](void (*change)(QuadraticProgram&)) {
+      QuadraticProgram q(2, 3);
+      change(q);
+      return ValidateQuadraticProgramDimensions(q).rfind("Inconsistent dimensions: ", 0) == 0;
+    };
+    if (!bad([](QuadraticProgram& q) { q.constraint_lower_bounds.resize(10); })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.constraint_upper_bounds.resize(10); })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.objective_vector.resize(10); })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.variable_lower_bounds.resize(10); })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.variable_upper_bounds.resize(10); })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.col_starts.resize(11); })) return code;  // 10 columns
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.objective_matrix_diagonal = std::vector<double>(10, 0.0); })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.variable_names = std::vector<std::string>{"x0"}; })) return code;
+    ++code;
+    if (!bad([](QuadraticProgram& q) { q.constraint_names = std::vector<std::string>{"c0"}; })) return code;
+    if (!pdlp_b200::IsLinearProgram(QuadraticProgram(2, 3))) return 30;
+  }
   std::printf("triplets ok\n");
   return 0;
 }

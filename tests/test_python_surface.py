@@ -210,3 +210,20 @@ def test_quadratic_program_to_string():  # quadratic_program_test.cc:477-556
     qp = fixtures.test_lp()
     qp.variable_lower_bounds = qp.variable_lower_bounds[:3]
     assert pdlp.to_string(qp).startswith("Quadratic program with inconsistent dimensions: ")
+
+
+@pytest.mark.parametrize("field,size", [("constraint_lower_bounds", 10), ("constraint_upper_bounds", 10), ("objective_vector", 10),
+                                        ("variable_lower_bounds", 10), ("variable_upper_bounds", 10), ("objective_matrix", 10),
+                                        ("variable_names", 1), ("constraint_names", 1), ("constraint_matrix", (10, 2)), ("constraint_matrix", (3, 10))])
+def test_validate_quadratic_program_dimensions_inconsistent(field, size):  # quadratic_program_test.cc:83-162
+    qp = pdlp.QuadraticProgram(2, 3)
+    pdlp.validate_quadratic_program_dimensions(qp)
+    if field == "constraint_matrix":
+        qp.constraint_matrix = scipy.sparse.csc_matrix(size)
+    elif field.endswith("_names"):
+        setattr(qp, field, ["n"] * size)
+    else:
+        setattr(qp, field, np.zeros(size))
+    with pytest.raises(ValueError, match="Inconsistent dimensions"):
+        pdlp.validate_quadratic_program_dimensions(qp)
+    assert pdlp.to_string(qp).startswith("Quadratic program with inconsistent dimensions: ")
