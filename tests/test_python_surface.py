@@ -227,3 +227,27 @@ def test_validate_quadratic_program_dimensions_inconsistent(field, size):  # qua
     with pytest.raises(ValueError, match="Inconsistent dimensions"):
         pdlp.validate_quadratic_program_dimensions(qp)
     assert pdlp.to_string(qp).startswith("Quadratic program with inconsistent dimensions: ")
+
+
+def _run_python_example():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return subprocess.run([sys.executable, os.path.join(root, "examples", "solve_simple_lp.py")], capture_output=True, text=True, timeout=300)
+
+
+def test_python_example_fails_loudly_without_a_gpu():
+    if pdlp.backend().device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = _run_python_example()
+    assert p.returncode != 0 and "no usable CUDA device" in p.stderr
+
+
+@pytest.mark.gpu
+def test_python_example_solves_the_sample_lp(b200_backend):  # samples/simple_pdlp_program.py
+    p = _run_python_example()
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Solve successful" in p.stdout
+    objective = [line for line in p.stdout.splitlines() if line.startswith("Primal objective:")]
+    assert objective and float(objective[0].split(":")[1]) == pytest.approx(-34.0, abs=1e-4)
