@@ -314,9 +314,12 @@ def pin_host_arrays(keep):
     """Page-locks the numpy arrays behind the PdlpProblemView (cudaHostRegister, no copy) so that the
     library's cudaMemcpyAsync calls read pinned memory. Returns the registered pointers; any failure
     just leaves that array pageable."""
-    import torch
-    rt = torch.cuda.cudart()
     done = []
+    try:
+        import torch
+        rt = torch.cuda.cudart()
+    except Exception:
+        return done
     for arr in keep.values():
         if not hasattr(arr, "ctypes") or getattr(arr, "nbytes", 0) < (1 << 16):
             continue
@@ -330,9 +333,11 @@ def pin_host_arrays(keep):
 
 
 def unpin_host_arrays(pointers):
+    if not pointers:
+        return
     import torch
     rt = torch.cuda.cudart()
-    for p in pointers or []:
+    for p in pointers:
         try:
             rt.cudaHostUnregister(p)
         except Exception:
