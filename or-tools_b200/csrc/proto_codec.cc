@@ -902,6 +902,7 @@ bool ForEachScalar(const Decoded& d, bool json, Emit emit) {
     if (!json) return RoundTripDouble(v);
     if (std::isnan(v)) return "\"NaN\"";
     if (std::isinf(v)) return v > 0 ? "\"Infinity\"" : "\"-Infinity\"";
+    if (v == 0.0 && std::signbit(v)) return "-0.0";  // "-0" is an integer to most JSON readers and loses the sign
     return RoundTripDouble(v);
   };
   auto integer = [&](int64_t v) -> std::string {
@@ -1091,6 +1092,18 @@ class JsonParser {
   void Skip() {
     while (p_ < end_ && std::isspace(static_cast<unsigned char>(*p_))) ++p_;
   }
+  bool Hex4(unsigned* v) {
+    if (end_ - p_ < 4) return false;
+    unsigned r = 0;
+    for (int k = 0; k < 4; ++k) {
+      const char h = p_[k];
+      if (!std::isxdigit(static_cast<unsigned char>(h))) return false;
+      r = r * 16 + static_cast<unsigned>(std::isdigit(static_cast<unsigned char>(h)) ? h - '0' : std::tolower(static_cast<unsigned char>(h)) - 'a' + 10);
+    }
+    p_ += 4;
+    *v = r;
+    return true;
+  }
   bool String(std::string* out) {
     if (p_ >= end_ || *p_ != '"') return Fail("expected a string");
     ++p_;
@@ -1110,20 +1123,27 @@ class JsonParser {
         case 'f': out->push_back('\f'); break;
         case '/': case '\\': case '"': out->push_back(c); break;
         case 'u': {
-          if (end_ - p_ < 4) return Fail("bad \\u escape");
           unsigned v = 0;
-          for (int k = 0; k < 4; ++k) {
-            const char h = *p_++;
-            if (!std::isxdigit(static_cast<unsigned char>(h))) return Fail("bad \\u escape");
-            v = v * 16 + (std::isdigit(static_cast<unsigned char>(h)) ? h - '0' : std::tolower(h) - 'a' + 10);
+          if (!Hex4(&v)) return Fail("bad \\u escape");
+          if (v >= 0xD800 && v <= 0xDBFF && end_ - p_ >= 6 && p_[0] == '\\' && p_[1] == 'u') {  // surrogate pair
+            const char* save = p_;
+            p_ += 2;
+            unsigned lo = 0;
+            if (Hex4(&lo) && lo >= 0xDC00 && lo <= 0xDFFF) v = 0x10000 + ((v - 0xD800) << 10) + (lo - 0xDC00);
+            else p_ = save;
           }
           if (v < 0x80) {
             out->push_back(static_cast<char>(v));
           } else if (v < 0x800) {
             out->push_back(static_cast<char>(0xC0 | (v >> 6)));
             out->push_back(static_cast<char>(0x80 | (v & 0x3F)));
-          } else {
+          } else if (v < 0x10000) {
             out->push_back(static_cast<char>(0xE0 | (v >> 12)));
+            out->push_back(static_cast<char>(0x80 | ((v >> 6) & 0x3F)));
+            out->push_back(static_cast<char>(0x80 | (v & 0x3F)));
+          } else {
+            out->push_back(static_cast<char>(0xF0 | (v >> 18)));
+            out->push_back(static_cast<char>(0x80 | ((v >> 12) & 0x3F)));
             out->push_back(static_cast<char>(0x80 | ((v >> 6) & 0x3F)));
             out->push_back(static_cast<char>(0x80 | (v & 0x3F)));
           }
