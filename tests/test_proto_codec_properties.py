@@ -93,3 +93,95 @@ def test_codec_round_trips_agree_with_the_protobuf_runtime(name, data):
         assert back == msg, encoded
     # binary -> binary is the identity on canonical input
     assert native_io.convert(name, blob, native_io.BINARY, native_io.BINARY) == blob
+
+
+# --------------------------------------------------------------------------------------------------
+# typed adapters: parameters, models, MPS
+# --------------------------------------------------------------------------------------------------
+EXAMPLES = int(os.environ.get("PDLP_B200_PROPERTY_EXAMPLES", "60"))
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(msg=messages(pdlp_proto.PrimalDualHybridGradientParamsProto))
+def test_parameter_pod_agrees_with_the_python_adapter(msg):
+    from test_native_io import same_pod
+    if len(msg.random_projection_seeds) > 8:
+        return
+    want = pdlp_proto.params_from_proto(msg).to_pod()
+    got = native_io.params_from_bytes(msg.SerializeToString())
+    same_pod(got, want)
+    same_pod(native_io.params_from_text(text_format.MessageToString(msg)), want)
+    again = pdlp_proto.PrimalDualHybridGradientParamsProto()
+    again.ParseFromString(native_io.params_serialize(got))
+    same_pod(pdlp_proto.params_from_proto(again).to_pod(), want)          # POD -> bytes -> POD is the identity
+
+
+@st.composite
+def models(draw):
+    import numpy as np
+    n = draw(st.integers(0, 6))
+    m = draw(st.integers(0, 5))
+    finite = st.floats(-1e6, 1e6, allow_nan=False)
+    bound = st.one_of(finite, st.just(math.inf), st.just(-math.inf))
+    msg = mp_model.MPModelProto()
+    for j in range(n):
+        v = msg.variable.add()
+        v.lower_bound, v.upper_bound, v.objective_coefficient = draw(bound), draw(bound), draw(finite)
+        if draw(st.booleans()):
+            v.name = "v%d" % j
+    for i in range(m):
+        c = msg.constraint.add()
+        c.lower_bound, c.upper_bound = draw(bound), draw(bound)
+        if n > 0:
+            idx = draw(st.lists(st.integers(0, n - 1), max_size=5))
+            c.var_index.extend(idx)
+            c.coefficient.extend(draw(st.lists(finite, min_size=len(idx), max_size=len(idx))))
+        if draw(st.booleans()):
+            c.name = "c%d" % i
+    msg.maximize = draw(st.booleans())
+    msg.objective_offset = draw(finite)
+    if n > 0 and draw(st.booleans()):
+        diag = draw(st.lists(st.integers(0, n - 1), max_size=3, unique=True))
+        msg.quadratic_objective.qvar1_index.extend(diag)
+        msg.quadratic_objective.qvar2_index.extend(diag)
+        msg.quadratic_objective.coefficient.extend(draw(st.lists(finite, min_size=len(diag), max_size=len(diag))))
+    if draw(st.booleans()):
+        msg.name = draw(st.text(alphabet="abc xyz", max_size=6))
+    return msg
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(msg=models(), names=st.booleans())
+def test_model_conversion_agrees_with_the_python_adapter(msg, names):
+    from test_native_io import same_qp
+    want = mp_model.qp_from_mp_model_proto(msg, relax_integer_variables=True, include_names=names)
+    got = native_io.qp_from_mp_model_proto_bytes(msg.SerializeToString(), True, include_names=names)
+    same_qp(got, want, names=names)
+    assert native_io.qp_to_mp_model_proto_bytes(got) == mp_model.qp_to_mp_model_proto(want).SerializeToString()
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large, HealthCheck.function_scoped_fixture])
+@given(msg=models())
+def test_mps_written_natively_is_read_alike_by_both_readers(msg, tmp_path):
+    import numpy as np
+    from ortools_b200 import qp_io
+    from test_native_io import same_qp
+    msg.ClearField("quadratic_objective")
+    qp = mp_model.qp_from_mp_model_proto(msg, True)
+    free = (qp.constraint_lower_bounds == -math.inf) & (qp.constraint_upper_bounds == math.inf)
+    crossed = qp.constraint_lower_bounds > qp.constraint_upper_bounds      # not expressible as a ranged MPS row
+    if free.any() or crossed.any() or np.isinf(qp.constraint_lower_bounds[qp.constraint_lower_bounds == qp.constraint_upper_bounds]).any():
+        return
+    if (qp.variable_lower_bounds > qp.variable_upper_bounds).any() or (qp.variable_lower_bounds == math.inf).any() or (qp.variable_upper_bounds == -math.inf).any():
+        return
+    path = str(tmp_path / "model.mps")
+    native_io.write_linear_program_to_mps(qp, path)
+    a, b = native_io.read_quadratic_program(path), qp_io.read_quadratic_program(path)
+    same_qp(a, b)
+    np.testing.assert_array_equal(a.constraint_matrix.toarray(), qp.constraint_matrix.toarray())
+    np.testing.assert_array_equal(a.objective_vector, qp.objective_vector)
+    np.testing.assert_array_equal(a.variable_lower_bounds, qp.variable_lower_bounds)
+    np.testing.assert_array_equal(a.variable_upper_bounds, qp.variable_upper_bounds)
+    np.testing.assert_array_equal(a.constraint_lower_bounds, qp.constraint_lower_bounds)
+    np.testing.assert_allclose(a.constraint_upper_bounds, qp.constraint_upper_bounds, rtol=1e-15, atol=1e-9)   # ranged rows: lower + (upper - lower)
+    assert a.objective_offset == qp.objective_offset and a.objective_scaling_factor == qp.objective_scaling_factor
