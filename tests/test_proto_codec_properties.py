@@ -185,3 +185,80 @@ def test_mps_written_natively_is_read_alike_by_both_readers(msg, tmp_path):
     np.testing.assert_array_equal(a.constraint_lower_bounds, qp.constraint_lower_bounds)
     np.testing.assert_allclose(a.constraint_upper_bounds, qp.constraint_upper_bounds, rtol=1e-15, atol=1e-9)   # ranged rows: lower + (upper - lower)
     assert a.objective_offset == qp.objective_offset and a.objective_scaling_factor == qp.objective_scaling_factor
+
+
+# --------------------------------------------------------------------------------------------------
+# differential test of the two MPS readers on structured random text (valid and invalid)
+# --------------------------------------------------------------------------------------------------
+NUMBERS = ["1", "-2.5", "1e3", "1E-2", "1D2", "2.5d-1", "+4", "inf", "-inf", "Infinity", "-INFINITY", "1e400", ".5", "5.", "0", "-0", "1e-320",
+           "nan", "abc", "0x10", "1e", "--1", "1.2.3"]
+ROW_NAMES = ["r0", "r1", "r2", "obj", "obj2", "nosuch"]
+COL_NAMES = ["x", "y", "z"]
+
+
+@st.composite
+def mps_texts(draw):
+    lines = ["NAME " + draw(st.sampled_from(["", "model", "two words"]))]
+    if draw(st.booleans()):
+        lines += draw(st.sampled_from([["OBJSENSE", "    MAX"], ["OBJSENSE MAXIMIZE"], ["OBJSENSE", " MIN"], ["OBJSENSEMAX"]]))
+    lines.append("ROWS")
+    lines.append(" N obj")
+    for r in ["r0", "r1", "r2"]:
+        if draw(st.booleans()):
+            lines.append(" %s %s" % (draw(st.sampled_from(["E", "L", "G", "e", "g", "N", "Q"])), r))
+    if draw(st.booleans()):
+        lines.append(" N obj2")
+    lines.append("COLUMNS")
+    for _ in range(draw(st.integers(0, 6))):
+        if draw(st.integers(0, 9)) == 0:
+            lines.append("    M1 'MARKER' '%s'" % draw(st.sampled_from(["INTORG", "INTEND"])))
+            continue
+        pairs = draw(st.integers(1, 2))
+        toks = [draw(st.sampled_from(COL_NAMES))]
+        for _ in range(pairs):
+            toks += [draw(st.sampled_from(ROW_NAMES)), draw(st.sampled_from(NUMBERS))]
+        lines.append("    " + " ".join(toks))
+    for section in ("RHS", "RANGES"):
+        if draw(st.booleans()):
+            lines.append(section)
+            for _ in range(draw(st.integers(0, 3))):
+                toks = [draw(st.sampled_from(ROW_NAMES)), draw(st.sampled_from(NUMBERS))]
+                if draw(st.booleans()):
+                    toks = ["SET"] + toks
+                if draw(st.integers(0, 3)) == 0:
+                    toks += [draw(st.sampled_from(ROW_NAMES)), draw(st.sampled_from(NUMBERS))]
+                lines.append("    " + " ".join(toks))
+    if draw(st.booleans()):
+        lines.append("BOUNDS")
+        for _ in range(draw(st.integers(0, 4))):
+            kind = draw(st.sampled_from(["LO", "UP", "FX", "FR", "MI", "PL", "BV", "LI", "UI", "SC", "XX", "up"]))
+            toks = [kind]
+            if draw(st.booleans()):
+                toks.append("BND")
+            toks.append(draw(st.sampled_from(COL_NAMES + ["w"])))
+            if kind.upper() in ("LO", "UP", "FX", "LI", "UI", "SC") or draw(st.integers(0, 4)) == 0:
+                toks.append(draw(st.sampled_from(NUMBERS)))
+            lines.append(" " + " ".join(toks))
+    if draw(st.integers(0, 5)) > 0:
+        lines.append("ENDATA")
+    if draw(st.integers(0, 6)) == 0:
+        lines.insert(draw(st.integers(0, len(lines))), draw(st.sampled_from(["* a comment", "", "WHATEVER", "    stray data", "QUADOBJ"])))
+    return "\n".join(lines) + "\n"
+
+
+@settings(max_examples=4 * EXAMPLES, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(text=mps_texts(), names=st.booleans())
+def test_both_mps_readers_agree_on_random_text(text, names):
+    from ortools_b200 import qp_io
+    from test_native_io import same_qp
+    want = error = None
+    try:
+        want = qp_io.parse_mps(text.splitlines(), include_names=names)
+    except qp_io.MpsError as e:
+        error = str(e)
+    if error is not None:
+        with pytest.raises(native_io.NativeIoError) as caught:
+            native_io.qp_from_mps_text(text, include_names=names)
+        assert str(caught.value).split(":")[0] == error.split(":")[0], (text, error, str(caught.value))      # the same line is blamed
+    else:
+        same_qp(native_io.qp_from_mps_text(text, include_names=names), want, names=names)
