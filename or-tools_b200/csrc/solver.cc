@@ -136,7 +136,8 @@ RelativeResiduals ComputeRelativeResiduals(const DetailedCriteria& oc, const Pdl
   r.l2_primal = s.l2_primal_residual / (rp + bn.l2_norm_constraint_bounds);
   r.l_inf_dual = s.l_inf_dual_residual / (rd + bn.l_inf_norm_primal_linear_objective);
   r.l2_dual = s.l2_dual_residual / (rd + bn.l2_norm_primal_linear_objective);
-  r.gap = (s.primal_objective - s.dual_objective) / (rg + std::abs(s.primal_objective) + std::abs(s.dual_objective));
+  const double abs_obj = std::abs(s.primal_objective) + std::abs(s.dual_objective);  // summed first, like termination.cc:266-268
+  r.gap = (s.primal_objective - s.dual_objective) / (rg + abs_obj);
   return r;
 }
 
