@@ -505,9 +505,25 @@ int32_t pdlp_b200_compute_localized_lagrangian_bounds_max_norm(PdlpDeviceProblem
 }
 
 // ---- problem-free vector entry points ---------------------------------------
+}  // extern "C"
+namespace {
+// Preconditions of SolveTrustRegion / SolveDiagonalTrustRegion (trust_region.h:58-89): a radius that is
+// not negative (nor NaN) and strictly positive norm weights. Checked on the host, before any device work.
+bool TrustRegionArgumentsOk(int64_t size, const double* weights, double target_radius) {
+  if (size < 0 || (size > 0 && weights == nullptr) || !(target_radius >= 0.0)) return false;
+  for (int64_t i = 0; i < size; ++i)
+    if (!(weights[i] > 0.0)) return false;
+  return true;
+}
+}  // namespace
+extern "C" {
 int32_t pdlp_b200_solve_trust_region(int32_t cuda_device, int64_t size, const double* objective, const double* lb, const double* ub,
                                      const double* center, const double* weights, double target_radius, double* solution, double* step_size,
                                      double* objective_value) {
+  // the reference CHECK-fails on these (trust_region.cc: "target_radius >= 0.0", "norm_weights_are_positive"); here they are a status
+  if (!TrustRegionArgumentsOk(size, weights, target_radius) || step_size == nullptr || objective_value == nullptr ||
+      (size > 0 && (objective == nullptr || lb == nullptr || ub == nullptr || center == nullptr || solution == nullptr)))
+    return PDLP_B200_STATUS_BAD_ARGUMENT;
   return Guard([&] {
     Device dev(cuda_device);
     PlainVec o(dev, objective, size), l(dev, lb, size), u(dev, ub, size), c(dev, center, size), w(dev, weights, size), s(dev, nullptr, size);
@@ -518,6 +534,9 @@ int32_t pdlp_b200_solve_trust_region(int32_t cuda_device, int64_t size, const do
 int32_t pdlp_b200_solve_diagonal_trust_region(int32_t cuda_device, int64_t size, const double* objective, const double* qdiag, const double* lb,
                                               const double* ub, const double* center, const double* weights, double target_radius, double tol,
                                               double* solution, double* step_size, double* objective_value) {
+  if (!TrustRegionArgumentsOk(size, weights, target_radius) || step_size == nullptr || objective_value == nullptr ||
+      (size > 0 && (objective == nullptr || qdiag == nullptr || lb == nullptr || ub == nullptr || center == nullptr || solution == nullptr)))
+    return PDLP_B200_STATUS_BAD_ARGUMENT;
   return Guard([&] {
     Device dev(cuda_device);
     PlainVec o(dev, objective, size), q(dev, qdiag, size), l(dev, lb, size), u(dev, ub, size), c(dev, center, size), w(dev, weights, size),

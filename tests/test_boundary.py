@@ -87,3 +87,17 @@ def test_param_validation_messages():
     p.major_iteration_frequency = 0
     ok, msg = be.validate_params(p)
     assert not ok and "major_iteration_frequency" in msg
+
+
+def test_trust_region_preconditions_are_statuses_not_crashes():
+    """trust_region_test.cc:503-583 (TrustRegionDeathTest): the reference CHECK-fails on a negative radius or
+    a non-positive norm weight; across the C ABI they are PDLP_B200_STATUS_BAD_ARGUMENT, decided on the
+    host before any device work (so this runs without a GPU)."""
+    be = pdlp.backend()
+    ones, zeros = [1.0, 1.0], [0.0, 0.0]
+    lo, hi = [-10.0, -10.0], [10.0, 10.0]
+    for weights, radius in (([1.0, 0.0], 1.0), ([1.0, -2.0], 1.0), ([1.0, float("nan")], 1.0), (ones, -1.0), (ones, float("nan"))):
+        with pytest.raises(RuntimeError, match="bad argument"):
+            be.solve_trust_region(ones, lo, hi, zeros, weights, radius)
+        with pytest.raises(RuntimeError, match="bad argument"):
+            be.solve_diagonal_trust_region(ones, ones, lo, hi, zeros, weights, radius, 1e-8)
