@@ -101,3 +101,14 @@ def test_trust_region_preconditions_are_statuses_not_crashes():
             be.solve_trust_region(ones, lo, hi, zeros, weights, radius)
         with pytest.raises(RuntimeError, match="bad argument"):
             be.solve_diagonal_trust_region(ones, ones, lo, hi, zeros, weights, radius, 1e-8)
+
+
+def test_public_headers_compile_as_c99_and_strict_cpp(tmp_path):
+    """include/*.h are plain C (the boundary has no C++ or torch types); the .hpp faces are warning-free C++17."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    for header in ("pdlp_b200.h", "pdlp_b200_io.h"):
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Wpedantic", "-Werror", "-I" + inc, "-fsyntax-only", "-x", "c", os.path.join(inc, header)])
+    src = tmp_path / "faces.cc"
+    src.write_text('#include "pdlp_b200.hpp"\n#include "pdlp_b200_io.hpp"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Wpedantic", "-Wshadow", "-Werror", "-I" + inc, "-fsyntax-only", str(src)])
