@@ -562,6 +562,38 @@ enum { PDLP_VECOP_DOT = 0, PDLP_VECOP_LINF_NORM = 1, PDLP_VECOP_L1_NORM = 2,
 int32_t pdlp_b200_vector_reduce(int32_t cuda_device, int32_t op, int64_t size, const double* a,
                                 const double* b, double* out);
 
+/* ---- layout inspection (host-only; no device needed) ---------------------- *
+ * The SELL-32 images of K (rows) and K^T (cols) exactly as the host builder
+ * lays them out for the device (csrc/sell_builder.cc) --
+ * the structure, not a product: the arrays are for checking that the image
+ * stores the caller's matrix entry for entry. Slots [0, num_virtual_padded) are
+ * the virtual slots of split rows (virt_pos = the row's position, -1 padding);
+ * slot num_virtual_padded + (p - num_split) is the row at position p >=
+ * num_split. Element j of slot s lives at slice_ptr[s / 32] + 32 j + s % 32;
+ * `col` holds positions of the OTHER image's order (row_of_pos maps a position
+ * back to the caller's index). Arrays are owned by the library.              */
+typedef struct PdlpSellLayout {
+  int64_t num_rows, num_cols, num_split, num_virtual, num_virtual_padded, num_slots, padded_nnz;
+  int32_t split_len;
+  int64_t* slice_ptr;    /* [num_slots / 32 + 1]  */
+  int32_t* slot_len;     /* [num_slots]           */
+  int32_t* col;          /* [padded_nnz]          */
+  double* val;           /* [padded_nnz]          */
+  int32_t* split_first;  /* [num_split + 1]       */
+  int32_t* virt_pos;     /* [num_virtual_padded]  */
+  int32_t* row_of_pos;   /* [num_rows]            */
+  int32_t* pos_of_row;   /* [num_rows]            */
+} PdlpSellLayout;
+/* [row_begin, row_end): the block of constraint rows to image (0, m for all;
+ * a row-sharded rank images only its block). sigma: sort window (4096).
+ * natural_primal_order (row-sharded solves): the row image stores the caller's
+ * column indices themselves, because primal vectors stay in the caller's order
+ * on every rank; the column image keeps its own position order.              */
+int32_t pdlp_b200_host_sell_layout(const PdlpProblemView* qp, int64_t row_begin, int64_t row_end,
+                                   int32_t sigma, int32_t natural_primal_order,
+                                   PdlpSellLayout* out_rows, PdlpSellLayout* out_cols);
+void pdlp_b200_sell_layout_free(PdlpSellLayout* layout);
+
 /* ---- misc ---------------------------------------------------------------- */
 /* Number of usable CUDA devices (0 if none); never fails. */
 int32_t pdlp_b200_device_count(void);

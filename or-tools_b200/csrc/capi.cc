@@ -141,6 +141,63 @@ int32_t pdlp_b200_params_validate(const PdlpParams* params, char* message, int64
   return e.empty() ? 1 : 0;
 }
 
+}  // extern "C"
+namespace {
+template <class T>
+T* CopyOut(const std::vector<T>& v) {
+  T* p = static_cast<T*>(std::malloc(std::max<size_t>(1, v.size()) * sizeof(T)));
+  if (p != nullptr && !v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(T));
+  return p;
+}
+void FillLayout(const SellHost& h, PdlpSellLayout* o) {
+  o->num_rows = h.num_rows;
+  o->num_cols = h.num_cols;
+  o->num_split = h.num_split;
+  o->num_virtual = h.num_virtual;
+  o->num_virtual_padded = h.num_virtual_padded;
+  o->num_slots = h.num_slots;
+  o->padded_nnz = h.padded_nnz;
+  o->split_len = h.split_len;
+  o->slice_ptr = CopyOut(h.slice_ptr);
+  o->slot_len = CopyOut(h.slot_len);
+  o->col = CopyOut(h.col);
+  o->val = CopyOut(h.val);
+  o->split_first = CopyOut(h.split_first);
+  o->virt_pos = CopyOut(h.virt_pos);
+  o->row_of_pos = CopyOut(h.row_of_pos);
+  o->pos_of_row = CopyOut(h.pos_of_row);
+}
+}  // namespace
+extern "C" {
+
+int32_t pdlp_b200_host_sell_layout(const PdlpProblemView* qp, int64_t row_begin, int64_t row_end, int32_t sigma, int32_t natural_primal_order,
+                                   PdlpSellLayout* out_rows, PdlpSellLayout* out_cols) {
+  if (qp == nullptr || out_rows == nullptr || out_cols == nullptr) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  std::memset(out_rows, 0, sizeof *out_rows);
+  std::memset(out_cols, 0, sizeof *out_cols);
+  try {
+    const QpHost h = BuildQpHost(*qp, row_begin, row_end, sigma, natural_primal_order != 0);
+    FillLayout(h.rows, out_rows);
+    FillLayout(h.cols, out_cols);
+    return PDLP_B200_STATUS_OK;
+  } catch (const std::exception&) {
+    return PDLP_B200_STATUS_BAD_ARGUMENT;
+  }
+}
+
+void pdlp_b200_sell_layout_free(PdlpSellLayout* layout) {
+  if (layout == nullptr) return;
+  std::free(layout->slice_ptr);
+  std::free(layout->slot_len);
+  std::free(layout->col);
+  std::free(layout->val);
+  std::free(layout->split_first);
+  std::free(layout->virt_pos);
+  std::free(layout->row_of_pos);
+  std::free(layout->pos_of_row);
+  std::memset(layout, 0, sizeof *layout);
+}
+
 int32_t pdlp_b200_device_count(void) { return Device::DeviceCount(); }
 const char* pdlp_b200_version(void) { return "pdlp_b200 0.1.0 (sm_100a)"; }
 int64_t pdlp_b200_sizeof(int32_t index) {
