@@ -33,6 +33,10 @@ struct Comm::Api {
   AllReduceFn all_reduce = nullptr;
   AllGatherFn all_gather = nullptr;
   GetErrorStringFn get_error_string = nullptr;
+  typedef int (*CommGetAsyncErrorFn)(NcclComm, int*);
+  typedef int (*CommAbortFn)(NcclComm);
+  CommGetAsyncErrorFn comm_get_async_error = nullptr;  // optional (NCCL >= 2.4)
+  CommAbortFn comm_abort = nullptr;
 
   static Api* Load(const char* path) {
     static std::mutex mu;
@@ -55,6 +59,8 @@ struct Comm::Api {
     a->all_reduce = reinterpret_cast<AllReduceFn>(dlsym(h, "ncclAllReduce"));
     a->all_gather = reinterpret_cast<AllGatherFn>(dlsym(h, "ncclAllGather"));
     a->get_error_string = reinterpret_cast<GetErrorStringFn>(dlsym(h, "ncclGetErrorString"));
+    a->comm_get_async_error = reinterpret_cast<CommGetAsyncErrorFn>(dlsym(h, "ncclCommGetAsyncError"));
+    a->comm_abort = reinterpret_cast<CommAbortFn>(dlsym(h, "ncclCommAbort"));
     if (!a->get_unique_id || !a->comm_init_rank || !a->comm_destroy || !a->all_reduce || !a->all_gather) {
       delete a;
       throw std::runtime_error("the NCCL library lacks a required symbol");
@@ -91,6 +97,23 @@ Comm::~Comm() {
     try { DestroyPeerArena(cached_arena_, nullptr); } catch (...) {}
   }
   if (comm_ != nullptr) api_->comm_destroy(comm_);
+}
+
+// Failure detection: an error NCCL noticed asynchronously (a peer process died, a
+// link went down) is turned into a CommError; the communicator is aborted first so that the other
+// ranks' pending collectives fail instead of hanging.
+void Comm::CheckAsyncError() {
+  if (comm_ == nullptr || api_->comm_get_async_error == nullptr) return;
+  int async = 0;
+  const int rc = api_->comm_get_async_error(comm_, &async);
+  if (rc == 0 && async == 0) return;
+  const int code = rc != 0 ? rc : async;
+  const std::string what = std::string("NCCL asynchronous error: ") + (api_->get_error_string ? api_->get_error_string(code) : "?");
+  if (api_->comm_abort != nullptr) {
+    api_->comm_abort(comm_);
+    comm_ = nullptr;
+  }
+  throw CommError(what);
 }
 
 void Comm::AllReduceSum(const double* send, double* recv, int64_t count, void* stream) {

@@ -7,9 +7,16 @@
 #define PDLP_B200_COMM_H_
 
 #include <cstdint>
+#include <stdexcept>
 #include <string>
 
 namespace pdlp_b200 {
+
+// A failure of the communicator itself (as opposed to a bad argument): the solve ends with
+// TERMINATION_REASON_OTHER on the rank that sees it.
+struct CommError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
 
 // One allocation per rank that every rank of the box maps into its own address
 // space (CUDA IPC over NVLink / NVSwitch peer memory): the fused exchange
@@ -56,6 +63,9 @@ class Comm {
   PeerArena* AcquirePeerArena(int64_t bytes, void* stream);
   void ReleasePeerArena(PeerArena* arena, void* stream);
   int64_t collectives() const { return collectives_; }
+  // ncclCommGetAsyncError: throws CommError (after ncclCommAbort) if NCCL has seen an
+  // asynchronous failure; polled by the solver at every checkpoint of a row-sharded solve.
+  void CheckAsyncError();
 
  private:
   struct Api;

@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <type_traits>
 
 #include "comm.h"
 #include "device_ops.h"
@@ -228,6 +229,53 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
 template <class T>
 __device__ __forceinline__ T* pick3(T* const (&p)[3], int i) { return i == 0 ? p[0] : (i == 1 ? p[1] : p[2]); }
 
+// ---- TMA (bulk asynchronous copy) staging of the value / index streams --------
+// The SELL streams are contiguous per warp, so they do not need the LSU at all:
+// one elected lane issues 1-D cp.async.bulk copies global -> shared (SASS UBLKCP)
+// that complete on an mbarrier (SYNCS); only the gathers of x stay on the
+// LSU -> L1 -> L2 request path, which is the unit that bounds the SpMV.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      "  .reg .pred p;\n"
+      "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "  selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// bytes: multiple of 16; dst / src 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar, unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+}  // namespace tma
+
 // The gathered vector is either fixed at launch or, inside the device-resident
 // step loop, one of three buffers selected by the state's candidate index.
 struct GatherSrc {
@@ -235,13 +283,28 @@ struct GatherSrc {
   const StepState* st;
 };
 
+// Step decision fused into the last kernel of an iteration: every block takes a
+// ticket after publishing its partial sums; the block that draws the last ticket
+// adds the three partial arrays in a fixed order (independent of which block it
+// is) and runs the accept test / step-size rule, so an iteration is three
+// launches and the decision costs one L2 round trip instead of a kernel.
+struct DecideTail {
+  StepState* st = nullptr;  // nullptr: no fused decision
+  const double *pp = nullptr, *pd = nullptr, *pt = nullptr;
+  int np = 0, nd = 0, nt = 0;
+  unsigned int* ticket = nullptr;
+};
+template <int BT>
+__device__ void run_decide_tail(const DecideTail& t);
+
 // Epi: struct Ctx; __device__ Ctx begin() const -- once per thread: resolves the rotating
 //      buffers and step scalars from the device state;
 //      struct Pre; __device__ Pre prefetch(const Ctx&, int64_t pos) const  -- issues the
 //      epilogue's own loads before the gather loop so that they overlap it;
 //      __device__ void operator()(const Ctx&, int64_t pos, double acc, double* red, const Pre&) const
 template <int MODE, int NS, class Epi, int BT, int V>
-__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks) {
+__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks,
+                                                                                              DecideTail tail) {
   pdl_trigger();
   pdl_wait();
   if (halt != nullptr && *halt != 0) return;
@@ -269,12 +332,112 @@ __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / B
     }
   }
   if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
+  if (tail.st != nullptr) run_decide_tail<BT>(tail);
+}
+
+// The same product with the value / index streams staged through shared memory
+// by the TMA engine (1-D cp.async.bulk + mbarrier), NST stages of U slots per
+// warp. A warp owns `chunks` CONSECUTIVE slices, so its part of val[] / col[] is
+// one contiguous range that lane 0 streams in pieces of U x 32 elements, each
+// piece completing on the stage's mbarrier; the lanes read their element of every
+// slot from shared memory (conflict-free) and only the gathers of x use the
+// LSU -> L2 request path. Slot -> thread map and reduction order are fixed, so
+// results are run-to-run deterministic (they differ in the last bits from
+// k_sell, whose blocks interleave the slices differently).
+template <int MODE, int NS, class Epi, int BT, int U, int NST>
+__global__ void __launch_bounds__(BT) k_sell_tma(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks, DecideTail tail) {
+  constexpr int NW = BT / 32;
+  __shared__ alignas(128) double s_val[NW][NST][U * 32];
+  __shared__ alignas(128) int32_t s_col[NW][NST][U * 32];
+  __shared__ alignas(8) unsigned long long s_bar[NW][NST];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < NST; ++st) tma::mbar_init(&s_bar[warp][st], 1);
+    tma::fence_barrier_init();
+  }
+  __syncwarp();
+  pdl_wait();
+  if (halt != nullptr && *halt != 0) return;  // (no copy has been issued yet)
+  const double* __restrict__ x = gs.st != nullptr ? pick3(gs.p, gs.st->cand) : gs.p[0];
+  double red[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) red[k] = 0.0;
+  const typename Epi::Ctx ctx = epi.begin();
+  const int64_t num_slices = a.num_slots >> 5;
+  const int64_t slice0 = (static_cast<int64_t>(blockIdx.x) * NW + warp) * chunks;
+  const int nsl = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(chunks), num_slices - slice0)));
+  if (nsl > 0) {
+    const int64_t e0 = a.slice_ptr[slice0];
+    const int R = static_cast<int>((a.slice_ptr[slice0 + nsl] - e0) >> 5);  // 32-element rows of this warp's stream
+    const int Q = (R + U - 1) / U;                                         // pieces
+    const double* __restrict__ gval = a.val + e0;
+    const int32_t* __restrict__ gcol = a.col + e0;
+    const unsigned long long policy = tma::policy_evict_first();
+    auto issue = [&](int q) {  // lane 0 only
+      const int rows = min(U, R - q * U);
+      const int st = q % NST;
+      tma::mbar_expect_tx(&s_bar[warp][st], static_cast<uint32_t>(rows) * 384u);
+      tma::bulk_g2s(&s_val[warp][st][0], gval + static_cast<int64_t>(q) * (U * 32), static_cast<uint32_t>(rows) * 256u, &s_bar[warp][st], policy);
+      tma::bulk_g2s(&s_col[warp][st][0], gcol + static_cast<int64_t>(q) * (U * 32), static_cast<uint32_t>(rows) * 128u, &s_bar[warp][st], policy);
+    };
+    if (lane == 0) {
+      for (int q = 0; q < min(NST, Q); ++q) issue(q);
+    }
+    int r = 0;  // rows of the stream consumed so far
+    int64_t e_prev = e0;
+    for (int c = 0; c < nsl; ++c) {
+      const int64_t slot = (slice0 + c) * 32 + lane;
+      const int64_t e_next = a.slice_ptr[slice0 + c + 1];
+      const int W = static_cast<int>((e_next - e_prev) >> 5);
+      e_prev = e_next;
+      const int n = a.slot_len[slot];
+      const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
+      const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
+      typename Epi::Pre pre;
+      if (own_row) pre = epi.prefetch(ctx, pos);
+      double acc = 0.0;
+      int j = 0;
+      while (j < W) {
+        const int q = r / U, o = r % U;
+        const int st = q % NST;
+        if (o == 0) tma::mbar_wait(&s_bar[warp][st], static_cast<uint32_t>((q / NST) & 1));
+        const int avail = min(U - o, W - j);
+        const double* sv = &s_val[warp][st][o * 32 + lane];
+        const int32_t* sc = &s_col[warp][st][o * 32 + lane];
+        const int mine = min(avail, n - j);  // slots of this piece that belong to this lane's row
+        double xv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) xv[u] = u < mine ? __ldg(x + sc[u * 32]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (u < mine) acc = combine<MODE>(acc, sv[u * 32], xv[u]);
+        r += avail;
+        j += avail;
+        if ((r % U) == 0 || r == R) {  // piece q fully consumed: refill its stage
+          __syncwarp();
+          if (lane == 0 && q + NST < Q) {
+            tma::fence_proxy_async();
+            issue(q + NST);
+          }
+        }
+      }
+      if (slot < a.num_virtual_padded) {
+        a.virt_partial[slot] = acc;
+      } else if (own_row) {
+        epi(ctx, pos, acc, red, pre);
+      }
+    }
+  }
+  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
+  if (tail.st != nullptr) run_decide_tail<BT>(tail);
 }
 
 // Split rows: one warp per row combines the partials of its virtual slots in
 // slot order and then runs the same epilogue.
 template <int MODE, int NS, class Epi>
-__global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, double* partials, const int32_t* halt) {
+__global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, double* partials, const int32_t* halt, DecideTail tail) {
   pdl_trigger();
   pdl_wait();
   if (halt != nullptr && *halt != 0) return;
@@ -294,6 +457,7 @@ __global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, dou
     }
   }
   if (NS > 0) block_reduce_store<NS, 0>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
+  if (tail.st != nullptr) run_decide_tail<kThreads>(tail);
 }
 
 // --------------------------------------------------------- PDHG step -------
@@ -318,7 +482,7 @@ struct StepPtrs {
 //   [scal_off, +4 G)   {||dx||^2, ||dy||^2, dx.(K^T y' - K^T y)} partials of rank h at 4 h
 //   [flags_off, +8 k)  barrier k: epoch last signalled by rank h at 8 k + h (u64)
 //   [epoch_off, +4)    this rank's own epoch counters (u64)
-//   [tr_off, +2*34*G)  trust-region bin totals of rank h for pass parity p at 34 (G p + h)
+//   [tr_off, +2*48*8)  trust-region round vector (kTrCols doubles) of rank h for round parity p at kTrCols (G p + h)
 struct PeerPtrs {
   int world, rank;
   double* base[kMaxPeers];
@@ -439,6 +603,13 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
     if (ratio > 0.0) b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
   }
   block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && st->rule == PDLP_ADAPTIVE_LINESEARCH_RULE) {
+    // the two pow() of this attempt's step-size decision, while the SpMV pair runs (see StepState)
+    const double total = static_cast<double>(st->num_rejected_steps + st->inner_iterations + st->iterations_completed + 1);
+    b.state->pow_reduction = pow(total + 1.0, -st->reduction_exponent);
+    b.state->pow_growth = pow(total + 1.0, -st->growth_exponent);
+    b.state->pow_total = total;
+  }
 }
 
 // PUSH: the all-gather of y' fused into the producing epilogue -- every new
@@ -566,11 +737,34 @@ __device__ __forceinline__ double block_sum_range(const double* __restrict__ p, 
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674) from the three
 // reduced scalars; one thread.
+// The two powers of the adaptive rule depend on the attempt count only, so a caller may
+// compute them (and load the state) while the partial sums are still in flight.
+__device__ __forceinline__ double decide_total(const StepState& s) {
+  return static_cast<double>(s.num_rejected_steps + s.inner_iterations + s.iterations_completed + 1);
+}
+__device__ __forceinline__ void decide_powers(const StepState& s, double& pow_reduction, double& pow_growth) {
+  pow_reduction = pow_growth = 0.0;
+  if (s.rule != PDLP_ADAPTIVE_LINESEARCH_RULE) return;
+  const double total = decide_total(s);
+  if (s.pow_total == total) {  // left by the primal-step kernel of this attempt
+    pow_reduction = s.pow_reduction;
+    pow_growth = s.pow_growth;
+  } else {
+    pow_reduction = pow(total + 1.0, -s.reduction_exponent);
+    pow_growth = pow(total + 1.0, -s.growth_exponent);
+  }
+}
+__device__ void decide_update(StepState* st_dev, StepState s, double pow_reduction, double pow_growth, double dx2, double dy2, double dot);
 __device__ void decide_update(StepState* st_dev, double dx2, double dy2, double dot) {
   // One load of the whole state into registers, one store at the end: the
   // decision is a chain of dependent scalar updates and must not pay an L2
   // round trip per field.
-  StepState s = *st_dev;
+  const StepState s = *st_dev;
+  double pr, pg;
+  decide_powers(s, pr, pg);
+  decide_update(st_dev, s, pr, pg, dx2, dy2, dot);
+}
+__device__ void decide_update(StepState* st_dev, StepState s, double pow_reduction, double pow_growth, double dx2, double dy2, double dot) {
   StepState* st = &s;
   const double eta = st->step_size, omega = st->primal_weight;
   const double movement = (0.5 * omega * dx2) + (0.5 / omega) * dy2;
@@ -596,9 +790,8 @@ __device__ void decide_update(StepState* st_dev, double dx2, double dy2, double 
   if (adaptive) {
     const double limit = nonlinearity > 0 ? movement / nonlinearity : kInfD;
     accepted = eta <= limit;
-    const double total = static_cast<double>(st->num_rejected_steps + st->inner_iterations + st->iterations_completed + 1);
-    const double first = isinf(limit) ? limit : (1.0 - pow(total + 1.0, -st->reduction_exponent)) * limit;
-    const double second = (1.0 + pow(total + 1.0, -st->growth_exponent)) * eta;
+    const double first = isinf(limit) ? limit : (1.0 - pow_reduction) * limit;
+    const double second = (1.0 + pow_growth) * eta;
     new_eta = fmin(first, second);
   }
   if (accepted) {
@@ -664,19 +857,103 @@ __device__ __forceinline__ void block_sum3(const double* __restrict__ p0, int n0
   }
 }
 
-// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
+// Tail of the last kernel of an iteration (see DecideTail): all threads of the block call it.
+template <int BT>
+__device__ void run_decide_tail(const DecideTail& t) {
+  __shared__ int s_last;
+  __shared__ double sh3[3][BT / 32];
+  if (threadIdx.x == 0) {
+    __threadfence();  // this block's partial sums are visible before its ticket
+    const unsigned int ticket = atomicAdd(t.ticket, 1u);
+    s_last = ticket == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last == 0) return;
+  __threadfence();
+  // Thread k adds p[k], p[k + BT], ...; then a shuffle tree and a fixed-order sum
+  // over the warps: the order depends on the array sizes only, never on which
+  // block happens to be the last one. __ldcg: the partials were written by other
+  // SMs during this launch, L1 must not serve them.
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < t.np; i += BT) s0 += __ldcg(t.pp + i);
+#pragma unroll 8
+  for (int i = threadIdx.x; i < t.nd; i += BT) s1 += __ldcg(t.pd + i);
+#pragma unroll 8
+  for (int i = threadIdx.x; i < t.nt; i += BT) s2 += __ldcg(t.pt + i);
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    sh3[0][threadIdx.x >> 5] = s0;
+    sh3[1][threadIdx.x >> 5] = s1;
+    sh3[2][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double sums[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    for (int w = 0; w < BT / 32; ++w) sums[k] += sh3[k][w];
+  *t.ticket = 0u;  // ready for the next launch (stream order makes it visible)
+  decide_update(t.st, sums[0], sums[1], sums[2]);
+}
+
+// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block. The three partial
+// arrays are contiguous ([pp | pd | pt]): one pass with every load in flight at once; meanwhile the
+// last warp loads the state and evaluates the two pow() of the rule, so the critical path after the
+// sums is a handful of flops and one store.
 __global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
   pdl_trigger();
   pdl_wait();
-  // The halt flag is read while the partial sums are already in flight (a halted
-  // attempt only wastes those loads): one L2 round trip less on the critical path.
-  const int32_t halted = *reinterpret_cast<const volatile int32_t*>(&st_dev->halt);
-  double sums[3];
+  __shared__ StepState sh_state;
+  __shared__ double sh_pow[2];
+  __shared__ double sh3[3][kDecideThreads / 32];
+  // (the state load is issued first and used only after the partial loads: both round trips overlap)
+  StepState loaded;
+  if (threadIdx.x == kDecideThreads - 1) loaded = *st_dev;
   // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
-  block_sum3(pp, np, pd, nd < 0 ? 0 : nd, pt, nt, sums);
-  if (halted != 0) return;
-  if (threadIdx.x != 0) return;
-  decide_update(st_dev, sums[0], nd < 0 ? *pd : sums[1], sums[2]);
+  const int n1 = nd < 0 ? 0 : nd;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (pd == pp + np && pt == pd + n1) {
+    const int total = np + n1 + nt;
+#pragma unroll 16
+    for (int i = threadIdx.x; i < total; i += kDecideThreads) {
+      const double v = pp[i];
+      if (i < np) s0 += v;
+      else if (i < np + n1) s1 += v;
+      else s2 += v;
+    }
+  } else {
+#pragma unroll 8
+    for (int i = threadIdx.x; i < np; i += kDecideThreads) s0 += pp[i];
+#pragma unroll 8
+    for (int i = threadIdx.x; i < n1; i += kDecideThreads) s1 += pd[i];
+#pragma unroll 8
+    for (int i = threadIdx.x; i < nt; i += kDecideThreads) s2 += pt[i];
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    sh3[0][threadIdx.x >> 5] = s0;
+    sh3[1][threadIdx.x >> 5] = s1;
+    sh3[2][threadIdx.x >> 5] = s2;
+  }
+  if (threadIdx.x == kDecideThreads - 1) {
+    sh_state = loaded;
+    decide_powers(loaded, sh_pow[0], sh_pow[1]);
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  double sums[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double t = threadIdx.x < kDecideThreads / 32 ? sh3[k][threadIdx.x] : 0.0;
+    sums[k] = warp_sum(t);
+  }
+  if (threadIdx.x != 0 || sh_state.halt != 0) return;
+  decide_update(st_dev, sh_state, sh_pow[0], sh_pow[1], sums[0], nd < 0 ? *pd : sums[1], sums[2]);
 }
 
 // ---- row-sharded variant of the step ---------------------------
@@ -805,11 +1082,15 @@ constexpr unsigned long long kMaxKey = 0x7FEFFFFFFFFFFFFFull;  // DBL_MAX
 struct TrSearchState {
   unsigned long long lo;
   int done, pad;   // no key with a nonzero contribution is left inside the bracket
+  int shift, width_shift;  // k_tr_solve: digit position of the next pass; the bracket is (lo, lo + 2^width_shift]
   double fixed_radius_sq, variable_coef;
   double radius_sq;
   double max_abs_objective;
   double step_size;
-  double lx, ly;
+  double frozen_a, frozen_b;     // k_tr_solve: sums of the elements already compacted away (below / above the bracket)
+  double lag_primal, lag_dual;   // k_tr_solve<JOINT>: Lagrangian value parts (sou.cc:446-527)
+  double radius;
+  double dist_primal_sq, dist_dual_sq;  // k_tr_solve<JOINT>: ||x - x0||^2, ||y - y0||^2 (when asked for)
 };
 
 // Joint problem elements, trust_region.cc:115-162 / 538-607.
@@ -830,6 +1111,51 @@ struct JointElem {
     if (lf) return lb;
     if (uf) return ub;
     return 0.0;
+  }
+  // k_tr_solve<JOINT> round 0: Lagrangian value parts (sou.cc:446-527) and squared distances to
+  // (x0, y0) from what get_k loaded (arithmetic only).
+  __device__ __forceinline__ void joint_extras(int64_t i, double obj, double center, double qd, double x0v, double coef, double& e0, double& e1,
+                                               double& d0, double& d1) const {
+    const double d = center - x0v;
+    if (i < n) {
+      const double op = qd * center;  // (q x; qd is 0 for an LP)
+      e0 += center * (obj - 0.5 * op);
+      d0 += d * d;
+    } else {
+      e1 += coef * center;
+      d1 += d * d;
+    }
+  }
+  __device__ __forceinline__ double weighted_distance_sq(double d0, double d1) const { return (0.5 * primal_weight) * d0 + (0.5 / primal_weight) * d1; }
+  // Branch-free accessors for a segment of one kind (KIND 0: primal elements i < n, 1: dual
+  // elements): the sweeps of k_tr_solve walk the two segments of a block's range separately so
+  // that the loads of several elements can be in flight together.
+  __device__ __forceinline__ int64_t split() const { return n; }
+  template <int KIND>
+  __device__ __forceinline__ void get_k(int64_t i, double& obj, double& lb, double& ub, double& center, double& w, double& qd, double& x0v, double& coef,
+                                        const double* x0, const double* y0) const {
+    if (KIND == 0) {
+      const int64_t ip = pbeg + i;
+      center = x[ip];
+      qd = q != nullptr ? q[ip] : 0.0;
+      obj = q != nullptr ? (c[ip] + qd * center - kty[ip]) : (c[ip] - kty[ip]);
+      lb = lv[ip];
+      ub = uv[ip];
+      w = 0.5 * primal_weight;
+      x0v = x0 != nullptr ? x0[ip] : center;
+      coef = 0.0;
+    } else {
+      const int64_t j = i - n;
+      const double lcv = lc[j], ucv = uc[j];
+      center = y[j];
+      coef = subgradient_coefficient(j);
+      obj = -(coef - kx[j]);
+      lb = isfinite(ucv) ? -kInfD : 0.0;
+      ub = isfinite(lcv) ? kInfD : 0.0;
+      w = 0.5 / primal_weight;
+      qd = 0.0;
+      x0v = y0 != nullptr ? y0[j] : center;
+    }
   }
   __device__ __forceinline__ void get(int64_t i, double& obj, double& lb, double& ub, double& center, double& w, double& qd) const {
     if (i < n) {
@@ -853,9 +1179,20 @@ struct JointElem {
 };
 struct VectorElem {
   const double *obj_, *lb_, *ub_, *center_, *w_, *q_;
+  int64_t n;  // (unused; k_tr_solve<JOINT> is never instantiated for explicit vectors)
+  __device__ __forceinline__ void joint_extras(int64_t, double, double, double, double, double, double&, double&, double&, double&) const {}
+  __device__ __forceinline__ double weighted_distance_sq(double, double) const { return 0.0; }
   __device__ __forceinline__ void get(int64_t i, double& obj, double& lb, double& ub, double& center, double& w, double& qd) const {
     obj = obj_[i]; lb = lb_[i]; ub = ub_[i]; center = center_[i]; w = w_[i];
     qd = q_ != nullptr ? q_[i] : 0.0;
+  }
+  __device__ __forceinline__ int64_t split() const { return INT64_MAX; }  // one kind only
+  template <int KIND>
+  __device__ __forceinline__ void get_k(int64_t i, double& obj, double& lb, double& ub, double& center, double& w, double& qd, double& x0v, double& coef,
+                                        const double*, const double*) const {
+    get(i, obj, lb, ub, center, w, qd);
+    x0v = center;
+    coef = 0.0;
   }
 };
 
@@ -986,126 +1323,542 @@ __device__ __forceinline__ void tr_pick(const double* tot, TrSearchState* st, in
   if (tot[best + 1] == 0.0 && tot[17 + best + 1] == 0.0) st->done = 1;
 }
 
-// ---- the whole threshold search in ONE persistent launch -----------------------
-// All radix-16 passes of the search run inside one cooperative launch: per pass
-// every thread bins its elements into 34 shared-memory accumulators of its own
-// (column tid: conflict-free, two read-modify-writes per element instead of 34
-// predicated adds), the block reduces them in a fixed order, a grid barrier
-// publishes the per-block partials, and EVERY block then adds the partials of
-// all blocks in the same order and takes the same bracket decision -- so no
-// second kernel, no host round trip, and the loop stops at the first pass that
-// leaves nothing inside the bracket. On a row-sharded solve block 0 also stores
-// the 34 totals into every rank's arena and the ranks meet at a peer barrier;
-// every block then adds the G x 34 totals in rank order.
-constexpr int kTrBlocksPerSm = 2;
-constexpr int kTrMaxBlocks = 320;  // grid cap of k_tr_search (multiple of 32)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) {}
-    __threadfence();
-  }
-  __syncthreads();
+__device__ __forceinline__ double projected_value(double center, double obj, double w, double lb, double ub, double step) {
+  const double full = center - step * obj / w;  // trust_region.h:223-228
+  return fmin(fmax(full, lb), ub);
 }
-template <bool PEER>
-__global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_search(int64_t total, const unsigned long long* __restrict__ keys, const double* __restrict__ a,
-                                                                        const double* __restrict__ bcoef, TrSearchState* st_dev, double* partials,
-                                                                        unsigned int* sync_counter, PeerPtrs peer, int32_t* peer_error, double radius) {
-  extern __shared__ double bins[];  // [34][kThreads]
-  __shared__ double tot[34];
-  __shared__ TrSearchState s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nb = gridDim.x;
-  if (tid == 0) s = *st_dev;
-  __syncthreads();
-  unsigned int syncs = 0;
-  const int64_t stride = static_cast<int64_t>(nb) * kThreads * kTrUnroll;
-  int pass = 0;
-  for (int shift = 60; shift >= 0 && s.done == 0; shift -= 4, ++pass) {
-    const unsigned long long lo = s.lo;
+
+// ---- the whole trust-region solve in ONE persistent cooperative launch -----------
+// k_tr_solve does what k_tr_prepare + k_tr_init + the radix passes + k_tr_finish (+ the reductions
+// around them) did in separate launches:
+//   round 0   every block walks its CONTIGUOUS range of the joint problem once: critical step
+//             sizes (as keys), a, b to scratch; max |objective|, the smallest positive and the
+//             largest finite critical step size, (JOINT) the Lagrangian value parts and the
+//             distance to the last restart point (= the radius).
+//   passes    radix-16 on the key bits, but STARTING at the bits where the smallest and the largest
+//             key differ (the top passes of a search from bit 60 split nothing). Every pass filters
+//             the block's list to the current bracket and compacts it in place (stable,
+//             block-local), so a pass costs as much as the bracket is populated; elements that left
+//             the bracket live on in the running sums frozen_a / frozen_b. Once the bracket holds
+//             at most kTrFinishCap elements the block that closes the round finishes the remaining
+//             passes alone (no more grid rounds).
+//   final     (JOINT) objective deltas at the solution (trust_region.cc:929-967).
+// A round ends with a ticket: the block that arrives last adds the per-block vectors in a fixed
+// order (independent of which block it is), exchanges them with the other ranks of a row-sharded
+// solve through the peer arenas, takes the bracket decision, publishes the state and bumps a
+// generation counter the other blocks wait for. One launch, one device->host copy.
+constexpr int kTrBlocksPerSm = 2;
+constexpr int kTrMaxBlocks = 320;    // grid cap
+constexpr int kTrCols = 42;          // doubles per round vector: 34 bins + extras
+constexpr int kTrFinishCap = 4096;   // bracket population below which one block finishes the search
+enum { kTrLagP = 34, kTrLagD = 35, kTrDistP = 36, kTrDistD = 37, kTrCount = 38, kTrFirstMax = 39, kTrMaxObj = 39, kTrMaxCrit = 40, kTrNegMinCrit = 41 };
+struct TrSolveArgs {
+  int64_t total;
+  unsigned long long* keys;
+  double *a, *b;             // scratch [total] each
+  TrSearchState* st;         // result (device)
+  double* partials;          // [blocks][kTrCols]
+  unsigned int* sync;        // [0] arrivals [1] generation; zero before the launch
+  double radius;             // < 0 (JOINT only): the weighted distance to (x0, y0), computed in round 0
+  const double *x0, *y0;
+  double* out;               // JOINT: {lagrangian primal part, dual part, primal delta, dual delta, radius, ||x-x0||^2, ||y-y0||^2}
+  int32_t* peer_error;
+  unsigned long long* cand_keys;  // [kTrFinishCap] each: the bracket's elements, gathered by the finishing block
+  double *cand_a, *cand_b;
+  unsigned long long* trace;  // PDLP_B200_TRACE=1: [0] count, then globaltimer (ns) stamps of block 0
+};
+__device__ __forceinline__ void tr_stamp(const TrSolveArgs& g) {
+  if (g.trace == nullptr || blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  const unsigned long long k = g.trace[0];
+  if (k < 30ull) { g.trace[1 + k] = t; g.trace[0] = k + 1ull; }
+}
+
+__device__ __forceinline__ void tr_pick_compact(const double* tot, TrSearchState* st, int shift) {
+  const unsigned long long lo = st->lo;
+  // A_j = frozen_a + bins 0..j of a; B_j = frozen_b + bins j+1..16 of b.
+  double suffix[18];
+  suffix[17] = st->frozen_b;
+  for (int j = 16; j >= 0; --j) suffix[j] = suffix[j + 1] + tot[17 + j];
+  double A = st->frozen_a;
+  int best = 0;
+  double bestA = A + tot[0], bestB = suffix[1];
+  for (int j = 0; j < 16; ++j) {
+    A += tot[j];
+    if (j == 0) continue;
+    const unsigned long long cj = lo + (static_cast<unsigned long long>(j) << shift);
+    if (cj > kMaxKey || cj < lo) break;
+    const double t = __longlong_as_double(static_cast<long long>(cj));
+    const double B = suffix[j + 1];
+    const double f = A + (B > 0.0 ? t * t * B : 0.0);
+    if (f <= st->radius_sq) { best = j; bestA = A; bestB = B; } else break;
+  }
+  st->lo = lo + (static_cast<unsigned long long>(best) << shift);
+  st->fixed_radius_sq = bestA;
+  st->variable_coef = bestB;
+  st->frozen_a = bestA;               // bins 0..best leave the list below the bracket
+  st->frozen_b = suffix[best + 2];    // bins best+2.. leave it above
+  st->width_shift = shift;            // the next bracket is (lo, lo + 2^shift]
+  st->shift = shift >= 4 ? shift - 4 : 0;
+  if ((tot[best + 1] == 0.0 && tot[17 + best + 1] == 0.0) || shift == 0) st->done = 1;
+}
+
+// Column sums of the per-thread bins of this block (warp w adds columns w, w + 8, ... over the 256
+// threads: lane-strided, then a shuffle tree); columns >= kTrFirstMax are maxima.
+__device__ __forceinline__ void tr_block_totals(const double* bins, double* dst, int K) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < K; j += kThreads / 32) {
+    double v;
+    if (j >= kTrFirstMax) {
+      v = -kInfD;
 #pragma unroll
-    for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
-    for (int64_t base = static_cast<int64_t>(blockIdx.x) * kThreads * kTrUnroll + tid; base < total; base += stride) {
-      unsigned long long key[kTrUnroll];
-      double av[kTrUnroll], bv[kTrUnroll];
-#pragma unroll
-      for (int u = 0; u < kTrUnroll; ++u) {
-        const int64_t i = base + static_cast<int64_t>(u) * kThreads;
-        const bool ok = i < total;
-        key[u] = ok ? keys[i] : 0ull;
-        av[u] = ok ? a[i] : 0.0;
-        bv[u] = ok ? bcoef[i] : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < kTrUnroll; ++u) {
-        int j0 = 0;
-        if (key[u] > lo) {
-          const unsigned long long d = (key[u] - lo - 1ull) >> shift;
-          j0 = d >= 15ull ? 16 : static_cast<int>(d) + 1;
-        }
-        bins[j0 * kThreads + tid] += av[u];
-        bins[(17 + j0) * kThreads + tid] += bv[u];
-      }
-    }
-    __syncthreads();
-    // block totals: warp w adds columns w, w + 8, ... over the 256 threads (lane-strided, then a shuffle tree)
-    double* mine = partials + (static_cast<int64_t>(pass & 1) * nb + blockIdx.x) * 34;
-    for (int j = warp; j < 34; j += kThreads / 32) {
-      double v = 0.0;
+      for (int t = lane; t < kThreads; t += 32) v = fmax(v, bins[j * kThreads + t]);
+      v = warp_max(v);
+    } else {
+      v = 0.0;
 #pragma unroll
       for (int t = lane; t < kThreads; t += 32) v += bins[j * kThreads + t];
       v = warp_sum(v);
-      if (lane == 0) mine[j] = v;
     }
-    grid_barrier(sync_counter, static_cast<unsigned int>(nb) * (++syncs));
-    // every block: the same fixed-order sum over the blocks
-    const double* all = partials + static_cast<int64_t>(pass & 1) * nb * 34;
-    // (all loads of a column are issued before the first add: the sum is a
-    // dependent chain and must not pay one L2 round trip per term)
-    for (int j = warp; j < 34; j += kThreads / 32) {
-      double term[kTrMaxBlocks / 32];
+    if (lane == 0) dst[j] = v;
+  }
+}
+
+// End of a round. In: bins[c][t] holds thread t's contribution to column c < K. Out (in the block
+// that arrived last, returns true there): tot[0..K) over all blocks and ranks. All threads of all
+// blocks call it; `round` counts the calls.
+template <bool PEER>
+__device__ bool tr_round(const TrSolveArgs& g, const PeerPtrs& peer, double* bins, double* tot, double (*part)[48], int* s_last, int K, unsigned round) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = gridDim.x;
+  __syncthreads();
+  tr_block_totals(bins, g.partials + static_cast<int64_t>(blockIdx.x) * kTrCols, K);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();  // (cumulative: the whole block's stores, ordered by the barrier, are visible before the ticket)
+    const unsigned int ticket = atomicAdd(g.sync, 1u);
+    *s_last = ticket == static_cast<unsigned int>(nb) * (round + 1u) - 1u ? 1 : 0;
+  }
+  __syncthreads();
+  if (*s_last == 0) return false;
+  __threadfence();
+  {  // fixed-order sum over the blocks: five interleaved row groups per column (240 threads), all
+     // loads of a thread in flight together, groups combined in order
+    constexpr int kGroups = 5, kBatch = 16;
+    const int colx = tid % 48, grp = tid / 48;
+    if (grp < kGroups && colx < K) {
+      const bool is_max = colx >= kTrFirstMax;
+      double v = is_max ? -kInfD : 0.0;
+      for (int b0 = grp; b0 < nb; b0 += kGroups * kBatch) {
+        double term[kBatch];
 #pragma unroll
-      for (int k = 0; k < kTrMaxBlocks / 32; ++k) {
-        const int b = lane + 32 * k;
-        term[k] = b < nb ? __ldcg(all + static_cast<int64_t>(b) * 34 + j) : 0.0;
+        for (int k = 0; k < kBatch; ++k) {
+          const int b = b0 + kGroups * k;
+          term[k] = b < nb ? __ldcg(g.partials + static_cast<int64_t>(b) * kTrCols + colx) : (is_max ? -kInfD : 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) v = is_max ? fmax(v, term[k]) : v + term[k];
       }
-      double v = 0.0;
-#pragma unroll
-      for (int k = 0; k < kTrMaxBlocks / 32; ++k) v += term[k];
-      v = warp_sum(v);
-      if (lane == 0) tot[j] = v;
+      part[grp][colx] = v;
     }
     __syncthreads();
-    if (PEER) {
-      const int64_t slot = peer.tr_off + static_cast<int64_t>(pass & 1) * 34 * peer.world;
-      if (blockIdx.x == 0 && warp == 0) {
-        for (int h = 0; h < peer.world; ++h) {
-          volatile double* dst = peer_base(peer, h) + slot + 34 * peer.rank;
-          dst[lane] = tot[lane];
-          if (lane < 2) dst[32 + lane] = tot[32 + lane];
-        }
-        peer_barrier(peer, 3, peer_error);
-      }
-      grid_barrier(sync_counter, static_cast<unsigned int>(nb) * (++syncs));
-      if (tid < 34) {
-        const volatile double* src = peer_base(peer, peer.rank) + slot;
-        double v = 0.0;
-        for (int h = 0; h < peer.world; ++h) v += src[34 * h + tid];
-        tot[tid] = v;
-      }
-      __syncthreads();
-      if (*reinterpret_cast<volatile int32_t*>(peer_error) != 0) break;  // a peer never arrived
+    if (tid < K) {
+      double v = part[0][tid];
+#pragma unroll
+      for (int k = 1; k < kGroups; ++k) v = tid >= kTrFirstMax ? fmax(v, part[k][tid]) : v + part[k][tid];
+      tot[tid] = v;
     }
-    if (tid == 0) tr_pick(tot, &s, shift);
     __syncthreads();
   }
-  if (blockIdx.x == 0 && tid == 0) {
-    // trust_region.cc:345-365, 429-444
-    if (radius == 0.0 || !(s.max_abs_objective > 0.0)) s.step_size = 0.0;
-    else s.step_size = s.variable_coef > 0.0 ? sqrt((s.radius_sq - s.fixed_radius_sq) / s.variable_coef) : DBL_MAX;
-    *st_dev = s;
+  if (PEER) {
+    const int64_t slot = peer.tr_off + static_cast<int64_t>(round & 1u) * kTrCols * peer.world;
+    if (warp == 0) {
+      for (int h = 0; h < peer.world; ++h) {
+        volatile double* dst = peer_base(peer, h) + slot + kTrCols * peer.rank;
+        if (lane < K) dst[lane] = tot[lane];
+        if (32 + lane < K) dst[32 + lane] = tot[32 + lane];
+      }
+      peer_barrier(peer, 3, g.peer_error);
+    }
+    __syncthreads();
+    if (tid < K) {
+      const volatile double* src = peer_base(peer, peer.rank) + slot;
+      double v = tid >= kTrFirstMax ? -kInfD : 0.0;
+      for (int h = 0; h < peer.world; ++h) v = tid >= kTrFirstMax ? fmax(v, src[kTrCols * h + tid]) : v + src[kTrCols * h + tid];
+      tot[tid] = v;
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// Publishes the state decided by the last block / waits for it in the others; afterwards the
+// shared copy `s` of every block equals the global state.
+__device__ __forceinline__ void tr_publish_or_wait(const TrSolveArgs& g, TrSearchState* s, bool last, unsigned round) {
+  constexpr int kWords = static_cast<int>(sizeof(TrSearchState) / sizeof(double));
+  if (last) {
+    __syncthreads();
+    if (threadIdx.x < kWords) reinterpret_cast<double*>(g.st)[threadIdx.x] = reinterpret_cast<const double*>(s)[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *reinterpret_cast<volatile unsigned int*>(g.sync + 1) = round + 1u;
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      while (*reinterpret_cast<volatile unsigned int*>(g.sync + 1) < round + 1u) {}
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x < kWords) reinterpret_cast<double*>(s)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(g.st) + threadIdx.x);
+  }
+  __syncthreads();
+}
+
+// bin (1..16) of a key inside the bracket (lo, lo + 16 << shift]
+__device__ __forceinline__ int tr_bin(unsigned long long key, unsigned long long lo, int shift) {
+  const unsigned long long d = (key - lo - 1ull) >> shift;
+  return d >= 15ull ? 16 : static_cast<int>(d) + 1;
+}
+
+template <class Elem, bool PEER, bool JOINT>
+__global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_solve(TrSolveArgs g, Elem el, PeerPtrs peer) {
+  extern __shared__ double bins[];  // [kTrCols][kThreads]
+  __shared__ double tot[kTrCols];
+  __shared__ double part[5][48];
+  __shared__ TrSearchState s;
+  __shared__ int s_last;
+  __shared__ int s_wtot[kTrUnroll][kThreads / 32];
+  static_assert(sizeof(TrSearchState) % sizeof(double) == 0 && sizeof(TrSearchState) / sizeof(double) <= kThreads, "state is copied as doubles");
+  static_assert(kTrCols <= 48 && 5 * 48 <= kThreads, "layout of the cross-block sum");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = gridDim.x;
+  constexpr int64_t kTile = static_cast<int64_t>(kThreads) * kTrUnroll;
+  const int64_t per = ((g.total + nb - 1) / nb + kTile - 1) / kTile * kTile;
+  const int64_t beg = min(g.total, static_cast<int64_t>(blockIdx.x) * per), end = min(g.total, beg + per);
+  unsigned round = 0;
+  tr_stamp(g);
+
+  // ---- round 0: prepare ---------------------------------------------------------------
+  {
+    double mx = 0.0, maxc = -kInfD, negminc = -kInfD, e0 = 0.0, e1 = 0.0, d0 = 0.0, d1 = 0.0;
+    // kTrUnroll elements per thread and trip, every load issued before the first store (the sweep
+    // is bound by memory latency at two 256-thread blocks per SM); the primal and the dual segment
+    // of the range are walked separately so that the accessors are branch-free
+    auto sweep = [&](auto kind, int64_t sb, int64_t se) {
+      constexpr int KIND = decltype(kind)::value;
+      for (int64_t base = sb + tid; base < se; base += kTile) {
+        double obj[kTrUnroll], lb[kTrUnroll], ub[kTrUnroll], center[kTrUnroll], w[kTrUnroll], qd[kTrUnroll];
+        double x0v[kTrUnroll], coef[kTrUnroll];
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int64_t i = min(base + static_cast<int64_t>(u) * kThreads, se - 1);  // (clamped: a valid, discarded load)
+          el.template get_k<KIND>(i, obj[u], lb[u], ub[u], center[u], w[u], qd[u], x0v[u], coef[u], g.x0, g.y0);
+        }
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int64_t i = base + static_cast<int64_t>(u) * kThreads;
+          if (i >= se) continue;
+          double crit, dist = 0.0;
+          if (obj[u] == 0.0) {
+            crit = kInfD;
+          } else {
+            dist = (obj[u] > 0.0 ? lb[u] : ub[u]) - center[u];  // DistanceAtCriticalStepSize
+            crit = -w[u] * dist / obj[u];                        // CriticalStepSize
+          }
+          const unsigned long long key = crit_key(crit);
+          g.keys[i] = key;
+          g.a[i] = w[u] * dist * dist;
+          g.b[i] = obj[u] * obj[u] / w[u];
+          mx = fmax(mx, fabs(obj[u]));
+          if (key > 0ull && key <= kMaxKey) {  // positive and finite
+            const double c = __longlong_as_double(static_cast<long long>(key));
+            maxc = fmax(maxc, c);
+            negminc = fmax(negminc, -c);
+          }
+          if (JOINT) el.joint_extras(i, obj[u], center[u], qd[u], x0v[u], coef[u], e0, e1, d0, d1);
+        }
+      }
+    };
+    const int64_t cut = el.split();
+    sweep(std::integral_constant<int, 0>(), beg, min(end, cut));
+    sweep(std::integral_constant<int, 1>(), max(beg, min(end, cut)), end);
+    bins[kTrLagP * kThreads + tid] = e0;
+    bins[kTrLagD * kThreads + tid] = e1;
+    bins[kTrDistP * kThreads + tid] = d0;
+    bins[kTrDistD * kThreads + tid] = d1;
+    bins[kTrCount * kThreads + tid] = 0.0;
+    bins[kTrMaxObj * kThreads + tid] = mx;
+    bins[kTrMaxCrit * kThreads + tid] = maxc;
+    bins[kTrNegMinCrit * kThreads + tid] = negminc;
+#pragma unroll
+    for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
+  }
+  tr_stamp(g);
+  bool last = tr_round<PEER>(g, peer, bins, tot, part, &s_last, kTrCols, round);
+  if (last && tid == 0) {
+    double radius = g.radius;
+    if (JOINT && radius < 0.0) radius = sqrt(el.weighted_distance_sq(tot[kTrDistP], tot[kTrDistD]));
+    s.done = 0;
+    s.pad = 0;
+    s.fixed_radius_sq = 0.0;
+    s.variable_coef = 0.0;
+    s.radius_sq = radius * radius;
+    s.max_abs_objective = fmax(0.0, tot[kTrMaxObj]);
+    s.step_size = 0.0;
+    s.frozen_a = 0.0;
+    s.frozen_b = 0.0;
+    s.lag_primal = tot[kTrLagP];
+    s.lag_dual = tot[kTrLagD];
+    s.radius = radius;
+    s.dist_primal_sq = tot[kTrDistP];
+    s.dist_dual_sq = tot[kTrDistD];
+    // first bracket: just below the smallest positive key up to the largest finite one, in 16 bins
+    s.lo = 0ull;
+    s.shift = 60;
+    if (tot[kTrMaxCrit] > 0.0) {
+      const unsigned long long maxkey = static_cast<unsigned long long>(__double_as_longlong(tot[kTrMaxCrit]));
+      const unsigned long long minkey = static_cast<unsigned long long>(__double_as_longlong(-tot[kTrNegMinCrit]));
+      s.lo = minkey - 1ull;
+      const unsigned long long span = maxkey - s.lo - 1ull;  // largest (key - lo - 1)
+      s.shift = span < 16ull ? 0 : 64 - __clzll(static_cast<long long>(span)) - 4;
+    }
+    s.width_shift = 64;  // no upper end yet
+    if (PEER && *reinterpret_cast<volatile int32_t*>(g.peer_error) != 0) s.done = 1;  // a peer never arrived
+  }
+  tr_publish_or_wait(g, &s, last, round);
+  ++round;
+  tr_stamp(g);
+
+  // ---- passes: filter to the bracket, compact in place, bin ------------------------------
+  int64_t len = end - beg;
+  bool first_pass = true;
+  while (s.done == 0) {
+    const int shift = s.shift;
+    const unsigned long long lo = s.lo;
+    const bool open_end = s.width_shift >= 64;
+    const unsigned long long width = open_end ? ~0ull : (1ull << s.width_shift);
+#pragma unroll
+    for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
+    if (first_pass) {
+      // Every positive key is inside the first bracket: a plain streaming pass (no compaction, no
+      // barriers); keys <= lo (zero keys) are the part below every bracket, bin 0.
+      for (int64_t base = beg + tid; base < end; base += kTile) {
+        unsigned long long key[kTrUnroll];
+        double av[kTrUnroll], bv[kTrUnroll];
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int64_t i = base + static_cast<int64_t>(u) * kThreads;
+          const bool ok = i < end;
+          key[u] = ok ? g.keys[i] : 0ull;
+          av[u] = ok ? g.a[i] : 0.0;
+          bv[u] = ok ? g.b[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int j0 = key[u] > lo ? tr_bin(key[u], lo, shift) : 0;
+          bins[j0 * kThreads + tid] += av[u];
+          if (j0 > 0) bins[(17 + j0) * kThreads + tid] += bv[u];
+        }
+      }
+    } else {
+      int64_t wpos = 0;
+      for (int64_t tbase = 0; tbase < len; tbase += kTile) {
+        unsigned long long key[kTrUnroll];
+        double av[kTrUnroll], bv[kTrUnroll];
+        bool surv[kTrUnroll];
+        int rank_in_warp[kTrUnroll];
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int64_t idx = tbase + static_cast<int64_t>(u) * kThreads + tid;
+          const bool ok = idx < len;
+          key[u] = ok ? g.keys[beg + idx] : 0ull;
+          surv[u] = ok && key[u] > lo && key[u] - lo <= width;
+          av[u] = surv[u] ? g.a[beg + idx] : 0.0;
+          bv[u] = surv[u] ? g.b[beg + idx] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const unsigned int ballot = __ballot_sync(0xffffffffu, surv[u]);
+          rank_in_warp[u] = __popc(ballot & ((1u << lane) - 1u));
+          if (lane == 0) s_wtot[u][warp] = __popc(ballot);
+          if (surv[u]) {
+            const int j0 = tr_bin(key[u], lo, shift);
+            bins[j0 * kThreads + tid] += av[u];
+            bins[(17 + j0) * kThreads + tid] += bv[u];
+          }
+        }
+        __syncthreads();  // every load of this tile is done before any of its survivors is written
+        int tile_total = 0;
+        int my_off[kTrUnroll];
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+#pragma unroll
+          for (int w = 0; w < kThreads / 32; ++w) {
+            if (w == warp) my_off[u] = tile_total;
+            tile_total += s_wtot[u][w];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          if (surv[u]) {
+            const int64_t dst = beg + wpos + my_off[u] + rank_in_warp[u];
+            g.keys[dst] = key[u];
+            g.a[dst] = av[u];
+            g.b[dst] = bv[u];
+          }
+        }
+        wpos += tile_total;
+        __syncthreads();  // s_wtot is reused; the compacted prefix is complete before the next tile's loads
+      }
+      len = wpos;
+    }
+    // (after the first pass the list is still the whole range: its population is unknown, report "large")
+    bins[kTrCount * kThreads + tid] = tid == 0 ? (first_pass ? 1.0e18 : static_cast<double>(len)) : 0.0;
+    first_pass = false;
+    last = tr_round<PEER>(g, peer, bins, tot, part, &s_last, kTrCount + 1, round);
+    if (last) {
+      if (tid == 0) {
+        tr_pick_compact(tot, &s, shift);
+        if (PEER && *reinterpret_cast<volatile int32_t*>(g.peer_error) != 0) s.done = 1;
+      }
+      __syncthreads();
+      // Few elements left in the bracket: this block finishes the remaining passes alone. It first
+      // gathers the compacted lists of all blocks (their lengths are column kTrCount of the
+      // partials) into one contiguous buffer -- every load independent of the others -- and then
+      // runs the passes over that buffer.
+      // (Row-sharded solves keep the grid rounds: every rank must take part in every exchange.)
+      if (!PEER && s.done == 0 && tot[kTrCount] <= static_cast<double>(kTrFinishCap)) {
+        __shared__ int s_start[kTrMaxBlocks + 1];
+        for (int b = tid; b < nb; b += kThreads) s_start[b + 1] = static_cast<int>(__ldcg(g.partials + static_cast<int64_t>(b) * kTrCols + kTrCount));
+        if (tid == 0) s_start[0] = 0;
+        __syncthreads();
+        if (warp == 0) {  // inclusive scan of the lengths: lane l owns a run of consecutive blocks
+          const int chunk = (nb + 31) / 32;
+          int local = 0;
+          for (int k = 0; k < chunk; ++k) {
+            const int b = lane * chunk + k;
+            if (b < nb) local += s_start[b + 1];
+          }
+          int incl = local;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          int run = incl - local;
+          for (int k = 0; k < chunk; ++k) {
+            const int b = lane * chunk + k;
+            if (b < nb) {
+              run += s_start[b + 1];
+              s_start[b + 1] = run;
+            }
+          }
+        }
+        __syncthreads();
+        const int ncand = s_start[nb];
+        for (int idx = tid; idx < ncand; idx += kThreads) {
+          int lo_b = 0, hi_b = nb;  // the block whose list holds candidate idx: s_start[b] <= idx < s_start[b + 1]
+          while (hi_b - lo_b > 1) {
+            const int mid = (lo_b + hi_b) >> 1;
+            if (s_start[mid] <= idx) lo_b = mid; else hi_b = mid;
+          }
+          const int64_t src = min(g.total, static_cast<int64_t>(lo_b) * per) + (idx - s_start[lo_b]);
+          g.cand_keys[idx] = __ldcg(g.keys + src);
+          g.cand_a[idx] = __ldcg(g.a + src);
+          g.cand_b[idx] = __ldcg(g.b + src);
+        }
+        __syncthreads();
+        while (s.done == 0) {
+          const int sh = s.shift;
+          const unsigned long long l2 = s.lo;
+          const unsigned long long w2 = 1ull << s.width_shift;
+#pragma unroll
+          for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
+          for (int base = tid; base < ncand; base += kThreads * kTrUnroll) {
+            unsigned long long key[kTrUnroll];
+            double av[kTrUnroll], bv[kTrUnroll];
+#pragma unroll
+            for (int u = 0; u < kTrUnroll; ++u) {
+              const int i = base + u * kThreads;
+              key[u] = i < ncand ? g.cand_keys[i] : 0ull;
+              av[u] = i < ncand ? g.cand_a[i] : 0.0;
+              bv[u] = i < ncand ? g.cand_b[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kTrUnroll; ++u) {
+              if (key[u] > l2 && key[u] - l2 <= w2) {
+                const int j0 = tr_bin(key[u], l2, sh);
+                bins[j0 * kThreads + tid] += av[u];
+                bins[(17 + j0) * kThreads + tid] += bv[u];
+              }
+            }
+          }
+          __syncthreads();
+          tr_block_totals(bins, tot, 34);
+          __syncthreads();
+          if (tid == 0) tr_pick_compact(tot, &s, sh);
+          __syncthreads();
+        }
+      }
+    }
+    tr_publish_or_wait(g, &s, last, round);
+    ++round;
+    tr_stamp(g);
+  }
+
+  // trust_region.cc:345-365, 429-444 (every block computes the same value from the same state)
+  double step = 0.0;
+  if (!(s.radius_sq == 0.0 || !(s.max_abs_objective > 0.0))) step = s.variable_coef > 0.0 ? sqrt((s.radius_sq - s.fixed_radius_sq) / s.variable_coef) : DBL_MAX;
+  if (!JOINT) {
+    if (blockIdx.x == 0 && tid == 0) {
+      s.step_size = step;
+      *g.st = s;
+    }
+    return;
+  }
+  // ---- final: objective deltas at the solution (trust_region.cc:929-967) ---------------
+  {
+    double f0 = 0.0, f1 = 0.0;
+    auto sweep = [&](auto kind, int64_t sb, int64_t se) {
+      constexpr int KIND = decltype(kind)::value;
+      for (int64_t base = sb + tid; base < se; base += kTile) {
+        double obj[kTrUnroll], lb[kTrUnroll], ub[kTrUnroll], center[kTrUnroll], w[kTrUnroll], qd[kTrUnroll], x0v[kTrUnroll], coef[kTrUnroll];
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int64_t i = min(base + static_cast<int64_t>(u) * kThreads, se - 1);
+          el.template get_k<KIND>(i, obj[u], lb[u], ub[u], center[u], w[u], qd[u], x0v[u], coef[u], nullptr, nullptr);
+        }
+#pragma unroll
+        for (int u = 0; u < kTrUnroll; ++u) {
+          const int64_t i = base + static_cast<int64_t>(u) * kThreads;
+          if (i >= se) continue;
+          const double sol = projected_value(center[u], obj[u], w[u], lb[u], ub[u], step);
+          if (KIND == 0) f0 += obj[u] * (sol - center[u]);
+          else f1 += (-obj[u]) * (sol - center[u]);
+        }
+      }
+    };
+    const int64_t cut = el.split();
+    sweep(std::integral_constant<int, 0>(), beg, min(end, cut));
+    sweep(std::integral_constant<int, 1>(), max(beg, min(end, cut)), end);
+    __syncthreads();
+    bins[0 * kThreads + tid] = f0;
+    bins[1 * kThreads + tid] = f1;
+  }
+  tr_stamp(g);
+  last = tr_round<PEER>(g, peer, bins, tot, part, &s_last, 2, round);
+  tr_stamp(g);
+  if (last && tid == 0) {
+    s.step_size = step;
+    *g.st = s;
+    g.out[0] = s.lag_primal;
+    g.out[1] = s.lag_dual;
+    g.out[2] = tot[0];
+    g.out[3] = tot[1];
+    g.out[4] = s.radius;
+    g.out[5] = s.dist_primal_sq;
+    g.out[6] = s.dist_dual_sq;
   }
 }
 
@@ -1117,11 +1870,20 @@ __global__ void k_tr_init(TrSearchState* st, double radius, const double* maxabs
   st->lo = 0ull;
   st->done = 0;
   st->pad = 0;
+  st->shift = 60;
+  st->width_shift = 64;
   st->fixed_radius_sq = 0.0;
   st->variable_coef = 0.0;
   st->radius_sq = radius * radius;
   st->max_abs_objective = mx;
   st->step_size = 0.0;
+  st->frozen_a = 0.0;
+  st->frozen_b = 0.0;
+  st->lag_primal = 0.0;
+  st->lag_dual = 0.0;
+  st->radius = radius;
+  st->dist_primal_sq = 0.0;
+  st->dist_dual_sq = 0.0;
 }
 __global__ void k_tr_finish(TrSearchState* st, double radius) {
   // trust_region.cc:345-365, 429-444
@@ -1129,10 +1891,6 @@ __global__ void k_tr_finish(TrSearchState* st, double radius) {
   st->step_size = st->variable_coef > 0.0 ? sqrt((st->radius_sq - st->fixed_radius_sq) / st->variable_coef) : DBL_MAX;
 }
 
-__device__ __forceinline__ double projected_value(double center, double obj, double w, double lb, double ub, double step) {
-  const double full = center - step * obj / w;  // trust_region.h:223-228
-  return fmin(fmax(full, lb), ub);
-}
 
 }  // namespace kernels
 
@@ -1172,6 +1930,8 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   CUDA_OK(cudaMalloc(&partials_, sizeof(double) * kMaxReduceBlocks * 40));
   CUDA_OK(cudaMalloc(&tr_peer_error_, 64));
   CUDA_OK(cudaMemset(tr_peer_error_, 0, 64));
+  CUDA_OK(cudaMalloc(&decide_ticket_, 64));
+  CUDA_OK(cudaMemset(decide_ticket_, 0, 64));
   CUDA_OK(cudaMalloc(&results_, sizeof(double) * 64));
   CUDA_OK(cudaMallocHost(&host_results_, sizeof(double) * 64));
 }
@@ -1180,6 +1940,7 @@ Device::~Device() {
   cudaSetDevice(device_);
   cudaFree(partials_);
   cudaFree(tr_peer_error_);
+  cudaFree(decide_ticket_);
   cudaFree(results_);
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
@@ -1286,7 +2047,7 @@ int SellThreads() {
   static const int bt = [] {
     const char* v = std::getenv("PDLP_B200_SELL_THREADS");
     const int t = (v != nullptr && *v != 0) ? std::atoi(v) : 128;
-    return (t == 256 || t == 512) ? t : 128;
+    return t == 256 ? t : 128;
   }();
   return bt;
 }
@@ -1294,6 +2055,13 @@ int SellVariant() {
   static const int v = [] {
     const char* e = std::getenv("PDLP_B200_SELL_VARIANT");
     return (e != nullptr && *e != 0) ? std::atoi(e) : 1;
+  }();
+  return v;
+}
+int SellCarveout() {  // PDLP_B200_SELL_CARVEOUT: preferred shared-memory carve-out (percent) of the TMA-staged kernels; -1 = driver default
+  static const int v = [] {
+    const char* e = std::getenv("PDLP_B200_SELL_CARVEOUT");
+    return (e != nullptr && *e != 0) ? std::atoi(e) : -1;
   }();
   return v;
 }
@@ -1326,6 +2094,11 @@ void launch_k(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStrea
   cfg.numAttrs = pdl ? 1 : 0;
   CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
+bool StepFusedDecide() {
+  // (off by default: one ticket per block of the K^T y' kernel costs more than the launch it saves -- profiles/r02b_ab_sell.txt)
+  static const bool v = [] { const char* e = std::getenv("PDLP_B200_FUSED_DECIDE"); return e != nullptr && e[0] == '1'; }();
+  return v;
+}
 bool StepPdl() {
   static const bool v = [] { const char* e = std::getenv("PDLP_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
   return v;
@@ -1333,23 +2106,53 @@ bool StepPdl() {
 
 template <int MODE, int NS, class Epi>
 void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, double* partials, const int32_t* halt, int64_t* launches,
-                 int* main_blocks, int* fix_blocks, bool pdl = false) {
+                 int* main_blocks, int* fix_blocks, bool pdl = false, DecideTail tail = DecideTail()) {
   const int nb = SellGrid(a);
   const int variant = SellVariant();
-#define PDLP_SELL_LAUNCH(BT, V) launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, nb, BT, stream, a, x, epi, partials, halt, SellChunks())
-#define PDLP_SELL_LAUNCH_V(BT) (variant == 1 ? PDLP_SELL_LAUNCH(BT, 1) : variant == 2 ? PDLP_SELL_LAUNCH(BT, 2) : PDLP_SELL_LAUNCH(BT, 0))
+  // the fused decision runs in the LAST kernel of the product: the fix-up when there are split rows
+  const DecideTail none;
+  const DecideTail& main_tail = a.num_split > 0 ? none : tail;
+  // variants: 0 plain, 1 / 2 software-pipelined register staging (4 / 8 slots), 3.. TMA staging
+  // (slots per stage x stages) 3: 8 x 2, 4: 4 x 2, 5: 2 x 2, 6: 2 x 4, 7: 4 x 3. Shared memory used for
+  // staging is taken from the L1 that tracks the outstanding gather misses, so the stages are small
+  // and the carve-out is pinned to what the resident blocks need.
+#define PDLP_SELL_LAUNCH(BT, V) launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, nb, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail)
+#define PDLP_SELL_LAUNCH_T(BT, U, NST)                                                                                              \
+  do {                                                                                                                              \
+    static bool carved = false;                                                                                                     \
+    if (!carved) {                                                                                                                  \
+      carved = true;                                                                                                                \
+      if (const int pct = SellCarveout(); pct >= 0)                                                                                 \
+        cudaFuncSetAttribute(k_sell_tma<MODE, NS, Epi, BT, U, NST>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);          \
+    }                                                                                                                               \
+    launch_k(pdl, k_sell_tma<MODE, NS, Epi, BT, U, NST>, nb, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail);       \
+  } while (0)
+#define PDLP_SELL_LAUNCH_V(BT)                                 \
+  do {                                                         \
+    if (variant == 3) PDLP_SELL_LAUNCH_T(128, 8, 2);           \
+    else if (variant == 4) PDLP_SELL_LAUNCH_T(128, 4, 2);      \
+    else if (variant == 5) PDLP_SELL_LAUNCH_T(128, 2, 2);      \
+    else if (variant == 6) PDLP_SELL_LAUNCH_T(128, 2, 4);      \
+    else if (variant == 7) PDLP_SELL_LAUNCH_T(128, 4, 3);      \
+    else if (variant == 1) PDLP_SELL_LAUNCH(BT, 1);            \
+    else if (variant == 2) PDLP_SELL_LAUNCH(BT, 2);            \
+    else PDLP_SELL_LAUNCH(BT, 0);                              \
+  } while (0)
   switch (SellThreads()) {
-    case 256: PDLP_SELL_LAUNCH_V(256); break;
-    case 512: PDLP_SELL_LAUNCH_V(512); break;
+    case 256:  // (static shared memory: 8 warps only fit the small stagings)
+      if (variant >= 3) PDLP_SELL_LAUNCH_T(256, 2, 2);
+      else PDLP_SELL_LAUNCH_V(256);
+      break;
     default: PDLP_SELL_LAUNCH_V(128); break;
   }
 #undef PDLP_SELL_LAUNCH_V
+#undef PDLP_SELL_LAUNCH_T
 #undef PDLP_SELL_LAUNCH
   ++*launches;
   int nf = 0;
   if (a.num_split > 0) {
     nf = static_cast<int>((a.num_split * 32 + kThreads - 1) / kThreads);
-    launch_k(pdl, k_sell_fixup<MODE, NS, Epi>, nf, kThreads, stream, a, epi, partials != nullptr ? partials + static_cast<int64_t>(nb) * NS : nullptr, halt);
+    launch_k(pdl, k_sell_fixup<MODE, NS, Epi>, nf, kThreads, stream, a, epi, partials != nullptr ? partials + static_cast<int64_t>(nb) * NS : nullptr, halt, tail);
     ++*launches;
   }
   if (main_blocks != nullptr) *main_blocks = nb;
@@ -1766,8 +2569,6 @@ double* Device::TrScratch(int64_t doubles) {
 }
 
 namespace kernels {
-// Runs the threshold search; leaves the step size in st->step_size (device).
-// Elements below `first` are skipped (replicated primal part on ranks > 0).
 static bool TrLegacy();
 static int TrSms();
 static long long PeerTimeoutCycles() {
@@ -1790,46 +2591,78 @@ static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_glob
   pp.timeout_cycles = PeerTimeoutCycles();
   return pp;
 }
+// Persistent solve (k_tr_solve). Returns false when it does not apply (PDLP_B200_TR_LEGACY=1, or a
+// row-sharded solve without peer arenas) and the caller must take the multi-launch path.
+// JOINT: x0 / y0 / out as in TrSolveArgs.
+template <class Elem, bool JOINT>
+bool tr_solve_persistent(cudaStream_t stream, Comm* comm, const PeerPtrs& peer, int32_t* peer_error, int64_t total, Elem el, double radius,
+                         const double* x0, const double* y0, double* scratch, double* partials, TrSearchState* st, double* out, int64_t* launches) {
+  const bool use_peer = comm != nullptr && peer.world > 1;
+  if (TrLegacy() || (comm != nullptr && !use_peer)) return false;
+  constexpr int64_t kTile = static_cast<int64_t>(kThreads) * kTrUnroll;
+  const int nbp = static_cast<int>(std::min<int64_t>(std::min<int64_t>(kTrMaxBlocks, static_cast<int64_t>(TrSms()) * kTrBlocksPerSm), std::max<int64_t>(1, (total + kTile - 1) / kTile)));
+  TrSolveArgs g;
+  g.total = total;
+  g.keys = reinterpret_cast<unsigned long long*>(scratch);
+  g.a = scratch + total;
+  g.b = scratch + 2 * total;
+  g.st = st;
+  g.partials = partials;
+  g.sync = reinterpret_cast<unsigned int*>(scratch + 3 * total + 32);
+  g.radius = radius;
+  g.x0 = x0;
+  g.y0 = y0;
+  g.out = out;
+  g.peer_error = peer_error;
+  g.cand_keys = reinterpret_cast<unsigned long long*>(scratch + 3 * total + 128);
+  g.cand_a = scratch + 3 * total + 128 + kTrFinishCap;
+  g.cand_b = scratch + 3 * total + 128 + 2 * kTrFinishCap;
+  static const bool trace = [] { const char* t = std::getenv("PDLP_B200_TRACE"); return t != nullptr && t[0] == '1'; }();
+  static int traced_calls = 0;
+  g.trace = nullptr;
+  if (trace && traced_calls < 8) {
+    g.trace = reinterpret_cast<unsigned long long*>(scratch + 3 * total + 34);  // (after the two sync words; scratch has 64 spare doubles... the stamps need 31)
+    CUDA_OK(cudaMemsetAsync(g.trace, 0, 31 * sizeof(unsigned long long), stream));
+  }
+  CUDA_OK(cudaMemsetAsync(g.sync, 0, 2 * sizeof(unsigned int), stream));
+  const size_t smem = sizeof(double) * kTrCols * kThreads;
+  PeerPtrs pp = peer;
+  void* args[] = {&g, &el, &pp};
+  const void* fn = use_peer ? reinterpret_cast<const void*>(k_tr_solve<Elem, true, JOINT>) : reinterpret_cast<const void*>(k_tr_solve<Elem, false, JOINT>);
+  // (per device, so set on every launch: a process may drive several devices)
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nbp), dim3(kThreads), args, smem, stream);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cooperative launch of k_tr_solve failed: ") + cudaGetErrorString(e));
+  *launches += 1;
+  if (g.trace != nullptr) {
+    ++traced_calls;
+    unsigned long long h[31];
+    CUDA_OK(cudaMemcpyAsync(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    std::fprintf(stderr, "[pdlp_b200 trace] k_tr_solve (%lld elements, %d blocks) phase us of block 0 [start | prepare | round 0 | passes ... | final sweep | final round]:", static_cast<long long>(total), nbp);
+    for (unsigned long long k = 1; k < h[0] && k < 30; ++k) std::fprintf(stderr, " %.1f", (h[1 + k] - h[k]) / 1000.0);
+    std::fprintf(stderr, "\n");
+  }
+  return true;
+}
+
+// Multi-launch threshold search (PDLP_B200_TR_LEGACY=1 and row-sharded solves whose ranks share no
+// peer arenas: the bin totals are all-reduced by NCCL between the passes). Leaves the step size in
+// st->step_size (device).
 template <class Elem>
-void tr_search(cudaStream_t stream, Comm* comm, const PeerPtrs& peer, int32_t* peer_error, int64_t total, int64_t first, Elem el, double radius,
-               double* scratch, double* partials, TrSearchState* st, double* totals, int64_t* launches) {
+void tr_search_multilaunch(cudaStream_t stream, Comm* comm, int64_t total, Elem el, double radius, double* scratch, double* partials,
+                           TrSearchState* st, double* totals, int64_t* launches) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(scratch);
   double* a = scratch + total;
   double* b = scratch + 2 * total;
   const int nb = static_cast<int>(std::min<int64_t>(148 * 2, std::max<int64_t>(1, (total + kThreads * kTrUnroll - 1) / (kThreads * kTrUnroll))));
   const int nb_prep = static_cast<int>(std::min<int64_t>(kMaxReduceBlocks, std::max<int64_t>(1, (total + kThreads * 2 - 1) / (kThreads * 2))));
-  k_tr_prepare<Elem><<<nb_prep, kThreads, 0, stream>>>(total, first, el, keys, a, b, partials);
+  k_tr_prepare<Elem><<<nb_prep, kThreads, 0, stream>>>(total, 0, el, keys, a, b, partials);
   k_tr_init<<<1, 32, 0, stream>>>(st, radius, partials, nb_prep);
   *launches += 2;
   if (comm != nullptr) {
     double* mx = reinterpret_cast<double*>(st) + offsetof(TrSearchState, max_abs_objective) / sizeof(double);
     comm->AllReduceMax(mx, mx, 1, stream);
-  }
-  const bool persistent = !TrLegacy();
-  if (persistent) {
-    // one cooperative launch (all blocks co-resident: SMs x kTrBlocksPerSm)
-    const int nbp = static_cast<int>(std::min<int64_t>(std::min<int64_t>(kTrMaxBlocks, static_cast<int64_t>(TrSms()) * kTrBlocksPerSm), std::max<int64_t>(1, (total + kThreads * kTrUnroll - 1) / (kThreads * kTrUnroll))));
-    unsigned int* counter = reinterpret_cast<unsigned int*>(totals + 40);
-    cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream);
-    double* part2 = partials;  // [2][nbp][34]
-    const size_t smem = sizeof(double) * 34 * kThreads;
-    const unsigned long long* ckeys = keys;
-    const double* ca = a;
-    const double* cb = b;
-    int64_t tot_arg = total;
-    double rad = radius;
-    void* args[] = {&tot_arg, &ckeys, &ca, &cb, &st, &part2, &counter, const_cast<PeerPtrs*>(&peer), &peer_error, &rad};
-    const bool use_peer = comm != nullptr && peer.world > 1;
-    // (per device, so set on every launch: a process may drive several devices)
-    cudaFuncSetAttribute(k_tr_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    cudaFuncSetAttribute(k_tr_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (comm == nullptr || use_peer) {
-      cudaError_t e = cudaLaunchCooperativeKernel(use_peer ? reinterpret_cast<const void*>(k_tr_search<true>) : reinterpret_cast<const void*>(k_tr_search<false>),
-                                                  dim3(nbp), dim3(kThreads), args, smem, stream);
-      if (e != cudaSuccess) throw std::runtime_error(std::string("cooperative launch of k_tr_search failed: ") + cudaGetErrorString(e));
-      *launches += 1;
-      return;
-    }
   }
   for (int shift = 60; shift >= 0; shift -= 4) {
     k_tr_pass<<<nb, kThreads, 0, stream>>>(total, keys, a, b, st, shift, partials);
@@ -1857,12 +2690,51 @@ static int TrSms() {
 
 void Device::LocalizedLagrangianBounds(const double* x, const double* y, const double* kx, const double* kty, const double* c, const double* q,
                                        const double* lv, const double* uv, const double* lc, const double* uc, double primal_weight, double radius,
-                                       bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t mm, double out[3]) {
+                                       bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t mm, double out[3], const double* x0,
+                                       const double* y0, double* extra_out) {
   // The primal side is replicated on a row-sharded solve: every rank counts its own slice of it.
   const int64_t pbeg = PrimalSliceBegin(n), plen = PrimalSliceEnd(n) - pbeg;
   const int64_t total = plen + mm;
   const JointElem el{x, y, kx, kty, c, q, lv, uv, lc, uc, primal_weight, plen, mm, pbeg};
-  const int64_t first = 0;
+  double* scratch = TrScratch(3 * total + 128 + 3 * kTrFinishCap);
+  TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * total);
+  const bool radius_from_distance = radius < 0.0 && x0 != nullptr && y0 != nullptr;
+
+  if (!use_diagonal_solver) {
+    // One persistent launch: Lagrangian value, radius (when asked for), threshold search, objective
+    // deltas (trust_region.cc:886-1016); one device->host copy.
+    const PeerPtrs tr_peer = MakeTrPeerPtrs(peer_arena_, peer_arena_n_, peer_arena_m_);
+    if (tr_solve_persistent<JointElem, true>(STREAM, comm_, tr_peer, tr_peer_error_, total, el, radius, radius_from_distance ? x0 : nullptr,
+                                             radius_from_distance ? y0 : nullptr, scratch, partials_, st, results_, &launches_)) {
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * 7, cudaMemcpyDeviceToHost, STREAM));
+      int32_t* err = reinterpret_cast<int32_t*>(host_results_ + 8);
+      *err = 0;
+      if (comm_ != nullptr && peer_arena_ != nullptr) CUDA_OK(cudaMemcpyAsync(err, tr_peer_error_, sizeof(int32_t), cudaMemcpyDeviceToHost, STREAM));
+      Sync();
+      if (*err != 0) throw std::runtime_error("peer-memory exchange timed out in the trust-region search: a rank did not arrive");
+      const double lagrangian = host_results_[0] + host_results_[1];
+      out[0] = lagrangian;
+      out[1] = lagrangian + host_results_[2];
+      out[2] = lagrangian + host_results_[3];
+      if (extra_out != nullptr) {
+        extra_out[0] = host_results_[4];
+        extra_out[1] = radius_from_distance ? host_results_[5] : -1.0;
+        extra_out[2] = radius_from_distance ? host_results_[6] : -1.0;
+      }
+      return;
+    }
+  }
+  double dist[2] = {-1.0, -1.0};
+  if (radius_from_distance) {
+    DistancesSq(x, x0, n, y, y0, mm, dist);
+    radius = std::sqrt((0.5 * primal_weight) * dist[0] + (0.5 / primal_weight) * dist[1]);
+  }
+  if (extra_out != nullptr) {
+    extra_out[0] = radius;
+    extra_out[1] = dist[0];
+    extra_out[2] = dist[1];
+  }
   // Lagrangian value = primal part + dual part (sou.cc:446-527).
   REDUCE_S(true, 2, 0, total, {
     if (i < plen) {
@@ -1876,18 +2748,10 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
     }
   });
   const double lagrangian = host_results_[0] + host_results_[1];
-  double* scratch = TrScratch(3 * total + 64);
-  TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * total);
 
   if (!use_diagonal_solver) {
-    tr_search(STREAM, comm_, MakeTrPeerPtrs(peer_arena_, peer_arena_n_, peer_arena_m_), tr_peer_error_, total, first, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
+    tr_search_multilaunch(STREAM, comm_, total, el, radius, scratch, partials_, st, scratch + 3 * total + 16, &launches_);
     CUDA_OK(cudaGetLastError());
-    if (comm_ != nullptr && peer_arena_ != nullptr) {
-      int32_t err = 0;
-      CUDA_OK(cudaMemcpyAsync(&err, tr_peer_error_, sizeof(err), cudaMemcpyDeviceToHost, STREAM));
-      Sync();
-      if (err != 0) throw std::runtime_error("peer-memory exchange timed out in the trust-region search: a rank did not arrive");
-    }
     // objective deltas at the solution (trust_region.cc:929-967)
     const TrSearchState* cst = st;
     REDUCE_S(true, 2, 0, total, {
@@ -1950,9 +2814,10 @@ void Device::LocalizedLagrangianBounds(const double* x, const double* y, const d
 void Device::SolveTrustRegion(const double* obj, const double* lb, const double* ub, const double* center, const double* w, double radius,
                               int64_t n, double* solution, double* step_size, double* objective_value) {
   const VectorElem el{obj, lb, ub, center, w, nullptr};
-  double* scratch = TrScratch(3 * n + 64);
+  double* scratch = TrScratch(3 * n + 128 + 3 * kTrFinishCap);
   TrSearchState* st = reinterpret_cast<TrSearchState*>(scratch + 3 * n);
-  tr_search(STREAM, nullptr, PeerPtrs{}, nullptr, n, 0, el, radius, scratch, partials_, st, scratch + 3 * n + 16, &launches_);
+  if (!tr_solve_persistent<VectorElem, false>(STREAM, nullptr, PeerPtrs{}, nullptr, n, el, radius, nullptr, nullptr, scratch, partials_, st, nullptr, &launches_))
+    tr_search_multilaunch(STREAM, nullptr, n, el, radius, scratch, partials_, st, scratch + 3 * n + 16, &launches_);
   CUDA_OK(cudaGetLastError());
   const TrSearchState* cst = st;
   REDUCE(1, 0, n, {
@@ -2014,8 +2879,9 @@ StepState* Device::AllocState() {
   return p;
 }
 void Device::UploadState(StepState* dev, const StepState& host) {
+  // (pageable source: the runtime stages the bytes before it returns, and the stream orders the
+  // copy before the step kernels -- no host synchronisation needed)
   CUDA_OK(cudaMemcpyAsync(dev, &host, sizeof(StepState), cudaMemcpyHostToDevice, STREAM));
-  Sync();
 }
 void Device::DownloadState(StepState& host, const StepState* dev) {
   CUDA_OK(cudaMemcpyAsync(&host, dev, sizeof(StepState), cudaMemcpyDeviceToHost, STREAM));
@@ -2157,12 +3023,24 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, np, b.exchange + b.n, -1, pt, nk);
       ++launches_;
     } else {
-      if (b.n > 0) {
-        launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr, pdl);
+      if (b.n > 0 && StepFusedDecide()) {
+        // three launches per iteration: the decision runs in the last block of the K^T y' kernel
+        DecideTail tail;
+        tail.st = b.state;
+        tail.pp = pp; tail.np = np;
+        tail.pd = pd; tail.nd = b.m > 0 ? nd_main + nd_fix : 0;
+        tail.pt = pt; tail.nt = nt_main + nt_fix;
+        tail.ticket = decide_ticket_;
+        launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr, pdl, tail);
+        if (slot >= 0) ev(slot, 3);
+      } else {
+        if (b.n > 0) {
+          launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr, pdl);
+        }
+        if (slot >= 0) ev(slot, 3);
+        launch_k(pdl, k_step_decide, 1, kDecideThreads, STREAM, b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
+        ++launches_;
       }
-      if (slot >= 0) ev(slot, 3);
-      launch_k(pdl, k_step_decide, 1, kDecideThreads, STREAM, b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
-      ++launches_;
     }
     if (slot >= 0) ev(slot, 4);
   }
@@ -2196,6 +3074,18 @@ void Device::TimelineStart(int id) {
   for (int k = 0; k < 2; ++k)
     if (timeline_ev_[id][k] == nullptr) { cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); timeline_ev_[id][k] = e; }
   CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timeline_ev_[id][0]), STREAM));
+}
+void Device::TimelineStop(int id) {
+  CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timeline_ev_[id][1]), STREAM));
+  timeline_pending_[id] = true;
+}
+double Device::TimelineCollectMs(int id) {
+  if (!timeline_pending_[id]) return 0.0;
+  timeline_pending_[id] = false;
+  CUDA_OK(cudaEventSynchronize(static_cast<cudaEvent_t>(timeline_ev_[id][1])));
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(timeline_ev_[id][0]), static_cast<cudaEvent_t>(timeline_ev_[id][1])));
+  return ms;
 }
 double Device::TimelineStopMs(int id) {
   CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timeline_ev_[id][1]), STREAM));

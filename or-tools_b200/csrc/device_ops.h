@@ -97,6 +97,10 @@ struct StepState {
   double reduction_exponent, growth_exponent;
   double last_dx2, last_dy2, last_nonlinearity, last_movement;
   int64_t attempts;                 // attempts actually executed (not no-ops)
+  // (total + 1)^-reduction_exponent and ^-growth_exponent of the adaptive rule for the attempt
+  // count `pow_total`: evaluated by the primal-step kernel, off the critical path of the decision
+  // (two double-precision pow() in one thread are ~5 us). Ignored unless pow_total matches.
+  double pow_reduction, pow_growth, pow_total;
 };
 enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent = 3, kHaltInnerLimit = 4, kHaltPeerTimeout = 5 };
 
@@ -118,7 +122,7 @@ struct PeerLayout {
     l.flags_off = l.scal_off + 4 * 8;
     l.epoch_off = l.flags_off + 8 * 4;
     l.tr_off = l.epoch_off + 4;
-    l.doubles = l.tr_off + 2 * 34 * 8;
+    l.doubles = l.tr_off + 2 * 48 * 8;
     return l;
   }
 };
@@ -274,10 +278,14 @@ class Device {
 
   // ---- trust region (trust_region.cc) ------------------------------------
   // Joint problem (trust_region.cc:115-162) over (x, y): returns lagrangian
-  // value, lower, upper (ComputeLocalizedLagrangianBounds, Euclidean norm).
+  // value, lower, upper (ComputeLocalizedLagrangianBounds, Euclidean norm). radius < 0 with x0 / y0
+  // given: the radius is the weighted distance of (x, y) to (x0, y0) (pdhg.cc:1998-2007), computed in the
+  // same launch; extra_out (3 doubles) receives {radius, ||x - x0||^2, ||y - y0||^2} (the last two -1 when
+  // the radius was given).
   void LocalizedLagrangianBounds(const double* x, const double* y, const double* kx, const double* kty, const double* c, const double* q,
                                  const double* lv, const double* uv, const double* lc, const double* uc, double primal_weight,
-                                 double radius, bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t m, double out[3]);
+                                 double radius, bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t m, double out[3],
+                                 const double* x0 = nullptr, const double* y0 = nullptr, double* extra_out = nullptr);
   // Explicit-vector problems (SolveTrustRegion / SolveDiagonalTrustRegion).
   void SolveTrustRegion(const double* obj, const double* lb, const double* ub, const double* center, const double* w, double radius,
                         int64_t n, double* solution, double* step_size, double* objective_value);
@@ -331,6 +339,8 @@ class Device {
   // Device-timeline stopwatch on the launching stream (CUDA events).
   void TimelineStart(int id);        // id in {0, 1}
   double TimelineStopMs(int id);     // synchronises
+  void TimelineStop(int id);         // records only; TimelineCollectMs (which synchronises) returns the time later
+  double TimelineCollectMs(int id);  // 0 if nothing is pending
   // Applies the deferred average update (if any) for both averages.
   void FlushAverages(const StepBuffers& b);
   // Peer exchange only: inside the step loop every rank advances just its slice
@@ -358,6 +368,7 @@ class Device {
   const PeerArena* peer_arena_ = nullptr;
   int64_t peer_arena_n_ = 0, peer_arena_m_ = 0;
   int32_t* tr_peer_error_ = nullptr;  // device flag: a peer did not arrive at a barrier of the trust-region search
+  unsigned int* decide_ticket_ = nullptr;  // ticket counter of the fused step decision (DecideTail)
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)
   double* tr_scratch_ = nullptr;
@@ -376,6 +387,7 @@ class Device {
   std::vector<int> timing_attempt_idx_;  // attempt index of each used slot in the last batch
   StepTimings step_timings_;
   void* timeline_ev_[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  bool timeline_pending_[2] = {false, false};
 };
 
 }  // namespace pdlp_b200

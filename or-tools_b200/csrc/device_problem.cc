@@ -387,12 +387,15 @@ void DeviceProblem::ReducedCosts(const double* x, const double* y, bool use_zero
 }
 
 void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const double* y, double primal_weight, double radius, const double* kx,
-                                                     const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4]) {
+                                                     const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4],
+                                                     const double* x0, const double* y0, double* dist_sq) {
   if (kx == nullptr) { Kx(x, tmp_m_[2]); kx = tmp_m_[2]; }
   if (kty == nullptr) { KTy(y, tmp_n_[2]); kty = tmp_n_[2]; }
-  double r3[3];
-  dev_->LocalizedLagrangianBounds(x, y, kx, kty, c_, q_, lv_, uv_, lc_, uc_, primal_weight, radius, use_diagonal_solver, diagonal_tol, n_, m_, r3);
-  out[0] = r3[0]; out[1] = r3[1]; out[2] = r3[2]; out[3] = radius;
+  double r3[3], extra[3];
+  dev_->LocalizedLagrangianBounds(x, y, kx, kty, c_, q_, lv_, uv_, lc_, uc_, primal_weight, radius, use_diagonal_solver, diagonal_tol, n_, m_, r3, x0, y0,
+                                  extra);
+  out[0] = r3[0]; out[1] = r3[1]; out[2] = r3[2]; out[3] = extra[0];
+  if (dist_sq != nullptr) { dist_sq[0] = extra[1]; dist_sq[1] = extra[2]; }
 }
 
 void DeviceProblem::ComputeLocalizedLagrangianBoundsMaxNorm(const double* x, const double* y, double primal_weight, double radius, const double* kx,

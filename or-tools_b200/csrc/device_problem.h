@@ -108,7 +108,9 @@ class DeviceProblem {
   void ReducedCosts(const double* x, const double* y, bool use_zero_primal_objective, double* out);
   // trust_region.cc:978-1016 (Euclidean). kx / kty may be null (computed).
   void ComputeLocalizedLagrangianBounds(const double* x, const double* y, double primal_weight, double radius, const double* kx,
-                                        const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4]);
+                                        const double* kty, bool use_diagonal_solver, double diagonal_tol, double out[4],
+                                        const double* x0 = nullptr, const double* y0 = nullptr,   // radius < 0: distance to (x0, y0)
+                                        double* dist_sq = nullptr);                                 // then also {||x - x0||^2, ||y - y0||^2}
 
   // trust_region.cc:855-884 (max norm): the primal and the dual trust-region problems are solved
   // separately with radii sqrt(2) r / sqrt(w) and sqrt(2) r sqrt(w). Not used by the solver

@@ -13,6 +13,8 @@
 //  * the Malitsky-Pock rule (pdhg.cc:2463-2556) is host-driven per inner step.
 #include "solver.h"
 
+#include "comm.h"
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -371,10 +373,13 @@ class DeviceSolve {
     return std::sqrt((0.5 * hs_.primal_weight) * d[0] + (0.5 / hs_.primal_weight) * d[1]);
   }
   LocalizedBounds BoundsAt(const double* x, const double* y, const double* kx, const double* kty) {
-    const double radius = DistanceTraveledFromLastStart(x, y);
-    double out[4];
-    P.ComputeLocalizedLagrangianBounds(x, y, hs_.primal_weight, radius, kx, kty, params_.use_diagonal_qp_trust_region_solver != 0,
-                                       params_.diagonal_qp_trust_region_solver_tolerance, out);
+    // radius = DistanceTraveledFromLastStart(x, y) (pdhg.cc:1998-2007), computed inside the same launch
+    double out[4], dist[2];
+    P.ComputeLocalizedLagrangianBounds(x, y, hs_.primal_weight, /*radius=*/-1.0, kx, kty, params_.use_diagonal_qp_trust_region_solver != 0,
+                                       params_.diagonal_qp_trust_region_solver_tolerance, out, x0_, y0_, dist);
+    // ||x - x0||^2, ||y - y0||^2 come out of the same launch: the primal weight update of a restart reuses them
+    if (x == X() && y == Y()) { dist_cur_[0] = dist[0]; dist_cur_[1] = dist[1]; dist_cur_ok_ = dist[0] >= 0.0; }
+    else if (x == buf_.avg_x && y == buf_.avg_y) { dist_avg_[0] = dist[0]; dist_avg_[1] = dist[1]; dist_avg_ok_ = dist[0] >= 0.0; }
     return {out[0], out[1], out[2], out[3]};
   }
   LocalizedBounds ComputeLocalizedBoundsAtCurrent() {  // pdhg.cc:2009-2021
@@ -413,6 +418,10 @@ class DeviceSolve {
   SolverResultCpp PickSolutionAndConstructSolverResult(const double* avg_x, const double* avg_y, const PdlpIterationStats& stats, int reason,
                                                        int output_type, SolveLogCpp log);
   void MaterializeDeltas();
+  // The iterate difference is only read by termination checks and overwritten by restarts to the
+  // average: it is materialised when one of the two happens, not after every chunk of steps.
+  bool delta_pending_ = false;
+  void EnsureDeltas() { if (delta_pending_) { MaterializeDeltas(); delta_pending_ = false; } }
   int NextCheckpoint(int k) const;
   Outcome RunDeviceSteps(int k, const volatile int32_t* interrupt);
   Outcome TakeMalitskyPockStep();
@@ -434,9 +443,12 @@ class DeviceSolve {
   // of the average. Valid only until the iterates or the averages change.
   double *pc_kx_cur_ = nullptr, *pc_kx_avg_ = nullptr, *pc_kty_avg_ = nullptr;
   bool pc_kx_cur_ok_ = false, pc_kx_avg_ok_ = false, pc_kty_avg_ok_ = false;
+  // squared distances of the current / average point to the last restart point, as left by BoundsAt
+  double dist_cur_[2] = {0, 0}, dist_avg_[2] = {0, 0};
+  bool dist_cur_ok_ = false, dist_avg_ok_ = false;
   void InvalidateProducts(bool current, bool average) {
-    if (current) pc_kx_cur_ok_ = false;
-    if (average) pc_kx_avg_ok_ = pc_kty_avg_ok_ = false;
+    if (current) pc_kx_cur_ok_ = dist_cur_ok_ = false;
+    if (average) pc_kx_avg_ok_ = pc_kty_avg_ok_ = dist_avg_ok_ = false;
   }
   const double* CachedKx(const double* x) {  // nullptr: not one of the cached points
     const bool mp = params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE;
@@ -543,7 +555,8 @@ int DeviceSolve::ChooseRestartToApply(bool is_major) {  // pdhg.cc:2109-2170
 
 double DeviceSolve::ComputeNewPrimalWeight() {  // pdhg.cc:2188-2214
   double d[2];
-  D.DistancesSq(X(), x0_, P.n(), Y(), y0_, P.m(), d);
+  if (dist_cur_ok_) { d[0] = dist_cur_[0]; d[1] = dist_cur_[1]; }
+  else D.DistancesSq(X(), x0_, P.n(), Y(), y0_, P.m(), d);
   const double primal_distance = std::sqrt(d[0]), dual_distance = std::sqrt(d[1]);
   constexpr double kNonzeroTol = 1.0e-10;
   if (primal_distance <= kNonzeroTol || primal_distance >= 1.0 / kNonzeroTol || dual_distance <= kNonzeroTol || dual_distance >= 1.0 / kNonzeroTol)
@@ -563,8 +576,10 @@ void DeviceSolve::ApplyRestartChoice(int restart) {  // pdhg.cc:2246-2296
       break;
     case PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE:
       if (params_.verbosity_level >= 4) logger_.Log(Fmt("Restarted to average on iteration %d after %d iterations", iterations_completed_, avg_x_terms_));
+      EnsureDeltas();  // x[cur] - x[prev] of the last accepted step, before x[cur] is overwritten
       D.CopyD2D(X(), buf_.avg_x, P.n());
       D.CopyD2D(Y(), buf_.avg_y, P.m());
+      dist_cur_[0] = dist_avg_[0]; dist_cur_[1] = dist_avg_[1]; dist_cur_ok_ = dist_avg_ok_;
       // the new current iterate is the average: its products are the average's
       if (pc_kty_avg_ok_ && params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE) {
         D.CopyD2D(Kty(), pc_kty_avg_, P.n());
@@ -592,6 +607,7 @@ void DeviceSolve::ApplyRestartChoice(int restart) {  // pdhg.cc:2246-2296
   ClearAverages();
   D.CopyD2D(x0_, X(), P.n());
   D.CopyD2D(y0_, Y(), P.m());
+  dist_cur_ok_ = dist_avg_ok_ = false;  // the restart point moved
 }
 
 PdlpIterationStats DeviceSolve::CreateSimpleIterationStats(int restart_used) const {  // pdhg.cc:1976-1996
@@ -672,6 +688,7 @@ void DeviceSolve::MaterializeDeltas() {
 // pdhg.cc:1567-1653
 std::optional<ReasonAndType> DeviceSolve::UpdateIterationStatsAndCheckTermination(bool force_numerical, bool interrupted,
                                                                                   const PdlpIterationStats& full_stats, PdlpIterationStats& stats) {
+  EnsureDeltas();
   ConvergenceAndInfeasibility(X(), Y(), Kty(), PDLP_POINT_TYPE_CURRENT_ITERATE, &stats.convergence_information[stats.num_convergence_information],
                               &stats.infeasibility_information[stats.num_infeasibility_information]);
   stats.num_convergence_information++;
@@ -997,28 +1014,33 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
   hs_.avg_weight_sum = avg_x_weight_;
   hs_.avg_num_terms = avg_x_terms_;
   hs_.pending_ratio = 0.0;
+  hs_.pow_total = -1.0;  // (nothing cached for this attempt count yet)
   PushState();
   WallTimer t;
+  device_step_ms_ += D.TimelineCollectMs(1);  // (the previous chunk's; its events are about to be reused)
   D.TimelineStart(1);
   for (;;) {
     const int remaining = std::max(1, hs_.k_stop - hs_.iterations_completed);
     const int64_t attempts_before = hs_.attempts;
-    D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining + 1, 4096));
+    // exactly the attempts that reach the checkpoint if every step is accepted; rejected
+    // steps (rare) are made up by another pass of this loop
+    D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining, 4096));
     D.DownloadState(hs_, buf_.state);
+    if (P.sharded() && D.comm() != nullptr) D.comm()->CheckAsyncError();
     D.CollectStepTimings(hs_.attempts - attempts_before);
     if (hs_.halt != kHaltNone) break;
   }
   phase_s_[3] += t.Get();
   WallTimer phase;
   D.FlushAverages(buf_);
-  D.DownloadState(hs_, buf_.state);
+  hs_.pending_ratio = 0.0;  // (all FlushAverages changes in the device state)
   if (hs_.halt == kHaltPeerTimeout) throw std::runtime_error("peer-memory exchange timed out: a rank of the row-sharded solve did not arrive");
   D.GatherPrimalSlices(buf_, hs_.cur, hs_.prev);
-  device_step_ms_ += D.TimelineStopMs(1);
+  D.TimelineStop(1);  // collected lazily: no host synchronisation here
   device_time_sec_ += t.Get();
   phase_s_[4] += phase.Get();
   phase.Start();
-  if (hs_.iterations_completed > k) MaterializeDeltas();
+  if (hs_.iterations_completed > k) delta_pending_ = true;
   phase_s_[5] += phase.Get();
   avg_x_weight_ = avg_y_weight_ = hs_.avg_weight_sum;
   avg_x_terms_ = avg_y_terms_ = hs_.avg_num_terms;
@@ -1134,6 +1156,7 @@ std::optional<SolverResultCpp> DeviceSolve::Advance(int target_iterations, const
     check_done_ = false;
     if (outcome == Outcome::kForceNumericalTermination) force_numerical_ = true;
   }
+  device_step_ms_ += D.TimelineCollectMs(1);
   if (!nested_) device_total_ms_ += D.TimelineStopMs(0);
   return done;
 }
@@ -1410,13 +1433,17 @@ SolverResultCpp PrimalDualHybridGradient(const PdlpProblemView& view, const Pdlp
   const double t_validate = t.Get();
   SolverResultCpp result;
   double t_problem = 0, t_solve = 0;
-  {
+  try {
     DeviceProblem problem(view, cuda_device, comm);
     t_problem = t.Get();
     DeviceSolve solve(problem, params, logger, std::move(callback));
     const std::string name = view.problem_name != nullptr ? std::string(view.problem_name) : std::string();
     result = solve.PreprocessAndSolve(std::move(initial_solution), interrupt_solve, view.problem_name != nullptr ? &name : nullptr);
     t_solve = t.Get();
+  } catch (const CommError& e) {
+    // the communicator failed under the solve (ncclCommGetAsyncError): no usable point, the
+    // reason is not one of the problem's (pdhg.cc has no analogue; SolveLog's catch-all applies)
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_OTHER, std::string("The row-sharded solve was aborted: ") + e.what(), logger);
   }
   if (trace)
     std::fprintf(stderr, "[pdlp_b200 trace] entry point wall seconds: validate %.4f, device problem (upload + SELL build) %.4f, preprocess + solve + result %.4f, teardown %.4f\n",

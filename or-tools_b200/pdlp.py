@@ -577,6 +577,17 @@ class Backend:
     def problem(self, qp, **kwargs):
         return DeviceProblem(self, qp, **kwargs)
 
+    # The two calls whose argument lists depend on the library behind the C ABI (a subclass
+    # binding another library overrides them).
+    def _problem_create(self, view, handle, cuda_device=0, num_threads=1, num_shards=0):
+        return self.fn("problem_create")(C.byref(view), C.c_int32(cuda_device), C.byref(handle))
+
+    def _localized_bounds(self, prob, args, max_norm, out):
+        if max_norm:  # PrimalDualNorm::kMaxNorm has its own entry point
+            prob._call("compute_localized_lagrangian_bounds_max_norm", *args[:6], out)
+        else:
+            prob._call("compute_localized_lagrangian_bounds", *args, out)
+
 
 class DeviceProblem:
     """A QP resident on the backend (ShardedQuadraticProgram equivalent)."""
@@ -587,10 +598,7 @@ class DeviceProblem:
         view, self._keep = qp._to_view()
         self.m, self.n, self.nnz = view.num_constraints, view.num_variables, view.num_nonzeros
         self.h = C.c_void_p()
-        if backend.prefix == "pdlp_oracle_":
-            rc = backend.fn("problem_create")(C.byref(view), C.c_int32(num_threads), C.c_int32(num_shards), C.byref(self.h))
-        else:
-            rc = backend.fn("problem_create")(C.byref(view), C.c_int32(cuda_device), C.byref(self.h))
+        rc = backend._problem_create(view, self.h, cuda_device=cuda_device, num_threads=num_threads, num_shards=num_shards)
         backend._check(rc, "problem_create")
 
     def close(self):
@@ -722,12 +730,7 @@ class DeviceProblem:
         out = (C.c_double * 4)()
         args = [capi.ptr_f64(x), capi.ptr_f64(y), C.c_double(primal_weight), C.c_double(radius), capi.ptr_f64(pp), capi.ptr_f64(dp),
                 C.c_int32(int(use_diagonal_qp_trust_region_solver)), C.c_double(diagonal_qp_trust_region_solver_tolerance)]
-        if self.b.prefix == "pdlp_oracle_":
-            args.append(C.c_int32(1 if max_norm else 0))
-        elif max_norm:  # PrimalDualNorm::kMaxNorm has its own entry point on the device library
-            self._call("compute_localized_lagrangian_bounds_max_norm", *args[:6], out)
-            return types.SimpleNamespace(lagrangian_value=out[0], lower_bound=out[1], upper_bound=out[2], radius=out[3])
-        self._call("compute_localized_lagrangian_bounds", *args, out)
+        self.b._localized_bounds(self, args, max_norm, out)
         return types.SimpleNamespace(lagrangian_value=out[0], lower_bound=out[1], upper_bound=out[2], radius=out[3])
 
 

@@ -8,7 +8,8 @@
 // imports or calls anything in this directory.
 //
 // Parity status: PINNED against the reference's own known-answer tests
-// (tests/test_oracle_*.py transcribe the vectors listed in SURVEY.md 8c). The
+// (tests/test_kernel_goldens.py, test_solver_goldens.py, test_termination.py, test_params_validation.py and
+// test_feasibility_polishing.py transcribe the vectors listed in SURVEY.md 8c). The
 // reference itself cannot be built in this image (needs Eigen 3.4.0,
 // abseil-cpp, protobuf + protoc, glop; none present, no network), so inner
 // products follow the published semantics of Eigen 3.4.0 sparse^T * dense

@@ -37,6 +37,14 @@ class OracleBackend(pdlp.Backend):
             build()
         super().__init__(LIB, "pdlp_oracle_")
 
+    # the oracle's problem takes the reference's thread / shard counts instead of a CUDA device,
+    # and one bounds entry point serves both norms
+    def _problem_create(self, view, handle, cuda_device=0, num_threads=1, num_shards=0):
+        return self.fn("problem_create")(C.byref(view), C.c_int32(num_threads), C.c_int32(num_shards), C.byref(handle))
+
+    def _localized_bounds(self, prob, args, max_norm, out):
+        prob._call("compute_localized_lagrangian_bounds", *args, C.c_int32(1 if max_norm else 0), out)
+
     def sharder_starts(self, num_elements, num_shards, masses=None):
         out = np.zeros(num_elements + 2, dtype=np.int64)
         mp = None if masses is None else np.ascontiguousarray(masses, dtype=np.int64)

@@ -351,14 +351,14 @@ def _nccl_worker(rank, world, port, out_dir, exchange):
 # peer-d: x~ and y' all-gathered through peer memory (column-slice image); peer-s: x~ all-gathered,
 # K^T y' partials reduce-scattered through peer memory; nccl: one NCCL all-reduce per step.
 @pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["peer-d", "peer-s", "nccl"])
-def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend, exchange):
+def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend, exchange, world):
     import torch
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (run with gpurun --gpus %d)" % (world, world))
     mp.spawn(_nccl_worker, args=(world, free_port(), str(tmp_path), exchange), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "nccl_rank%d.npz" % r)) for r in range(world)]
     for name, scale in (("c2", 0.004), ("c3", 0.002), ("c5", 0.003)):
@@ -375,8 +375,9 @@ def test_row_sharded_solve_matches_single_gpu(tmp_path, b200_backend, exchange):
             assert pobj == pytest.approx(ci.primal_objective, rel=1e-5, abs=1e-5)
             assert dobj == pytest.approx(ci.dual_objective, rel=1e-5, abs=1e-5)
         # every rank returns the same full-length vectors
-        np.testing.assert_array_equal(parts[0][name + "_x"], parts[1][name + "_x"])
-        np.testing.assert_array_equal(parts[0][name + "_y"], parts[1][name + "_y"])
+        for part in parts[1:]:
+            np.testing.assert_array_equal(parts[0][name + "_x"], part[name + "_x"])
+            np.testing.assert_array_equal(parts[0][name + "_y"], part[name + "_y"])
         p = pdlp.PrimalDualHybridGradientParams()
         p.restart_strategy = p.NO_RESTARTS
         p.primal_weight_update_smoothing = 0.0

@@ -203,3 +203,43 @@ def test_c2_full_size_properties(b200_backend):
     ci = chosen(res.solve_log)
     assert ci.primal_objective == pytest.approx(info["objective"], rel=5e-4)
     assert ci.dual_objective == pytest.approx(info["objective"], rel=5e-4)
+
+
+def fixed_iteration_params(iterations):
+    p = P()
+    p.restart_strategy = P.NO_RESTARTS
+    p.primal_weight_update_smoothing = 0.0
+    p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = 0.0
+    p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = 0.0
+    p.termination_criteria.iteration_limit = iterations
+    p.num_threads = 16
+    return p
+
+
+@pytest.mark.gpu
+def test_c3_full_size_meets_oracle(b200_backend, oracle_backend):
+    """C3 at FULL size (8 022 x 10 M, 40 M nonzeros; 45 rows of more than 10^5 nonzeros, the longest
+    979 143): the split-row path (virtual slots + k_sell_fixup) against the CPU oracle -- the SpMV
+    pair within 1e-12 and 16 fixed PDHG iterations (restarts disabled) within 1e-9."""
+    qp, _ = synthetic.c3(scale=1.0)
+    k = qp.constraint_matrix
+    lens = np.diff(k.tocsr().indptr)
+    assert lens.max() > 500_000 and (lens > 100_000).sum() >= 10
+    rng = np.random.default_rng(11)
+    x, y = rng.normal(size=k.shape[1]), rng.normal(size=k.shape[0])
+    dev, ref = b200_backend.problem(qp), oracle_backend.problem(qp)
+    a, b = dev.matrix_vector_product(x), ref.matrix_vector_product(x)
+    assert np.max(np.abs(a - b) / (abs(k) @ np.abs(x) + 1e-300)) < 1e-12
+    a, b = dev.transposed_matrix_vector_product(y), ref.transposed_matrix_vector_product(y)
+    assert np.max(np.abs(a - b) / (abs(k).T @ np.abs(y) + 1e-300)) < 1e-12
+    dev.close()
+    ref.close()
+    p = fixed_iteration_params(16)
+    got = b200_backend.primal_dual_hybrid_gradient(qp, p)
+    want = oracle_backend.primal_dual_hybrid_gradient(qp, p)
+    assert got.solve_log.termination_reason == want.solve_log.termination_reason == TR.TERMINATION_REASON_ITERATION_LIMIT
+    assert got.solve_log.iteration_count == want.solve_log.iteration_count == 16
+    assert got.solve_log.solution_stats.cumulative_rejected_steps == want.solve_log.solution_stats.cumulative_rejected_steps
+    for u, v in ((got.primal_solution, want.primal_solution), (got.dual_solution, want.dual_solution)):
+        assert np.linalg.norm(u - v) <= 1e-9 * max(1.0, np.linalg.norm(v))
+    assert got.solve_log.solution_stats.step_size == pytest.approx(want.solve_log.solution_stats.step_size, rel=1e-9)

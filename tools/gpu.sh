@@ -45,6 +45,10 @@ for stage in "$@"; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $OUT/${TAG}_launches_raw.csv \
         python bench.py --steps 130 --warmup 3 --no-e2e --no-cpu > $OUT/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
       python tools/compact_launches.py $OUT/${TAG}_launches_raw.csv $OUT/${TAG}_launches.csv "bench.py --steps 130 --warmup 3 (C2, 1 B200), ncu gpu__time_duration.sum --clock-control none"; head -30 $OUT/${TAG}_launches.csv ;;
+    launches-driver)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $OUT/${TAG}_launches_driver_raw.csv \
+        python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu > $OUT/${TAG}_launches_driver.log 2>&1; echo "launch list rc=$?"
+      python tools/compact_launches.py $OUT/${TAG}_launches_driver_raw.csv $OUT/${TAG}_launches_driver.csv "bench.py --steps 20 --warmup 5 (C2, 1 B200), ncu gpu__time_duration.sum --clock-control none"; head -40 $OUT/${TAG}_launches_driver.csv ;;
     bench)
       PDLP_B200_TRACE=1 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; line $OUT/${TAG}_bench.json
       grep "trace\]" $OUT/${TAG}_bench.err | head -8
