@@ -37,6 +37,8 @@ struct Comm::Api {
   typedef int (*CommAbortFn)(NcclComm);
   CommGetAsyncErrorFn comm_get_async_error = nullptr;  // optional (NCCL >= 2.4)
   CommAbortFn comm_abort = nullptr;
+  typedef int (*GroupFn)();
+  GroupFn group_start = nullptr, group_end = nullptr;  // optional: several collectives in one launch
 
   static Api* Load(const char* path) {
     static std::mutex mu;
@@ -61,6 +63,8 @@ struct Comm::Api {
     a->get_error_string = reinterpret_cast<GetErrorStringFn>(dlsym(h, "ncclGetErrorString"));
     a->comm_get_async_error = reinterpret_cast<CommGetAsyncErrorFn>(dlsym(h, "ncclCommGetAsyncError"));
     a->comm_abort = reinterpret_cast<CommAbortFn>(dlsym(h, "ncclCommAbort"));
+    a->group_start = reinterpret_cast<GroupFn>(dlsym(h, "ncclGroupStart"));
+    a->group_end = reinterpret_cast<GroupFn>(dlsym(h, "ncclGroupEnd"));
     if (!a->get_unique_id || !a->comm_init_rank || !a->comm_destroy || !a->all_reduce || !a->all_gather) {
       delete a;
       throw std::runtime_error("the NCCL library lacks a required symbol");
@@ -132,6 +136,8 @@ void Comm::AllGatherBytes(const void* send, void* recv, int64_t bytes_per_rank, 
   api_->Check(api_->all_gather(send, recv, static_cast<size_t>(bytes_per_rank), kNcclInt8, comm_, static_cast<cudaStream_t>(stream)), "ncclAllGather");
   ++collectives_;
 }
+void Comm::GroupStart() { if (api_->group_start != nullptr && api_->group_end != nullptr) api_->Check(api_->group_start(), "ncclGroupStart"); }
+void Comm::GroupEnd() { if (api_->group_start != nullptr && api_->group_end != nullptr) api_->Check(api_->group_end(), "ncclGroupEnd"); }
 void Comm::AllGatherInPlace(double* buf, int64_t count_per_rank, void* stream) {
   if (count_per_rank <= 0) return;
   api_->Check(api_->all_gather(buf + static_cast<int64_t>(rank_) * count_per_rank, buf, static_cast<size_t>(count_per_rank), kNcclFloat64, comm_,

@@ -50,6 +50,9 @@ class Comm {
   void AllGatherBytes(const void* send, void* recv, int64_t bytes_per_rank, void* stream);
   // In-place all-gather of equal fp64 slices: rank r's slice is buf[r * count_per_rank ...).
   void AllGatherInPlace(double* buf, int64_t count_per_rank, void* stream);
+  // ncclGroupStart / ncclGroupEnd around several collectives: one launch instead of one each.
+  void GroupStart();
+  void GroupEnd();
   // Collective: allocates `bytes` (zero-filled) on every rank and maps all of
   // them everywhere. Returns nullptr (on every rank) when peer mapping is not
   // possible on this box; the caller then keeps the NCCL exchange.

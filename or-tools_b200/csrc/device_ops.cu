@@ -185,7 +185,7 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
     // right after the gathers of chunk k, so the DRAM latency of the streams
     // overlaps the L2 latency of the gathers and the gather queue never drains
     // while a warp waits for its next indices.
-    constexpr int U = V == 1 ? 4 : 8;
+    constexpr int U = (V == 1 || V == 8) ? 4 : 8;
     if (n >= U) {
       double v[U];
       int c[U];
@@ -283,19 +283,28 @@ struct GatherSrc {
   const StepState* st;
 };
 
-// Step decision fused into the last kernel of an iteration: every block takes a
-// ticket after publishing its partial sums; the block that draws the last ticket
-// adds the three partial arrays in a fixed order (independent of which block it
-// is) and runs the accept test / step-size rule, so an iteration is three
-// launches and the decision costs one L2 round trip instead of a kernel.
-struct DecideTail {
-  StepState* st = nullptr;  // nullptr: no fused decision
-  const double *pp = nullptr, *pd = nullptr, *pt = nullptr;
-  int np = 0, nd = 0, nt = 0;
-  unsigned int* ticket = nullptr;
+// The step decision runs at the HEAD of the last kernel of an attempt. All three sums it needs
+// are known before K^T y' is even computed: ||dx||^2 from the primal kernel, and ||dy||^2 and the
+// nonlinearity dx . K^T dy = (K dx) . dy from the dual kernel, because K dx = (K x~ - K x) / 2 is
+// available row by row once K x of the current iterate is kept (StepPtrs::kx). So block 0 of the
+// K^T y' kernel adds the partials and takes the decision while the other blocks already stream the
+// matrix: the decision is off the critical path and an attempt is three launches. The state is
+// double-buffered: the kernels of an attempt read slot `in`, the decision writes slot `out`, the
+// next attempt reads that one.
+struct DecideHead {
+  const StepState* in = nullptr;  // nullptr: no decision in this launch
+  StepState* out = nullptr;
+  const double* pp = nullptr;     // ||dx||^2 partials of the primal-step kernel
+  int np = 0;
+  const double* pd = nullptr;     // {||dy||^2, (K dx) . dy} partials of the dual kernel, [block][2]
+  int nd = 0;
+  // Row-sharded solves: already reduced {||dx||^2, ||dy||^2, (K dx) . dy} triples, one per rank,
+  // at scal[k * scal_stride + 0..2], added in rank order (replaces pd, and pp when scal_has_dx2).
+  const double* scal = nullptr;
+  int scal_count = 0, scal_stride = 0, scal_has_dx2 = 0;
 };
 template <int BT>
-__device__ void run_decide_tail(const DecideTail& t);
+__device__ void run_decide_head(const DecideHead& h);
 
 // Epi: struct Ctx; __device__ Ctx begin() const -- once per thread: resolves the rotating
 //      buffers and step scalars from the device state;
@@ -303,11 +312,18 @@ __device__ void run_decide_tail(const DecideTail& t);
 //      epilogue's own loads before the gather loop so that they overlap it;
 //      __device__ void operator()(const Ctx&, int64_t pos, double acc, double* red, const Pre&) const
 template <int MODE, int NS, class Epi, int BT, int V>
-__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks,
-                                                                                              DecideTail tail) {
+__global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : V == 8 ? 896 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks,
+                                                                                              DecideHead head) {
   pdl_trigger();
   pdl_wait();
   if (halt != nullptr && *halt != 0) return;
+  if (head.in != nullptr && blockIdx.x == 0) {
+    // the launch has one extra block, the FIRST one scheduled, and it only takes the step decision
+    // (see DecideHead): apart from the row loop, so that its registers do not count against the loop's
+    run_decide_head<BT>(head);
+    return;
+  }
+  const int64_t blk = static_cast<int64_t>(blockIdx.x) - (head.in != nullptr ? 1 : 0);
   const double* __restrict__ x = gs.st != nullptr ? pick3(gs.p, gs.st->cand) : gs.p[0];
   double red[NS > 0 ? NS : 1];
 #pragma unroll
@@ -318,7 +334,7 @@ __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / B
   // still balances the (window-sorted, hence uneven) rows; the slot -> thread
   // map is fixed, so the partial sums stay deterministic.
   for (int c = 0; c < chunks; ++c) {
-    const int64_t slot = (static_cast<int64_t>(blockIdx.x) * chunks + c) * BT + threadIdx.x;
+    const int64_t slot = (blk * chunks + c) * BT + threadIdx.x;
     if (slot >= a.num_slots) break;
     const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
     const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
@@ -331,8 +347,7 @@ __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / B
       epi(ctx, pos, acc, red, pre);
     }
   }
-  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
-  if (tail.st != nullptr) run_decide_tail<BT>(tail);
+  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + blk * NS);
 }
 
 // The same product with the value / index streams staged through shared memory
@@ -345,7 +360,7 @@ __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : 1280) / B
 // results are run-to-run deterministic (they differ in the last bits from
 // k_sell, whose blocks interleave the slices differently).
 template <int MODE, int NS, class Epi, int BT, int U, int NST>
-__global__ void __launch_bounds__(BT) k_sell_tma(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks, DecideTail tail) {
+__global__ void __launch_bounds__(BT) k_sell_tma(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks, DecideHead head) {
   constexpr int NW = BT / 32;
   __shared__ alignas(128) double s_val[NW][NST][U * 32];
   __shared__ alignas(128) int32_t s_col[NW][NST][U * 32];
@@ -360,13 +375,18 @@ __global__ void __launch_bounds__(BT) k_sell_tma(SellDev a, GatherSrc gs, Epi ep
   __syncwarp();
   pdl_wait();
   if (halt != nullptr && *halt != 0) return;  // (no copy has been issued yet)
+  if (head.in != nullptr && blockIdx.x == 0) {
+    run_decide_head<BT>(head);
+    return;
+  }
+  const int64_t blk = static_cast<int64_t>(blockIdx.x) - (head.in != nullptr ? 1 : 0);
   const double* __restrict__ x = gs.st != nullptr ? pick3(gs.p, gs.st->cand) : gs.p[0];
   double red[NS > 0 ? NS : 1];
 #pragma unroll
   for (int k = 0; k < NS; ++k) red[k] = 0.0;
   const typename Epi::Ctx ctx = epi.begin();
   const int64_t num_slices = a.num_slots >> 5;
-  const int64_t slice0 = (static_cast<int64_t>(blockIdx.x) * NW + warp) * chunks;
+  const int64_t slice0 = (blk * NW + warp) * chunks;
   const int nsl = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(chunks), num_slices - slice0)));
   if (nsl > 0) {
     const int64_t e0 = a.slice_ptr[slice0];
@@ -430,14 +450,13 @@ __global__ void __launch_bounds__(BT) k_sell_tma(SellDev a, GatherSrc gs, Epi ep
       }
     }
   }
-  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
-  if (tail.st != nullptr) run_decide_tail<BT>(tail);
+  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + blk * NS);
 }
 
 // Split rows: one warp per row combines the partials of its virtual slots in
 // slot order and then runs the same epilogue.
 template <int MODE, int NS, class Epi>
-__global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, double* partials, const int32_t* halt, DecideTail tail) {
+__global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, double* partials, const int32_t* halt) {
   pdl_trigger();
   pdl_wait();
   if (halt != nullptr && *halt != 0) return;
@@ -457,7 +476,6 @@ __global__ void __launch_bounds__(kThreads) k_sell_fixup(SellDev a, Epi epi, dou
     }
   }
   if (NS > 0) block_reduce_store<NS, 0>(red, nullptr, partials + static_cast<int64_t>(blockIdx.x) * NS);
-  if (tail.st != nullptr) run_decide_tail<kThreads>(tail);
 }
 
 // --------------------------------------------------------- PDHG step -------
@@ -466,11 +484,12 @@ struct StepPtrs {
   double* x[3];
   double* y[3];
   double* kty[3];
+  double* kx[3];   // K x of the iterates (dual length): K x' = (K x~ + K x) / 2 comes out of the dual kernel
   double* x_tilde;
   double* avg_x;
   double* avg_y;
   const double *c, *q, *lv, *uv, *lc, *uc;
-  StepState* state;
+  StepState* state;  // the slot the kernels of this attempt read
 };
 
 // Peer-memory exchange of the row-sharded step loop: every rank's
@@ -482,11 +501,12 @@ struct StepPtrs {
 //   [scal_off, +4 G)   {||dx||^2, ||dy||^2, dx.(K^T y' - K^T y)} partials of rank h at 4 h
 //   [flags_off, +8 k)  barrier k: epoch last signalled by rank h at 8 k + h (u64)
 //   [epoch_off, +4)    this rank's own epoch counters (u64)
+//   [cand_off, +G seg) trust-region finish: rank h's bracket candidates (keys | a | b | count) at cand_off + h * PeerLayout::kTrCandSegment
 //   [tr_off, +2*48*8)  trust-region round vector (kTrCols doubles) of rank h for round parity p at kTrCols (G p + h)
 struct PeerPtrs {
   int world, rank;
   double* base[kMaxPeers];
-  int64_t xt_off, partial_off, y_off, scal_off, flags_off, epoch_off, tr_off;
+  int64_t xt_off, partial_off, y_off, scal_off, flags_off, epoch_off, tr_off, cand_off;
   int64_t row_begin;   // this rank's first position in the box-wide dual order
   long long timeout_cycles;  // a peer that does not arrive within this many SM clocks halts the loop
   int64_t begin, end;  // this rank's slice of the primal vector (begin is even)
@@ -615,16 +635,18 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
 // PUSH: the all-gather of y' fused into the producing epilogue -- every new
 // dual value is also stored into every rank's arena at its box-wide position.
 template <bool PUSH>
-struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1
+struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1; nonlinearity of pdhg.cc:2588-2592 on the row side
   StepPtrs b;
   PeerPtrs peer;
-  struct Ctx { const double* yc; double* yn; double sigma, ratio; };
+  struct Ctx { const double* yc; double* yn; const double* kxc; double* kxn; double sigma, ratio; };
   struct Pre { double yc, lc, uc, avg; };
   __device__ __forceinline__ Ctx begin() const {
     const StepState* st = b.state;
     Ctx c;
     c.yc = pick3(b.y, st->cur);
     c.yn = pick3(b.y, st->cand);
+    c.kxc = pick3(b.kx, st->cur);
+    c.kxn = pick3(b.kx, st->cand);
     c.sigma = st->step_size * st->primal_weight;
     c.ratio = st->pending_ratio;
     return c;
@@ -637,11 +659,14 @@ struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1
     p.avg = c.ratio > 0.0 ? b.avg_y[pos] : 0.0;
     return p;
   }
-  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kx, double* red, const Pre& p) const {
+  // kxt = (K x~)_pos with x~ = 2 x' - x, so K x' = (kxt + K x) / 2 and K (x' - x) = (kxt - K x) / 2
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kxt, double* red, const Pre& p) const {
+    const double kxc = c.kxc[pos];  // (loaded here, not prefetched: the row loop is at its register limit)
     if (c.ratio > 0.0) b.avg_y[pos] = p.avg + c.ratio * (p.yc - p.avg);
-    const double t = p.yc - c.sigma * kx;
+    const double t = p.yc - c.sigma * kxt;
     const double yn = fmax(fmin(0.0, t + c.sigma * p.uc), t + c.sigma * p.lc);
     c.yn[pos] = yn;
+    c.kxn[pos] = 0.5 * (kxt + kxc);
     if (PUSH) {
 #pragma unroll
       for (int h = 0; h < kMaxPeers; ++h)
@@ -649,6 +674,7 @@ struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1
     }
     const double d = yn - p.yc;
     red[0] += d * d;
+    red[1] += (0.5 * (kxt - kxc)) * d;  // (K dx)_pos dy_pos: summed over the rows it is dx . K^T dy
   }
 };
 struct DualEpi : DualEpiT<false> {};
@@ -659,29 +685,13 @@ inline DualEpi MakeDualEpi(const StepPtrs& p) {
   return e;
 }
 
-struct KtyEpi {  // pdhg.cc:2588-2592, 1949-1959
+struct KtyEpi {  // K^T y' of the candidate (pdhg.cc:1949-1959); the nonlinearity is computed on the row side
   StepPtrs b;
-  struct Ctx { const double *x_cand, *x_cur, *kty_cur; double* kty_cand; };
-  struct Pre { double dx, kty; };
-  __device__ __forceinline__ Ctx begin() const {
-    const StepState* st = b.state;
-    Ctx c;
-    c.x_cand = pick3(b.x, st->cand);
-    c.x_cur = pick3(b.x, st->cur);
-    c.kty_cur = pick3(b.kty, st->cur);
-    c.kty_cand = pick3(b.kty, st->cand);
-    return c;
-  }
-  __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const {
-    Pre p;
-    p.dx = c.x_cand[pos] - c.x_cur[pos];
-    p.kty = c.kty_cur[pos];
-    return p;
-  }
-  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kty_next, double* red, const Pre& p) const {
-    c.kty_cand[pos] = kty_next;
-    red[0] += p.dx * (kty_next - p.kty);
-  }
+  struct Ctx { double* kty_cand; };
+  struct Pre {};
+  __device__ __forceinline__ Ctx begin() const { return Ctx{pick3(b.kty, b.state->cand)}; }
+  __device__ __forceinline__ Pre prefetch(const Ctx&, int64_t) const { return Pre(); }
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kty_next, double*, const Pre&) const { c.kty_cand[pos] = kty_next; }
 };
 
 // All-gather exchange: K^T y' for this rank's column slice only. Position p of the
@@ -690,28 +700,11 @@ struct KtyEpiSlice {
   StepPtrs b;
   const int32_t* perm;
   int64_t col0;
-  struct Ctx { const double *x_cand, *x_cur, *kty_cur; double* kty_cand; };
-  struct Pre { double dx, kty; int32_t idx; };
-  __device__ __forceinline__ Ctx begin() const {
-    const StepState* st = b.state;
-    Ctx c;
-    c.x_cand = pick3(b.x, st->cand) + col0;
-    c.x_cur = pick3(b.x, st->cur) + col0;
-    c.kty_cur = pick3(b.kty, st->cur) + col0;
-    c.kty_cand = pick3(b.kty, st->cand) + col0;
-    return c;
-  }
-  __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const {
-    Pre p;
-    p.idx = __ldg(perm + pos);
-    p.dx = c.x_cand[p.idx] - c.x_cur[p.idx];
-    p.kty = c.kty_cur[p.idx];
-    return p;
-  }
-  __device__ __forceinline__ void operator()(const Ctx& c, int64_t, double kty_next, double* red, const Pre& p) const {
-    c.kty_cand[p.idx] = kty_next;
-    red[0] += p.dx * (kty_next - p.kty);
-  }
+  struct Ctx { double* kty_cand; };
+  struct Pre { int32_t idx; };
+  __device__ __forceinline__ Ctx begin() const { return Ctx{pick3(b.kty, b.state->cand) + col0}; }
+  __device__ __forceinline__ Pre prefetch(const Ctx&, int64_t pos) const { return Pre{__ldg(perm + pos)}; }
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t, double kty_next, double*, const Pre& p) const { c.kty_cand[p.idx] = kty_next; }
 };
 
 constexpr int kDecideThreads = 1024;
@@ -734,9 +727,8 @@ __device__ __forceinline__ double block_sum_range(const double* __restrict__ p, 
   return t;  // valid in warp 0
 }
 
-// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block.
 // Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674) from the three
-// reduced scalars; one thread.
+// reduced scalars; one thread. Reads the state slot of this attempt, writes the other one.
 // The two powers of the adaptive rule depend on the attempt count only, so a caller may
 // compute them (and load the state) while the partial sums are still in flight.
 __device__ __forceinline__ double decide_total(const StepState& s) {
@@ -754,16 +746,8 @@ __device__ __forceinline__ void decide_powers(const StepState& s, double& pow_re
     pow_growth = pow(total + 1.0, -s.growth_exponent);
   }
 }
-__device__ void decide_update(StepState* st_dev, StepState s, double pow_reduction, double pow_growth, double dx2, double dy2, double dot);
-__device__ void decide_update(StepState* st_dev, double dx2, double dy2, double dot) {
-  // One load of the whole state into registers, one store at the end: the
-  // decision is a chain of dependent scalar updates and must not pay an L2
-  // round trip per field.
-  const StepState s = *st_dev;
-  double pr, pg;
-  decide_powers(s, pr, pg);
-  decide_update(st_dev, s, pr, pg, dx2, dy2, dot);
-}
+// (One load of the whole state into registers by the caller, one store at the end: the decision
+// is a chain of dependent scalar updates and must not pay an L2 round trip per field.)
 __device__ void decide_update(StepState* st_dev, StepState s, double pow_reduction, double pow_growth, double dx2, double dy2, double dot) {
   StepState* st = &s;
   const double eta = st->step_size, omega = st->primal_weight;
@@ -826,61 +810,21 @@ __device__ void decide_update(StepState* st_dev, StepState s, double pow_reducti
   *st_dev = s;
 }
 
-// Three fixed-order sums at once: all loads of the three partial arrays are in
-// flight together and one shuffle tree + one shared-memory exchange serves all
-// of them (the decision kernel is pure latency on the critical path of a step).
-__device__ __forceinline__ void block_sum3(const double* __restrict__ p0, int n0, const double* __restrict__ p1, int n1,
-                                           const double* __restrict__ p2, int n2, double out[3]) {
-  __shared__ double sh3[3][kDecideThreads / 32];
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll 8
-  for (int i = threadIdx.x; i < n0; i += kDecideThreads) s0 += p0[i];
-#pragma unroll 8
-  for (int i = threadIdx.x; i < n1; i += kDecideThreads) s1 += p1[i];
-#pragma unroll 16
-  for (int i = threadIdx.x; i < n2; i += kDecideThreads) s2 += p2[i];
-  s0 = warp_sum(s0);
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) {
-    sh3[0][threadIdx.x >> 5] = s0;
-    sh3[1][threadIdx.x >> 5] = s1;
-    sh3[2][threadIdx.x >> 5] = s2;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double t = threadIdx.x < kDecideThreads / 32 ? sh3[k][threadIdx.x] : 0.0;
-      out[k] = warp_sum(t);
-    }
-  }
-}
-
-// Tail of the last kernel of an iteration (see DecideTail): all threads of the block call it.
-template <int BT>
-__device__ void run_decide_tail(const DecideTail& t) {
-  __shared__ int s_last;
+// Fixed-order sums of the step partials by one block of BT threads: out = {sum pp[0..np),
+// sum pd[2 b], sum pd[2 b + 1]}, valid in thread 0. Thread t adds elements t, t + BT, ...; then a
+// shuffle tree and a fixed-order sum over the warps: the order depends on the sizes only.
+template <int BT, bool VOLATILE_L2>
+__device__ __forceinline__ void step_partial_sums(const double* pp, int np, const double* pd, int nd, double out[3]) {
   __shared__ double sh3[3][BT / 32];
-  if (threadIdx.x == 0) {
-    __threadfence();  // this block's partial sums are visible before its ticket
-    const unsigned int ticket = atomicAdd(t.ticket, 1u);
-    s_last = ticket == gridDim.x - 1 ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last == 0) return;
-  __threadfence();
-  // Thread k adds p[k], p[k + BT], ...; then a shuffle tree and a fixed-order sum
-  // over the warps: the order depends on the array sizes only, never on which
-  // block happens to be the last one. __ldcg: the partials were written by other
-  // SMs during this launch, L1 must not serve them.
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll 8
-  for (int i = threadIdx.x; i < t.np; i += BT) s0 += __ldcg(t.pp + i);
+  for (int i = threadIdx.x; i < np; i += BT) s0 += VOLATILE_L2 ? __ldcg(pp + i) : pp[i];
 #pragma unroll 8
-  for (int i = threadIdx.x; i < t.nd; i += BT) s1 += __ldcg(t.pd + i);
-#pragma unroll 8
-  for (int i = threadIdx.x; i < t.nt; i += BT) s2 += __ldcg(t.pt + i);
+  for (int i = threadIdx.x; i < nd; i += BT) {
+    const double2 v = VOLATILE_L2 ? __ldcg(reinterpret_cast<const double2*>(pd) + i) : reinterpret_cast<const double2*>(pd)[i];
+    s1 += v.x;
+    s2 += v.y;
+  }
   s0 = warp_sum(s0);
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -890,114 +834,87 @@ __device__ void run_decide_tail(const DecideTail& t) {
     sh3[2][threadIdx.x >> 5] = s2;
   }
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  double sums[3] = {0.0, 0.0, 0.0};
+  out[0] = out[1] = out[2] = 0.0;
+  if (threadIdx.x == 0) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-    for (int w = 0; w < BT / 32; ++w) sums[k] += sh3[k][w];
-  *t.ticket = 0u;  // ready for the next launch (stream order makes it visible)
-  decide_update(t.st, sums[0], sums[1], sums[2]);
+    for (int k = 0; k < 3; ++k)
+      for (int w = 0; w < BT / 32; ++w) out[k] += sh3[k][w];
+  }
 }
 
-// Accept test and step-size update (pdhg.cc:2574-2640, 2651-2674), one block. The three partial
-// arrays are contiguous ([pp | pd | pt]): one pass with every load in flight at once; meanwhile the
-// last warp loads the state and evaluates the two pow() of the rule, so the critical path after the
-// sums is a handful of flops and one store.
-__global__ void __launch_bounds__(kDecideThreads) k_step_decide(StepState* st_dev, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
+// Head of the last kernel of an attempt (see DecideHead): all threads of block 0 call it, after
+// pdl_wait. The state is loaded first and used last, so its round trip overlaps the partial loads.
+template <int BT>
+__device__ void run_decide_head(const DecideHead& h) {
+  StepState loaded;
+  if (threadIdx.x == 0) loaded = *h.in;
+  double sums[3];
+  step_partial_sums<BT, false>(h.scal != nullptr && h.scal_has_dx2 ? nullptr : h.pp, h.scal != nullptr && h.scal_has_dx2 ? 0 : h.np,
+                               h.scal != nullptr ? nullptr : h.pd, h.scal != nullptr ? 0 : h.nd, sums);
+  if (threadIdx.x != 0) return;
+  if (h.scal != nullptr) {
+    const volatile double* sc = h.scal;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < h.scal_count; ++k) {
+      if (h.scal_has_dx2) t0 += sc[k * h.scal_stride + 0];
+      t1 += sc[k * h.scal_stride + 1];
+      t2 += sc[k * h.scal_stride + 2];
+    }
+    if (h.scal_has_dx2) sums[0] = t0;
+    sums[1] = t1;
+    sums[2] = t2;
+  }
+  double pr, pg;
+  decide_powers(loaded, pr, pg);
+  decide_update(h.out, loaded, pr, pg, sums[0], sums[1], sums[2]);
+}
+
+// The decision as a kernel of its own: problems without variables (no K^T y' kernel to carry it).
+__global__ void __launch_bounds__(kThreads) k_decide_only(DecideHead head) {
   pdl_trigger();
   pdl_wait();
-  __shared__ StepState sh_state;
-  __shared__ double sh_pow[2];
-  __shared__ double sh3[3][kDecideThreads / 32];
-  // (the state load is issued first and used only after the partial loads: both round trips overlap)
-  StepState loaded;
-  if (threadIdx.x == kDecideThreads - 1) loaded = *st_dev;
-  // nd < 0: *pd already holds the all-reduced ||dy||^2 (row-sharded solve)
-  const int n1 = nd < 0 ? 0 : nd;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  if (pd == pp + np && pt == pd + n1) {
-    const int total = np + n1 + nt;
-#pragma unroll 16
-    for (int i = threadIdx.x; i < total; i += kDecideThreads) {
-      const double v = pp[i];
-      if (i < np) s0 += v;
-      else if (i < np + n1) s1 += v;
-      else s2 += v;
-    }
-  } else {
-#pragma unroll 8
-    for (int i = threadIdx.x; i < np; i += kDecideThreads) s0 += pp[i];
-#pragma unroll 8
-    for (int i = threadIdx.x; i < n1; i += kDecideThreads) s1 += pd[i];
-#pragma unroll 8
-    for (int i = threadIdx.x; i < nt; i += kDecideThreads) s2 += pt[i];
-  }
-  s0 = warp_sum(s0);
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if ((threadIdx.x & 31) == 0) {
-    sh3[0][threadIdx.x >> 5] = s0;
-    sh3[1][threadIdx.x >> 5] = s1;
-    sh3[2][threadIdx.x >> 5] = s2;
-  }
-  if (threadIdx.x == kDecideThreads - 1) {
-    sh_state = loaded;
-    decide_powers(loaded, sh_pow[0], sh_pow[1]);
-  }
-  __syncthreads();
-  if (threadIdx.x >= 32) return;
-  double sums[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const double t = threadIdx.x < kDecideThreads / 32 ? sh3[k][threadIdx.x] : 0.0;
-    sums[k] = warp_sum(t);
-  }
-  if (threadIdx.x != 0 || sh_state.halt != 0) return;
-  decide_update(st_dev, sh_state, sh_pow[0], sh_pow[1], sums[0], nd < 0 ? *pd : sums[1], sums[2]);
+  if (head.in->halt != 0) return;
+  run_decide_head<kThreads>(head);
 }
 
-// ---- row-sharded variant of the step ---------------------------
-// The primal side is replicated, the dual side is this rank's row block. After
-// the local K^T y' partial (scattered to column order) one all-reduce of
-// [n + 1] doubles completes both K^T y' and ||dy||^2; then k_kty_finish does
-// what KtyEpi does on one GPU.
+// ---- row-sharded variants of the step ----------------------------
+// NCCL exchange: the primal side is replicated, the dual side is this rank's row block. The local
+// {||dy||^2, (K dx) . dy} go to exchange[n], exchange[n + 1]; the local K^T y' partial (scattered to
+// column order) to exchange[0..n); one all-reduce of n + 2 doubles completes all of them; then
+// k_kty_finish stores K^T y' and its block 0 takes the decision.
 __global__ void __launch_bounds__(kDecideThreads) k_sum_to_slot(const StepState* st, const double* pd, int nd, double* slot) {
   pdl_trigger();
   pdl_wait();
   if (st->halt != 0) return;
-  const double v = block_sum_range(pd, nd);
-  if (threadIdx.x == 0) *slot = v;
+  double sums[3];
+  step_partial_sums<kDecideThreads, false>(nullptr, 0, pd, nd, sums);
+  if (threadIdx.x == 0) {
+    slot[0] = sums[1];
+    slot[1] = sums[2];
+  }
 }
-__global__ void __launch_bounds__(kThreads) k_kty_finish(StepPtrs b, const double* __restrict__ reduced, double* partials) {
+__global__ void __launch_bounds__(kThreads) k_kty_finish(StepPtrs b, const double* __restrict__ reduced, DecideHead head) {
   pdl_trigger();
   pdl_wait();
   const StepState* st = b.state;
   if (st->halt != 0) return;
-  double s = 0.0;
+  if (blockIdx.x == 0) run_decide_head<kThreads>(head);
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  if (i < b.n) {
-    const double v = reduced[i];
-    pick3(b.kty, st->cand)[i] = v;
-    s = (pick3(b.x, st->cand)[i] - pick3(b.x, st->cur)[i]) * (v - pick3(b.kty, st->cur)[i]);
-  }
-  block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
+  if (i < b.n) pick3(b.kty, st->cand)[i] = reduced[i];
 }
 
 // Peer exchange: the reduce-scatter of the K^T y' partials fused into the
 // consumer. This rank pulls its slice of every rank's partial out of the peer
 // arenas (128-bit loads over NVLink), adds them in rank order (the same order
-// on every rank), stores K^T y' and accumulates the nonlinearity partials.
-__global__ void __launch_bounds__(kThreads) k_kty_finish_peer(StepPtrs b, PeerPtrs peer, double* partials) {
+// on every rank) and stores K^T y'; block 0 takes the decision first.
+__global__ void __launch_bounds__(kThreads) k_kty_finish_peer(StepPtrs b, PeerPtrs peer, DecideHead head) {
   pdl_trigger();
   pdl_wait();
   const StepState* st = b.state;
   if (st->halt != 0) return;
-  double s = 0.0;
+  if (blockIdx.x == 0) run_decide_head<kThreads>(head);
   const int64_t i0 = peer.begin + (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * 2;
   double* __restrict__ kc = pick3(b.kty, st->cand);
-  const double* __restrict__ xc = pick3(b.x, st->cand);
-  const double* __restrict__ xo = pick3(b.x, st->cur);
-  const double* __restrict__ ko = pick3(b.kty, st->cur);
   if (i0 + 1 < peer.end) {
     double2 v = make_double2(0.0, 0.0);
 #pragma unroll
@@ -1008,51 +925,39 @@ __global__ void __launch_bounds__(kThreads) k_kty_finish_peer(StepPtrs b, PeerPt
         v.y += t.y;
       }
     }
-    const double2 a = *reinterpret_cast<const double2*>(xc + i0);
-    const double2 o = *reinterpret_cast<const double2*>(xo + i0);
-    const double2 k = *reinterpret_cast<const double2*>(ko + i0);
     *reinterpret_cast<double2*>(kc + i0) = v;
-    s = (a.x - o.x) * (v.x - k.x) + (a.y - o.y) * (v.y - k.y);
   } else if (i0 < peer.end) {
     double v = 0.0;
 #pragma unroll
     for (int h = 0; h < kMaxPeers; ++h)
       if (h < peer.world) v += peer.base[h][peer.partial_off + i0];
     kc[i0] = v;
-    s = (xc[i0] - xo[i0]) * (v - ko[i0]);
   }
-  block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
 }
 
-// Step decision of the peer exchange: local fixed-order sums, the three
-// partials stored into every rank's arena, the cross-GPU barrier, then every
-// rank adds the G x 3 partials in rank order and takes the same decision.
-__global__ void __launch_bounds__(kDecideThreads) k_step_decide_peer(StepState* st_dev, PeerPtrs peer, const double* pp, int np, const double* pd, int nd,
-                                                                     const double* pt, int nt) {
+// Peer exchange, between the dual kernel and the K^T y' side: this rank's fixed-order sums
+// {||dx||^2, ||dy||^2, (K dx) . dy} are stored into every rank's arena and the ranks meet at barrier
+// `which` -- the same barrier that publishes y' (all-gather exchange) or the K^T y' partials
+// (reduce-scatter exchange). Afterwards every rank's decision head adds the G triples in rank
+// order and takes the identical decision: no barrier of its own for the decision.
+__global__ void __launch_bounds__(kDecideThreads) k_sum_push_barrier(StepState* st, PeerPtrs peer, int which, const double* pp, int np, const double* pd, int nd) {
   pdl_trigger();
   pdl_wait();
-  if (st_dev->halt != 0) return;
+  if (st->halt != 0) return;
   double sums[3];
-  block_sum3(pp, np, pd, nd, pt, nt, sums);
+  step_partial_sums<kDecideThreads, false>(pp, np, pd, nd, sums);
+  __shared__ double sh[3];
+  if (threadIdx.x == 0) { sh[0] = sums[0]; sh[1] = sums[1]; sh[2] = sums[2]; }
+  __syncthreads();
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   if (lane < peer.world) {
     volatile double* dst = peer_base(peer, lane) + peer.scal_off + 4 * peer.rank;
-    dst[0] = sums[0];
-    dst[1] = sums[1];
-    dst[2] = sums[2];
+    dst[0] = sh[0];
+    dst[1] = sh[1];
+    dst[2] = sh[2];
   }
-  peer_barrier(peer, 2, &st_dev->halt);
-  if (lane != 0) return;
-  if (*reinterpret_cast<volatile int32_t*>(&st_dev->halt) != 0) return;  // a peer never arrived
-  const volatile double* sc = peer_base(peer, peer.rank) + peer.scal_off;
-  double t[3] = {0.0, 0.0, 0.0};
-  for (int h = 0; h < peer.world; ++h) {
-    t[0] += sc[4 * h + 0];
-    t[1] += sc[4 * h + 1];
-    t[2] += sc[4 * h + 2];
-  }
-  decide_update(st_dev, t[0], t[1], t[2]);
+  peer_barrier(peer, which, &st->halt);
 }
 
 // [pbegin, pend): the part of the primal average this rank maintains (all of
@@ -1530,6 +1435,7 @@ __global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_solve(TrSolveAr
   __shared__ int s_last;
   __shared__ int s_wtot[kTrUnroll][kThreads / 32];
   static_assert(sizeof(TrSearchState) % sizeof(double) == 0 && sizeof(TrSearchState) / sizeof(double) <= kThreads, "state is copied as doubles");
+  static_assert(kTrFinishCap == PeerLayout::kTrCandCap, "arena segment size");
   static_assert(kTrCols <= 48 && 5 * 48 <= kThreads, "layout of the cross-block sum");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = gridDim.x;
@@ -1727,8 +1633,10 @@ __global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_solve(TrSolveAr
       // gathers the compacted lists of all blocks (their lengths are column kTrCount of the
       // partials) into one contiguous buffer -- every load independent of the others -- and then
       // runs the passes over that buffer.
-      // (Row-sharded solves keep the grid rounds: every rank must take part in every exchange.)
-      if (!PEER && s.done == 0 && tot[kTrCount] <= static_cast<double>(kTrFinishCap)) {
+      // Row-sharded solves: every rank stores its candidates into every rank's arena, the ranks
+      // meet once more, and then each of them runs the same passes over the same concatenation (in
+      // rank order): identical decisions, no further exchange.
+      if (s.done == 0 && tot[kTrCount] <= static_cast<double>(kTrFinishCap)) {
         __shared__ int s_start[kTrMaxBlocks + 1];
         for (int b = tid; b < nb; b += kThreads) s_start[b + 1] = static_cast<int>(__ldcg(g.partials + static_cast<int64_t>(b) * kTrCols + kTrCount));
         if (tid == 0) s_start[0] = 0;
@@ -1757,6 +1665,7 @@ __global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_solve(TrSolveAr
         }
         __syncthreads();
         const int ncand = s_start[nb];
+        constexpr int64_t kSeg = PeerLayout::kTrCandSegment;
         for (int idx = tid; idx < ncand; idx += kThreads) {
           int lo_b = 0, hi_b = nb;  // the block whose list holds candidate idx: s_start[b] <= idx < s_start[b + 1]
           while (hi_b - lo_b > 1) {
@@ -1764,42 +1673,73 @@ __global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_solve(TrSolveAr
             if (s_start[mid] <= idx) lo_b = mid; else hi_b = mid;
           }
           const int64_t src = min(g.total, static_cast<int64_t>(lo_b) * per) + (idx - s_start[lo_b]);
-          g.cand_keys[idx] = __ldcg(g.keys + src);
-          g.cand_a[idx] = __ldcg(g.a + src);
-          g.cand_b[idx] = __ldcg(g.b + src);
+          const unsigned long long key = __ldcg(g.keys + src);
+          const double av = __ldcg(g.a + src), bv = __ldcg(g.b + src);
+          if (PEER) {
+            for (int h = 0; h < peer.world; ++h) {
+              double* seg = peer_base(peer, h) + peer.cand_off + kSeg * peer.rank;
+              reinterpret_cast<unsigned long long*>(seg)[idx] = key;
+              seg[kTrFinishCap + idx] = av;
+              seg[2 * kTrFinishCap + idx] = bv;
+            }
+          } else {
+            g.cand_keys[idx] = key;
+            g.cand_a[idx] = av;
+            g.cand_b[idx] = bv;
+          }
+        }
+        int nseg = 1;
+        if (PEER) {
+          if (tid == 0)
+            for (int h = 0; h < peer.world; ++h) *reinterpret_cast<volatile long long*>(peer_base(peer, h) + peer.cand_off + kSeg * peer.rank + 3 * kTrFinishCap) = ncand;
+          __syncthreads();  // all stores of the block are issued before the (system-scope) fence of the barrier
+          if (warp == 0) peer_barrier(peer, 3, g.peer_error);
+          nseg = peer.world;
         }
         __syncthreads();
-        while (s.done == 0) {
-          const int sh = s.shift;
-          const unsigned long long l2 = s.lo;
-          const unsigned long long w2 = 1ull << s.width_shift;
+        if (!(PEER && *reinterpret_cast<volatile int32_t*>(g.peer_error) != 0)) {
+          while (s.done == 0) {
+            const int sh = s.shift;
+            const unsigned long long l2 = s.lo;
+            const unsigned long long w2 = 1ull << s.width_shift;
 #pragma unroll
-          for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
-          for (int base = tid; base < ncand; base += kThreads * kTrUnroll) {
-            unsigned long long key[kTrUnroll];
-            double av[kTrUnroll], bv[kTrUnroll];
+            for (int j = 0; j < 34; ++j) bins[j * kThreads + tid] = 0.0;
+            for (int h = 0; h < nseg; ++h) {  // rank order, then list order: the same on every rank
+              const double* seg = PEER ? peer_base(peer, peer.rank) + peer.cand_off + kSeg * h : nullptr;
+              const unsigned long long* ck = PEER ? reinterpret_cast<const unsigned long long*>(seg) : g.cand_keys;
+              const double* ca = PEER ? seg + kTrFinishCap : g.cand_a;
+              const double* cb = PEER ? seg + 2 * kTrFinishCap : g.cand_b;
+              const int cnt = PEER ? static_cast<int>(*reinterpret_cast<const volatile long long*>(seg + 3 * kTrFinishCap)) : ncand;
+              for (int base = tid; base < cnt; base += kThreads * kTrUnroll) {
+                unsigned long long key[kTrUnroll];
+                double av[kTrUnroll], bv[kTrUnroll];
 #pragma unroll
-            for (int u = 0; u < kTrUnroll; ++u) {
-              const int i = base + u * kThreads;
-              key[u] = i < ncand ? g.cand_keys[i] : 0ull;
-              av[u] = i < ncand ? g.cand_a[i] : 0.0;
-              bv[u] = i < ncand ? g.cand_b[i] : 0.0;
-            }
+                for (int u = 0; u < kTrUnroll; ++u) {
+                  const int i = base + u * kThreads;
+                  key[u] = i < cnt ? __ldcg(ck + i) : 0ull;
+                  av[u] = i < cnt ? __ldcg(ca + i) : 0.0;
+                  bv[u] = i < cnt ? __ldcg(cb + i) : 0.0;
+                }
 #pragma unroll
-            for (int u = 0; u < kTrUnroll; ++u) {
-              if (key[u] > l2 && key[u] - l2 <= w2) {
-                const int j0 = tr_bin(key[u], l2, sh);
-                bins[j0 * kThreads + tid] += av[u];
-                bins[(17 + j0) * kThreads + tid] += bv[u];
+                for (int u = 0; u < kTrUnroll; ++u) {
+                  if (key[u] > l2 && key[u] - l2 <= w2) {
+                    const int j0 = tr_bin(key[u], l2, sh);
+                    bins[j0 * kThreads + tid] += av[u];
+                    bins[(17 + j0) * kThreads + tid] += bv[u];
+                  }
+                }
               }
             }
+            __syncthreads();
+            tr_block_totals(bins, tot, 34);
+            __syncthreads();
+            if (tid == 0) tr_pick_compact(tot, &s, sh);
+            __syncthreads();
           }
-          __syncthreads();
-          tr_block_totals(bins, tot, 34);
-          __syncthreads();
-          if (tid == 0) tr_pick_compact(tot, &s, sh);
-          __syncthreads();
+        } else if (tid == 0) {
+          s.done = 1;  // a peer never arrived
         }
+        __syncthreads();
       }
     }
     tr_publish_or_wait(g, &s, last, round);
@@ -1930,8 +1870,6 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   CUDA_OK(cudaMalloc(&partials_, sizeof(double) * kMaxReduceBlocks * 40));
   CUDA_OK(cudaMalloc(&tr_peer_error_, 64));
   CUDA_OK(cudaMemset(tr_peer_error_, 0, 64));
-  CUDA_OK(cudaMalloc(&decide_ticket_, 64));
-  CUDA_OK(cudaMemset(decide_ticket_, 0, 64));
   CUDA_OK(cudaMalloc(&results_, sizeof(double) * 64));
   CUDA_OK(cudaMallocHost(&host_results_, sizeof(double) * 64));
 }
@@ -1940,7 +1878,6 @@ Device::~Device() {
   cudaSetDevice(device_);
   cudaFree(partials_);
   cudaFree(tr_peer_error_);
-  cudaFree(decide_ticket_);
   cudaFree(results_);
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
@@ -2094,11 +2031,6 @@ void launch_k(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStrea
   cfg.numAttrs = pdl ? 1 : 0;
   CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
-bool StepFusedDecide() {
-  // (off by default: one ticket per block of the K^T y' kernel costs more than the launch it saves -- profiles/r02b_ab_sell.txt)
-  static const bool v = [] { const char* e = std::getenv("PDLP_B200_FUSED_DECIDE"); return e != nullptr && e[0] == '1'; }();
-  return v;
-}
 bool StepPdl() {
   static const bool v = [] { const char* e = std::getenv("PDLP_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
   return v;
@@ -2106,17 +2038,18 @@ bool StepPdl() {
 
 template <int MODE, int NS, class Epi>
 void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, double* partials, const int32_t* halt, int64_t* launches,
-                 int* main_blocks, int* fix_blocks, bool pdl = false, DecideTail tail = DecideTail()) {
+                 int* main_blocks, int* fix_blocks, bool pdl = false, DecideHead head = DecideHead()) {
   const int nb = SellGrid(a);
-  const int variant = SellVariant();
-  // the fused decision runs in the LAST kernel of the product: the fix-up when there are split rows
-  const DecideTail none;
-  const DecideTail& main_tail = a.num_split > 0 ? none : tail;
-  // variants: 0 plain, 1 / 2 software-pipelined register staging (4 / 8 slots), 3.. TMA staging
+  // the dual kernel (two reductions, a 6-operand epilogue) is 4 % faster with 72 registers at 7 blocks
+  // per SM than squeezed into 64 at 8; the store-only kernels prefer the 8 blocks (profiles/r02m_ab.txt)
+  const int variant = (SellVariant() == 1 && NS == 2) ? 8 : SellVariant();
+  const DecideHead& main_tail = head;  // (an extra block of the main kernel takes the step decision when asked to)
+  // variants: 0 plain, 1 / 2 software-pipelined register staging (4 / 8 slots; 8 = 1 with 72 registers, 7 blocks per SM), 3.. TMA staging
   // (slots per stage x stages) 3: 8 x 2, 4: 4 x 2, 5: 2 x 2, 6: 2 x 4, 7: 4 x 3. Shared memory used for
   // staging is taken from the L1 that tracks the outstanding gather misses, so the stages are small
   // and the carve-out is pinned to what the resident blocks need.
-#define PDLP_SELL_LAUNCH(BT, V) launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, nb, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail)
+  const int grid = nb + (head.in != nullptr ? 1 : 0);  // (+ the block that only takes the step decision)
+#define PDLP_SELL_LAUNCH(BT, V) launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, grid, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail)
 #define PDLP_SELL_LAUNCH_T(BT, U, NST)                                                                                              \
   do {                                                                                                                              \
     static bool carved = false;                                                                                                     \
@@ -2125,7 +2058,7 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
       if (const int pct = SellCarveout(); pct >= 0)                                                                                 \
         cudaFuncSetAttribute(k_sell_tma<MODE, NS, Epi, BT, U, NST>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);          \
     }                                                                                                                               \
-    launch_k(pdl, k_sell_tma<MODE, NS, Epi, BT, U, NST>, nb, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail);       \
+    launch_k(pdl, k_sell_tma<MODE, NS, Epi, BT, U, NST>, grid, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail);     \
   } while (0)
 #define PDLP_SELL_LAUNCH_V(BT)                                 \
   do {                                                         \
@@ -2135,6 +2068,7 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
     else if (variant == 6) PDLP_SELL_LAUNCH_T(128, 2, 4);      \
     else if (variant == 7) PDLP_SELL_LAUNCH_T(128, 4, 3);      \
     else if (variant == 1) PDLP_SELL_LAUNCH(BT, 1);            \
+    else if (variant == 8) PDLP_SELL_LAUNCH(BT, 8);            \
     else if (variant == 2) PDLP_SELL_LAUNCH(BT, 2);            \
     else PDLP_SELL_LAUNCH(BT, 0);                              \
   } while (0)
@@ -2152,7 +2086,7 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
   int nf = 0;
   if (a.num_split > 0) {
     nf = static_cast<int>((a.num_split * 32 + kThreads - 1) / kThreads);
-    launch_k(pdl, k_sell_fixup<MODE, NS, Epi>, nf, kThreads, stream, a, epi, partials != nullptr ? partials + static_cast<int64_t>(nb) * NS : nullptr, halt, tail);
+    launch_k(pdl, k_sell_fixup<MODE, NS, Epi>, nf, kThreads, stream, a, epi, partials != nullptr ? partials + static_cast<int64_t>(nb) * NS : nullptr, halt);
     ++*launches;
   }
   if (main_blocks != nullptr) *main_blocks = nb;
@@ -2587,7 +2521,7 @@ static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_glob
   pp.rank = arena->rank;
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(arena->base[h]);
   const PeerLayout l = PeerLayout::For(n, m_global, pp.world);
-  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off; pp.cand_off = l.cand_off;
   pp.timeout_cycles = PeerTimeoutCycles();
   return pp;
 }
@@ -2872,10 +2806,10 @@ void Device::SolveDiagonalTrustRegion(const double* obj, const double* qdiag, co
 }
 
 // ---- PDHG step ----------------------------------------------------------------
-StepState* Device::AllocState() {
+StepState* Device::AllocState() {  // two slots (see DecideHead)
   StepState* p = nullptr;
-  CUDA_OK(cudaMalloc(&p, sizeof(StepState)));
-  CUDA_OK(cudaMemset(p, 0, sizeof(StepState)));
+  CUDA_OK(cudaMalloc(&p, 2 * sizeof(StepState)));
+  CUDA_OK(cudaMemset(p, 0, 2 * sizeof(StepState)));
   return p;
 }
 void Device::UploadState(StepState* dev, const StepState& host) {
@@ -2887,11 +2821,21 @@ void Device::DownloadState(StepState& host, const StepState* dev) {
   CUDA_OK(cudaMemcpyAsync(&host, dev, sizeof(StepState), cudaMemcpyDeviceToHost, STREAM));
   Sync();
 }
+int Device::DownloadLatestState(StepState& host, const StepState* slots, int preferred_slot) {
+  StepState both[2];
+  CUDA_OK(cudaMemcpyAsync(both, slots, 2 * sizeof(StepState), cudaMemcpyDeviceToHost, STREAM));
+  Sync();
+  // every executed decision increments `attempts` while it moves the state to the other slot
+  int slot = preferred_slot;
+  if (both[1 - preferred_slot].attempts > both[preferred_slot].attempts) slot = 1 - preferred_slot;
+  host = both[slot];
+  return slot;
+}
 
 static StepPtrs MakePtrs(const Device::StepBuffers& b) {
   StepPtrs p;
   p.n = b.n; p.m = b.m;
-  for (int k = 0; k < 3; ++k) { p.x[k] = b.x[k]; p.y[k] = b.y[k]; p.kty[k] = b.kty[k]; }
+  for (int k = 0; k < 3; ++k) { p.x[k] = b.x[k]; p.y[k] = b.y[k]; p.kty[k] = b.kty[k]; p.kx[k] = b.kx[k]; }
   p.x_tilde = b.x_tilde; p.avg_x = b.avg_x; p.avg_y = b.avg_y;
   p.c = b.c; p.q = b.q; p.lv = b.lv; p.uv = b.uv; p.lc = b.lc; p.uc = b.uc;
   p.state = b.state;
@@ -2906,7 +2850,7 @@ static PeerPtrs MakePeerPtrs(const Device::StepBuffers& b) {
   pp.rank = b.arena->rank;
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(b.arena->base[h]);
   const PeerLayout l = PeerLayout::For(b.n, b.m_global, pp.world);
-  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off;
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off; pp.cand_off = l.cand_off;
   pp.row_begin = b.row_begin;
   pp.timeout_cycles = PeerTimeoutCycles();
   pp.begin = b.slice_begin;
@@ -2914,8 +2858,8 @@ static PeerPtrs MakePeerPtrs(const Device::StepBuffers& b) {
   return pp;
 }
 
-void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count) {
-  const StepPtrs p = MakePtrs(b);
+void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count, int first_slot) {
+  StepPtrs p = MakePtrs(b);
   const bool use_peer = b.arena != nullptr;
   const bool pdl = StepPdl();
   const PeerPtrs peer = MakePeerPtrs(b);
@@ -2923,11 +2867,8 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const int np = static_cast<int>(std::max<int64_t>(1, ((primal_work + 1) / 2 + kThreads - 1) / kThreads));
   const int nd_main = SellGrid(rows);
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
-  const int nt_main = SellGrid(cols);
-  const int nt_fix = cols.num_split > 0 ? static_cast<int>((cols.num_split * 32 + kThreads - 1) / kThreads) : 0;
-  const int ns_main = b.cols_slice != nullptr ? SellGrid(*b.cols_slice) : 0;
-  const int ns_fix = b.cols_slice != nullptr && b.cols_slice->num_split > 0 ? static_cast<int>((b.cols_slice->num_split * 32 + kThreads - 1) / kThreads) : 0;
-  const int64_t need = static_cast<int64_t>(np) + nd_main + nd_fix + std::max<int64_t>(std::max<int64_t>(nt_main + nt_fix, ns_main + ns_fix), Blocks(b.n)) + 8;
+  const int nd = b.m > 0 ? nd_main + nd_fix : 0;
+  const int64_t need = static_cast<int64_t>(np) + 2 * static_cast<int64_t>(nd_main + nd_fix) + 8;
   if (need > step_partials_size_) {
     cudaFree(step_partials_);
     step_partials_ = nullptr;
@@ -2935,15 +2876,25 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
     CUDA_OK(cudaMemset(step_partials_, 0, sizeof(double) * need));
     step_partials_size_ = need;
   }
-  double* pp = step_partials_;
-  double* pd = pp + np;
-  double* pt = pd + nd_main + nd_fix;
-  const int32_t* halt = &b.state->halt;
+  double* pd = step_partials_;              // [nd][2] (16-byte aligned: read as double2)
+  double* pp = pd + 2 * (nd_main + nd_fix);  // [np]
   constexpr int kMaxSamples = 64;
   timing_attempt_idx_.clear();
   timing_peer_ = use_peer;
   auto ev = [&](int slot, int k) { CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timing_events_[slot * kEvPerSlot + k]), STREAM)); };
   for (int it = 0; it < count; ++it) {
+    // the kernels of this attempt read state slot `in`; its decision writes the other slot
+    StepState* st_in = b.state + ((first_slot + it) & 1);
+    StepState* st_out = b.state + ((first_slot + it + 1) & 1);
+    p.state = st_in;
+    const int32_t* halt = &st_in->halt;
+    DecideHead head;
+    head.in = st_in;
+    head.out = st_out;
+    head.pp = pp;
+    head.np = b.n > 0 ? np : 0;
+    head.pd = pd;
+    head.nd = nd;
     int slot = -1;
     if (step_timing_ && it % step_timing_stride_ == 0 && static_cast<int>(timing_attempt_idx_.size()) < kMaxSamples) {
       slot = static_cast<int>(timing_attempt_idx_.size());
@@ -2955,92 +2906,84 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       timing_attempt_idx_.push_back(it);
       ev(slot, 0);
     }
+    if (use_peer) {
+      // the decision adds the G triples {||dx||^2, ||dy||^2, (K dx) . dy} that k_sum_push_barrier stored into this rank's arena
+      head.scal = peer.base[peer.rank] + peer.scal_off;
+      head.scal_count = peer.world;
+      head.scal_stride = 4;
+      head.scal_has_dx2 = 1;
+    }
     if (use_peer && b.cols_slice != nullptr) {
-      // all-gather exchange; sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual + y' stores | - | barrier | K^T y' slice + nonlinearity | decision (+ barrier)
+      // all-gather exchange; sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual + y' stores | - | sums + barrier | K^T y' slice (+ decision) | -
       launch_k(pdl, k_primal_step<true>, np, kThreads, STREAM, p, peer, pp);
       if (slot >= 0) ev(slot, 1);
-      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 0, b.state);
+      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 0, st_in);
       launches_ += 2;
       if (slot >= 0) ev(slot, 2);
       if (b.m > 0) {
         DualEpiT<true> de;
         de.b = p;
         de.peer = peer;
-        launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, de, pd, halt, &launches_, nullptr, nullptr, pdl);
+        launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, de, pd, halt, &launches_, nullptr, nullptr, pdl);
       }
       if (slot >= 0) { ev(slot, 3); ev(slot, 4); }
-      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 1, b.state);
+      launch_k(pdl, k_sum_push_barrier, 1, kDecideThreads, STREAM, st_in, peer, 1, pp, np, pd, nd);
       ++launches_;
       if (slot >= 0) ev(slot, 5);
-      launch_sell<kDot, 1>(STREAM, *b.cols_slice, GatherSrc{{peer.base[peer.rank] + peer.y_off, nullptr, nullptr}, nullptr}, KtyEpiSlice{p, b.slice_perm, b.slice_begin}, pt, halt,
-                           &launches_, nullptr, nullptr, pdl);
-      if (slot >= 0) ev(slot, 6);
-      launch_k(pdl, k_step_decide_peer, 1, kDecideThreads, STREAM, b.state, peer, pp, np, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, ns_main + ns_fix);
-      ++launches_;
-      if (slot >= 0) ev(slot, 7);
+      launch_sell<kDot, 0>(STREAM, *b.cols_slice, GatherSrc{{peer.base[peer.rank] + peer.y_off, nullptr, nullptr}, nullptr}, KtyEpiSlice{p, b.slice_perm, b.slice_begin}, nullptr, halt,
+                           &launches_, nullptr, nullptr, pdl, head);
+      if (slot >= 0) { ev(slot, 6); ev(slot, 7); }
       continue;
     }
     if (use_peer) {
-      // sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual | K^T y' partial | barrier | slice pull + finish | decision (+ barrier)
+      // reduce-scatter exchange; sub-phases (events 0..7): primal slice + x~ stores | barrier | K x~ + dual | K^T y' partial | sums + barrier | slice pull (+ decision) | -
       launch_k(pdl, k_primal_step<true>, np, kThreads, STREAM, p, peer, pp);
       if (slot >= 0) ev(slot, 1);
-      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 0, b.state);
+      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 0, st_in);
       launches_ += 2;
       if (slot >= 0) ev(slot, 2);
       if (b.m > 0) {
-        launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
+        launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
       }
       if (slot >= 0) ev(slot, 3);
-      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{peer.base[peer.rank] + peer.partial_off, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, ScatterEpi{peer.base[peer.rank] + peer.partial_off, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
       if (slot >= 0) ev(slot, 4);
-      launch_k(pdl, k_peer_barrier, 1, 32, STREAM, peer, 1, b.state);
+      launch_k(pdl, k_sum_push_barrier, 1, kDecideThreads, STREAM, st_in, peer, 1, pp, np, pd, nd);
       if (slot >= 0) ev(slot, 5);
-      launch_k(pdl, k_kty_finish_peer, np, kThreads, STREAM, p, peer, pt);
+      launch_k(pdl, k_kty_finish_peer, np, kThreads, STREAM, p, peer, head);
       launches_ += 2;
-      if (slot >= 0) ev(slot, 6);
-      launch_k(pdl, k_step_decide_peer, 1, kDecideThreads, STREAM, b.state, peer, pp, np, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, np);
-      ++launches_;
-      if (slot >= 0) ev(slot, 7);
+      if (slot >= 0) { ev(slot, 6); ev(slot, 7); }
       continue;
     }
     launch_k(pdl, k_primal_step<false>, np, kThreads, STREAM, p, peer, pp);
     ++launches_;
     if (slot >= 0) ev(slot, 1);
     if (b.m > 0) {
-      launch_sell<kDot, 1>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
+      launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
     }
     if (slot >= 0) ev(slot, 2);
     if (comm_ != nullptr) {
-      // local ||dy||^2 -> exchange[n]; local K^T y' partial -> exchange[0..n) in column order
-      k_sum_to_slot<<<1, kDecideThreads, 0, STREAM>>>(b.state, pd, b.m > 0 ? nd_main + nd_fix : 0, b.exchange + b.n);
+      // NCCL exchange: local {||dy||^2, (K dx) . dy} -> exchange[n], exchange[n + 1]; local K^T y' partial -> exchange[0..n) in column order
+      k_sum_to_slot<<<1, kDecideThreads, 0, STREAM>>>(st_in, pd, nd, b.exchange + b.n);
       ++launches_;
-      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, ScatterEpi{b.exchange, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
-      comm_->AllReduceSum(b.exchange, b.exchange, b.n + 1, stream_);
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, ScatterEpi{b.exchange, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
+      comm_->AllReduceSum(b.exchange, b.exchange, b.n + 2, stream_);
+      head.scal = b.exchange + b.n - 1;  // (so that entries 1, 2 of the "triple" are exchange[n], exchange[n + 1]; ||dx||^2 comes from pp: the primal side is replicated)
+      head.scal_count = 1;
+      head.scal_stride = 0;
+      head.scal_has_dx2 = 0;
       const int nk = Blocks(b.n);
-      k_kty_finish<<<nk, kThreads, 0, STREAM>>>(p, b.exchange, pt);
+      k_kty_finish<<<nk, kThreads, 0, STREAM>>>(p, b.exchange, head);
       ++launches_;
       if (slot >= 0) ev(slot, 3);
-      k_step_decide<<<1, kDecideThreads, 0, STREAM>>>(b.state, pp, np, b.exchange + b.n, -1, pt, nk);
-      ++launches_;
+    } else if (b.n > 0) {
+      // three launches per attempt: block 0 of the K^T y' kernel takes the decision while the others stream the matrix
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, KtyEpi{p}, nullptr, halt, &launches_, nullptr, nullptr, pdl, head);
+      if (slot >= 0) ev(slot, 3);
     } else {
-      if (b.n > 0 && StepFusedDecide()) {
-        // three launches per iteration: the decision runs in the last block of the K^T y' kernel
-        DecideTail tail;
-        tail.st = b.state;
-        tail.pp = pp; tail.np = np;
-        tail.pd = pd; tail.nd = b.m > 0 ? nd_main + nd_fix : 0;
-        tail.pt = pt; tail.nt = nt_main + nt_fix;
-        tail.ticket = decide_ticket_;
-        launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr, pdl, tail);
-        if (slot >= 0) ev(slot, 3);
-      } else {
-        if (b.n > 0) {
-          launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, b.state}, KtyEpi{p}, pt, halt, &launches_, nullptr, nullptr, pdl);
-        }
-        if (slot >= 0) ev(slot, 3);
-        launch_k(pdl, k_step_decide, 1, kDecideThreads, STREAM, b.state, pp, b.n > 0 ? np : 0, pd, b.m > 0 ? nd_main + nd_fix : 0, pt, b.n > 0 ? nt_main + nt_fix : 0);
-        ++launches_;
-      }
+      launch_k(pdl, k_decide_only, 1, kThreads, STREAM, head);
+      ++launches_;
+      if (slot >= 0) ev(slot, 3);
     }
     if (slot >= 0) ev(slot, 4);
   }
@@ -3097,17 +3040,24 @@ double Device::TimelineStopMs(int id) {
 
 void Device::GatherPrimalSlices(const StepBuffers& b, int cur, int prev) {
   if (b.arena == nullptr || comm_ == nullptr) return;
-  for (double* v : {b.x[cur], b.x[prev], b.kty[cur], b.avg_x}) comm_->AllGatherInPlace(v, b.slice_stride, stream_);
+  // prev < 0: the previous iterate is only read by the iterate difference, which is materialised
+  // lazily (it then asks for that one vector with cur < 0)
+  comm_->GroupStart();
+  if (cur >= 0)
+    for (double* v : {b.x[cur], b.kty[cur], b.avg_x}) comm_->AllGatherInPlace(v, b.slice_stride, stream_);
+  if (prev >= 0) comm_->AllGatherInPlace(b.x[prev], b.slice_stride, stream_);
+  comm_->GroupEnd();
 }
 
-void Device::FlushAverages(const StepBuffers& b) {
-  const StepPtrs p = MakePtrs(b);
+void Device::FlushAverages(const StepBuffers& b, int slot) {
+  StepPtrs p = MakePtrs(b);
+  p.state = b.state + slot;
   const int64_t total = b.n + b.m;
   if (total > 0) {
     k_flush_average<<<Blocks(total), kThreads, 0, STREAM>>>(p, total, b.arena != nullptr ? b.slice_begin : 0, b.arena != nullptr ? b.slice_end : b.n);
     ++launches_;
   }
-  k_clear_pending<<<1, 1, 0, STREAM>>>(b.state);
+  k_clear_pending<<<1, 1, 0, STREAM>>>(b.state + slot);
   LAUNCHED();
 }
 

@@ -109,7 +109,9 @@ enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent
 // `stride` (even) columns; n_pad = world * stride is also the allocated length
 // of every primal vector so that slices can be all-gathered in place.
 struct PeerLayout {
-  int64_t stride = 0, n_pad = 0, xt_off = 0, partial_off = 0, y_off = 0, scal_off = 0, flags_off = 0, epoch_off = 0, tr_off = 0, doubles = 0;
+  int64_t stride = 0, n_pad = 0, xt_off = 0, partial_off = 0, y_off = 0, scal_off = 0, flags_off = 0, epoch_off = 0, tr_off = 0, cand_off = 0, doubles = 0;
+  static constexpr int64_t kTrCandCap = 4096;                  // = kTrFinishCap of the trust-region solve
+  static constexpr int64_t kTrCandSegment = 3 * kTrCandCap + 8;  // per rank: keys, a, b of its candidates + their count
   static PeerLayout For(int64_t n, int64_t m_global, int world) {
     PeerLayout l;
     l.stride = 2 * ((n + 2 * world - 1) / (2 * world));
@@ -122,7 +124,8 @@ struct PeerLayout {
     l.flags_off = l.scal_off + 4 * 8;
     l.epoch_off = l.flags_off + 8 * 4;
     l.tr_off = l.epoch_off + 4;
-    l.doubles = l.tr_off + 2 * 48 * 8;
+    l.cand_off = l.tr_off + 2 * 48 * 8;
+    l.doubles = l.cand_off + kTrCandSegment * 8;
     return l;
   }
 };
@@ -299,11 +302,12 @@ class Device {
     double* x[3] = {nullptr, nullptr, nullptr};
     double* y[3] = {nullptr, nullptr, nullptr};
     double* kty[3] = {nullptr, nullptr, nullptr};
+    double* kx[3] = {nullptr, nullptr, nullptr};  // K x of the iterates (maintained by the dual kernel)
     double* x_tilde = nullptr;
     double* avg_x = nullptr;
     double* avg_y = nullptr;
     const double *c = nullptr, *q = nullptr, *lv = nullptr, *uv = nullptr, *lc = nullptr, *uc = nullptr;
-    StepState* state = nullptr;  // device
+    StepState* state = nullptr;  // device, TWO slots: an attempt reads one, its decision writes the other
     // row-sharded solve only: [n + 1] exchange buffer for the K^T y' partial
     // (+ this rank's ||dy||^2 in the last slot) and the scatter permutation
     double* exchange = nullptr;
@@ -319,19 +323,21 @@ class Device {
     const SellDev* cols_slice = nullptr;
     const int32_t* slice_perm = nullptr;
   };
-  StepState* AllocState();
+  StepState* AllocState();  // two slots
   void UploadState(StepState* dev, const StepState& host);
   void DownloadState(StepState& host, const StepState* dev);
-  // Enqueues `count` attempts of the fused 3-kernel step; attempts after the
-  // device sets `halt` are no-ops. Does not synchronise.
-  void EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count);
+  // Both slots; returns the index of the one the last executed decision wrote (preferred_slot on a tie).
+  int DownloadLatestState(StepState& host, const StepState* slots, int preferred_slot);
+  // Enqueues `count` attempts of the fused 3-kernel step, the first one reading state slot
+  // `first_slot`; attempts after the device sets `halt` are no-ops. Does not synchronise.
+  void EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count, int first_slot);
   // Per-kernel CUDA-event sampling of the step loop (bench / profiling only).
   // While enabled, every `stride`-th attempt of an EnqueueSteps batch is
   // bracketed by events on the launching stream; CollectStepTimings (call it
   // after the batch has been synchronised) adds the samples whose attempt
   // index is < `executed_attempts` (later ones were halted no-ops).
   // Kernel classes: 0 primal step, 1 K x~ + dual epilogue (+fix-up),
-  // 2 K^T y' + nonlinearity epilogue (+fix-up), 3 step decision.
+  // 2 K^T y' (+fix-up; its block 0 takes the step decision), 3 row-sharded solves only: sums + barrier.
   struct StepTimings { double ms[4] = {0, 0, 0, 0}; int64_t samples[4] = {0, 0, 0, 0}; };
   void EnableStepTiming(bool on, int stride = 8);
   void CollectStepTimings(int64_t executed_attempts);
@@ -342,7 +348,7 @@ class Device {
   void TimelineStop(int id);         // records only; TimelineCollectMs (which synchronises) returns the time later
   double TimelineCollectMs(int id);  // 0 if nothing is pending
   // Applies the deferred average update (if any) for both averages.
-  void FlushAverages(const StepBuffers& b);
+  void FlushAverages(const StepBuffers& b, int slot);
   // Peer exchange only: inside the step loop every rank advances just its slice
   // of x, K^T y and the primal average; this all-gathers the slices of
   // x[cur], x[prev], kty[cur] and avg_x so that the replicated primal side is
@@ -368,7 +374,6 @@ class Device {
   const PeerArena* peer_arena_ = nullptr;
   int64_t peer_arena_n_ = 0, peer_arena_m_ = 0;
   int32_t* tr_peer_error_ = nullptr;  // device flag: a peer did not arrive at a barrier of the trust-region search
-  unsigned int* decide_ticket_ = nullptr;  // ticket counter of the fused step decision (DecideTail)
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)
   double* tr_scratch_ = nullptr;

@@ -94,7 +94,7 @@ DeviceProblem::DeviceProblem(const PdlpProblemView& view, int cuda_device, Comm*
     nnz_ = h.nnz;
   }
   if (comm_ != nullptr) {
-    exchange_ = dev_->AllocF64(n_ + 1);
+    exchange_ = dev_->AllocF64(n_ + 2);  // K^T y' partial + {||dy||^2, (K dx) . dy}
     layout_ = PeerLayout::For(n_, m_global_, comm_->world_size());
     slice_begin_ = std::min<int64_t>(n_, layout_.stride * comm_->rank());
     slice_end_ = std::min<int64_t>(n_, slice_begin_ + layout_.stride);

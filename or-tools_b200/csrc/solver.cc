@@ -307,8 +307,8 @@ class DeviceSolve {
       std::fprintf(stderr, "[pdlp_b200 trace] host wall seconds: restart-choice %.4f termination-check %.4f apply-restart %.4f step-loop %.4f flush+gather %.4f deltas %.4f\n",
                    phase_s_[0], phase_s_[1], phase_s_[2], phase_s_[3], phase_s_[4], phase_s_[5]);
     }
-    for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); }
-    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, kx_cur_, kx_next_, delta_x_, delta_y_, pc_kx_cur_, pc_kx_avg_, pc_kty_avg_, polish_x_, polish_y_}) D.Free(v);
+    for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); D.Free(buf_.kx[k]); }
+    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, delta_x_, delta_y_, pc_kx_avg_, pc_kty_avg_, polish_x_, polish_y_}) D.Free(v);
     if (!nested_) { D.Free(dc_); D.Free(dr_); }
     D.Free(buf_.state);
   }
@@ -331,11 +331,12 @@ class DeviceSolve {
   double* X() const { return buf_.x[hs_.cur]; }
   double* Y() const { return buf_.y[hs_.cur]; }
   double* Kty() const { return buf_.kty[hs_.cur]; }
+  double* Kx() const { return buf_.kx[hs_.cur]; }  // K x of the current iterate (kept by the dual kernel: K x' = (K x~ + K x) / 2)
   bool PrimalAvgHasWeight() const { return avg_x_weight_ > 0.0; }
   bool DualAvgHasWeight() const { return avg_y_weight_ > 0.0; }
   const double* PrimalAverage() const { return PrimalAvgHasWeight() ? buf_.avg_x : X(); }  // pdhg.cc:2172-2186
   const double* DualAverage() const { return DualAvgHasWeight() ? buf_.avg_y : Y(); }
-  void PushState() { D.UploadState(buf_.state, hs_); }
+  void PushState() { D.UploadState(buf_.state, hs_); state_slot_ = 0; }  // (slot 0 of the two device slots)
   void ClearAverages() {
     InvalidateProducts(false, true);
     D.Fill(buf_.avg_x, 0.0, P.n());
@@ -364,7 +365,7 @@ class DeviceSolve {
     hs_.avg_num_terms = 1;
   }
   void SetCurrentPrimalAndDualProducts() {  // pdhg.cc:1961-1974
-    if (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE) P.Kx(X(), kx_cur_);
+    P.Kx(X(), Kx());  // (the reference keeps K x only under Malitsky-Pock; here the dual kernel maintains it for every rule)
     P.KTy(Y(), Kty());
   }
   double DistanceTraveledFromLastStart(const double* x, const double* y) {  // pdhg.cc:1998-2007
@@ -410,6 +411,7 @@ class DeviceSolve {
   bool Interrupted(const volatile int32_t* interrupt) {
     const bool local = interrupt != nullptr && *interrupt != 0;
     if (!P.sharded()) return local;
+    if (!interrupt_polled_) return false;  // no rank was given a flag (agreed on in Advance): nothing to exchange
     return D.RootValue(local ? 1.0 : 0.0) != 0.0;
   }
   void ConvergenceAndInfeasibility(const double* x, const double* y, const double* kty_or_null, int type, PdlpConvergenceInformation* conv,
@@ -421,6 +423,7 @@ class DeviceSolve {
   // The iterate difference is only read by termination checks and overwritten by restarts to the
   // average: it is materialised when one of the two happens, not after every chunk of steps.
   bool delta_pending_ = false;
+  bool prev_slices_gathered_ = true;  // x[prev] is whole on every rank
   void EnsureDeltas() { if (delta_pending_) { MaterializeDeltas(); delta_pending_ = false; } }
   int NextCheckpoint(int k) const;
   Outcome RunDeviceSteps(int k, const volatile int32_t* interrupt);
@@ -437,26 +440,21 @@ class DeviceSolve {
   Device::StepBuffers buf_;
   StepState hs_{};
   double *x0_ = nullptr, *y0_ = nullptr;            // last restart point
-  double *kx_cur_ = nullptr, *kx_next_ = nullptr;    // Malitsky-Pock product cache
-  // Products of the points a major iteration looks at more than once (restart
-  // test, termination check, restart): K x of the current iterate and K x / K^T y
-  // of the average. Valid only until the iterates or the averages change.
-  double *pc_kx_cur_ = nullptr, *pc_kx_avg_ = nullptr, *pc_kty_avg_ = nullptr;
-  bool pc_kx_cur_ok_ = false, pc_kx_avg_ok_ = false, pc_kty_avg_ok_ = false;
+  int state_slot_ = 0;  // which of the two device state slots is current
+  // Products of the average that a major iteration looks at more than once (restart test,
+  // termination check, restart): K x / K^T y. Valid only until the averages change. (K x and
+  // K^T y of the current iterate are iterate buffers of the step loop.)
+  double *pc_kx_avg_ = nullptr, *pc_kty_avg_ = nullptr;
+  bool pc_kx_avg_ok_ = false, pc_kty_avg_ok_ = false;
   // squared distances of the current / average point to the last restart point, as left by BoundsAt
   double dist_cur_[2] = {0, 0}, dist_avg_[2] = {0, 0};
   bool dist_cur_ok_ = false, dist_avg_ok_ = false;
   void InvalidateProducts(bool current, bool average) {
-    if (current) pc_kx_cur_ok_ = dist_cur_ok_ = false;
+    if (current) dist_cur_ok_ = false;
     if (average) pc_kx_avg_ok_ = pc_kty_avg_ok_ = dist_avg_ok_ = false;
   }
   const double* CachedKx(const double* x) {  // nullptr: not one of the cached points
-    const bool mp = params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE;
-    if (x == X()) {
-      if (mp) return kx_cur_;
-      if (!pc_kx_cur_ok_) { P.Kx(x, pc_kx_cur_); pc_kx_cur_ok_ = true; }
-      return pc_kx_cur_;
-    }
+    if (x == X()) return Kx();
     if (x == buf_.avg_x) {
       if (!pc_kx_avg_ok_) { P.Kx(x, pc_kx_avg_); pc_kx_avg_ok_ = true; }
       return pc_kx_avg_;
@@ -581,17 +579,9 @@ void DeviceSolve::ApplyRestartChoice(int restart) {  // pdhg.cc:2246-2296
       D.CopyD2D(Y(), buf_.avg_y, P.m());
       dist_cur_[0] = dist_avg_[0]; dist_cur_[1] = dist_avg_[1]; dist_cur_ok_ = dist_avg_ok_;
       // the new current iterate is the average: its products are the average's
-      if (pc_kty_avg_ok_ && params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE) {
-        D.CopyD2D(Kty(), pc_kty_avg_, P.n());
-      } else {
-        SetCurrentPrimalAndDualProducts();
-      }
-      if (pc_kx_avg_ok_) {
-        D.CopyD2D(pc_kx_cur_, pc_kx_avg_, P.m());
-        pc_kx_cur_ok_ = true;
-      } else {
-        pc_kx_cur_ok_ = false;
-      }
+      if (pc_kty_avg_ok_) D.CopyD2D(Kty(), pc_kty_avg_, P.n()); else P.KTy(Y(), Kty());
+      if (pc_kx_avg_ok_) D.CopyD2D(Kx(), pc_kx_avg_, P.m()); else P.Kx(X(), Kx());
+
       break;
   }
   hs_.primal_weight = ComputeNewPrimalWeight();
@@ -675,6 +665,10 @@ void DeviceSolve::AddPointMetadata(const double* x, const double* y, int type, P
 }
 
 void DeviceSolve::MaterializeDeltas() {
+  if (!prev_slices_gathered_) {  // (row-sharded peer exchange: inside the loop every rank advances only its slice of x)
+    D.GatherPrimalSlices(buf_, -1, hs_.prev);
+    prev_slices_gathered_ = true;
+  }
   // current_primal_delta_ / current_dual_delta_ of the last accepted step
   // (pdhg.cc:2604-2605) are x[cur]-x[prev] and y[cur]-y[prev]: the third
   // buffer keeps `prev` intact across rejected candidates. Called right after
@@ -799,7 +793,8 @@ std::optional<SolverResultCpp> DeviceSolve::MajorIterationAndTerminationCheck(bo
   const int restart = force_numerical ? PDLP_RESTART_CHOICE_NO_RESTART : ChooseRestartToApply(is_major);
   phase_s_[0] += phase.Get();
   PdlpIterationStats stats = CreateSimpleIterationStats(restart);
-  if (P.sharded()) stats.cumulative_time_sec = D.RootValue(stats.cumulative_time_sec);  // one clock decides the time limit
+  // one clock decides the time limit (a host round trip through the communicator: only when there is a limit)
+  if (P.sharded() && std::isfinite(params_.termination_criteria.time_sec_limit)) stats.cumulative_time_sec = D.RootValue(stats.cumulative_time_sec);
   const PdlpIterationStats full_work_stats = AddWorkStats(stats, work_from_feasibility_polishing_);
   const bool interrupted = Interrupted(interrupt);
   const auto simple = CheckSimpleTerminationCriteria(params_.termination_criteria, full_work_stats, interrupted);
@@ -1024,18 +1019,19 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
     const int64_t attempts_before = hs_.attempts;
     // exactly the attempts that reach the checkpoint if every step is accepted; rejected
     // steps (rare) are made up by another pass of this loop
-    D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining, 4096));
-    D.DownloadState(hs_, buf_.state);
+    D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining, 4096), state_slot_);
+    state_slot_ = D.DownloadLatestState(hs_, buf_.state, state_slot_);
     if (P.sharded() && D.comm() != nullptr) D.comm()->CheckAsyncError();
     D.CollectStepTimings(hs_.attempts - attempts_before);
     if (hs_.halt != kHaltNone) break;
   }
   phase_s_[3] += t.Get();
   WallTimer phase;
-  D.FlushAverages(buf_);
+  D.FlushAverages(buf_, state_slot_);
   hs_.pending_ratio = 0.0;  // (all FlushAverages changes in the device state)
   if (hs_.halt == kHaltPeerTimeout) throw std::runtime_error("peer-memory exchange timed out: a rank of the row-sharded solve did not arrive");
-  D.GatherPrimalSlices(buf_, hs_.cur, hs_.prev);
+  D.GatherPrimalSlices(buf_, hs_.cur, -1);
+  prev_slices_gathered_ = false;
   D.TimelineStop(1);  // collected lazily: no host synchronisation here
   device_time_sec_ += t.Get();
   phase_s_[4] += phase.Get();
@@ -1075,7 +1071,8 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
   const double contraction = params_.malitsky_pock_linesearch_contraction_factor;
   const double dual_weight = omega * omega;
   int inner_iterations = 0;
-  P.Kx(x_next, kx_next_);
+  double* kx_next = buf_.kx[hs_.cand];
+  P.Kx(x_next, kx_next);
   for (bool accepted = false; !accepted; ++inner_iterations) {
     if (inner_iterations >= 60) {
       logger_.Log(Fmt("WARNING: Inner iteration limit reached at iteration %d", iterations_completed_));
@@ -1084,7 +1081,7 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
       break;
     }
     const double new_ratio = new_primal_step_size / primal_step_size;
-    D.DualStepFromProducts(Y(), kx_cur_, kx_next_, P.lc(), P.uc(), dual_weight * new_primal_step_size, new_ratio, y_next, m);
+    D.DualStepFromProducts(Y(), Kx(), kx_next, P.lc(), P.uc(), dual_weight * new_primal_step_size, new_ratio, y_next, m);
     P.KTy(y_next, kty_next);
     const double delta_dual_norm = std::sqrt(D.SumSqDiff(y_next, Y(), m, P.sharded()));
     const double delta_dual_prod_norm = std::sqrt(D.SumSqDiff(Kty(), kty_next, n));
@@ -1098,7 +1095,6 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
       hs_.prev = hs_.cur;
       hs_.cur = hs_.cand;
       hs_.cand = old_prev;
-      std::swap(kx_cur_, kx_next_);
       MaterializeDeltas();
       AverageAdd(true, X(), new_primal_step_size);
       AverageAdd(false, Y(), new_primal_step_size);
@@ -1178,10 +1174,10 @@ void DeviceSolve::FillStatus(PdlpSessionStatus* out) const {
   //  primal step: reads x, c, K^T y, l_v, u_v (+Q), writes x', x~; deferred average R/W.
   out->kernel_algorithmic_bytes[0] = 8.0 * (9.0 + qn) * n;
   //  K x~ + dual epilogue: K-by-rows (8 B value + 4 B index per nonzero, 4 B row offset),
-  //  gathers x~ once, reads y, l_c, u_c, writes y'; deferred dual average R/W.
-  out->kernel_algorithmic_bytes[1] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (m + 1) + 8.0 * n + 8.0 * 6.0 * m;
-  //  K^T y' + nonlinearity epilogue: K-by-columns, gathers y' once, writes K^T y', reads x', x, K^T y.
-  out->kernel_algorithmic_bytes[2] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (n + 1) + 8.0 * m + 8.0 * 4.0 * n;
+  //  gathers x~ once, reads y, l_c, u_c, K x, writes y', K x'; deferred dual average R/W.
+  out->kernel_algorithmic_bytes[1] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (m + 1) + 8.0 * n + 8.0 * 8.0 * m;
+  //  K^T y': K-by-columns, gathers y' once, writes K^T y' (the nonlinearity is a by-product of the dual kernel).
+  out->kernel_algorithmic_bytes[2] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (n + 1) + 8.0 * m + 8.0 * n;
   out->kernel_algorithmic_bytes[3] = 0.0;
 }
 
@@ -1220,18 +1216,16 @@ void DeviceSolve::AllocateIterates() {
   const int64_t n = P.n(), m = P.m();
   buf_.n = n;
   buf_.m = m;
-  for (int k = 0; k < 3; ++k) { buf_.x[k] = P.NewPrimal(); buf_.y[k] = P.NewDual(); buf_.kty[k] = P.NewPrimal(); }
+  for (int k = 0; k < 3; ++k) { buf_.x[k] = P.NewPrimal(); buf_.y[k] = P.NewDual(); buf_.kty[k] = P.NewPrimal(); buf_.kx[k] = P.NewDual(); }
   buf_.x_tilde = P.NewPrimal();
   buf_.avg_x = P.NewPrimal();
   buf_.avg_y = P.NewDual();
   x0_ = P.NewPrimal();
   y0_ = P.NewDual();
   delta_x_ = P.NewPrimal();
-  pc_kx_cur_ = P.NewDual();
   pc_kx_avg_ = P.NewDual();
   pc_kty_avg_ = P.NewPrimal();
   delta_y_ = P.NewDual();
-  if (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE) { kx_cur_ = P.NewDual(); kx_next_ = P.NewDual(); }
   buf_.c = P.c(); buf_.q = P.q(); buf_.lv = P.lv(); buf_.uv = P.uv(); buf_.lc = P.lc(); buf_.uc = P.uc();
   buf_.state = D.AllocState();
   buf_.exchange = P.exchange();

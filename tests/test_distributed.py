@@ -3,8 +3,9 @@
 CPU (not gpu): the row partition exported by the C ABI, and a world_size-2
 ``gloo`` run of the exchange protocol the CUDA path uses inside the step loop
 (each rank advances a slice of the primal vector and its block of dual rows;
-per PDHG step: all-gather of the x~ slices, reduce-scatter of the K^T y'
-partials added in rank order, three partial sums per rank added in rank order),
+per PDHG step: all-gather of the x~ slices, then -- together -- the reduce-scatter
+of the K^T y' partials added in rank order and three partial sums per rank added
+in rank order; the nonlinearity is the row-side sum (K dx) . dy),
 restated in numpy and compared with the unsharded iteration.
 
 GPU (needs >= 2 devices): the real thing over NCCL against the 1-GPU solve.
@@ -129,6 +130,7 @@ def _protocol_worker(rank, world, port, out_dir):
     lc, uc = qp.constraint_lower_bounds[b:e], qp.constraint_upper_bounds[b:e]
     x, y = np.zeros(c1 - c0), np.zeros(e - b)       # this rank's slice of x, block of y
     kty = np.zeros(c1 - c0)
+    kx = np.zeros(e - b)                             # K x of the current iterate, kept by the dual kernel
     step, weight = 0.1, 1.0
     rejected, done, trace = 0, 0, []
 
@@ -145,23 +147,27 @@ def _protocol_worker(rank, world, port, out_dir):
             tau, sigma = step / weight, step * weight
             xn = np.clip(x - tau * (c - kty), lv, uv)              # primal half step on the slice
             xt = all_gather_slices(2 * xn - x)                     # exchange 1: x~ slices -> whole x~ everywhere
-            t = y - sigma * (kg @ xt)                              # row-local dual half step
+            kxt = kg @ xt                                          # K x~ = 2 K x' - K x on the row block
+            t = y - sigma * kxt                                    # row-local dual half step
             yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
+            kxn = 0.5 * (kxt + kx)                                 # K x'
+            dx, dy = xn - x, yn - y
+            # the nonlinearity dx . K^T dy = (K dx) . dy is known on the row side: all three sums
+            # travel with exchange 2, the decision needs no exchange of its own
+            scal = torch.tensor([dx @ dx, dy @ dy, (0.5 * (kxt - kx)) @ dy], dtype=torch.float64)
             partial = torch.from_numpy(kg.T @ yn)                  # [n] partial of K^T y'
             # exchange 2: reduce-scatter of the partials (each rank adds its slice of every
             # rank's partial in rank order); gloo has no reduce_scatter, so gather + fixed-order sum
             parts = [torch.zeros(n, dtype=torch.float64) for _ in range(world)]
             dist.all_gather(parts, partial)
-            ktyn = np.zeros(c1 - c0)
-            for h in range(world):
-                ktyn = ktyn + parts[h].numpy()[c0:c1]
-            dx = xn - x
-            scal = torch.tensor([dx @ dx, (yn - y) @ (yn - y), dx @ (ktyn - kty)], dtype=torch.float64)
             per_rank = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
-            dist.all_gather(per_rank, scal)                        # exchange 3: three partial sums per rank,
+            dist.all_gather(per_rank, scal)                        # ... and the three partial sums per rank,
             tot = np.zeros(3)                                      # added in rank order on every rank
             for h in range(world):
                 tot = tot + per_rank[h].numpy()
+            ktyn = np.zeros(c1 - c0)
+            for h in range(world):
+                ktyn = ktyn + parts[h].numpy()[c0:c1]
             movement = 0.5 * weight * tot[0] + 0.5 / weight * tot[1]
             nonlin = -tot[2]
             limit = movement / nonlin if nonlin > 0 else np.inf
@@ -172,7 +178,7 @@ def _protocol_worker(rank, world, port, out_dir):
             step = min(first, second)
             trace.append(accepted)
             if accepted:
-                x, y, kty = xn, yn, ktyn.copy()
+                x, y, kty, kx = xn, yn, ktyn.copy(), kxn
                 rejected += inner
                 done += 1
                 break
@@ -220,6 +226,7 @@ def _protocol_worker_all_gather(rank, world, port, out_dir):
     c, lv, uv = qp.objective_vector[c0:c1], qp.variable_lower_bounds[c0:c1], qp.variable_upper_bounds[c0:c1]
     lc, uc = qp.constraint_lower_bounds[b:e], qp.constraint_upper_bounds[b:e]
     x, y, kty = np.zeros(c1 - c0), np.zeros(e - b), np.zeros(c1 - c0)
+    kx = np.zeros(e - b)
     step, weight = 0.1, 1.0
     rejected, done, trace = 0, 0, []
     max_rows = max(e1 - b1 for b1, e1 in blocks)
@@ -242,14 +249,16 @@ def _protocol_worker_all_gather(rank, world, port, out_dir):
             tau, sigma = step / weight, step * weight
             xn = np.clip(x - tau * (c - kty), lv, uv)
             xt = all_gather(2 * xn - x, stride, n, col_offsets)            # exchange 1: x~
-            t = y - sigma * (k_rows @ xt)
+            kxt = k_rows @ xt
+            t = y - sigma * kxt
             yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
-            y_full = all_gather(yn, max_rows, m, blocks)                   # exchange 2: y'
-            ktyn = k_cols_t @ y_full                                       # whole products of the slice
-            dx = xn - x
-            scal = torch.tensor([dx @ dx, (yn - y) @ (yn - y), dx @ (ktyn - kty)], dtype=torch.float64)
+            kxn = 0.5 * (kxt + kx)
+            dx, dy = xn - x, yn - y
+            scal = torch.tensor([dx @ dx, dy @ dy, (0.5 * (kxt - kx)) @ dy], dtype=torch.float64)
+            y_full = all_gather(yn, max_rows, m, blocks)                   # exchange 2: y' ...
             per_rank = [torch.zeros(3, dtype=torch.float64) for _ in range(world)]
-            dist.all_gather(per_rank, scal)                                # exchange 3
+            dist.all_gather(per_rank, scal)                                # ... with the three sums
+            ktyn = k_cols_t @ y_full                                       # whole products of the slice
             tot = np.zeros(3)
             for h in range(world):
                 tot = tot + per_rank[h].numpy()
@@ -263,7 +272,7 @@ def _protocol_worker_all_gather(rank, world, port, out_dir):
             step = min(first, second)
             trace.append(accepted)
             if accepted:
-                x, y, kty = xn, yn, ktyn.copy()
+                x, y, kty, kx = xn, yn, ktyn.copy(), kxn
                 rejected += inner
                 done += 1
                 break

@@ -64,6 +64,20 @@ for stage in "$@"; do
         env $(echo $v | tr ',' ' ') timeout 300 python bench.py --no-e2e --no-cpu > $OUT/${TAG}_ab_$(echo $v | tr -c 'A-Za-z0-9_\n' '_').json 2>/dev/null
         echo "-- $v"; line $OUT/${TAG}_ab_$(echo $v | tr -c 'A-Za-z0-9_\n' '_').json
       done ;;
+    pytest-dist)   # multi-GPU parity tests (run under gpurun --gpus N); the log is kept under profiles/ by hand
+      timeout 1700 python -m pytest tests/test_distributed.py -m gpu -q -rs > $OUT/${TAG}_pytest_dist.log 2>&1; echo "pytest rc=$?"; tail -15 $OUT/${TAG}_pytest_dist.log ;;
+    bench-n)       # bench.py on NGPU GPUs (driver window) with the per-phase trace; C4 sub-record at C4_SCALE
+      T="python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus ${NGPU:-2}"
+      PDLP_B200_TRACE=1 timeout 1500 $T --steps 20 --warmup 5 --c4-scale ${C4_SCALE:-1.0} ${BENCH_EXTRA:-} > $OUT/${TAG}_bench_n${NGPU:-2}.json 2> $OUT/${TAG}_bench_n${NGPU:-2}.err
+      line $OUT/${TAG}_bench_n${NGPU:-2}.json
+      grep -E "trace\] (step|rank 0|SELL|entry)|\[bench\]" $OUT/${TAG}_bench_n${NGPU:-2}.err | head -24
+      python - $OUT/${TAG}_bench_n${NGPU:-2}.json <<'PY'
+import json,sys
+d=json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{')][-1])
+print('c4', json.dumps(d.get('c4')))
+print('e2e_cold', json.dumps(d.get('e2e_cold')))
+PY
+      ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
