@@ -85,8 +85,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+RULE = "adaptive"   # --rule: adaptive (reference default) | malitsky_pock | constant
+
+
 def make_params(pdlp, eps, iteration_limit=None, num_threads=1):
     p = pdlp.PrimalDualHybridGradientParams()
+    if RULE == "malitsky_pock":
+        p.linesearch_rule = p.MALITSKY_POCK_LINESEARCH_RULE
+    elif RULE == "constant":
+        p.linesearch_rule = p.CONSTANT_STEP_SIZE_RULE
     p.termination_criteria.simple_optimality_criteria.eps_optimal_absolute = eps
     p.termination_criteria.simple_optimality_criteria.eps_optimal_relative = eps
     if iteration_limit is not None:
@@ -109,7 +116,7 @@ def workload_name(args):
 def config_dict(args, m, n, nnz):
     """`config` of the JSON line: the workload only, identical in both arms (ours / reference)."""
     return {"workload": workload_name(args), "rows": m, "cols": n, "nnz": nnz, "step": "one PDHG iteration (restart/termination work included)",
-            "params": "reference defaults; eps_optimal 0 in the resident leg, %g in the e2e solve" % args.eps,
+            "params": "reference defaults%s; eps_optimal 0 in the resident leg, %g in the e2e solve" % ("" if args.rule == "adaptive" else " except linesearch_rule=" + args.rule, args.eps),
             "l2": "inputs larger than L2 (two matrix images, %.0f MB, streamed every iteration; no flush needed)" % (2 * nnz * 12 / 1e6)}
 
 
@@ -466,9 +473,12 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU PDHG loop for the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--rule", default="adaptive", choices=["adaptive", "malitsky_pock", "constant"], help="step-size rule (A/B runs; the headline is the reference default)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 sub-record of a multi-GPU run")
     ap.add_argument("--c4-scale", type=float, default=1.0)
     args = ap.parse_args()
+    global RULE
+    RULE = args.rule
     args.warmup = max(3, args.warmup)
     if args.impl == "reference":
         if args.cpu_budget == 25.0:

@@ -763,7 +763,7 @@ __device__ void decide_update(StepState* st_dev, StepState s, double pow_reducti
     // kForceNumericalTermination: the loop is left without incrementing
     // inner_iterations, then num_rejected_steps_ += inner_iterations - 1.
     st->halt = movement == 0.0 ? kHaltZeroMovement : kHaltDivergent;
-    st->pending_ratio = 0.0;
+    st->pending_ratio = st->pending_ratio_dual = st->pending_ratio0 = 0.0;
     if (adaptive) st->num_rejected_steps += st->inner_iterations - 1;
     st->inner_iterations = 0;
     *st_dev = s;
@@ -790,6 +790,8 @@ __device__ void decide_update(StepState* st_dev, StepState s, double pow_reducti
     } else {
       st->pending_ratio = 0.0;
     }
+    st->pending_ratio_dual = st->pending_ratio;
+    st->pending_ratio0 = 0.0;
     st->avg_num_terms += 1;
     st->num_rejected_steps += st->inner_iterations;
     st->inner_iterations = 0;
@@ -798,7 +800,7 @@ __device__ void decide_update(StepState* st_dev, StepState s, double pow_reducti
     const double kkt = static_cast<double>(st->iterations_completed) + static_cast<double>(st->num_rejected_steps);
     if (st->iterations_completed >= st->k_stop || kkt >= st->kkt_pass_limit) st->halt = kHaltCheckpoint;
   } else {
-    st->pending_ratio = 0.0;
+    st->pending_ratio = st->pending_ratio_dual = st->pending_ratio0 = 0.0;
     st->step_size = new_eta;
     st->inner_iterations += 1;
     if (st->inner_iterations >= 60) {
@@ -964,17 +966,190 @@ __global__ void __launch_bounds__(kDecideThreads) k_sum_push_barrier(StepState* 
 // it unless the peer exchange slices the primal update).
 __global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t total, int64_t pbegin, int64_t pend) {
   StepState* st = b.state;
-  const double ratio = st->pending_ratio;
-  if (ratio <= 0.0) return;
+  const double r0 = st->pending_ratio0, r1 = st->pending_ratio, rd = st->pending_ratio_dual;
+  if (!(r0 > 0.0 || r1 > 0.0 || rd > 0.0)) return;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (i < b.n) {
-    if (i >= pbegin && i < pend) b.avg_x[i] += ratio * (pick3(b.x, st->cur)[i] - b.avg_x[i]);
+    if (i >= pbegin && i < pend) {
+      double av = b.avg_x[i];
+      if (r0 > 0.0) av += r0 * (pick3(b.x, st->prev)[i] - av);
+      if (r1 > 0.0) av += r1 * (pick3(b.x, st->cur)[i] - av);
+      b.avg_x[i] = av;
+    }
   } else if (i < total) {
     const int64_t j = i - b.n;
-    b.avg_y[j] += ratio * (pick3(b.y, st->cur)[j] - b.avg_y[j]);
+    if (rd > 0.0) b.avg_y[j] += rd * (pick3(b.y, st->cur)[j] - b.avg_y[j]);
   }
 }
-__global__ void k_clear_pending(StepState* st) { st->pending_ratio = 0.0; }
+__global__ void k_clear_pending(StepState* st) { st->pending_ratio = st->pending_ratio_dual = st->pending_ratio0 = 0.0; }
+
+// ---- Malitsky-Pock rule on the device (pdhg.cc:2463-2556) ---------------------------
+// One attempt = one inner iteration of the line search; the kernels of an attempt read state slot
+// `in`, k_mp_decide writes the other slot. x' and K x' are computed by the first attempt of an
+// iteration only (mp_skip_primal marks the retries).
+__global__ void __launch_bounds__(kThreads) k_mp_primal(StepPtrs b, double* partials) {
+  pdl_trigger();
+  pdl_wait();
+  const StepState* st = b.state;
+  if (st->halt != 0 || st->mp_skip_primal != 0) return;
+  const double* __restrict__ xc = pick3(b.x, st->cur);
+  const double* __restrict__ xp = pick3(b.x, st->prev);
+  double* __restrict__ xn = pick3(b.x, st->cand);
+  const double* __restrict__ kty = pick3(b.kty, st->cur);
+  const double tau = st->step_size / st->primal_weight;
+  const double r0 = st->pending_ratio0, r1 = st->pending_ratio;
+  double s = 0.0;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i < b.n) {
+    const double x = xc[i];
+    double t = x - tau * (b.c[i] - kty[i]);
+    if (b.q != nullptr) t = t / (tau * b.q[i] + 1.0);
+    const double nx = fmax(fmin(t, b.uv[i]), b.lv[i]);
+    xn[i] = nx;
+    const double d = nx - x;
+    s = d * d;
+    if (r0 > 0.0 || r1 > 0.0) {  // deferred ShardedWeightedAverage::Add of the accepted step (and of its starting point)
+      double av = b.avg_x[i];
+      if (r0 > 0.0) av += r0 * (xp[i] - av);
+      if (r1 > 0.0) av += r1 * (x - av);
+      b.avg_x[i] = av;
+    }
+  }
+  block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
+}
+struct KxStoreEpi {  // K x' of the candidate into kx[cand]
+  StepPtrs b;
+  struct Ctx { double* kx_cand; };
+  struct Pre {};
+  __device__ __forceinline__ Ctx begin() const { return Ctx{pick3(b.kx, b.state->cand)}; }
+  __device__ __forceinline__ Pre prefetch(const Ctx&, int64_t) const { return Pre(); }
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double v, double*, const Pre&) const { c.kx_cand[pos] = v; }
+};
+__global__ void __launch_bounds__(kThreads) k_mp_dual(StepPtrs b, double* partials) {  // pdhg.cc:1905-1910, 1923-1928 with the trial step
+  pdl_trigger();
+  pdl_wait();
+  const StepState* st = b.state;
+  if (st->halt != 0) return;
+  const double* __restrict__ yc = pick3(b.y, st->cur);
+  double* __restrict__ yn = pick3(b.y, st->cand);
+  const double* __restrict__ kxc = pick3(b.kx, st->cur);
+  const double* __restrict__ kxn = pick3(b.kx, st->cand);
+  const double omega = st->primal_weight;
+  const double tau = st->step_size / omega, new_tau = st->mp_new_tau;
+  const double theta = new_tau / tau;
+  const double sigma = (omega * omega) * new_tau;
+  const double rd = st->pending_ratio_dual;
+  double s = 0.0;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i < b.m) {
+    const double y = yc[i];
+    const double t = y - sigma * (-theta * kxc[i] + (theta + 1) * kxn[i]);
+    const double ny = fmax(fmin(0.0, t + sigma * b.uc[i]), t + sigma * b.lc[i]);
+    yn[i] = ny;
+    const double d = ny - y;
+    s = d * d;
+    if (rd > 0.0) b.avg_y[i] += rd * (y - b.avg_y[i]);
+  }
+  block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
+}
+struct KtyDiffEpi {  // K^T y' of the trial into kty[cand], ||K^T y - K^T y'||^2
+  StepPtrs b;
+  struct Ctx { const double* kty_cur; double* kty_cand; };
+  struct Pre { double kty; };
+  __device__ __forceinline__ Ctx begin() const { return Ctx{pick3(b.kty, b.state->cur), pick3(b.kty, b.state->cand)}; }
+  __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const { return Pre{c.kty_cur[pos]}; }
+  __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double v, double* red, const Pre& p) const {
+    c.kty_cand[pos] = v;
+    const double d = p.kty - v;
+    red[0] += d * d;
+  }
+};
+__global__ void __launch_bounds__(kDecideThreads) k_mp_decide(const StepState* in, StepState* out, const double* pp, int np, const double* pd, int nd, const double* pt, int nt) {
+  pdl_trigger();
+  pdl_wait();
+  StepState loaded;
+  if (threadIdx.x == 0) loaded = *in;
+  __shared__ double sh3[3][kDecideThreads / 32];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < np; i += kDecideThreads) s0 += pp[i];
+#pragma unroll 4
+  for (int i = threadIdx.x; i < nd; i += kDecideThreads) s1 += pd[i];
+#pragma unroll 8
+  for (int i = threadIdx.x; i < nt; i += kDecideThreads) s2 += pt[i];
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) {
+    sh3[0][threadIdx.x >> 5] = s0;
+    sh3[1][threadIdx.x >> 5] = s1;
+    sh3[2][threadIdx.x >> 5] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0 || loaded.halt != 0) return;
+  double dx2 = 0.0, dy2 = 0.0, dk2 = 0.0;
+  for (int w = 0; w < kDecideThreads / 32; ++w) { dx2 += sh3[0][w]; dy2 += sh3[1][w]; dk2 += sh3[2][w]; }
+  StepState s = loaded;
+  s.attempts += 1;
+  const double omega = s.primal_weight;
+  const double tau = s.step_size / omega, new_tau = s.mp_new_tau;
+  const double theta = new_tau / tau;
+  if (omega * new_tau * sqrt(dk2) <= s.mp_contraction * sqrt(dy2)) {
+    s.step_size = new_tau * omega;
+    s.mp_ratio = theta;
+    // averaging (pdhg.cc:2514-2532): the starting point enters an empty primal average first
+    s.pending_ratio0 = 0.0;
+    if (!(s.avg_weight_sum_primal > 0.0)) {
+      const double w0 = new_tau * theta;
+      if (w0 > 0.0) {
+        s.pending_ratio0 = 1.0;
+        s.avg_weight_sum_primal = w0;
+      }
+      s.avg_num_terms_primal += 1;
+    }
+    if (new_tau > 0.0) {
+      s.pending_ratio = new_tau / (s.avg_weight_sum_primal + new_tau);
+      s.avg_weight_sum_primal += new_tau;
+      s.pending_ratio_dual = new_tau / (s.avg_weight_sum + new_tau);
+      s.avg_weight_sum += new_tau;
+    } else {
+      s.pending_ratio = s.pending_ratio_dual = 0.0;
+    }
+    s.avg_num_terms_primal += 1;
+    s.avg_num_terms += 1;
+    const int old_prev = s.prev;
+    s.prev = s.cur;
+    s.cur = s.cand;
+    s.cand = old_prev;
+    const double movement = (0.5 * omega * dx2) + (0.5 / omega) * dy2;
+    s.last_dx2 = dx2;
+    s.last_dy2 = dy2;
+    s.last_movement = movement;
+    s.last_nonlinearity = 0.0;
+    s.num_rejected_steps += s.inner_iterations;
+    s.inner_iterations = 0;
+    if (movement == 0.0 || movement > 1.0e100) {
+      s.halt = movement == 0.0 ? kHaltZeroMovement : kHaltDivergent;  // (the host counts this iteration, as for the other rules)
+    } else {
+      s.iterations_completed += 1;
+      s.mp_new_tau = new_tau * (1.0 + s.mp_interpolation * (sqrt(1.0 + theta) - 1.0));
+      const double kkt = static_cast<double>(s.iterations_completed) + 0.5 * static_cast<double>(s.num_rejected_steps);
+      if (s.iterations_completed >= s.k_stop || kkt >= s.kkt_pass_limit) s.halt = kHaltCheckpoint;
+    }
+    s.mp_skip_primal = s.halt != 0 ? 1 : 0;
+  } else {
+    s.mp_new_tau = s.mp_downscaling * new_tau;
+    s.inner_iterations += 1;
+    s.pending_ratio = s.pending_ratio_dual = s.pending_ratio0 = 0.0;
+    s.mp_skip_primal = 1;
+    if (s.inner_iterations >= 60) {
+      s.halt = kHaltInnerLimit;
+      s.num_rejected_steps += s.inner_iterations;
+      s.inner_iterations = 0;
+    }
+  }
+  *out = s;
+}
 
 // ------------------------------------------------------ trust region -------
 __device__ __forceinline__ unsigned long long crit_key(double crit) {
@@ -2986,6 +3161,46 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       if (slot >= 0) ev(slot, 3);
     }
     if (slot >= 0) ev(slot, 4);
+  }
+  CUDA_OK(cudaGetLastError());
+}
+
+void Device::EnqueueMalitskyPockSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count, int first_slot) {
+  StepPtrs p = MakePtrs(b);
+  const bool pdl = StepPdl();
+  const int np = Blocks(b.n), nd = Blocks(b.m);
+  const int nt_main = SellGrid(cols);
+  const int nt_fix = cols.num_split > 0 ? static_cast<int>((cols.num_split * 32 + kThreads - 1) / kThreads) : 0;
+  const int64_t need = static_cast<int64_t>(np) + nd + nt_main + nt_fix + 8;
+  if (need > step_partials_size_) {
+    cudaFree(step_partials_);
+    step_partials_ = nullptr;
+    CUDA_OK(cudaMalloc(&step_partials_, sizeof(double) * need));
+    CUDA_OK(cudaMemset(step_partials_, 0, sizeof(double) * need));
+    step_partials_size_ = need;
+  }
+  double* pp = step_partials_;
+  double* pd = pp + np;
+  double* pt = pd + nd;
+  timing_attempt_idx_.clear();
+  for (int it = 0; it < count; ++it) {
+    StepState* st_in = b.state + ((first_slot + it) & 1);
+    StepState* st_out = b.state + ((first_slot + it + 1) & 1);
+    p.state = st_in;
+    if (b.n > 0) {
+      launch_k(pdl, k_mp_primal, np, kThreads, STREAM, p, pp);
+      ++launches_;
+      if (b.m > 0)  // K x' of the candidate, first attempt of an iteration only
+        launch_sell<kDot, 0>(STREAM, rows, GatherSrc{{b.x[0], b.x[1], b.x[2]}, st_in}, KxStoreEpi{p}, nullptr, &st_in->mp_skip_primal, &launches_, nullptr, nullptr, pdl);
+    }
+    if (b.m > 0) {
+      launch_k(pdl, k_mp_dual, nd, kThreads, STREAM, p, pd);
+      ++launches_;
+    }
+    if (b.n > 0) launch_sell<kDot, 1>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, KtyDiffEpi{p}, pt, &st_in->halt, &launches_, nullptr, nullptr, pdl);
+    launch_k(pdl, k_mp_decide, 1, kDecideThreads, STREAM, static_cast<const StepState*>(st_in), st_out, static_cast<const double*>(pp), b.n > 0 ? np : 0,
+             static_cast<const double*>(pd), b.m > 0 ? nd : 0, static_cast<const double*>(pt), b.n > 0 ? nt_main + nt_fix : 0);
+    ++launches_;
   }
   CUDA_OK(cudaGetLastError());
 }

@@ -101,6 +101,15 @@ struct StepState {
   // count `pow_total`: evaluated by the primal-step kernel, off the critical path of the decision
   // (two double-precision pow() in one thread are ~5 us). Ignored unless pow_total matches.
   double pow_reduction, pow_growth, pow_total;
+  // Malitsky-Pock rule on the device (pdhg.cc:2463-2556): one attempt = one inner iteration.
+  double mp_new_tau;                // trial primal step size of this attempt
+  double mp_ratio;                  // ratio_last_two_step_sizes_
+  double mp_interpolation, mp_downscaling, mp_contraction;
+  int32_t mp_skip_primal;           // != 0: a retry (x' and K x' of this iteration exist) or halted
+  int32_t avg_num_terms_primal;     // under Malitsky-Pock the primal average has its own weight / count
+  double avg_weight_sum_primal;     //   (the starting point enters it once after every restart)
+  double pending_ratio0;            // deferred update of the primal average with the PREVIOUS iterate (that entry)
+  double pending_ratio_dual;        // deferred update of the dual average (= pending_ratio under the other rules)
 };
 enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent = 3, kHaltInnerLimit = 4, kHaltPeerTimeout = 5 };
 
@@ -355,7 +364,10 @@ class Device {
   // whole again before restart / termination work reads it.
   void GatherPrimalSlices(const StepBuffers& b, int cur, int prev);
 
-  // Unfused pieces for the Malitsky-Pock rule (pdhg.cc:2463-2556).
+  // Device-resident Malitsky-Pock loop: `count` inner iterations (attempts), five launches each
+  // (x' once per iteration | K x' once | dual trial | K^T y' + ||K^T y - K^T y'||^2 | decision).
+  void EnqueueMalitskyPockSteps(const StepBuffers& b, const SellDev& rows, const SellDev& cols, int count, int first_slot);
+  // Unfused pieces for the Malitsky-Pock rule (pdhg.cc:2463-2556): row-sharded solves drive it from the host.
   void PrimalStep(const double* x, const double* kty, const double* c, const double* q, const double* lv, const double* uv,
                   double tau, double* x_next, int64_t n);
   void DualStepFromProducts(const double* y, const double* kx_cur, const double* kx_next, const double* lc, const double* uc,

@@ -1414,7 +1414,10 @@ int32_t SolveProto(std::string_view request, bool relax_integer_variables, const
   PdlpResult result;
   std::memset(&result, 0, sizeof result);
   const int32_t rc = pdlp_b200_primal_dual_hybrid_gradient(&model.view, &params, nullptr, 0, nullptr, 0, interrupt_solve, nullptr, nullptr, nullptr, &result);
-  if (rc != PDLP_B200_STATUS_OK) return rc;
+  if (rc != PDLP_B200_STATUS_OK) {
+    pdlp_b200_result_free(&result);  // (a failed solve may already own a termination string)
+    return rc;
+  }
   int status = kMpSolverNotSolved;
   switch (result.termination_reason) {
     case PDLP_TERMINATION_REASON_OPTIMAL: status = kMpSolverOptimal; break;
@@ -1628,6 +1631,7 @@ int32_t pdlp_b200_qp_to_mp_model_proto(const PdlpProblemView* qp, const char* co
                                        PdlpBlob* out, char* error, int64_t error_capacity) {
   return HostGuard(error, error_capacity, [&]() -> int32_t {
     if (qp == nullptr || out == nullptr) return BadArgument(error, error_capacity, "null argument");
+    if (const std::string bad = ValidateView(*qp); !bad.empty()) return BadArgument(error, error_capacity, bad);
     std::string wire, err;
     if (!QpToMpModelWire(*qp, variable_names, constraint_names, &wire, &err)) return BadArgument(error, error_capacity, err);
     return ToBlob(wire, out);
@@ -1638,6 +1642,7 @@ int32_t pdlp_b200_write_linear_program_to_mps(const PdlpProblemView* qp, const c
                                               const char* path, char* error, int64_t error_capacity) {
   return HostGuard(error, error_capacity, [&]() -> int32_t {
     if (qp == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
+    if (const std::string bad = ValidateView(*qp); !bad.empty()) return BadArgument(error, error_capacity, bad);
     std::string text, err;
     if (!LinearProgramToMps(*qp, variable_names, constraint_names, &text, &err) || !WriteFile(path, text, &err))
       return BadArgument(error, error_capacity, err);
@@ -1650,6 +1655,7 @@ int32_t pdlp_b200_write_quadratic_program_to_mp_model_proto(const PdlpProblemVie
                                                             int64_t error_capacity) {
   return HostGuard(error, error_capacity, [&]() -> int32_t {
     if (qp == nullptr || path == nullptr) return BadArgument(error, error_capacity, "null argument");
+    if (const std::string bad = ValidateView(*qp); !bad.empty()) return BadArgument(error, error_capacity, bad);
     std::string wire, err;
     if (!QpToMpModelWire(*qp, variable_names, constraint_names, &wire, &err) || !WriteFile(path, wire, &err))
       return BadArgument(error, error_capacity, err);

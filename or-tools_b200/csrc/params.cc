@@ -181,4 +181,30 @@ std::string ValidateParams(const PdlpParams& p) {  // :171-298
   return "";
 }
 
+// Structure of the caller's CSC view, shared by every entry point that walks the arrays on the
+// host (the format writers; the device path checks the same things while it builds the images):
+// consistent vector sizes, non-null arrays, col_starts[0] == 0, monotone col_starts,
+// col_starts[n] == num_nonzeros and 0 <= row < m.
+std::string ValidateView(const PdlpProblemView& v) {
+  const int64_t n = v.num_variables, m = v.num_constraints;
+  if (n < 0 || m < 0 || v.num_nonzeros < 0) return "negative dimension";
+  auto size_ok = [](int64_t given, int64_t want) { return given < 0 || given == want; };
+  if (!size_ok(v.variable_lower_bounds_size, n) || !size_ok(v.variable_upper_bounds_size, n) || !size_ok(v.objective_vector_size, n) ||
+      !size_ok(v.constraint_lower_bounds_size, m) || !size_ok(v.constraint_upper_bounds_size, m) ||
+      (v.objective_matrix_diagonal != nullptr && !size_ok(v.objective_matrix_size, n)))
+    return "Inconsistent dimensions: a vector of the problem view does not match the constraint matrix";
+  if (n > 0 && (v.variable_lower_bounds == nullptr || v.variable_upper_bounds == nullptr || v.objective_vector == nullptr)) return "null vector in the problem view";
+  if (m > 0 && (v.constraint_lower_bounds == nullptr || v.constraint_upper_bounds == nullptr)) return "null vector in the problem view";
+  if (v.col_starts == nullptr) return n == 0 && v.num_nonzeros == 0 ? "" : "col_starts is null";
+  if (v.col_starts[0] != 0) return "col_starts[0] is not 0";
+  for (int64_t c = 0; c < n; ++c)
+    if (v.col_starts[c + 1] < v.col_starts[c]) return "col_starts is not monotone";
+  if (v.col_starts[n] != v.num_nonzeros)
+    return "col_starts[n] = " + std::to_string(static_cast<long long>(v.col_starts[n])) + " differs from num_nonzeros = " + std::to_string(static_cast<long long>(v.num_nonzeros));
+  if (v.num_nonzeros > 0 && (v.row_indices == nullptr || v.values == nullptr)) return "null matrix array in the problem view";
+  for (int64_t k = 0; k < v.num_nonzeros; ++k)
+    if (v.row_indices[k] < 0 || v.row_indices[k] >= m) return "row index out of range";
+  return "";
+}
+
 }  // namespace pdlp_b200

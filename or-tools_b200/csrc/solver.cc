@@ -239,6 +239,7 @@ std::string ValidateDimensions(const PdlpProblemView& v) {  // quadratic_program
   if (con_lb != con_ub) return Fmt("Inconsistent dimensions: constraint lower bound vector has size %lld while constraint upper bound vector has size %lld", con_lb, con_ub);
   if (con_lb != m) return Fmt("Inconsistent dimensions: constraint lower bound vector has size %lld while constraint matrix has %lld rows ", con_lb, m);
   return "";
+
 }
 
 // ---- feasibility polishing helpers (pdhg.cc:2298-2358, 2684-2700, 2867-2886) ------------
@@ -426,6 +427,13 @@ class DeviceSolve {
   bool prev_slices_gathered_ = true;  // x[prev] is whole on every rank
   void EnsureDeltas() { if (delta_pending_) { MaterializeDeltas(); delta_pending_ = false; } }
   int NextCheckpoint(int k) const;
+  // Iterations between two polls of the time limit / interrupt flag (the reference polls every
+  // iteration): about 50 ms of measured iteration time, at least one and at most 32 iterations.
+  int PollStride() const {
+    if (iterations_completed_ <= 0 || !(device_time_sec_ > 0.0)) return 32;
+    const double seconds_per_iteration = device_time_sec_ / iterations_completed_;
+    return static_cast<int>(std::max(1.0, std::min(32.0, 0.05 / seconds_per_iteration)));
+  }
   Outcome RunDeviceSteps(int k, const volatile int32_t* interrupt);
   Outcome TakeMalitskyPockStep();
   void LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) const;
@@ -985,14 +993,15 @@ int DeviceSolve::NextCheckpoint(int k) const {
   if (params_.use_feasibility_polishing && iteration_type_ == PDLP_ITERATION_TYPE_NORMAL) consider(next_feasibility_polishing_iteration_);
   if (params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
     // artificial restart (pdhg.cc:2120-2130): first k' with terms + (k'-k) >= k'/2
-    const int terms = avg_x_terms_;
+    // (under Malitsky-Pock the first accepted step after a restart adds TWO terms to the primal average)
+    const int terms = avg_x_terms_ + (params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE && !PrimalAvgHasWeight() ? 1 : 0);
     for (int64_t j = 1;; ++j) {
       if (terms + j >= (static_cast<int64_t>(k) + j) / 2) { consider(static_cast<int64_t>(k) + j); break; }
       if (k + j >= best) break;
     }
   }
   // time limit / interrupt are polled at checkpoints: keep them close.
-  if (std::isfinite(tc.time_sec_limit)) consider(static_cast<int64_t>(k) + 32);
+  if (std::isfinite(tc.time_sec_limit)) consider(static_cast<int64_t>(k) + PollStride());
   return best;
 }
 
@@ -1003,12 +1012,23 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
   hs_.inner_iterations = 0;
   hs_.halt = kHaltNone;
   int k_stop = NextCheckpoint(k);
-  if (interrupt_polled_) k_stop = std::min(k_stop, k + 32);
+  if (interrupt_polled_) k_stop = std::min(k_stop, k + PollStride());
   hs_.k_stop = k_stop;
   hs_.kkt_pass_limit = params_.termination_criteria.kkt_matrix_pass_limit - work_from_feasibility_polishing_.cumulative_kkt_matrix_passes;
-  hs_.avg_weight_sum = avg_x_weight_;
-  hs_.avg_num_terms = avg_x_terms_;
-  hs_.pending_ratio = 0.0;
+  const bool mp = params_.linesearch_rule == PDLP_MALITSKY_POCK_LINESEARCH_RULE;
+  hs_.avg_weight_sum = mp ? avg_y_weight_ : avg_x_weight_;
+  hs_.avg_num_terms = mp ? avg_y_terms_ : avg_x_terms_;
+  hs_.avg_weight_sum_primal = avg_x_weight_;
+  hs_.avg_num_terms_primal = avg_x_terms_;
+  hs_.pending_ratio = hs_.pending_ratio_dual = hs_.pending_ratio0 = 0.0;
+  if (mp) {  // the trial step of the first attempt (pdhg.cc:2473-2480); later ones are set by the device decision
+    hs_.mp_ratio = ratio_last_two_step_sizes_;
+    hs_.mp_interpolation = params_.malitsky_pock_step_size_interpolation;
+    hs_.mp_downscaling = params_.malitsky_pock_step_size_downscaling_factor;
+    hs_.mp_contraction = params_.malitsky_pock_linesearch_contraction_factor;
+    hs_.mp_new_tau = (hs_.step_size / hs_.primal_weight) * (1.0 + hs_.mp_interpolation * (std::sqrt(1.0 + hs_.mp_ratio) - 1.0));
+    hs_.mp_skip_primal = 0;
+  }
   hs_.pow_total = -1.0;  // (nothing cached for this attempt count yet)
   PushState();
   WallTimer t;
@@ -1019,7 +1039,8 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
     const int64_t attempts_before = hs_.attempts;
     // exactly the attempts that reach the checkpoint if every step is accepted; rejected
     // steps (rare) are made up by another pass of this loop
-    D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining, 4096), state_slot_);
+    if (mp) D.EnqueueMalitskyPockSteps(buf_, P.rows(), P.cols(), std::min(remaining, 4096), state_slot_);
+    else D.EnqueueSteps(buf_, P.rows(), P.cols(), std::min(remaining, 4096), state_slot_);
     state_slot_ = D.DownloadLatestState(hs_, buf_.state, state_slot_);
     if (P.sharded() && D.comm() != nullptr) D.comm()->CheckAsyncError();
     D.CollectStepTimings(hs_.attempts - attempts_before);
@@ -1038,8 +1059,11 @@ DeviceSolve::Outcome DeviceSolve::RunDeviceSteps(int k, const volatile int32_t* 
   phase.Start();
   if (hs_.iterations_completed > k) delta_pending_ = true;
   phase_s_[5] += phase.Get();
-  avg_x_weight_ = avg_y_weight_ = hs_.avg_weight_sum;
-  avg_x_terms_ = avg_y_terms_ = hs_.avg_num_terms;
+  avg_y_weight_ = hs_.avg_weight_sum;
+  avg_y_terms_ = hs_.avg_num_terms;
+  avg_x_weight_ = mp ? hs_.avg_weight_sum_primal : hs_.avg_weight_sum;
+  avg_x_terms_ = mp ? hs_.avg_num_terms_primal : hs_.avg_num_terms;
+  if (mp) ratio_last_two_step_sizes_ = hs_.mp_ratio;
   num_rejected_steps_ = hs_.num_rejected_steps;
   iterations_completed_ = hs_.iterations_completed;
   if (hs_.halt == kHaltCheckpoint) return Outcome::kSuccessful;
@@ -1120,7 +1144,8 @@ DeviceSolve::Outcome DeviceSolve::TakeMalitskyPockStep() {
 std::optional<SolverResultCpp> DeviceSolve::Advance(int target_iterations, const volatile int32_t* interrupt_solve) {
   target_stop_ = target_iterations;
   interrupt_polled_ = D.MaxOverRanks(interrupt_solve != nullptr ? 1.0 : 0.0) != 0.0;
-  const bool device_loop = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE;
+  // (row-sharded Malitsky-Pock solves are still driven from the host, one synchronisation per inner step)
+  const bool device_loop = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE || !P.sharded();
   if (!nested_) D.TimelineStart(0);
   std::optional<SolverResultCpp> done;
   for (;;) {
@@ -1405,6 +1430,8 @@ std::optional<SolverResultCpp> ValidateInputs(const PdlpProblemView& view, const
   if (!perr.empty()) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "INVALID_ARGUMENT: " + perr, logger);
   const std::string derr = ValidateDimensions(view);
   if (!derr.empty()) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "INVALID_ARGUMENT: " + derr, logger);
+  if (view.num_variables > 0 && view.col_starts != nullptr && view.col_starts[view.num_variables] != view.num_nonzeros)
+    return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "INVALID_ARGUMENT: col_starts[num_variables] differs from num_nonzeros", logger);
   if (view.objective_scaling_factor == 0) return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM, "The objective scaling factor cannot be zero.", logger);
   if (params.use_feasibility_polishing && view.objective_matrix_diagonal != nullptr)
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PARAMETER, "use_feasibility_polishing is only implemented for linear programs.", logger);
@@ -1451,6 +1478,7 @@ struct SolveSession::Impl {
   std::unique_ptr<DeviceProblem> problem;
   std::unique_ptr<DeviceSolve> solve;
   std::optional<SolverResultCpp> finished;  // scaled-point result or input error
+  std::optional<SolverResultCpp> original;  // the result in the caller's space (built by the first Finish)
   bool input_error = false;
 };
 
@@ -1506,8 +1534,10 @@ SolverResultCpp SolveSession::Finish() {
     Advance(std::numeric_limits<int>::max(), &stop);
   }
   if (im.input_error) return *im.finished;
-  SolverResultCpp r = im.solve->ConstructOriginalSolverResult(*im.finished);
-  return r;
+  // Unscaling works in place on the device copy of the chosen point and fires the termination
+  // callback: done once, later calls return the same result.
+  if (!im.original.has_value()) im.original = im.solve->ConstructOriginalSolverResult(*im.finished);
+  return *im.original;
 }
 
 // ---- termination.h as host-only C entry points (no device needed): the scalar predicates the

@@ -65,6 +65,9 @@ using StatsCallback = std::function<void(const PdlpIterationCallbackInfo&)>;
 // params.cc
 void SetDefaultParams(PdlpParams* p);
 std::string ValidateParams(const PdlpParams& p);  // "" if valid, else the reference's message
+// "" if the CSC view is well-formed (dimensions, col_starts[0] == 0, monotone col_starts,
+// col_starts[n] == num_nonzeros, 0 <= row < m); every host-side walker of the arrays calls it first.
+std::string ValidateView(const PdlpProblemView& v);
 
 // PrimalDualHybridGradient (pdhg.cc:3107-3152) on the CUDA device. Throws
 // std::runtime_error only for CUDA / device failures; every solver-level

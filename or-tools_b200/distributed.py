@@ -79,8 +79,8 @@ class Context:
             self.h, C.byref(view), C.byref(pod), capi.ptr_f64(x0), C.c_int64(0 if x0 is None else x0.size),
             capi.ptr_f64(y0), C.c_int64(0 if y0 is None else y0.size), None, capi.MESSAGE_CALLBACK(), capi.STATS_CALLBACK(), None, C.byref(res))
         del keep
-        self.b._check(rc, "primal_dual_hybrid_gradient_distributed")
         try:
+            self.b._check(rc, "primal_dual_hybrid_gradient_distributed")
             return self.b._result_from_pod(res)
         finally:
             self.b.fn("result_free", None)(C.byref(res))

@@ -531,8 +531,8 @@ class Backend:
                    capi.ptr_f64(y0), C.c_int64(0 if y0 is None else y0.size),
                    flag_ptr, msg_cb, st_cb, None, C.byref(res))
         del keep
-        self._check(rc, "primal_dual_hybrid_gradient")
         try:
+            self._check(rc, "primal_dual_hybrid_gradient")
             if result_pod_consumer is not None:
                 result_pod_consumer(res)
             return self._result_from_pod(res)

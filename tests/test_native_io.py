@@ -652,3 +652,37 @@ def test_format_layer_survives_mutation_fuzzing(tmp_path):
     if p.returncode != 0 and ("cannot find -lasan" in p.stderr or "libasan" in p.stderr and "No such file" in p.stderr):
         pytest.skip("no sanitizer runtime in this toolchain")
     assert p.returncode == 0 and "fuzz ok: 4000 inputs" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+def test_writers_reject_a_malformed_view():
+    """The format writers walk the caller's CSC arrays on the host: a view whose row indices, column starts
+    or nonzero count are inconsistent is refused with BAD_ARGUMENT instead of being indexed."""
+    import ctypes as C
+    from ortools_b200 import _capi as capi
+    qp = fixtures.test_lp()
+    be = pdlp.backend()
+    blob = native_io.PdlpBlob()
+    err = C.create_string_buffer(256)
+    fn = be.fn("qp_to_mp_model_proto")
+
+    def call(mutate):
+        view, keep = qp._to_view()
+        mutate(view, keep)
+        rc = fn(C.byref(view), None, None, C.byref(blob), err, C.c_int64(256))
+        del keep
+        return rc
+
+    assert call(lambda v, k: None) == 0
+    be.fn("blob_free", None)(C.byref(blob))
+
+    def bad_row(v, k):
+        k["row_indices"][1] = v.num_constraints + 3
+    assert call(bad_row) != 0 and b"row index" in err.value
+
+    def bad_nnz(v, k):
+        v.num_nonzeros = v.num_nonzeros + 1
+    assert call(bad_nnz) != 0 and b"num_nonzeros" in err.value
+
+    def bad_starts(v, k):
+        k["col_starts"][1] = k["col_starts"][2] + 1
+    assert call(bad_starts) != 0 and b"monotone" in err.value
