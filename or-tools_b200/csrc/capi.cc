@@ -37,19 +37,13 @@ char* DupString(const std::string& s) {
   std::memcpy(p, s.c_str(), s.size() + 1);
   return p;
 }
-double* DupVec(const std::vector<double>& v) {
-  if (v.empty()) return nullptr;
-  double* p = static_cast<double*>(std::malloc(v.size() * sizeof(double)));
-  std::memcpy(p, v.data(), v.size() * sizeof(double));
-  return p;
-}
 void FillResult(SolverResultCpp&& r, PdlpResult* out) {
   std::memset(out, 0, sizeof(*out));
   out->primal_size = static_cast<int64_t>(r.primal_solution.size());
   out->dual_size = static_cast<int64_t>(r.dual_solution.size());
-  out->primal_solution = DupVec(r.primal_solution);
-  out->dual_solution = DupVec(r.dual_solution);
-  out->reduced_costs = DupVec(r.reduced_costs);
+  out->primal_solution = r.primal_solution.release();  // (malloc storage handed over, no copy)
+  out->dual_solution = r.dual_solution.release();
+  out->reduced_costs = r.reduced_costs.release();
   const SolveLogCpp& l = r.solve_log;
   out->instance_name = l.instance_name ? DupString(*l.instance_name) : nullptr;
   out->termination_reason = l.termination_reason;

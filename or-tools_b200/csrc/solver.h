@@ -2,7 +2,10 @@
 #ifndef PDLP_B200_SOLVER_H_
 #define PDLP_B200_SOLVER_H_
 
+#include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <new>
 #include <memory>
 #include <optional>
 #include <string>
@@ -45,8 +48,40 @@ struct SolveLogCpp {
   double device_iteration_time_sec = 0;
 };
 
+// A malloc-backed array of doubles whose storage can be handed to the C ABI result without a copy
+// (PdlpResult's arrays are released with free()); resize leaves the elements uninitialised (they
+// are the destination of a device->host copy).
+class HostVec {
+ public:
+  HostVec() = default;
+  HostVec(const HostVec& o) { assign(o.p_, o.n_); }
+  HostVec(HostVec&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  HostVec& operator=(const HostVec& o) { if (this != &o) assign(o.p_, o.n_); return *this; }
+  HostVec& operator=(HostVec&& o) noexcept { if (this != &o) { std::free(p_); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; } return *this; }
+  ~HostVec() { std::free(p_); }
+  void resize(size_t n) {
+    std::free(p_);
+    p_ = n > 0 ? static_cast<double*>(std::malloc(n * sizeof(double))) : nullptr;
+    if (n > 0 && p_ == nullptr) throw std::bad_alloc();
+    n_ = n;
+  }
+  double* data() { return p_; }
+  const double* data() const { return p_; }
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  double* release() { double* p = p_; p_ = nullptr; n_ = 0; return p; }  // the caller frees it with free()
+
+ private:
+  void assign(const double* p, size_t n) {
+    resize(n);
+    if (n > 0) std::memcpy(p_, p, n * sizeof(double));
+  }
+  double* p_ = nullptr;
+  size_t n_ = 0;
+};
+
 struct SolverResultCpp {
-  std::vector<double> primal_solution, dual_solution, reduced_costs;
+  HostVec primal_solution, dual_solution, reduced_costs;
   SolveLogCpp solve_log;
 };
 

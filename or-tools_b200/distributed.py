@@ -81,9 +81,10 @@ class Context:
         del keep
         try:
             self.b._check(rc, "primal_dual_hybrid_gradient_distributed")
-            return self.b._result_from_pod(res)
-        finally:
+        except BaseException:
             self.b.fn("result_free", None)(C.byref(res))
+            raise
+        return self.b._result_from_pod(res)  # (takes ownership of res)
 
     def session(self, qp, params):
         s = pdlp.SolveSession.__new__(pdlp.SolveSession)

@@ -464,6 +464,21 @@ def _cstr(ptr):
 
 
 # --------------------------------------------------------------------------
+class _ResultOwner:
+    """Frees a PdlpResult (result_free of the backend it came from) when the numpy views of its
+    solution vectors are gone."""
+
+    def __init__(self, backend, res):
+        self._free = backend.fn("result_free", None)
+        self._res = res
+
+    def __del__(self):
+        try:
+            self._free(C.byref(self._res))
+        except Exception:
+            pass
+
+
 # Backend: binds one shared library exporting the C ABI with a given prefix.
 # --------------------------------------------------------------------------
 class Backend:
@@ -535,14 +550,24 @@ class Backend:
             self._check(rc, "primal_dual_hybrid_gradient")
             if result_pod_consumer is not None:
                 result_pod_consumer(res)
-            return self._result_from_pod(res)
-        finally:
+        except BaseException:
             self.fn("result_free", None)(C.byref(res))
+            raise
+        return self._result_from_pod(res)  # (takes ownership of res)
 
     def _result_from_pod(self, res):
+        """SolverResult from the POD. The three solution vectors are NOT copied: they are numpy
+        views of the library's buffers, which are released (result_free) when the last of them is
+        garbage-collected -- the caller of this method must not free `res` itself."""
         out = SolverResult()
+        owner = _ResultOwner(self, res)
+
         def vec(p, n):
-            return np.ctypeslib.as_array(p, shape=(n,)).copy() if n > 0 and p else np.zeros(0)
+            if n <= 0 or not p:
+                return np.zeros(0)
+            buf = (C.c_double * n).from_address(C.addressof(p.contents))
+            buf._owner = owner  # the buffer object is the array's base: it keeps the owner alive
+            return np.frombuffer(buf, dtype=np.float64)
         out.primal_solution = vec(res.primal_solution, res.primal_size)
         out.dual_solution = vec(res.dual_solution, res.dual_size)
         out.reduced_costs = vec(res.reduced_costs, res.primal_size)
@@ -832,11 +857,12 @@ class SolveSession:
 
     def finish(self):
         res = capi.PdlpResult()
-        self.b._check(self.b.fn("session_finish")(self.h, C.byref(res)), "session_finish")
         try:
-            return self.b._result_from_pod(res)
-        finally:
+            self.b._check(self.b.fn("session_finish")(self.h, C.byref(res)), "session_finish")
+        except BaseException:
             self.b.fn("result_free", None)(C.byref(res))
+            raise
+        return self.b._result_from_pod(res)  # (takes ownership of res)
 
     def close(self):
         if self.h:
