@@ -311,11 +311,23 @@ __device__ void run_decide_head(const DecideHead& h);
 //      struct Pre; __device__ Pre prefetch(const Ctx&, int64_t pos) const  -- issues the
 //      epilogue's own loads before the gather loop so that they overlap it;
 //      __device__ void operator()(const Ctx&, int64_t pos, double acc, double* red, const Pre&) const
+// Work queue of a persistent launch (the step loop's SpMV pair): the grid is sized to what is
+// resident at once, every block takes tiles (= what a block of an ordinary launch would do, same
+// slot -> thread map, same per-tile partial sums: results do not depend on the schedule) from an
+// atomic counter until none is left, so no SM idles through a last partial wave. The counter is
+// zeroed by the OTHER kernel of the pair (which runs strictly before / after this one).
+struct TileQueue {
+  unsigned int* counter = nullptr;  // nullptr: ordinary launch, one tile per block
+  unsigned int* reset = nullptr;    // the other kernel's counter, zeroed by this launch
+  int num_tiles = 0;
+};
+
 template <int MODE, int NS, class Epi, int BT, int V>
 __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : V == 8 ? 896 : 1280) / BT)) k_sell(SellDev a, GatherSrc gs, Epi epi, double* partials, const int32_t* halt, int chunks,
-                                                                                              DecideHead head) {
+                                                                                              DecideHead head, TileQueue q) {
   pdl_trigger();
   pdl_wait();
+  if (q.reset != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *q.reset = 0u;
   if (halt != nullptr && *halt != 0) return;
   if (head.in != nullptr && blockIdx.x == 0) {
     // the launch has one extra block, the FIRST one scheduled, and it only takes the step decision
@@ -323,31 +335,39 @@ __global__ void __launch_bounds__(BT, ((V == 2 ? 768 : V == 1 ? 1024 : V == 8 ? 
     run_decide_head<BT>(head);
     return;
   }
-  const int64_t blk = static_cast<int64_t>(blockIdx.x) - (head.in != nullptr ? 1 : 0);
+  const int64_t first = static_cast<int64_t>(blockIdx.x) - (head.in != nullptr ? 1 : 0);
+  const int64_t workers = static_cast<int64_t>(gridDim.x) - (head.in != nullptr ? 1 : 0);
   const double* __restrict__ x = gs.st != nullptr ? pick3(gs.p, gs.st->cand) : gs.p[0];
-  double red[NS > 0 ? NS : 1];
-#pragma unroll
-  for (int k = 0; k < NS; ++k) red[k] = 0.0;
   const typename Epi::Ctx ctx = epi.begin();
-  // `chunks` consecutive groups of BT slots per block: fewer per-block partial
-  // sums for the decision kernel to add while the hardware block scheduler
-  // still balances the (window-sorted, hence uneven) rows; the slot -> thread
-  // map is fixed, so the partial sums stay deterministic.
-  for (int c = 0; c < chunks; ++c) {
-    const int64_t slot = (blk * chunks + c) * BT + threadIdx.x;
-    if (slot >= a.num_slots) break;
-    const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
-    const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
-    typename Epi::Pre pre;
-    if (own_row) pre = epi.prefetch(ctx, pos);
-    const double acc = sell_row<MODE, V>(a, slot, x);
-    if (slot < a.num_virtual_padded) {
-      a.virt_partial[slot] = acc;
-    } else if (own_row) {
-      epi(ctx, pos, acc, red, pre);
+  __shared__ int64_t s_next;
+  // `chunks` consecutive groups of BT slots per tile: the slot -> thread map is fixed, so the
+  // partial sums stay deterministic.
+  for (int64_t blk = first;;) {
+    if (q.counter != nullptr && threadIdx.x == 0) s_next = workers + atomicAdd(q.counter, 1u);  // (used after this tile: latency hidden)
+    double red[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) red[k] = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t slot = (blk * chunks + c) * BT + threadIdx.x;
+      if (slot >= a.num_slots) break;
+      const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
+      const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
+      typename Epi::Pre pre;
+      if (own_row) pre = epi.prefetch(ctx, pos);
+      const double acc = sell_row<MODE, V>(a, slot, x);
+      if (slot < a.num_virtual_padded) {
+        a.virt_partial[slot] = acc;
+      } else if (own_row) {
+        epi(ctx, pos, acc, red, pre);
+      }
     }
+    if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + blk * NS);
+    if (q.counter == nullptr) break;
+    __syncthreads();
+    blk = s_next;
+    __syncthreads();  // (every thread has read s_next before thread 0 overwrites it)
+    if (blk >= q.num_tiles) break;
   }
-  if (NS > 0) block_reduce_store<NS, 0, BT>(red, nullptr, partials + blk * NS);
 }
 
 // The same product with the value / index streams staged through shared memory
@@ -2045,6 +2065,8 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   CUDA_OK(cudaMalloc(&partials_, sizeof(double) * kMaxReduceBlocks * 40));
   CUDA_OK(cudaMalloc(&tr_peer_error_, 64));
   CUDA_OK(cudaMemset(tr_peer_error_, 0, 64));
+  CUDA_OK(cudaMalloc(&tile_counters_, 64));
+  CUDA_OK(cudaMemset(tile_counters_, 0, 64));
   CUDA_OK(cudaMalloc(&results_, sizeof(double) * 64));
   CUDA_OK(cudaMallocHost(&host_results_, sizeof(double) * 64));
 }
@@ -2053,6 +2075,7 @@ Device::~Device() {
   cudaSetDevice(device_);
   cudaFree(partials_);
   cudaFree(tr_peer_error_);
+  cudaFree(tile_counters_);
   cudaFree(results_);
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
@@ -2185,10 +2208,32 @@ int SellChunks() {
   }();
   return v;
 }
-// Blocks of a k_sell launch: one block per SellChunks() groups of SellThreads() slots.
-int SellGrid(const SellDev& a) {
-  const int64_t per_block = static_cast<int64_t>(SellThreads()) * SellChunks();
+// Tiles of a k_sell launch: one per `chunks` groups of SellThreads() slots (an ordinary launch has one block per tile).
+int SellGridFor(const SellDev& a, int chunks) {
+  const int64_t per_block = static_cast<int64_t>(SellThreads()) * chunks;
   return static_cast<int>(std::max<int64_t>(1, (a.num_slots + per_block - 1) / per_block));
+}
+int SellGrid(const SellDev& a) { return SellGridFor(a, SellChunks()); }
+// Step loop only: persistent SpMV launches with a tile queue (PDLP_B200_SELL_PERSIST=0 disables) and their groups per tile
+bool SellPersist() {
+  static const bool v = [] { const char* e = std::getenv("PDLP_B200_SELL_PERSIST"); return !(e != nullptr && e[0] == '0'); }();
+  return v;
+}
+int SellPersistChunks() {
+  static const int v = [] {
+    const char* e = std::getenv("PDLP_B200_SELL_PERSIST_CHUNKS");
+    const int c = (e != nullptr && *e != 0) ? std::atoi(e) : 1;
+    return std::max(1, std::min(64, c));
+  }();
+  return v;
+}
+int SmCount() {
+  static const int v = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+  }();
+  return v;
 }
 // Launch with (pdl) or without the programmatic-dependent-launch attribute.
 template <class... KArgs, class... Args>
@@ -2213,8 +2258,10 @@ bool StepPdl() {
 
 template <int MODE, int NS, class Epi>
 void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, double* partials, const int32_t* halt, int64_t* launches,
-                 int* main_blocks, int* fix_blocks, bool pdl = false, DecideHead head = DecideHead()) {
-  const int nb = SellGrid(a);
+                 int* main_blocks, int* fix_blocks, bool pdl = false, DecideHead head = DecideHead(), TileQueue queue = TileQueue(), int chunks = 0) {
+  if (chunks <= 0) chunks = SellChunks();
+  const int nb = SellGridFor(a, chunks);
+  queue.num_tiles = nb;
   // the dual kernel (two reductions, a 6-operand epilogue) is 4 % faster with 72 registers at 7 blocks
   // per SM than squeezed into 64 at 8; the store-only kernels prefer the 8 blocks (profiles/r02m_ab.txt)
   const int variant = (SellVariant() == 1 && NS == 2) ? 8 : SellVariant();
@@ -2224,7 +2271,16 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
   // staging is taken from the L1 that tracks the outstanding gather misses, so the stages are small
   // and the carve-out is pinned to what the resident blocks need.
   const int grid = nb + (head.in != nullptr ? 1 : 0);  // (+ the block that only takes the step decision)
-#define PDLP_SELL_LAUNCH(BT, V) launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, grid, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail)
+#define PDLP_SELL_LAUNCH(BT, V)                                                                                                       \
+  do {                                                                                                                                \
+    int g__ = grid;                                                                                                                   \
+    if (queue.counter != nullptr) {  /* persistent: as many workers as are resident at once (+ the decision block) */                 \
+      int per_sm__ = 0;                                                                                                               \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm__, k_sell<MODE, NS, Epi, BT, V>, BT, 0);                                  \
+      g__ = std::min(nb, std::max(1, per_sm__) * SmCount()) + (head.in != nullptr ? 1 : 0);                                           \
+    }                                                                                                                                 \
+    launch_k(pdl, k_sell<MODE, NS, Epi, BT, V>, g__, BT, stream, a, x, epi, partials, halt, chunks, main_tail, queue);                \
+  } while (0)
 #define PDLP_SELL_LAUNCH_T(BT, U, NST)                                                                                              \
   do {                                                                                                                              \
     static bool carved = false;                                                                                                     \
@@ -2233,7 +2289,7 @@ void launch_sell(cudaStream_t stream, const SellDev& a, GatherSrc x, Epi epi, do
       if (const int pct = SellCarveout(); pct >= 0)                                                                                 \
         cudaFuncSetAttribute(k_sell_tma<MODE, NS, Epi, BT, U, NST>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);          \
     }                                                                                                                               \
-    launch_k(pdl, k_sell_tma<MODE, NS, Epi, BT, U, NST>, grid, BT, stream, a, x, epi, partials, halt, SellChunks(), main_tail);     \
+    launch_k(pdl, k_sell_tma<MODE, NS, Epi, BT, U, NST>, grid, BT, stream, a, x, epi, partials, halt, chunks, main_tail);           \
   } while (0)
 #define PDLP_SELL_LAUNCH_V(BT)                                 \
   do {                                                         \
@@ -3040,7 +3096,18 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const PeerPtrs peer = MakePeerPtrs(b);
   const int64_t primal_work = use_peer ? b.slice_end - b.slice_begin : b.n;
   const int np = static_cast<int>(std::max<int64_t>(1, ((primal_work + 1) / 2 + kThreads - 1) / kThreads));
-  const int nd_main = SellGrid(rows);
+  // one GPU: the SpMV pair runs as persistent launches with a tile queue (no partial last wave)
+  const bool persist = SellPersist() && !use_peer && comm_ == nullptr && SellVariant() < 3;
+  const int pair_chunks = persist ? SellPersistChunks() : SellChunks();
+  TileQueue q_dual, q_kty;
+  if (persist) {
+    q_dual.counter = tile_counters_;
+    q_dual.reset = tile_counters_ + 1;
+    q_kty.counter = tile_counters_ + 1;
+    q_kty.reset = tile_counters_;
+    CUDA_OK(cudaMemsetAsync(tile_counters_, 0, 2 * sizeof(unsigned int), STREAM));
+  }
+  const int nd_main = SellGridFor(rows, pair_chunks);
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int nd = b.m > 0 ? nd_main + nd_fix : 0;
   const int64_t need = static_cast<int64_t>(np) + 2 * static_cast<int64_t>(nd_main + nd_fix) + 8;
@@ -3134,7 +3201,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
     ++launches_;
     if (slot >= 0) ev(slot, 1);
     if (b.m > 0) {
-      launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
+      launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{b.x_tilde, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl, DecideHead(), q_dual, pair_chunks);
     }
     if (slot >= 0) ev(slot, 2);
     if (comm_ != nullptr) {
@@ -3153,7 +3220,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       if (slot >= 0) ev(slot, 3);
     } else if (b.n > 0) {
       // three launches per attempt: block 0 of the K^T y' kernel takes the decision while the others stream the matrix
-      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, KtyEpi{p}, nullptr, halt, &launches_, nullptr, nullptr, pdl, head);
+      launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, KtyEpi{p}, nullptr, halt, &launches_, nullptr, nullptr, pdl, head, q_kty, pair_chunks);
       if (slot >= 0) ev(slot, 3);
     } else {
       launch_k(pdl, k_decide_only, 1, kThreads, STREAM, head);

@@ -386,6 +386,7 @@ class Device {
   const PeerArena* peer_arena_ = nullptr;
   int64_t peer_arena_n_ = 0, peer_arena_m_ = 0;
   int32_t* tr_peer_error_ = nullptr;  // device flag: a peer did not arrive at a barrier of the trust-region search
+  unsigned int* tile_counters_ = nullptr;  // tile queues of the persistent SpMV pair of the step loop (one per kernel)
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)
   double* tr_scratch_ = nullptr;

@@ -35,12 +35,20 @@ for stage in "$@"; do
     sanitize)
       timeout 1500 tools/sanitize.sh > $OUT/${TAG}_sanitize.log 2>&1; echo "sanitize rc=$?"; grep -E "^===|ERROR SUMMARY|RACECHECK SUMMARY" $OUT/${TAG}_sanitize.log ;;
     ncu-full)
-      # warm-up launches (problem build, rescaling, first iterations) are skipped so only live step launches are captured
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell|k_primal_step|k_step_decide' -s 60 -c 12 \
-        -o $OUT/${TAG}_step -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_step.log 2>&1; echo "ncu step rc=$?"
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_tr_' -s 4 -c 4 \
-        -o $OUT/${TAG}_tr -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_tr.log 2>&1; echo "ncu tr rc=$?"
-      ls -la $OUT/${TAG}_step.ncu-rep $OUT/${TAG}_tr.ncu-rep ;;
+      # warm-up launches (problem build, rescaling, first iterations) are skipped so only live step launches are captured;
+      # the reports are summarised ON THE BOX (gpurun_out is capped at 64 MiB) and only the CSVs travel back
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell|k_primal_step' -s 60 -c 9 \
+        -o /tmp/${TAG}_step -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_step.log 2>&1; echo "ncu step rc=$?"
+      python tools/ncu_summary.py /tmp/${TAG}_step.ncu-rep $OUT/${TAG}_ncu_full_step_c2.csv --traffic-out $OUT/${TAG}_traffic.json c2
+      ncu -i /tmp/${TAG}_step.ncu-rep --page source --csv --kernel-name regex:DualEpi 2>/dev/null | head -700 > $OUT/${TAG}_ncu_source_dualepi.csv
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_tr_' -s 4 -c 2 \
+        -o /tmp/${TAG}_tr -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_tr.log 2>&1; echo "ncu tr rc=$?"
+      python tools/ncu_summary.py /tmp/${TAG}_tr.ncu-rep $OUT/${TAG}_ncu_full_tr_c2.csv
+      # the TMA-staged variant of the same step kernels, for the counter comparison
+      PDLP_B200_SELL_VARIANT=5 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell_tma' -s 60 -c 6 \
+        -o /tmp/${TAG}_step_tma -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_step_tma.log 2>&1; echo "ncu tma rc=$?"
+      python tools/ncu_summary.py /tmp/${TAG}_step_tma.ncu-rep $OUT/${TAG}_ncu_full_step_tma_c2.csv
+      ls -la $OUT/${TAG}_ncu_full_*.csv ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $OUT/${TAG}_launches_raw.csv \
         python bench.py --steps 130 --warmup 3 --no-e2e --no-cpu > $OUT/${TAG}_launches.log 2>&1; echo "launch list rc=$?"

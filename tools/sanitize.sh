@@ -3,7 +3,8 @@
 # detection"): memcheck, racecheck (shared-memory hazards in the block reductions, the trust-region
 # bins, the radix sort of the device builder), initcheck and synccheck. Run on a GPU box:
 #   gpurun --timeout 900 -- 'tools/sanitize.sh > gpurun_out/sanitize.log 2>&1'
-# Each pass solves TestLp / TinyLp / a 2000 x 4000 random LP through the C ABI, builds the SELL pair on
+# Each pass solves TestLp / TinyLp / a diagonal QP / a 2000 x 4000 random LP (adaptive and Malitsky-Pock
+# rules; restarts, i.e. the persistent trust-region kernel, included) through the C ABI, builds the SELL pair on
 # the device and runs the kernel-level entry points; the summaries go to profiles/ by hand.
 set -u
 cd "$(dirname "$0")/.."
@@ -36,6 +37,11 @@ qp.objective_vector = rng.uniform(0, 1, n)
 p.termination_criteria.iteration_limit = 192
 r = be.primal_dual_hybrid_gradient(qp, p)
 print("random", pdlp.TerminationReason.Name(r.solve_log.termination_reason), r.solve_log.iteration_count, flush=True)
+p.linesearch_rule = p.MALITSKY_POCK_LINESEARCH_RULE   # the device-resident Malitsky-Pock loop
+p.termination_criteria.iteration_limit = 96
+r = be.primal_dual_hybrid_gradient(qp, p)
+print("random, Malitsky-Pock", pdlp.TerminationReason.Name(r.solve_log.termination_reason), r.solve_log.iteration_count, flush=True)
+p.linesearch_rule = p.ADAPTIVE_LINESEARCH_RULE
 prob = be.problem(qp)
 prob.matrix_vector_product(rng.normal(size=n)); prob.transposed_matrix_vector_product(rng.normal(size=m))
 print(prob.compute_stats().constraint_matrix_num_nonzeros, flush=True)
@@ -46,6 +52,14 @@ for tool in memcheck racecheck initcheck synccheck; do
   timeout 600 "$SAN" --tool "$tool" --error-exitcode 9 --print-limit 20 "$PY" -c "$SCRIPT" 2>&1 | grep -v "^$" | tail -40
   rc=${PIPESTATUS[0]}
   echo "=== $tool exit code $rc"
+  [ "$rc" -ne 0 ] && status=1
+done
+# the TMA-staged SELL variant (cp.async.bulk + mbarrier), memcheck + racecheck only
+for tool in memcheck racecheck; do
+  echo "=== compute-sanitizer --tool $tool (PDLP_B200_SELL_VARIANT=5, TMA staging)"
+  PDLP_B200_SELL_VARIANT=5 timeout 600 "$SAN" --tool "$tool" --error-exitcode 9 --print-limit 20 "$PY" -c "$SCRIPT" 2>&1 | grep -v "^$" | tail -12
+  rc=${PIPESTATUS[0]}
+  echo "=== $tool (TMA variant) exit code $rc"
   [ "$rc" -ne 0 ] && status=1
 done
 exit $status
