@@ -2214,9 +2214,12 @@ int SellGridFor(const SellDev& a, int chunks) {
   return static_cast<int>(std::max<int64_t>(1, (a.num_slots + per_block - 1) / per_block));
 }
 int SellGrid(const SellDev& a) { return SellGridFor(a, SellChunks()); }
-// Step loop only: persistent SpMV launches with a tile queue (PDLP_B200_SELL_PERSIST=0 disables) and their groups per tile
+// Step loop only: persistent SpMV launches with a tile queue (PDLP_B200_SELL_PERSIST=1) and their groups per tile.
+// Off by default: measured equal to the ordinary launches (220.3 vs 220.5 us per iteration on C2,
+// profiles/r02s_ab_persistent.txt) -- the hardware block scheduler plus programmatic dependent launch
+// already keep the SMs fed through the last wave; the kernels are bound by the gather request rate.
 bool SellPersist() {
-  static const bool v = [] { const char* e = std::getenv("PDLP_B200_SELL_PERSIST"); return !(e != nullptr && e[0] == '0'); }();
+  static const bool v = [] { const char* e = std::getenv("PDLP_B200_SELL_PERSIST"); return e != nullptr && e[0] == '1'; }();
   return v;
 }
 int SellPersistChunks() {
