@@ -213,9 +213,16 @@ __global__ void __launch_bounds__(kT) k_virtual_counts(int64_t num_split, const 
   const int64_t i = gtid();
   if (i < num_split) nv[i] = (len[row_of_pos[i]] + split_len - 1) / split_len;
 }
+// Virtual slots of a split row are filled in TEAMS: the slots of the row that share a 32-slot slice
+// take the elements of their common range round-robin (member k of a team of t gets elements
+// e0 + k, e0 + k + t, ...), so that at every step of the row loop the lanes of the team read
+// CONSECUTIVE entries of the row -- for a row whose columns are contiguous (transportation /
+// multicommodity structure) the gathers of x coalesce into two 128-byte lines per warp instead of
+// 32 sectors. slot_off = first element, slot_stride = t.
 __global__ void __launch_bounds__(kT) k_virtual_slots(int64_t num_virtual, int64_t num_split, const int64_t* __restrict__ split_first64, const int32_t* __restrict__ row_of_pos,
                                                       const int64_t* __restrict__ len, int64_t split_len, int32_t* __restrict__ slot_len,
-                                                      int32_t* __restrict__ slot_row, int64_t* __restrict__ slot_off, int32_t* __restrict__ virt_pos) {
+                                                      int32_t* __restrict__ slot_row, int64_t* __restrict__ slot_off, int32_t* __restrict__ slot_stride,
+                                                      int32_t* __restrict__ virt_pos, int teams) {
   const int64_t v = gtid();
   if (v >= num_virtual) return;
   int64_t lo = 0, hi = num_split;  // last i with split_first[i] <= v
@@ -224,10 +231,16 @@ __global__ void __launch_bounds__(kT) k_virtual_slots(int64_t num_virtual, int64
     if (split_first64[mid] <= v) lo = mid; else hi = mid;
   }
   const int32_t row = row_of_pos[lo];
-  const int64_t off = (v - split_first64[lo]) * split_len;
-  slot_len[v] = static_cast<int32_t>(min(split_len, len[row] - off));
+  const int64_t first = split_first64[lo], last = split_first64[lo + 1];  // the row's slots [first, last)
+  // its team inside this slice (teams == 0, PDLP_B200_TEAM_SLOTS=0: every slot alone, entries [k T, (k + 1) T) of the row)
+  const int64_t ts = teams ? max(first, (v >> 5) << 5) : v, te = teams ? min(last, ((v >> 5) + 1) << 5) : v + 1;
+  const int64_t t = te - ts, k = v - ts;
+  const int64_t e0 = (ts - first) * split_len, e1 = min(len[row], (te - first) * split_len);
+  const int64_t team_len = e1 - e0;
+  slot_len[v] = team_len > k ? static_cast<int32_t>((team_len - k + t - 1) / t) : 0;
   slot_row[v] = row;
-  slot_off[v] = off;
+  slot_off[v] = e0 + k;
+  slot_stride[v] = static_cast<int32_t>(t);
   virt_pos[v] = static_cast<int32_t>(lo);
 }
 __global__ void __launch_bounds__(kT) k_plain_slots(int64_t rows, int64_t num_split, int64_t nvp, const int32_t* __restrict__ row_of_pos, const int64_t* __restrict__ len,
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(kT) k_iota(int64_t n, int32_t* p) {
 // is the other orientation's original index of an entry and `other_pos` its
 // position map (nullptr = keep original indices).
 __global__ void __launch_bounds__(kT) k_fill_sell(int64_t num_slots, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ slot_len,
-                                                  const int32_t* __restrict__ slot_row, const int64_t* __restrict__ slot_off,
+                                                  const int32_t* __restrict__ slot_row, const int64_t* __restrict__ slot_off, const int32_t* __restrict__ slot_stride,
                                                   const int64_t* __restrict__ row_start, const int32_t* __restrict__ order,
                                                   const int32_t* __restrict__ idx_of_entry, const double* __restrict__ cval,
                                                   const int32_t* __restrict__ other_pos, int32_t* __restrict__ col, double* __restrict__ val) {
@@ -330,9 +343,10 @@ __global__ void __launch_bounds__(kT) k_fill_sell(int64_t num_slots, const int64
   if (row < 0) return;
   const int64_t base = slice_ptr[slot >> 5] + (slot & 31);
   const int64_t src0 = row_start[row] + slot_off[slot];
+  const int64_t stride = slot_stride[slot];
   const int len = slot_len[slot];
   for (int j = 0; j < len; ++j) {
-    const int64_t e = order != nullptr ? order[src0 + j] : src0 + j;
+    const int64_t e = order != nullptr ? order[src0 + j * stride] : src0 + j * stride;
     const int32_t other = idx_of_entry[e];
     col[base + static_cast<int64_t>(j) * 32] = other_pos != nullptr ? other_pos[other] : other;
     val[base + static_cast<int64_t>(j) * 32] = cval[e];
@@ -341,7 +355,7 @@ __global__ void __launch_bounds__(kT) k_fill_sell(int64_t num_slots, const int64
 
 // values of the column copy back into the caller's CSC order
 __global__ void __launch_bounds__(kT) k_unfill_values(int64_t num_slots, const int64_t* __restrict__ slice_ptr, const int32_t* __restrict__ slot_len,
-                                                      const int32_t* __restrict__ slot_row, const int64_t* __restrict__ slot_off,
+                                                      const int32_t* __restrict__ slot_row, const int64_t* __restrict__ slot_off, const int32_t* __restrict__ slot_stride,
                                                       const int64_t* __restrict__ row_start, const double* __restrict__ val, double* __restrict__ out) {
   const int64_t slot = gtid();
   if (slot >= num_slots) return;
@@ -349,8 +363,9 @@ __global__ void __launch_bounds__(kT) k_unfill_values(int64_t num_slots, const i
   if (row < 0) return;
   const int64_t base = slice_ptr[slot >> 5] + (slot & 31);
   const int64_t dst0 = row_start[row] + slot_off[slot];
+  const int64_t stride = slot_stride[slot];
   const int len = slot_len[slot];
-  for (int j = 0; j < len; ++j) out[dst0 + j] = val[base + static_cast<int64_t>(j) * 32];
+  for (int j = 0; j < len; ++j) out[dst0 + j * stride] = val[base + static_cast<int64_t>(j) * 32];
 }
 
 }  // namespace build_kernels
@@ -460,6 +475,7 @@ struct Orientation {
   int32_t* pos_of_row = nullptr;  // temp (needed by the other orientation's fill)
   int32_t* slot_row = nullptr;    // persistent only for the column copy
   int64_t* slot_off = nullptr;
+  int32_t* slot_stride = nullptr;  // 1, or the team size of a virtual slot (k_virtual_slots)
 };
 
 void BuildOrientation(cudaStream_t stream, Scanner& scan, Temps& tmp, int64_t rows, int64_t gathered_len, const int64_t* len, int32_t split_len, int sigma,
@@ -508,14 +524,16 @@ void BuildOrientation(cudaStream_t stream, Scanner& scan, Temps& tmp, int64_t ro
   CUDA_OK(cudaMalloc(&out->virt_partial, sizeof(double) * (nvp + 32)));
   o->slot_row = DevAlloc<int32_t>(num_slots);
   o->slot_off = DevAlloc<int64_t>(num_slots);
+  o->slot_stride = DevAlloc<int32_t>(num_slots);
   CUDA_OK(cudaMemsetAsync(out->slot_len, 0, sizeof(int32_t) * std::max<int64_t>(num_slots, 1), stream));
   CUDA_OK(cudaMemsetAsync(o->slot_off, 0, sizeof(int64_t) * std::max<int64_t>(num_slots, 1), stream));
   if (num_slots > 0) k_fill_i32<<<Blk(num_slots), kT, 0, stream>>>(num_slots, o->slot_row, -1);
+  if (num_slots > 0) k_fill_i32<<<Blk(num_slots), kT, 0, stream>>>(num_slots, o->slot_stride, 1);
   if (nvp > 0) k_fill_i32<<<Blk(nvp), kT, 0, stream>>>(nvp, out->virt_pos, -1);
   k_narrow_i32<<<Blk(num_split + 1), kT, 0, stream>>>(num_split + 1, split_first64, out->split_first);
   if (num_virtual > 0)
     k_virtual_slots<<<Blk(num_virtual), kT, 0, stream>>>(num_virtual, num_split, split_first64, o->row_of_pos, len, split_len, out->slot_len, o->slot_row, o->slot_off,
-                                                         out->virt_pos);
+                                                         o->slot_stride, out->virt_pos, EnvIntB("PDLP_B200_TEAM_SLOTS", 1) != 0 ? 1 : 0);
   if (rows - num_split > 0)
     k_plain_slots<<<Blk(rows - num_split), kT, 0, stream>>>(rows, num_split, nvp, o->row_of_pos, len, out->slot_len, o->slot_row, o->slot_off);
   *launches += 5;
@@ -643,10 +661,10 @@ void Device::BuildSellPair(const PdlpProblemView& v, int64_t row_begin, int64_t 
   }
   // ---- fill both images
   if (rows_out->num_slots > 0)
-    k_fill_sell<<<Blk(rows_out->num_slots), kT, 0, stream>>>(rows_out->num_slots, rows_out->slice_ptr, rows_out->slot_len, orow.slot_row, orow.slot_off, row_start, order,
+    k_fill_sell<<<Blk(rows_out->num_slots), kT, 0, stream>>>(rows_out->num_slots, rows_out->slice_ptr, rows_out->slot_len, orow.slot_row, orow.slot_off, orow.slot_stride, row_start, order,
                                                              ecol, cval, natural_primal_order ? nullptr : ocol.pos_of_row, rows_out->col, rows_out->val);
   if (cols_out->num_slots > 0)
-    k_fill_sell<<<Blk(cols_out->num_slots), kT, 0, stream>>>(cols_out->num_slots, cols_out->slice_ptr, cols_out->slot_len, ocol.slot_row, ocol.slot_off, kt_start, nullptr,
+    k_fill_sell<<<Blk(cols_out->num_slots), kT, 0, stream>>>(cols_out->num_slots, cols_out->slice_ptr, cols_out->slot_len, ocol.slot_row, ocol.slot_off, ocol.slot_stride, kt_start, nullptr,
                                                              key, cval, orow.pos_of_row, cols_out->col, cols_out->val);
   launches_ += 2;
   CUDA_OK(cudaGetLastError());
@@ -655,6 +673,7 @@ void Device::BuildSellPair(const PdlpProblemView& v, int64_t row_begin, int64_t 
     std::fprintf(stderr, "[pdlp_b200 trace] SELL build: device passes %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_build0).count());
   cudaFree(orow.slot_row);
   cudaFree(orow.slot_off);
+  cudaFree(orow.slot_stride);
   *dual_perm = orow.row_of_pos;
   *primal_perm = ocol.row_of_pos;
   info->n = n;
@@ -662,6 +681,7 @@ void Device::BuildSellPair(const PdlpProblemView& v, int64_t row_begin, int64_t 
   info->nnz = nnz;
   info->col_slot_row = ocol.slot_row;
   info->col_slot_off = ocol.slot_off;
+  info->col_slot_stride = ocol.slot_stride;
   info->col_start = kt_start;
 }
 
@@ -718,7 +738,7 @@ void Device::BuildColumnSliceImage(const PdlpProblemView& v, int64_t col_begin, 
   Orientation ocol;
   BuildOrientation(stream, scan, tmp, n, m_full, col_len, ChooseSplitLenDev(total), sigma, out, &ocol, &launches_);
   if (out->num_slots > 0) {
-    k_fill_sell<<<Blk(out->num_slots), kT, 0, stream>>>(out->num_slots, out->slice_ptr, out->slot_len, ocol.slot_row, ocol.slot_off, kt_start, nullptr, key, cval,
+    k_fill_sell<<<Blk(out->num_slots), kT, 0, stream>>>(out->num_slots, out->slice_ptr, out->slot_len, ocol.slot_row, ocol.slot_off, ocol.slot_stride, kt_start, nullptr, key, cval,
                                                         row_pos_global, out->col, out->val);
     launches_ += 1;
   }
@@ -726,12 +746,14 @@ void Device::BuildColumnSliceImage(const PdlpProblemView& v, int64_t col_begin, 
   CUDA_OK(cudaStreamSynchronize(stream));
   cudaFree(ocol.slot_row);
   cudaFree(ocol.slot_off);
+  cudaFree(ocol.slot_stride);
   *row_of_pos_out = ocol.row_of_pos;
 }
 
 void Device::FreeBuildInfo(DeviceBuildInfo& info) {
   cudaFree(info.col_slot_row);
   cudaFree(info.col_slot_off);
+  cudaFree(info.col_slot_stride);
   cudaFree(info.col_start);
   info = DeviceBuildInfo();
 }
@@ -740,7 +762,7 @@ void Device::DownloadValuesCscFromSell(const SellDev& cols, const DeviceBuildInf
   if (info.nnz <= 0) return;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   double* out = DevAlloc<double>(info.nnz);
-  k_unfill_values<<<Blk(cols.num_slots), kT, 0, stream>>>(cols.num_slots, cols.slice_ptr, cols.slot_len, info.col_slot_row, info.col_slot_off, info.col_start, cols.val, out);
+  k_unfill_values<<<Blk(cols.num_slots), kT, 0, stream>>>(cols.num_slots, cols.slice_ptr, cols.slot_len, info.col_slot_row, info.col_slot_off, info.col_slot_stride, info.col_start, cols.val, out);
   ++launches_;
   CUDA_OK(cudaMemcpyAsync(values_host, out, sizeof(double) * info.nnz, cudaMemcpyDeviceToHost, stream));
   CUDA_OK(cudaStreamSynchronize(stream));

@@ -143,7 +143,8 @@ struct PeerLayout {
 struct DeviceBuildInfo {
   int64_t n = 0, m = 0, nnz = 0;
   int32_t* col_slot_row = nullptr;  // [cols.num_slots] original column of a slot (-1 = padding)
-  int64_t* col_slot_off = nullptr;  // [cols.num_slots] offset of the slot inside its column
+  int64_t* col_slot_off = nullptr;  // [cols.num_slots] first element of the slot inside its column
+  int32_t* col_slot_stride = nullptr;  // [cols.num_slots] distance between consecutive elements of the slot (team size of a virtual slot, else 1)
   int64_t* col_start = nullptr;     // [n + 1] starts of the (row-block) columns in CSC order
 };
 

@@ -430,10 +430,15 @@ void DeviceProblem::DownloadValuesCsc(double* values) {
     const int32_t col = s.row_of_pos[pos];
     const int64_t dst = col_starts_[col];
     if (pos < s.num_split) {
-      int64_t off = 0;
-      for (int32_t v = s.split_first[pos]; v < s.split_first[pos + 1]; ++v, off += T) {
+      // virtual slots are filled in teams (sell_builder.cc FillSell): member k of a team of t holds entries e0 + k + t j
+      const int64_t first = s.split_first[pos], last = s.split_first[pos + 1];
+      for (int64_t v = first; v < last; ++v) {
+        const char* team_env = std::getenv("PDLP_B200_TEAM_SLOTS");
+        const bool teams = !(team_env != nullptr && team_env[0] == '0');
+        const int64_t ts = teams ? std::max<int64_t>(first, (v >> 5) << 5) : v, te = teams ? std::min<int64_t>(last, ((v >> 5) + 1) << 5) : v + 1;
+        const int64_t t = te - ts, k = v - ts, e0 = (ts - first) * T;
         const int64_t base = s.slice_ptr[v >> 5] + (v & 31);
-        for (int32_t j = 0; j < s.slot_len[v]; ++j) values[dst + off + j] = sell[base + static_cast<int64_t>(j) * 32];
+        for (int32_t j = 0; j < s.slot_len[v]; ++j) values[dst + e0 + k + t * j] = sell[base + static_cast<int64_t>(j) * 32];
       }
     } else {
       const int64_t slot = s.num_virtual_padded + (pos - s.num_split);

@@ -120,16 +120,25 @@ void FillSell(const Csr& a, const std::vector<int32_t>* other_pos_of_row, int64_
   if (s.num_slots >= (int64_t{1} << 31)) throw std::runtime_error("too many rows for int32 slot indices");
   s.slot_len.assign(s.num_slots, 0);
   s.virt_pos.assign(s.num_virtual_padded, -1);
-  // (source row, first entry) of every slot
+  // (first entry, distance between consecutive entries) of every slot. The virtual slots of a
+  // split row that share a slice form a team and take the entries of their common range
+  // round-robin (device_build.cu k_virtual_slots: same layout, bitwise the same products).
   std::vector<int64_t> slot_src(s.num_slots, -1);
+  std::vector<int32_t> slot_stride(s.num_slots, 1);
   for (int64_t i = 0; i < s.num_split; ++i) {
     const int32_t r = s.row_of_pos[i];
     const int64_t len = a.start[r + 1] - a.start[r];
-    int64_t v = s.split_first[i];
-    for (int64_t off = 0; off < len; off += T, ++v) {
-      s.slot_len[v] = static_cast<int32_t>(std::min<int64_t>(T, len - off));
+    const int64_t first = s.split_first[i], last = s.split_first[i + 1];
+    for (int64_t v = first; v < last; ++v) {
+      const bool teams = EnvInt("PDLP_B200_TEAM_SLOTS", 1) != 0;
+      const int64_t ts = teams ? std::max<int64_t>(first, (v >> 5) << 5) : v, te = teams ? std::min<int64_t>(last, ((v >> 5) + 1) << 5) : v + 1;
+      const int64_t t = te - ts, k = v - ts;
+      const int64_t e0 = (ts - first) * T, e1 = std::min<int64_t>(len, (te - first) * T);
+      const int64_t team_len = e1 - e0;
+      s.slot_len[v] = team_len > k ? static_cast<int32_t>((team_len - k + t - 1) / t) : 0;
       s.virt_pos[v] = static_cast<int32_t>(i);
-      slot_src[v] = a.start[r] + off;
+      slot_src[v] = a.start[r] + e0 + k;
+      slot_stride[v] = static_cast<int32_t>(t);
     }
   }
   for (int64_t p = s.num_split; p < rows; ++p) {
@@ -158,9 +167,10 @@ void FillSell(const Csr& a, const std::vector<int32_t>* other_pos_of_row, int64_
         const int64_t src = slot_src[slot];
         const int32_t len = src < 0 ? 0 : s.slot_len[slot];
         const int64_t base = s.slice_ptr[sl] + l;
+        const int64_t stride = slot_stride[slot];
         for (int32_t j = 0; j < len; ++j) {
-          s.col[base + static_cast<int64_t>(j) * 32] = other_pos_of_row != nullptr ? (*other_pos_of_row)[a.idx[src + j]] : a.idx[src + j];
-          s.val[base + static_cast<int64_t>(j) * 32] = a.val[src + j];
+          s.col[base + static_cast<int64_t>(j) * 32] = other_pos_of_row != nullptr ? (*other_pos_of_row)[a.idx[src + j * stride]] : a.idx[src + j * stride];
+          s.val[base + static_cast<int64_t>(j) * 32] = a.val[src + j * stride];
         }
         for (int64_t j = len; j < w; ++j) {
           s.col[base + j * 32] = 0;
