@@ -324,16 +324,26 @@ def run_ours(args):
         view_keep = qp._to_view()
         qp._to_view = lambda: view_keep
         pinned = pin_host_arrays(view_keep[1])   # the contract's "pinned host memory": page-lock the caller's buffers in place
-        barrier()
-        t0 = time.time()
-        if world == 1:
-            res = be.primal_dual_hybrid_gradient(qp, params)
-        else:
-            from ortools_b200 import distributed
-            res = distributed.context().primal_dual_hybrid_gradient(qp, params)
-        barrier()
+        walls = []
+        res = None
+        for _ in range(max(1, args.e2e_repeats)):  # the same solve repeated: the median is reported, every wall time listed
+            res = None                             # (the previous result's buffers are released first)
+            barrier()
+            t0 = time.time()
+            if world == 1:
+                res = be.primal_dual_hybrid_gradient(qp, params)
+            else:
+                from ortools_b200 import distributed
+                res = distributed.context().primal_dual_hybrid_gradient(qp, params)
+            barrier()
+            dt = time.time() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            walls.append(dt)
         if res is not None:
-            e2e_s = time.time() - t0
+            e2e_s = sorted(walls)[len(walls) // 2]
             lg = res.solve_log
             line["e2e"] = {"value": lg.iteration_count / e2e_s, "unit": "iterations/s",
                            "h2d_bytes_per_step": problem_bytes(qp) / max(1, lg.iteration_count),
@@ -348,8 +358,9 @@ def run_ours(args):
                 line["e2e"]["dual_objective"] = ci[0].dual_objective
             if "objective" in info:
                 line["e2e"]["planted_objective"] = info["objective"]
+            line["e2e"]["wall_s_all"] = walls
             line["e2e"]["host_buffers"] = "pinned in place (cudaHostRegister, %d arrays)" % len(pinned) if pinned else "pageable"
-            line["e2e"]["what"] = "warm: a later solve of the same process (memory pool, communicator and peer arenas exist; caller buffers page-locked outside the timed region)"
+            line["e2e"]["what"] = "warm: later solves of the same process (memory pool, communicator and peer arenas exist; caller buffers page-locked outside the timed region); median of wall_s_all"
         unpin_host_arrays(pinned)
         if e2e_cold is not None:
             line["e2e_cold"] = e2e_cold
@@ -481,6 +492,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--eps", type=float, default=1e-4)
     ap.add_argument("--e2e-iteration-limit", type=int, default=200000)
+    ap.add_argument("--e2e-repeats", type=int, default=3, help="the warm e2e solve is repeated this many times; the median wall time is reported")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU PDHG loop for the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

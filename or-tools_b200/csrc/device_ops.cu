@@ -2490,6 +2490,26 @@ void Device::DualStepFromProducts(const double* y, const double* kx_cur, const d
 }
 
 // ---- reductions -------------------------------------------------------------
+// Where the next reduction leaves its results. Outside a batch: the start of results_, copied to
+// the host and synchronised at once (host_results_[0..)). Inside a batch (BeginBatch .. EndBatch)
+// every reduction gets its own range, nothing is copied until EndBatch makes ONE device->host copy
+// and ONE synchronisation for all of them; the *Launch functions return the offset to read at.
+double* Device::ReduceTarget(int count) {
+  if (!batch_active_) { last_result_off_ = 0; return results_; }
+  if (batch_off_ + count > 64) throw std::runtime_error("reduction batch overflows the result buffer");
+  last_result_off_ = batch_off_;
+  batch_off_ += (count + 1) / 2 * 2;
+  return results_ + last_result_off_;
+}
+void Device::BeginBatch() {
+  batch_active_ = true;
+  batch_off_ = 0;
+}
+void Device::EndBatch() {
+  batch_active_ = false;
+  if (batch_off_ > 0) CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * batch_off_, cudaMemcpyDeviceToHost, STREAM));
+  Sync();
+}
 // `sharded`: the reduced elements are row-sharded across ranks (dual side), so
 // the sums / maxes are completed by an all-reduce; replicated (primal side)
 // reductions are identical on every rank and need none. Joint reductions count
@@ -2499,14 +2519,17 @@ void Device::DualStepFromProducts(const double* y, const double* kx_cur, const d
     const int nb__ = ReduceBlocks(n);                                                                                             \
     k_reduce<NS, NM><<<nb__, kThreads, 0, STREAM>>>((n), [=] __device__(int64_t i, double* s, double* m) __VA_ARGS__, partials_); \
     LAUNCHED();                                                                                                            \
-    k_reduce_final<NS, NM><<<1, kThreads, 0, STREAM>>>(nb__, partials_, results_);                                         \
+    double* res__ = ReduceTarget((NS) + (NM));                                                                             \
+    k_reduce_final<NS, NM><<<1, kThreads, 0, STREAM>>>(nb__, partials_, res__);                                            \
     LAUNCHED();                                                                                                            \
     if ((sharded) && comm_ != nullptr) {                                                                                   \
-      if ((NS) > 0) comm_->AllReduceSum(results_, results_, (NS), stream_);                                                \
-      if ((NM) > 0) comm_->AllReduceMax(results_ + (NS), results_ + (NS), (NM), stream_);                                  \
+      if ((NS) > 0) comm_->AllReduceSum(res__, res__, (NS), stream_);                                                      \
+      if ((NM) > 0) comm_->AllReduceMax(res__ + (NS), res__ + (NS), (NM), stream_);                                        \
     }                                                                                                                      \
-    CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * ((NS) + (NM)), cudaMemcpyDeviceToHost, STREAM));     \
-    Sync();                                                                                                                \
+    if (!batch_active_) {                                                                                                  \
+      CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * ((NS) + (NM)), cudaMemcpyDeviceToHost, STREAM));   \
+      Sync();                                                                                                              \
+    }                                                                                                                      \
   } while (0)
 #define REDUCE(NS, NM, n, ...) REDUCE_S(false, NS, NM, n, __VA_ARGS__)
 // Reduction over replicated primal-length vectors: on a row-sharded solve every
@@ -2518,14 +2541,17 @@ void Device::DualStepFromProducts(const double* y, const double* kx_cur, const d
     const int nb__ = ReduceBlocks(len__);                                                                                         \
     k_reduce<NS, NM><<<nb__, kThreads, 0, STREAM>>>(len__, [=] __device__(int64_t i__, double* s, double* m) { const int64_t i = i__ + off__; __VA_ARGS__ }, partials_); \
     LAUNCHED();                                                                                                            \
-    k_reduce_final<NS, NM><<<1, kThreads, 0, STREAM>>>(nb__, partials_, results_);                                         \
+    double* res__ = ReduceTarget((NS) + (NM));                                                                             \
+    k_reduce_final<NS, NM><<<1, kThreads, 0, STREAM>>>(nb__, partials_, res__);                                            \
     LAUNCHED();                                                                                                            \
     if (PrimalSliced(n)) {                                                                                                 \
-      if ((NS) > 0) comm_->AllReduceSum(results_, results_, (NS), stream_);                                                \
-      if ((NM) > 0) comm_->AllReduceMax(results_ + (NS), results_ + (NS), (NM), stream_);                                  \
+      if ((NS) > 0) comm_->AllReduceSum(res__, res__, (NS), stream_);                                                      \
+      if ((NM) > 0) comm_->AllReduceMax(res__ + (NS), res__ + (NS), (NM), stream_);                                        \
     }                                                                                                                      \
-    CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * ((NS) + (NM)), cudaMemcpyDeviceToHost, STREAM));     \
-    Sync();                                                                                                                \
+    if (!batch_active_) {                                                                                                  \
+      CUDA_OK(cudaMemcpyAsync(host_results_, results_, sizeof(double) * ((NS) + (NM)), cudaMemcpyDeviceToHost, STREAM));   \
+      Sync();                                                                                                              \
+    }                                                                                                                      \
   } while (0)
 
 double Device::Dot(const double* a, const double* b, int64_t n, bool sharded) { REDUCE_S(sharded, 1, 0, n, { s[0] += a[i] * b[i]; }); return host_results_[0]; }
@@ -2593,6 +2619,10 @@ bool Device::AllNonNegative(const double* v, int64_t n) {
 
 MSideStats Device::DualSideStats(const double* y, const double* kx, const double* lc, const double* uc, const double* dr, double cw_offset,
                                  bool homogeneous, int64_t mm) {
+  return ReadDualSideStats(DualSideStatsLaunch(y, kx, lc, uc, dr, cw_offset, homogeneous, mm));
+}
+int Device::DualSideStatsLaunch(const double* y, const double* kx, const double* lc, const double* uc, const double* dr, double cw_offset,
+                                bool homogeneous, int64_t mm) {
   REDUCE_S(true, 3, 3, mm, {  // iteration_stats.cc:66-134, 328-350
     const double rs = dr != nullptr ? dr[i] : 1.0;
     const double ub = (homogeneous && isfinite(uc[i])) ? 0.0 : uc[i];
@@ -2611,14 +2641,22 @@ MSideStats Device::DualSideStats(const double* y, const double* kx, const double
     m[2] = fmax(m[2], fabs(ys));
     s[2] += ys * ys;
   });
+  return last_result_off_;
+}
+MSideStats Device::ReadDualSideStats(int off) const {
+  const double* h = host_results_ + off;
   MSideStats r;
-  r.sumsq_residual = host_results_[0]; r.bounds_term = host_results_[1]; r.sumsq_scaled = host_results_[2];
-  r.linf_residual = std::max(0.0, host_results_[3]); r.cw_residual = std::max(0.0, host_results_[4]); r.linf_scaled = std::max(0.0, host_results_[5]);
+  r.sumsq_residual = h[0]; r.bounds_term = h[1]; r.sumsq_scaled = h[2];
+  r.linf_residual = std::max(0.0, h[3]); r.cw_residual = std::max(0.0, h[4]); r.linf_scaled = std::max(0.0, h[5]);
   return r;
 }
 
 NSideStats Device::PrimalSideStats(const double* x, const double* xb, const double* kty, const double* c, const double* q, const double* lv,
                                    const double* uv, const double* dc, double cw_offset, bool zero_objective, bool handle_as_residuals, int64_t n) {
+  return ReadPrimalSideStats(PrimalSideStatsLaunch(x, xb, kty, c, q, lv, uv, dc, cw_offset, zero_objective, handle_as_residuals, n));
+}
+int Device::PrimalSideStatsLaunch(const double* x, const double* xb, const double* kty, const double* c, const double* q, const double* lv,
+                                  const double* uv, const double* dc, double cw_offset, bool zero_objective, bool handle_as_residuals, int64_t n) {
   REDUCE_P(6, 4, n, {  // iteration_stats.cc:189-270, 273-323
     const double cs = dc != nullptr ? dc[i] : 1.0;
     const double xi = x[i];
@@ -2649,11 +2687,15 @@ NSideStats Device::PrimalSideStats(const double* x, const double* xb, const doub
     s[5] += xs * xs;
     m[3] = fmax(m[3], fabs(qx));
   });
+  return last_result_off_;
+}
+NSideStats Device::ReadPrimalSideStats(int off) const {
+  const double* h = host_results_ + off;
   NSideStats r;
-  r.correction = host_results_[0]; r.full_correction = host_results_[1]; r.sumsq_residual = host_results_[2];
-  r.objective_dot = host_results_[3]; r.quadratic = host_results_[4]; r.sumsq_scaled = host_results_[5];
-  r.linf_residual = std::max(0.0, host_results_[6]); r.cw_residual = std::max(0.0, host_results_[7]);
-  r.linf_scaled = std::max(0.0, host_results_[8]); r.linf_qx = std::max(0.0, host_results_[9]);
+  r.correction = h[0]; r.full_correction = h[1]; r.sumsq_residual = h[2];
+  r.objective_dot = h[3]; r.quadratic = h[4]; r.sumsq_scaled = h[5];
+  r.linf_residual = std::max(0.0, h[6]); r.cw_residual = std::max(0.0, h[7]);
+  r.linf_scaled = std::max(0.0, h[8]); r.linf_qx = std::max(0.0, h[9]);
   return r;
 }
 
@@ -2682,16 +2724,25 @@ double Device::LagrangianDualGradient(const double* y, const double* kx, const d
   return host_results_[0];
 }
 void Device::ActiveSetPrimal(const double* x, const double* x0, const double* lv, const double* uv, int64_t n, int64_t out[2]) {
+  ReadCounts(ActiveSetPrimalLaunch(x, x0, lv, uv, n), out);
+}
+void Device::ReadCounts(int off, int64_t out[2]) const {
+  out[0] = static_cast<int64_t>(host_results_[off]);
+  out[1] = static_cast<int64_t>(host_results_[off + 1]);
+}
+int Device::ActiveSetPrimalLaunch(const double* x, const double* x0, const double* lv, const double* uv, int64_t n) {
   REDUCE_P(2, 0, n, {
     const bool a = x[i] > lv[i] && x[i] < uv[i];
     const bool b = x0[i] > lv[i] && x0[i] < uv[i];
     s[0] += a ? 1.0 : 0.0;
     s[1] += (a != b) ? 1.0 : 0.0;
   });
-  out[0] = static_cast<int64_t>(host_results_[0]);
-  out[1] = static_cast<int64_t>(host_results_[1]);
+  return last_result_off_;
 }
 void Device::ActiveSetDual(const double* y, const double* y0, const double* lc, const double* uc, int64_t mm, int64_t out[2]) {
+  ReadCounts(ActiveSetDualLaunch(y, y0, lc, uc, mm), out);
+}
+int Device::ActiveSetDualLaunch(const double* y, const double* y0, const double* lc, const double* uc, int64_t mm) {
   REDUCE_S(true, 2, 0, mm, {
     const bool free_row = lc[i] == -kInfD && uc[i] == kInfD;
     const bool a = y[i] != 0.0 || free_row;
@@ -2699,8 +2750,7 @@ void Device::ActiveSetDual(const double* y, const double* y0, const double* lc, 
     s[0] += a ? 1.0 : 0.0;
     s[1] += (a != b) ? 1.0 : 0.0;
   });
-  out[0] = static_cast<int64_t>(host_results_[0]);
-  out[1] = static_cast<int64_t>(host_results_[1]);
+  return last_result_off_;
 }
 
 namespace kernels {

@@ -273,6 +273,19 @@ class Device {
   bool BoundsValid(const double* lb, const double* ub, int64_t n, bool sharded = false);           // HasValidBounds
   bool AllNonNegative(const double* v, int64_t n);
 
+  // Several reductions, ONE device->host copy and synchronisation: between BeginBatch and EndBatch
+  // the *Launch functions only enqueue and return where their results will be; Read* after EndBatch.
+  void BeginBatch();
+  void EndBatch();
+  int DualSideStatsLaunch(const double* y, const double* kx, const double* lc, const double* uc, const double* dr, double cw_offset,
+                          bool homogeneous_bounds, int64_t m);
+  int PrimalSideStatsLaunch(const double* x, const double* x_for_bounds, const double* kty, const double* c, const double* q, const double* lv,
+                            const double* uv, const double* dc, double cw_offset, bool zero_objective, bool handle_as_residuals, int64_t n);
+  int ActiveSetPrimalLaunch(const double* x, const double* x0, const double* lv, const double* uv, int64_t n);
+  int ActiveSetDualLaunch(const double* y, const double* y0, const double* lc, const double* uc, int64_t m);
+  MSideStats ReadDualSideStats(int off) const;
+  NSideStats ReadPrimalSideStats(int off) const;
+  void ReadCounts(int off, int64_t out[2]) const;
   // KKT reductions (iteration_stats.cc:66-350). dr/dc may be null (= ones).
   MSideStats DualSideStats(const double* y, const double* kx, const double* lc, const double* uc, const double* dr,
                            double cw_offset, bool homogeneous_bounds, int64_t m);
@@ -395,6 +408,9 @@ class Device {
   double* step_partials_ = nullptr;
   int64_t step_partials_size_ = 0;
   double* TrScratch(int64_t doubles);
+  double* ReduceTarget(int count);
+  bool batch_active_ = false;
+  int batch_off_ = 0, last_result_off_ = 0;
   // step timing
   bool step_timing_ = false;
   int step_timing_stride_ = 8;

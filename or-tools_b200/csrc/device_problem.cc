@@ -329,8 +329,12 @@ PdlpConvergenceInformation DeviceProblem::ComputeConvergenceInformation(bool han
   if (kx == nullptr) { Kx(x, tmp_m_[0]); kx = tmp_m_[0]; }
   const double* kty = kty_or_null;
   if (kty == nullptr) { KTy(y, tmp_n_[0]); kty = tmp_n_[0]; }
-  const MSideStats ms = d.DualSideStats(y, kx, lc_, uc_, dr, cw_primal_offset, /*homogeneous=*/false, m_);
-  const NSideStats ns = d.PrimalSideStats(x, x, kty, c_, q_, lv_, uv_, dc, cw_dual_offset, /*zero_objective=*/false, handle_as_residuals, n_);
+  d.BeginBatch();  // both sides in one host round trip
+  const int om = d.DualSideStatsLaunch(y, kx, lc_, uc_, dr, cw_primal_offset, /*homogeneous=*/false, m_);
+  const int on = d.PrimalSideStatsLaunch(x, x, kty, c_, q_, lv_, uv_, dc, cw_dual_offset, /*zero_objective=*/false, handle_as_residuals, n_);
+  d.EndBatch();
+  const MSideStats ms = d.ReadDualSideStats(om);
+  const NSideStats ns = d.ReadPrimalSideStats(on);
   r.l_inf_primal_residual = ms.linf_residual;
   r.l2_primal_residual = std::sqrt(ms.sumsq_residual);
   r.l_inf_componentwise_primal_residual = ms.cw_residual;
@@ -362,9 +366,13 @@ PdlpInfeasibilityInformation DeviceProblem::ComputeInfeasibilityInformation(bool
   Kx(primal_ray, tmp_m_[1]);
   // dual ray side: gradient = -K^T ray; DualResidualNorms against the bounds at
   // `primal_for_residual_tests`; primal ray side: objective terms + norms.
-  const NSideStats ns_dual = d.PrimalSideStats(primal_ray, primal_for_residual_tests, kty, c_, q_, lv_, uv_, dc, 0.0, /*zero_objective=*/true,
-                                               handle_as_residuals, n_);
-  const MSideStats ms = d.DualSideStats(dual_ray, tmp_m_[1], lc_, uc_, dr, 0.0, /*homogeneous=*/true, m_);
+  d.BeginBatch();  // both sides in one host round trip
+  const int on = d.PrimalSideStatsLaunch(primal_ray, primal_for_residual_tests, kty, c_, q_, lv_, uv_, dc, 0.0, /*zero_objective=*/true,
+                                         handle_as_residuals, n_);
+  const int om = d.DualSideStatsLaunch(dual_ray, tmp_m_[1], lc_, uc_, dr, 0.0, /*homogeneous=*/true, m_);
+  d.EndBatch();
+  const NSideStats ns_dual = d.ReadPrimalSideStats(on);
+  const MSideStats ms = d.ReadDualSideStats(om);
   const double l_inf_primal = ns_dual.linf_scaled;
   const double l_inf_dual = ms.linf_scaled;
   const double dual_ray_objective = ms.bounds_term + ns_dual.correction;

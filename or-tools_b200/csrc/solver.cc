@@ -661,8 +661,12 @@ void DeviceSolve::AddPointMetadata(const double* x, const double* y, int type, P
   }
   if (type != PDLP_POINT_TYPE_ITERATE_DIFFERENCE) {  // SetActiveSetInformation, pdhg.cc:1476-1545
     int64_t pc[2], dcnt[2];
-    D.ActiveSetPrimal(x, x0_, P.lv(), P.uv(), P.n(), pc);
-    D.ActiveSetDual(y, y0_, P.lc(), P.uc(), P.m(), dcnt);
+    D.BeginBatch();  // both counts in one host round trip
+    const int op = D.ActiveSetPrimalLaunch(x, x0_, P.lv(), P.uv(), P.n());
+    const int od = D.ActiveSetDualLaunch(y, y0_, P.lc(), P.uc(), P.m());
+    D.EndBatch();
+    D.ReadCounts(op, pc);
+    D.ReadCounts(od, dcnt);
     md.has_active_set_information = 1;
     md.active_primal_variable_count = pc[0];
     md.active_primal_variable_change = pc[1];
