@@ -157,7 +157,11 @@ __device__ __forceinline__ double combine(double acc, double v, double xv) {
 // One thread per slot; lanes of a warp read consecutive addresses of the
 // slice (coalesced 256 B value / 128 B index requests, streamed with
 // evict-first); x is gathered through L2.
-template <int MODE, int V>
+// CG: the gathered vector changes while the kernel runs (the persistent step loop of a row-sharded
+// solve, k_peer_loop): gathers go to L2 (ld.global.cg), never through the non-coherent L1 path.
+template <bool CG>
+__device__ __forceinline__ double gather_ld(const double* p) { return CG ? __ldcg(p) : __ldg(p); }
+template <int MODE, int V, bool CG = false>
 __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const double* __restrict__ x) {
   const int64_t base = a.slice_ptr[slot >> 5] + (slot & 31);
   const int n = a.slot_len[slot];
@@ -176,7 +180,7 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
         c[u] = __ldcs(col + static_cast<int64_t>(j + u) * 32);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) xv[u] = __ldg(x + c[u]);
+      for (int u = 0; u < 4; ++u) xv[u] = gather_ld<CG>(x + c[u]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc = combine<MODE>(acc, v[u], xv[u]);
     }
@@ -197,7 +201,7 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
       for (;;) {
         double xv[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = __ldg(x + c[u]);
+        for (int u = 0; u < U; ++u) xv[u] = gather_ld<CG>(x + c[u]);
         j += U;
         const bool more = j + U <= n;
         double vn[U];
@@ -220,7 +224,7 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
       }
     }
   }
-  for (; j < n; ++j) acc = combine<MODE>(acc, __ldcs(val + static_cast<int64_t>(j) * 32), __ldg(x + __ldcs(col + static_cast<int64_t>(j) * 32)));
+  for (; j < n; ++j) acc = combine<MODE>(acc, __ldcs(val + static_cast<int64_t>(j) * 32), gather_ld<CG>(x + __ldcs(col + static_cast<int64_t>(j) * 32)));
   return acc;
 }
 
@@ -1002,6 +1006,332 @@ __global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t 
   }
 }
 __global__ void k_clear_pending(StepState* st) { st->pending_ratio = st->pending_ratio_dual = st->pending_ratio0 = 0.0; }
+
+// ---- the row-sharded step loop as ONE persistent cooperative launch ----------
+// At 1/8 of a problem per rank the five launches and two barrier kernels of an attempt cost more
+// than the work in them (C2 on 8 GPUs: K x~ 31 us for 12 us of work). k_peer_loop runs a whole
+// chunk of attempts in one launch, one block per SM: the phases of an attempt are separated by
+// grid barriers (a ticket; the block that arrives last also meets the other ranks -- barrier A /
+// B of DESIGN.md 5 -- before it releases the grid), every rank takes the identical decision from
+// the G triples, and the loop leaves when the decision sets `halt` (checkpoint reached, numerical
+// halt) -- a rejected step costs no host round trip.
+//   P   primal slice step, x~ stored into every arena, ||dx||^2 per block       | grid + peer barrier A
+//   D   K[R_g,:] x~ + dual update (+ y' stored into every arena, MODE 0)         | MODE 1: grid barrier
+//   T1  (MODE 1, reduce-scatter) (K[R_g,:])^T y' partial into the own arena
+//       the last block adds the per-block {||dx||^2, ||dy||^2, (K dx).dy} in block order and
+//       stores the triple into every arena                                      | grid + peer barrier B
+//   T   MODE 0: (K[:,C_g])^T y' from the all-gathered y'; MODE 1: pull slice C_g of every rank's
+//       partial (128-bit peer loads), add in rank order. One warp first takes the step decision
+//       and writes the other state slot.                                        | grid barrier
+// Work is mapped to warps / threads STATICALLY: every row-wise vector is read and written by the
+// same thread in every attempt, and the partial sums do not depend on a schedule. Slices go to
+// the W warps of the grid in rounds of W, in alternating direction (warp w takes slice r W + w in
+// even rounds, r W + W - 1 - w in odd ones): the images are sorted by row length inside windows
+// whose size divides W, so a plain stride-W map would hand one warp the longest slices of every
+// window (measured: +60 % on the K^T y' phase of C2). Data another SM or GPU produced inside the launch
+// (x~, y', K^T y, the partials, the state) is read with ld.global.cg / volatile loads only: the
+// L1 of an SM is not coherent across the phases of one kernel.
+struct PeerLoopArgs {
+  StepPtrs p;        // p.state: slot 0 of the two state slots
+  PeerPtrs peer;
+  SellDev rows;      // K[R_g,:]
+  SellDev cols;      // MODE 0: (K[:,C_g])^T, indices in the box-wide dual order; MODE 1: (K[R_g,:])^T
+  const int32_t* perm;   // MODE 0: column (relative to col0) of a position of the slice image; MODE 1: column of a position
+  int64_t col0;
+  double* block_partials;  // [blocks][4]: ||dx||^2, ||dy||^2, (K dx).dy
+  unsigned int* sync;      // [0] arrivals [1] generation [2] error (a peer never arrived); zero before the launch
+  int first_slot, max_attempts;
+  unsigned long long* trace;  // nullptr, or [0] attempts, [1..6] summed ns of the phases (block 0)
+};
+enum { kLoopSyncPlain = 0, kLoopSyncPeer = 1, kLoopSyncSumsPeer = 2 };
+
+// Grid barrier number `bar` of the launch (all threads of all blocks). The block that arrives last
+// optionally adds the block partials and stores the triple into every arena (kLoopSyncSumsPeer),
+// then meets the other ranks at peer barrier `which` before it releases the grid. Returns true
+// when a peer never arrived.
+__device__ __forceinline__ bool loop_grid_sync(const PeerLoopArgs& g, unsigned& bar, int kind, int which, int* s_err) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned last = 0;
+    if (lane == 0) {
+      // (cumulative: the block's stores -- local and into the peers' arenas -- ordered by the barrier above)
+      if (kind == kLoopSyncPlain) __threadfence(); else __threadfence_system();
+      const unsigned ticket = atomicAdd(g.sync, 1u);
+      last = ticket == gridDim.x * (bar + 1u) - 1u ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last != 0u) {
+      __threadfence();
+      if (kind == kLoopSyncSumsPeer) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) {  // block order: lane-strided, then a shuffle tree
+          s0 += __ldcg(g.block_partials + 4 * b + 0);
+          s1 += __ldcg(g.block_partials + 4 * b + 1);
+          s2 += __ldcg(g.block_partials + 4 * b + 2);
+        }
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane < g.peer.world) {
+          volatile double* dst = peer_base(g.peer, lane) + g.peer.scal_off + 4 * g.peer.rank;
+          dst[0] = s0;
+          dst[1] = s1;
+          dst[2] = s2;
+        }
+      }
+      if (kind != kLoopSyncPlain) peer_barrier(g.peer, which, reinterpret_cast<int32_t*>(g.sync + 2));
+      if (lane == 0) {
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(g.sync + 1) = bar + 1u;
+      }
+    } else if (lane == 0) {
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned int*>(g.sync + 1) < bar + 1u) {
+        if (clock64() - t0 > 2 * g.peer.timeout_cycles) {  // (the releasing block itself gives up after timeout_cycles)
+          *reinterpret_cast<volatile int*>(g.sync + 2) = kHaltPeerTimeout;
+          break;
+        }
+      }
+      __threadfence();
+    }
+    if (lane == 0) *s_err = *reinterpret_cast<volatile int*>(g.sync + 2);
+  }
+  __syncthreads();
+  ++bar;
+  return *s_err != 0;
+}
+
+// The step decision of k_peer_loop (one thread; run_decide_head of the multi-launch path): the G
+// triples in rank order, the same on every rank. Not inlined: its registers (two pow()) must not
+// count against the row loops.
+__device__ __noinline__ void loop_decide(StepState* st_out, const StepState* st_smem, const double* scal, int world) {
+  const volatile double* sc = scal;
+  double dx2 = 0.0, dy2 = 0.0, dot = 0.0;
+  for (int k = 0; k < world; ++k) {
+    dx2 += sc[4 * k + 0];
+    dy2 += sc[4 * k + 1];
+    dot += sc[4 * k + 2];
+  }
+  StepState loaded = *st_smem;
+  loaded.pow_total = -1.0;  // (nobody precomputed the powers of this attempt)
+  double pr, pg;
+  decide_powers(loaded, pr, pg);
+  decide_update(st_out, loaded, pr, pg, dx2, dy2, dot);
+}
+
+__device__ __forceinline__ unsigned long long loop_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int MODE, int BT>
+__global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
+  constexpr int kWords = static_cast<int>(sizeof(StepState) / sizeof(double));
+  static_assert(sizeof(StepState) % sizeof(double) == 0 && kWords <= BT, "the state is copied as doubles");
+  __shared__ StepState s_st;
+  __shared__ int s_err;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * BT;
+  const int64_t gthread = static_cast<int64_t>(blockIdx.x) * BT + tid;
+  const int64_t nwarps = nthreads >> 5, gwarp = gthread >> 5;
+  const StepPtrs& b = g.p;
+  const PeerPtrs& peer = g.peer;
+  const bool has_q = b.q != nullptr;
+  const bool tracing = g.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool decider = gwarp == nwarps - 1;
+  unsigned bar = 0;
+  if (tid == 0) s_err = 0;
+  for (int it = 0; it < g.max_attempts; ++it) {
+    StepState* st_in = b.state + ((g.first_slot + it) & 1);
+    StepState* st_out = b.state + ((g.first_slot + it + 1) & 1);
+    __syncthreads();  // (everybody is done with the previous attempt's copy)
+    if (tid < kWords) reinterpret_cast<double*>(&s_st)[tid] = __ldcg(reinterpret_cast<const double*>(st_in) + tid);
+    __syncthreads();
+    if (s_st.halt != 0) break;  // (the same state on every block and rank)
+    const int cur = s_st.cur, cand = s_st.cand;
+    const double ratio = s_st.pending_ratio;
+    unsigned long long t0 = 0;
+    if (tracing) t0 = loop_now();
+
+    // ---- P: primal slice step (k_primal_step<PEER>) ------------------------------------
+    {
+      const double* __restrict__ xc = pick3(b.x, cur);
+      double* __restrict__ xn = pick3(b.x, cand);
+      const double* kty = pick3(b.kty, cur);
+      const double tau = s_st.step_size / s_st.primal_weight;
+      double s = 0.0;
+      for (int64_t i0 = peer.begin + 2 * gthread; i0 < peer.end; i0 += 2 * nthreads) {
+        if (i0 + 1 < peer.end) {
+          const double2 x2 = *reinterpret_cast<const double2*>(xc + i0);
+          const double2 k2 = __ldcg(reinterpret_cast<const double2*>(kty + i0));
+          const double2 c2 = *reinterpret_cast<const double2*>(b.c + i0);
+          const double2 l2 = *reinterpret_cast<const double2*>(b.lv + i0);
+          const double2 u2 = *reinterpret_cast<const double2*>(b.uv + i0);
+          double t0v = x2.x - tau * (c2.x - k2.x), t1v = x2.y - tau * (c2.y - k2.y);
+          if (has_q) {
+            const double2 q2 = *reinterpret_cast<const double2*>(b.q + i0);
+            t0v = t0v / (tau * q2.x + 1.0);
+            t1v = t1v / (tau * q2.y + 1.0);
+          }
+          double2 nx;
+          nx.x = fmax(fmin(t0v, u2.x), l2.x);
+          nx.y = fmax(fmin(t1v, u2.y), l2.y);
+          const double d0 = nx.x - x2.x, d1 = nx.y - x2.y;
+          *reinterpret_cast<double2*>(xn + i0) = nx;
+          double2 xt;
+          xt.x = nx.x + d0;
+          xt.y = nx.y + d1;
+#pragma unroll
+          for (int h = 0; h < kMaxPeers; ++h)
+            if (h < peer.world) *reinterpret_cast<double2*>(peer.base[h] + peer.xt_off + i0) = xt;
+          s += d0 * d0 + d1 * d1;
+          if (ratio > 0.0) {
+            double2 av = *reinterpret_cast<const double2*>(b.avg_x + i0);
+            av.x += ratio * (x2.x - av.x);
+            av.y += ratio * (x2.y - av.y);
+            *reinterpret_cast<double2*>(b.avg_x + i0) = av;
+          }
+        } else {
+          const double x = xc[i0];
+          double t = x - tau * (b.c[i0] - __ldcg(kty + i0));
+          if (has_q) t = t / (tau * b.q[i0] + 1.0);
+          const double nx = fmax(fmin(t, b.uv[i0]), b.lv[i0]);
+          const double d = nx - x;
+          xn[i0] = nx;
+#pragma unroll
+          for (int h = 0; h < kMaxPeers; ++h)
+            if (h < peer.world) peer.base[h][peer.xt_off + i0] = nx + d;
+          s += d * d;
+          if (ratio > 0.0) b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
+        }
+      }
+      block_reduce_store<1, 0, BT>(&s, nullptr, g.block_partials + 4 * blockIdx.x);
+    }
+    unsigned long long t1 = 0;
+    if (tracing) t1 = loop_now();
+    if (loop_grid_sync(g, bar, kLoopSyncPeer, 0, &s_err)) break;
+    unsigned long long t2 = 0;
+    if (tracing) t2 = loop_now();
+
+    // ---- D: K[R_g,:] x~ and the dual update (k_sell + DualEpi) --------------------------
+    {
+      DualEpiT<MODE == 0> epi;
+      epi.b = b;
+      epi.peer = peer;
+      typename DualEpiT<MODE == 0>::Ctx ctx;
+      ctx.yc = pick3(b.y, cur);
+      ctx.yn = pick3(b.y, cand);
+      ctx.kxc = pick3(b.kx, cur);
+      ctx.kxn = pick3(b.kx, cand);
+      ctx.sigma = s_st.step_size * s_st.primal_weight;
+      ctx.ratio = ratio;
+      const double* xt = peer.base[peer.rank] + peer.xt_off;
+      const SellDev& a = g.rows;
+      const int64_t nsl = a.num_slots >> 5;
+      double red[2] = {0.0, 0.0};
+      for (int64_t r = 0, base = 0; base < nsl; ++r, base += nwarps) {
+        const int64_t sl = base + ((r & 1) ? nwarps - 1 - gwarp : gwarp);  // (see the mapping note above the kernel)
+        if (sl >= nsl) continue;
+        const int64_t slot = (sl << 5) + lane;
+        const int64_t pos = a.num_split + (slot - a.num_virtual_padded);  // (no split rows: the host takes the multi-launch path for those)
+        const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
+        typename DualEpiT<MODE == 0>::Pre pre;
+        if (own_row) pre = epi.prefetch(ctx, pos);
+        const double acc = sell_row<kDot, 1, true>(a, slot, xt);
+        if (own_row) epi(ctx, pos, acc, red, pre);
+      }
+      block_reduce_store<2, 0, BT>(red, nullptr, g.block_partials + 4 * blockIdx.x + 1);
+    }
+    unsigned long long t3 = 0;
+    if (tracing) t3 = loop_now();
+    if (MODE == 1) {
+      // ---- T1: the local partial (K[R_g,:])^T y' into the own arena, column order --------
+      if (loop_grid_sync(g, bar, kLoopSyncPlain, 0, &s_err)) break;
+      const double* yn = pick3(b.y, cand);
+      double* partial = peer.base[peer.rank] + peer.partial_off;
+      const SellDev& a = g.cols;
+      const int64_t nsl = a.num_slots >> 5;
+      for (int64_t r = 0, base = 0; base < nsl; ++r, base += nwarps) {
+        const int64_t sl = base + ((r & 1) ? nwarps - 1 - gwarp : gwarp);  // (see the mapping note above the kernel)
+        if (sl >= nsl) continue;
+        const int64_t slot = (sl << 5) + lane;
+        const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
+        const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
+        int32_t dst = 0;
+        if (own_row) dst = __ldg(g.perm + pos);
+        const double acc = sell_row<kDot, 1, true>(a, slot, yn);
+        if (own_row) partial[dst] = acc;
+      }
+    }
+    unsigned long long t4 = 0;
+    if (tracing) t4 = loop_now();
+    if (loop_grid_sync(g, bar, kLoopSyncSumsPeer, 1, &s_err)) break;
+    unsigned long long t5 = 0;
+    if (tracing) t5 = loop_now();
+
+    // ---- the decision (one warp; run_decide_head of the multi-launch path) --------------
+    if (decider && lane == 0) loop_decide(st_out, &s_st, peer.base[peer.rank] + peer.scal_off, peer.world);
+    // ---- T: K^T y' of the candidate for this rank's column slice -------------------------
+    double* kc = pick3(b.kty, cand);
+    if (MODE == 0) {
+      const double* yall = peer.base[peer.rank] + peer.y_off;
+      const SellDev& a = g.cols;
+      const int64_t nsl = a.num_slots >> 5;
+      for (int64_t r = 0, base = 0; base < nsl; ++r, base += nwarps) {
+        const int64_t sl = base + ((r & 1) ? nwarps - 1 - gwarp : gwarp);  // (see the mapping note above the kernel)
+        if (sl >= nsl) continue;
+        const int64_t slot = (sl << 5) + lane;
+        const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
+        const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
+        int32_t dst = 0;
+        if (own_row) dst = __ldg(g.perm + pos);
+        const double acc = sell_row<kDot, 1, true>(a, slot, yall);
+        if (own_row) kc[g.col0 + dst] = acc;
+      }
+    } else {
+      for (int64_t i0 = peer.begin + 2 * gthread; i0 < peer.end; i0 += 2 * nthreads) {
+        if (i0 + 1 < peer.end) {
+          double2 v = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int h = 0; h < kMaxPeers; ++h) {
+            if (h < peer.world) {
+              const double2 t = __ldcg(reinterpret_cast<const double2*>(peer.base[h] + peer.partial_off + i0));
+              v.x += t.x;
+              v.y += t.y;
+            }
+          }
+          *reinterpret_cast<double2*>(kc + i0) = v;
+        } else {
+          double v = 0.0;
+#pragma unroll
+          for (int h = 0; h < kMaxPeers; ++h)
+            if (h < peer.world) v += __ldcg(peer.base[h] + peer.partial_off + i0);
+          kc[i0] = v;
+        }
+      }
+    }
+    unsigned long long t6 = 0;
+    if (tracing) t6 = loop_now();
+    if (loop_grid_sync(g, bar, kLoopSyncPlain, 0, &s_err)) break;
+    if (tracing) {
+      const unsigned long long t7 = loop_now();
+      g.trace[0] += 1ull;
+      g.trace[1] += t1 - t0;  // P
+      g.trace[2] += t2 - t1;  // grid + peer barrier A
+      g.trace[3] += t3 - t2;  // D
+      g.trace[4] += t4 - t3;  // (MODE 1: grid barrier + T1)
+      g.trace[5] += t5 - t4;  // sums + grid + peer barrier B
+      g.trace[6] += t6 - t5;  // decision + T
+      g.trace[7] += t7 - t6;  // closing grid barrier
+    }
+  }
+  if (s_err != 0 && blockIdx.x == 0 && tid == 0) {  // a peer never arrived: both slots say so, whatever the host reads
+    b.state[0].halt = kHaltPeerTimeout;
+    b.state[1].halt = kHaltPeerTimeout;
+  }
+}
 
 // ---- Malitsky-Pock rule on the device (pdhg.cc:2463-2556) ---------------------------
 // One attempt = one inner iteration of the line search; the kernels of an attempt read state slot
@@ -2067,6 +2397,8 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   CUDA_OK(cudaMemset(tr_peer_error_, 0, 64));
   CUDA_OK(cudaMalloc(&tile_counters_, 64));
   CUDA_OK(cudaMemset(tile_counters_, 0, 64));
+  CUDA_OK(cudaMalloc(&loop_sync_, 256));
+  CUDA_OK(cudaMemset(loop_sync_, 0, 256));
   CUDA_OK(cudaMalloc(&results_, sizeof(double) * 64));
   CUDA_OK(cudaMallocHost(&host_results_, sizeof(double) * 64));
 }
@@ -2076,6 +2408,7 @@ Device::~Device() {
   cudaFree(partials_);
   cudaFree(tr_peer_error_);
   cudaFree(tile_counters_);
+  cudaFree(loop_sync_);
   cudaFree(results_);
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
@@ -2253,6 +2586,11 @@ void launch_k(bool pdl, void (*kernel)(KArgs...), int grid, int block, cudaStrea
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+// PDLP_B200_PEER_LOOP: 0 the row-sharded step loop as separate launches per attempt, 2 always k_peer_loop, 1 (default) by size.
+int PeerLoop() {
+  static const int v = [] { const char* e = std::getenv("PDLP_B200_PEER_LOOP"); return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }();
+  return v;
 }
 bool StepPdl() {
   static const bool v = [] { const char* e = std::getenv("PDLP_B200_PDL"); return !(e != nullptr && e[0] == '0'); }();
@@ -3163,7 +3501,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const int nd_main = SellGridFor(rows, pair_chunks);
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int nd = b.m > 0 ? nd_main + nd_fix : 0;
-  const int64_t need = static_cast<int64_t>(np) + 2 * static_cast<int64_t>(nd_main + nd_fix) + 8;
+  const int64_t need = std::max<int64_t>(static_cast<int64_t>(np) + 2 * static_cast<int64_t>(nd_main + nd_fix) + 8, 4 * static_cast<int64_t>(num_sms_) + 8);
   if (need > step_partials_size_) {
     cudaFree(step_partials_);
     step_partials_ = nullptr;
@@ -3177,6 +3515,44 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   timing_attempt_idx_.clear();
   timing_peer_ = use_peer;
   auto ev = [&](int slot, int k) { CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timing_events_[slot * kEvPerSlot + k]), STREAM)); };
+  // k_peer_loop maps slices to warps statically, and the SMs of a B200 do not run a request-bound row loop
+  // at the same speed (GPCs of 16 / 18 / 20 SMs share a crossbar port: measured spread 25 %): it wins
+  // where an attempt is launch- and barrier-bound (at most kPeerLoopRounds slices per warp and image),
+  // the separate launches -- whose blocks the hardware scheduler balances -- win above that.
+  // PDLP_B200_PEER_LOOP=0 / 2 forces the launches / the loop.
+  const SellDev& kty_image = b.cols_slice != nullptr ? *b.cols_slice : cols;
+  constexpr int kLoopThreads = 1024;
+  constexpr int64_t kPeerLoopRounds = 3;
+  const int64_t loop_warps = static_cast<int64_t>(num_sms_) * (kLoopThreads / 32);
+  const bool loop_small = std::max(rows.num_slots, kty_image.num_slots) / 32 <= kPeerLoopRounds * loop_warps;
+  if (use_peer && (PeerLoop() == 2 || (PeerLoop() == 1 && loop_small)) && b.m > 0 && b.n > 0 && rows.num_split == 0 && kty_image.num_split == 0) {
+    // the whole chunk of attempts as one persistent cooperative launch (k_peer_loop); it leaves when the
+    // decision halts, so rejected steps need no second pass (the cap only bounds a state that never halts)
+    PeerLoopArgs g;
+    g.p = p;
+    g.p.state = b.state;
+    g.peer = peer;
+    g.rows = rows;
+    g.cols = b.cols_slice != nullptr ? *b.cols_slice : cols;
+    g.perm = b.cols_slice != nullptr ? b.slice_perm : b.primal_scatter;
+    g.col0 = b.slice_begin;
+    g.block_partials = step_partials_;
+    g.sync = loop_sync_;
+    g.first_slot = first_slot;
+    g.max_attempts = count + 64;
+    static const bool trace_env = [] { const char* t = std::getenv("PDLP_B200_TRACE"); return t != nullptr && t[0] == '1'; }();
+    g.trace = (step_timing_ || trace_env) ? reinterpret_cast<unsigned long long*>(loop_sync_ + 16) : nullptr;
+    CUDA_OK(cudaMemsetAsync(loop_sync_, 0, 128, STREAM));
+    const void* fn = b.cols_slice != nullptr ? reinterpret_cast<const void*>(k_peer_loop<0, kLoopThreads>) : reinterpret_cast<const void*>(k_peer_loop<1, kLoopThreads>);
+    void* args[] = {&g};
+    const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(num_sms_), dim3(kLoopThreads), args, 0, STREAM);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cooperative launch of k_peer_loop failed: ") + cudaGetErrorString(e));
+    ++launches_;
+    timing_attempt_idx_.clear();
+    timing_peer_ = true;
+    loop_traced_ = g.trace != nullptr;
+    return;
+  }
   for (int it = 0; it < count; ++it) {
     // the kernels of this attempt read state slot `in`; its decision writes the other slot
     StepState* st_in = b.state + ((first_slot + it) & 1);
@@ -3331,6 +3707,25 @@ void Device::EnableStepTiming(bool on, int stride) {
   timing_attempt_idx_.clear();
 }
 void Device::CollectStepTimings(int64_t executed_attempts) {
+  if (loop_traced_) {
+    // k_peer_loop: block 0 summed the phase times of every attempt (globaltimer, ns):
+    // [0] attempts, P | barrier A | D | (T1) | sums + barrier B | decision + T | closing barrier
+    loop_traced_ = false;
+    unsigned long long h[8];
+    CUDA_OK(cudaMemcpyAsync(h, loop_sync_ + 16, sizeof(h), cudaMemcpyDeviceToHost, STREAM));
+    Sync();
+    static const int kLoopClass[7] = {0, 0, 1, 2, 2, 2, 3};
+    if (h[0] > 0) {
+      for (int k = 0; k < 7; ++k) {
+        const double ms = static_cast<double>(h[1 + k]) * 1e-6;
+        step_timings_.ms[kLoopClass[k]] += ms;
+        detail_ms_[k] += ms;
+      }
+      for (int k = 0; k < 4; ++k) step_timings_.samples[k] += static_cast<int64_t>(h[0]);
+      detail_samples_ += static_cast<int64_t>(h[0]);
+    }
+    return;
+  }
   // sub-phase -> public kernel class (device_ops.h): peer exchange has 7 sub-phases, otherwise the 4 classes themselves
   static const int kPeerClass[7] = {0, 0, 1, 2, 2, 2, 3};
   const int phases = timing_peer_ ? 7 : 4;

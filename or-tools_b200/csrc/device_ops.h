@@ -401,6 +401,8 @@ class Device {
   int64_t peer_arena_n_ = 0, peer_arena_m_ = 0;
   int32_t* tr_peer_error_ = nullptr;  // device flag: a peer did not arrive at a barrier of the trust-region search
   unsigned int* tile_counters_ = nullptr;  // tile queues of the persistent SpMV pair of the step loop (one per kernel)
+  unsigned int* loop_sync_ = nullptr;      // k_peer_loop: [0..2] grid-barrier words, [16..32) phase-time sums (u64)
+  bool loop_traced_ = false;               // the last EnqueueSteps launched k_peer_loop with the phase trace on
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)
   double* tr_scratch_ = nullptr;
