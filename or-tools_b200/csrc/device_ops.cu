@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
   static_assert(sizeof(StepState) % sizeof(double) == 0 && kWords <= BT, "the state is copied as doubles");
   __shared__ StepState s_st;
   __shared__ int s_err;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * BT;
   const int64_t gthread = static_cast<int64_t>(blockIdx.x) * BT + tid;
   const int64_t nwarps = nthreads >> 5, gwarp = gthread >> 5;
@@ -2420,6 +2420,8 @@ Device::~Device() {
   }
   for (void* e : timing_events_) cudaEventDestroy(static_cast<cudaEvent_t>(e));
   for (auto& pr : timeline_ev_) for (void* e : pr) if (e != nullptr) cudaEventDestroy(static_cast<cudaEvent_t>(e));
+  for (void* e : pair_ev_) if (e != nullptr) cudaEventDestroy(static_cast<cudaEvent_t>(e));
+  if (stream2_ != nullptr) cudaStreamDestroy(static_cast<cudaStream_t>(stream2_));
   if (stream_ != nullptr) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
 }
 
@@ -3152,11 +3154,12 @@ static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_glob
 // JOINT: x0 / y0 / out as in TrSolveArgs.
 template <class Elem, bool JOINT>
 bool tr_solve_persistent(cudaStream_t stream, Comm* comm, const PeerPtrs& peer, int32_t* peer_error, int64_t total, Elem el, double radius,
-                         const double* x0, const double* y0, double* scratch, double* partials, TrSearchState* st, double* out, int64_t* launches) {
+                         const double* x0, const double* y0, double* scratch, double* partials, TrSearchState* st, double* out, int64_t* launches,
+                         int blocks_per_sm = kTrBlocksPerSm) {
   const bool use_peer = comm != nullptr && peer.world > 1;
   if (TrLegacy() || (comm != nullptr && !use_peer)) return false;
   constexpr int64_t kTile = static_cast<int64_t>(kThreads) * kTrUnroll;
-  const int nbp = static_cast<int>(std::min<int64_t>(std::min<int64_t>(kTrMaxBlocks, static_cast<int64_t>(TrSms()) * kTrBlocksPerSm), std::max<int64_t>(1, (total + kTile - 1) / kTile)));
+  const int nbp = static_cast<int>(std::min<int64_t>(std::min<int64_t>(kTrMaxBlocks, static_cast<int64_t>(TrSms()) * blocks_per_sm), std::max<int64_t>(1, (total + kTile - 1) / kTile)));
   TrSolveArgs g;
   g.total = total;
   g.keys = reinterpret_cast<unsigned long long*>(scratch);
@@ -3243,6 +3246,55 @@ static int TrSms() {
   return n;
 }
 }  // namespace kernels
+
+// The restart test needs the bounds at the average AND at the current iterate (pdhg.cc:2109-2170):
+// two independent joint problems. One GPU: two persistent launches on two streams, one block per
+// SM each (both co-resident), so the latency-bound rounds of one solve overlap the other's; one
+// host synchronisation for both. Not used on a row-sharded solve (both would exchange through the
+// same arena segments) or with the diagonal solver: returns false and the caller solves them in turn.
+bool Device::LocalizedLagrangianBoundsPair(const double* const x[2], const double* const y[2], const double* const kx[2], const double* const kty[2],
+                                           const double* c, const double* q, const double* lv, const double* uv, const double* lc, const double* uc,
+                                           double primal_weight, int64_t n, int64_t mm, const double* x0, const double* y0, double out[2][3],
+                                           double extra_out[2][3]) {
+  static const bool enabled = [] { const char* e = std::getenv("PDLP_B200_TR_PAIR"); return !(e != nullptr && e[0] == '0'); }();
+  if (!enabled || comm_ != nullptr || TrLegacy() || x0 == nullptr || y0 == nullptr) return false;
+  const int64_t total = n + mm;
+  const int64_t per = ((3 * total + 128 + 3 * kTrFinishCap) + 63) / 64 * 64;
+  double* scratch = TrScratch(2 * per);
+  if (stream2_ == nullptr) {
+    cudaStream_t s2;
+    CUDA_OK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+    stream2_ = s2;
+    for (void*& e : pair_ev_) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e = ev; }
+  }
+  cudaStream_t s2 = static_cast<cudaStream_t>(stream2_);
+  PeerPtrs no_peer;
+  std::memset(&no_peer, 0, sizeof(no_peer));
+  CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(pair_ev_[0]), STREAM));   // (the second stream starts after what the first has queued so far)
+  CUDA_OK(cudaStreamWaitEvent(s2, static_cast<cudaEvent_t>(pair_ev_[0]), 0));
+  for (int k = 0; k < 2; ++k) {
+    const JointElem el{x[k], y[k], kx[k], kty[k], c, q, lv, uv, lc, uc, primal_weight, n, mm, 0};
+    double* sc = scratch + k * per;
+    if (!tr_solve_persistent<JointElem, true>(k == 0 ? STREAM : s2, nullptr, no_peer, tr_peer_error_, total, el, -1.0, x0, y0, sc, partials_ + k * (kMaxReduceBlocks * 20),
+                                              reinterpret_cast<TrSearchState*>(sc + 3 * total), results_ + 16 * k, &launches_, 1))
+      throw std::runtime_error("persistent trust-region launch refused");
+    CUDA_OK(cudaMemcpyAsync(host_results_ + 16 * k, results_ + 16 * k, sizeof(double) * 7, cudaMemcpyDeviceToHost, k == 0 ? STREAM : s2));
+  }
+  CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(pair_ev_[1]), s2));
+  CUDA_OK(cudaStreamWaitEvent(STREAM, static_cast<cudaEvent_t>(pair_ev_[1]), 0));
+  Sync();
+  for (int k = 0; k < 2; ++k) {
+    const double* r = host_results_ + 16 * k;
+    const double lagrangian = r[0] + r[1];
+    out[k][0] = lagrangian;
+    out[k][1] = lagrangian + r[2];
+    out[k][2] = lagrangian + r[3];
+    extra_out[k][0] = r[4];
+    extra_out[k][1] = r[5];
+    extra_out[k][2] = r[6];
+  }
+  return true;
+}
 
 void Device::LocalizedLagrangianBounds(const double* x, const double* y, const double* kx, const double* kty, const double* c, const double* q,
                                        const double* lv, const double* uv, const double* lc, const double* uc, double primal_weight, double radius,

@@ -312,6 +312,12 @@ class Device {
                                  const double* lv, const double* uv, const double* lc, const double* uc, double primal_weight,
                                  double radius, bool use_diagonal_solver, double diagonal_tol, int64_t n, int64_t m, double out[3],
                                  const double* x0 = nullptr, const double* y0 = nullptr, double* extra_out = nullptr);
+  // The same for TWO points at once (index 0 / 1; radius = weighted distance to (x0, y0)): concurrent launches,
+  // one host synchronisation. false: not applicable here, solve them one by one. extra_out as above.
+  bool LocalizedLagrangianBoundsPair(const double* const x[2], const double* const y[2], const double* const kx[2], const double* const kty[2],
+                                     const double* c, const double* q, const double* lv, const double* uv, const double* lc, const double* uc,
+                                     double primal_weight, int64_t n, int64_t m, const double* x0, const double* y0, double out[2][3],
+                                     double extra_out[2][3]);
   // Explicit-vector problems (SolveTrustRegion / SolveDiagonalTrustRegion).
   void SolveTrustRegion(const double* obj, const double* lb, const double* ub, const double* center, const double* w, double radius,
                         int64_t n, double* solution, double* step_size, double* objective_value);
@@ -392,6 +398,8 @@ class Device {
   int device_ = 0;
   Comm* comm_ = nullptr;
   void* stream_ = nullptr;
+  void* stream2_ = nullptr;                 // second stream of LocalizedLagrangianBoundsPair (created on first use)
+  void* pair_ev_[2] = {nullptr, nullptr};   // fork / join events of the pair
   double* partials_ = nullptr;   // reduction scratch
   double* results_ = nullptr;    // small device result vector
   double* host_results_ = nullptr;  // pinned

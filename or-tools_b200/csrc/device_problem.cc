@@ -406,6 +406,19 @@ void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const doub
   if (dist_sq != nullptr) { dist_sq[0] = extra[1]; dist_sq[1] = extra[2]; }
 }
 
+bool DeviceProblem::ComputeLocalizedLagrangianBoundsPair(const double* const x[2], const double* const y[2], const double* const kx[2],
+                                                         const double* const kty[2], double primal_weight, bool use_diagonal_solver, const double* x0,
+                                                         const double* y0, double out[2][4], double dist_sq[2][2]) {
+  if (use_diagonal_solver || sharded()) return false;
+  double r3[2][3], extra[2][3];
+  if (!dev_->LocalizedLagrangianBoundsPair(x, y, kx, kty, c_, q_, lv_, uv_, lc_, uc_, primal_weight, n_, m_, x0, y0, r3, extra)) return false;
+  for (int k = 0; k < 2; ++k) {
+    out[k][0] = r3[k][0]; out[k][1] = r3[k][1]; out[k][2] = r3[k][2]; out[k][3] = extra[k][0];
+    dist_sq[k][0] = extra[k][1]; dist_sq[k][1] = extra[k][2];
+  }
+  return true;
+}
+
 void DeviceProblem::ComputeLocalizedLagrangianBoundsMaxNorm(const double* x, const double* y, double primal_weight, double radius, const double* kx,
                                                             const double* kty, double out[4]) {
   if (sharded()) throw std::runtime_error("max-norm localized Lagrangian bounds are not available on a row-sharded problem");

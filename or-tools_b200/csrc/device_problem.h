@@ -115,6 +115,11 @@ class DeviceProblem {
   // trust_region.cc:855-884 (max norm): the primal and the dual trust-region problems are solved
   // separately with radii sqrt(2) r / sqrt(w) and sqrt(2) r sqrt(w). Not used by the solver
   // (pdhg.cc asks for the Euclidean norm); single GPU only.
+  // Both points of the restart test in one go (Device::LocalizedLagrangianBoundsPair); kx / kty must be given.
+  // out[k] = {lagrangian, lower, upper, radius}, dist_sq[k] = {||x - x0||^2, ||y - y0||^2}. false: not applicable.
+  bool ComputeLocalizedLagrangianBoundsPair(const double* const x[2], const double* const y[2], const double* const kx[2], const double* const kty[2],
+                                            double primal_weight, bool use_diagonal_solver, const double* x0, const double* y0, double out[2][4],
+                                            double dist_sq[2][2]);
   void ComputeLocalizedLagrangianBoundsMaxNorm(const double* x, const double* y, double primal_weight, double radius, const double* kx,
                                                const double* kty, double out[4]);
 

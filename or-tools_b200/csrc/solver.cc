@@ -392,6 +392,26 @@ class DeviceSolve {
     const double* ay = DualAverage();
     return BoundsAt(ax, ay, CachedKx(ax), CachedKty(ay));
   }
+  // Both points of the restart test (pdhg.cc:2109-2170 evaluates them back to back): concurrently on one GPU.
+  void ComputeLocalizedBoundsAtAverageAndCurrent(LocalizedBounds& avg, LocalizedBounds& cur) {
+    const double* ax = PrimalAverage();
+    const double* ay = DualAverage();
+    const double* const xs[2] = {ax, X()};
+    const double* const ys[2] = {ay, Y()};
+    const double* const kxs[2] = {CachedKx(ax), CachedKx(X())};
+    const double* const ktys[2] = {CachedKty(ay), Kty()};
+    double out[2][4], dist[2][2];
+    if (kxs[0] != nullptr && ktys[0] != nullptr &&
+        P.ComputeLocalizedLagrangianBoundsPair(xs, ys, kxs, ktys, hs_.primal_weight, params_.use_diagonal_qp_trust_region_solver != 0, x0_, y0_, out, dist)) {
+      avg = {out[0][0], out[0][1], out[0][2], out[0][3]};
+      cur = {out[1][0], out[1][1], out[1][2], out[1][3]};
+      if (ax == buf_.avg_x && ay == buf_.avg_y) { dist_avg_[0] = dist[0][0]; dist_avg_[1] = dist[0][1]; dist_avg_ok_ = dist[0][0] >= 0.0; }
+      dist_cur_[0] = dist[1][0]; dist_cur_[1] = dist[1][1]; dist_cur_ok_ = dist[1][0] >= 0.0;
+      return;
+    }
+    avg = ComputeLocalizedBoundsAtAverage();
+    cur = ComputeLocalizedBoundsAtCurrent();
+  }
   static bool AverageHasBetterPotential(const LocalizedBounds& avg, const LocalizedBounds& cur) {  // :2041-2048
     return BoundGap(avg) / Sq(avg.radius) < BoundGap(cur) / Sq(cur.radius);
   }
@@ -524,8 +544,8 @@ int DeviceSolve::DetermineDistanceBasedRestartChoice() {  // pdhg.cc:2074-2107
   const double dist_avg = DistanceTraveledFromLastStart(buf_.avg_x, buf_.avg_y);
   if ((dist_avg / period) < params_.sufficient_reduction_for_restart *
                                 (distance_info_.distance_moved_last_restart_period / distance_info_.length_of_last_restart_period)) {
-    const LocalizedBounds avg = ComputeLocalizedBoundsAtAverage();
-    const LocalizedBounds cur = ComputeLocalizedBoundsAtCurrent();
+    LocalizedBounds avg, cur;
+    ComputeLocalizedBoundsAtAverageAndCurrent(avg, cur);
     return AverageHasBetterPotential(avg, cur) ? PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE : PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
   }
   return PDLP_RESTART_CHOICE_NO_RESTART;
@@ -535,8 +555,8 @@ int DeviceSolve::ChooseRestartToApply(bool is_major) {  // pdhg.cc:2109-2170
   if (!PrimalAvgHasWeight() && !DualAvgHasWeight()) return PDLP_RESTART_CHOICE_NO_RESTART;
   const int restart_length = avg_x_terms_;
   if (restart_length >= iterations_completed_ / 2 && params_.restart_strategy == PDLP_ADAPTIVE_HEURISTIC) {
-    const LocalizedBounds avg = ComputeLocalizedBoundsAtAverage();
-    const LocalizedBounds cur = ComputeLocalizedBoundsAtCurrent();
+    LocalizedBounds avg, cur;
+    ComputeLocalizedBoundsAtAverageAndCurrent(avg, cur);
     return AverageHasBetterPotential(avg, cur) ? PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE : PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
   }
   if (!is_major) return PDLP_RESTART_CHOICE_NO_RESTART;
@@ -544,8 +564,8 @@ int DeviceSolve::ChooseRestartToApply(bool is_major) {  // pdhg.cc:2109-2170
     case PDLP_NO_RESTARTS: return PDLP_RESTART_CHOICE_WEIGHTED_AVERAGE_RESET;
     case PDLP_EVERY_MAJOR_ITERATION: return PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE;
     case PDLP_ADAPTIVE_HEURISTIC: {
-      const LocalizedBounds avg = ComputeLocalizedBoundsAtAverage();
-      const LocalizedBounds cur = ComputeLocalizedBoundsAtCurrent();
+      LocalizedBounds avg, cur;
+      ComputeLocalizedBoundsAtAverageAndCurrent(avg, cur);
       double gap;
       int choice;
       if (AverageHasBetterPotential(avg, cur)) { gap = BoundGap(avg) / avg.radius; choice = PDLP_RESTART_CHOICE_RESTART_TO_AVERAGE; }
