@@ -512,6 +512,11 @@ struct StepPtrs {
   double* x_tilde;
   double* avg_x;
   double* avg_y;
+  // Row-sharded peer solves only (else nullptr): K x and K^T y of the average, maintained with the
+  // averages themselves (the products are linear in the iterate, and K x / K^T y of every iterate
+  // exist) -- the restart test then needs no product of the average, i.e. no all-reduce of n doubles.
+  double* avg_kx;
+  double* avg_kty;
   const double *c, *q, *lv, *uv, *lc, *uc;
   StepState* state;  // the slot the kernels of this attempt read
 };
@@ -628,6 +633,12 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
       av.x += ratio * (x2.x - av.x);
       av.y += ratio * (x2.y - av.y);
       *reinterpret_cast<double2*>(b.avg_x + i0) = av;
+      if (PEER && b.avg_kty != nullptr) {
+        double2 ak = *reinterpret_cast<const double2*>(b.avg_kty + i0);
+        ak.x += ratio * (k2.x - ak.x);
+        ak.y += ratio * (k2.y - ak.y);
+        *reinterpret_cast<double2*>(b.avg_kty + i0) = ak;
+      }
     }
   } else if (i0 < iend) {
     const double x = xc[i0];
@@ -644,7 +655,10 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
       b.x_tilde[i0] = nx + d;
     }
     s = d * d;
-    if (ratio > 0.0) b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
+    if (ratio > 0.0) {
+      b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
+      if (PEER && b.avg_kty != nullptr) b.avg_kty[i0] += ratio * (kty[i0] - b.avg_kty[i0]);
+    }
   }
   block_reduce_store<1, 0>(&s, nullptr, partials + blockIdx.x);
   if (blockIdx.x == 0 && threadIdx.x == 0 && st->rule == PDLP_ADAPTIVE_LINESEARCH_RULE) {
@@ -658,7 +672,7 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
 
 // PUSH: the all-gather of y' fused into the producing epilogue -- every new
 // dual value is also stored into every rank's arena at its box-wide position.
-template <bool PUSH>
+template <bool PUSH, bool AVGK = false>  // AVGK: also maintains K x of the average (StepPtrs::avg_kx; peer exchange only)
 struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1; nonlinearity of pdhg.cc:2588-2592 on the row side
   StepPtrs b;
   PeerPtrs peer;
@@ -686,7 +700,10 @@ struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1; nonlinearity of pdhg.cc:
   // kxt = (K x~)_pos with x~ = 2 x' - x, so K x' = (kxt + K x) / 2 and K (x' - x) = (kxt - K x) / 2
   __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kxt, double* red, const Pre& p) const {
     const double kxc = c.kxc[pos];  // (loaded here, not prefetched: the row loop is at its register limit)
-    if (c.ratio > 0.0) b.avg_y[pos] = p.avg + c.ratio * (p.yc - p.avg);
+    if (c.ratio > 0.0) {
+      b.avg_y[pos] = p.avg + c.ratio * (p.yc - p.avg);
+      if (AVGK && b.avg_kx != nullptr) b.avg_kx[pos] += c.ratio * (kxc - b.avg_kx[pos]);
+    }
     const double t = p.yc - c.sigma * kxt;
     const double yn = fmax(fmin(0.0, t + c.sigma * p.uc), t + c.sigma * p.lc);
     c.yn[pos] = yn;
@@ -999,10 +1016,14 @@ __global__ void __launch_bounds__(kThreads) k_flush_average(StepPtrs b, int64_t 
       if (r0 > 0.0) av += r0 * (pick3(b.x, st->prev)[i] - av);
       if (r1 > 0.0) av += r1 * (pick3(b.x, st->cur)[i] - av);
       b.avg_x[i] = av;
+      if (b.avg_kty != nullptr && r1 > 0.0) b.avg_kty[i] += r1 * (pick3(b.kty, st->cur)[i] - b.avg_kty[i]);  // (r0 is Malitsky-Pock only: not maintained there)
     }
   } else if (i < total) {
     const int64_t j = i - b.n;
-    if (rd > 0.0) b.avg_y[j] += rd * (pick3(b.y, st->cur)[j] - b.avg_y[j]);
+    if (rd > 0.0) {
+      b.avg_y[j] += rd * (pick3(b.y, st->cur)[j] - b.avg_y[j]);
+      if (b.avg_kx != nullptr) b.avg_kx[j] += rd * (pick3(b.kx, st->cur)[j] - b.avg_kx[j]);
+    }
   }
 }
 __global__ void k_clear_pending(StepState* st) { st->pending_ratio = st->pending_ratio_dual = st->pending_ratio0 = 0.0; }
@@ -1192,10 +1213,17 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
             av.x += ratio * (x2.x - av.x);
             av.y += ratio * (x2.y - av.y);
             *reinterpret_cast<double2*>(b.avg_x + i0) = av;
+            if (b.avg_kty != nullptr) {
+              double2 ak = *reinterpret_cast<const double2*>(b.avg_kty + i0);
+              ak.x += ratio * (k2.x - ak.x);
+              ak.y += ratio * (k2.y - ak.y);
+              *reinterpret_cast<double2*>(b.avg_kty + i0) = ak;
+            }
           }
         } else {
           const double x = xc[i0];
-          double t = x - tau * (b.c[i0] - __ldcg(kty + i0));
+          const double kv = __ldcg(kty + i0);
+          double t = x - tau * (b.c[i0] - kv);
           if (has_q) t = t / (tau * b.q[i0] + 1.0);
           const double nx = fmax(fmin(t, b.uv[i0]), b.lv[i0]);
           const double d = nx - x;
@@ -1204,7 +1232,10 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
           for (int h = 0; h < kMaxPeers; ++h)
             if (h < peer.world) peer.base[h][peer.xt_off + i0] = nx + d;
           s += d * d;
-          if (ratio > 0.0) b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
+          if (ratio > 0.0) {
+            b.avg_x[i0] += ratio * (x - b.avg_x[i0]);
+            if (b.avg_kty != nullptr) b.avg_kty[i0] += ratio * (kv - b.avg_kty[i0]);
+          }
         }
       }
       block_reduce_store<1, 0, BT>(&s, nullptr, g.block_partials + 4 * blockIdx.x);
@@ -1217,10 +1248,10 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
 
     // ---- D: K[R_g,:] x~ and the dual update (k_sell + DualEpi) --------------------------
     {
-      DualEpiT<MODE == 0> epi;
+      DualEpiT<MODE == 0, true> epi;
       epi.b = b;
       epi.peer = peer;
-      typename DualEpiT<MODE == 0>::Ctx ctx;
+      typename DualEpiT<MODE == 0, true>::Ctx ctx;
       ctx.yc = pick3(b.y, cur);
       ctx.yn = pick3(b.y, cand);
       ctx.kxc = pick3(b.kx, cur);
@@ -1237,7 +1268,7 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
         const int64_t slot = (sl << 5) + lane;
         const int64_t pos = a.num_split + (slot - a.num_virtual_padded);  // (no split rows: the host takes the multi-launch path for those)
         const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
-        typename DualEpiT<MODE == 0>::Pre pre;
+        typename DualEpiT<MODE == 0, true>::Pre pre;
         if (own_row) pre = epi.prefetch(ctx, pos);
         const double acc = sell_row<kDot, 1, true>(a, slot, xt);
         if (own_row) epi(ctx, pos, acc, red, pre);
@@ -3511,6 +3542,8 @@ static StepPtrs MakePtrs(const Device::StepBuffers& b) {
   p.n = b.n; p.m = b.m;
   for (int k = 0; k < 3; ++k) { p.x[k] = b.x[k]; p.y[k] = b.y[k]; p.kty[k] = b.kty[k]; p.kx[k] = b.kx[k]; }
   p.x_tilde = b.x_tilde; p.avg_x = b.avg_x; p.avg_y = b.avg_y;
+  p.avg_kx = b.arena != nullptr ? b.avg_kx : nullptr;   // (maintained by the peer-exchange kernels only)
+  p.avg_kty = b.arena != nullptr ? b.avg_kty : nullptr;
   p.c = b.c; p.q = b.q; p.lv = b.lv; p.uv = b.uv; p.lc = b.lc; p.uc = b.uc;
   p.state = b.state;
   return p;
@@ -3644,7 +3677,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       launches_ += 2;
       if (slot >= 0) ev(slot, 2);
       if (b.m > 0) {
-        DualEpiT<true> de;
+        DualEpiT<true, true> de;
         de.b = p;
         de.peer = peer;
         launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, de, pd, halt, &launches_, nullptr, nullptr, pdl);
@@ -3666,7 +3699,10 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
       launches_ += 2;
       if (slot >= 0) ev(slot, 2);
       if (b.m > 0) {
-        launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, MakeDualEpi(p), pd, halt, &launches_, nullptr, nullptr, pdl);
+        DualEpiT<false, true> de;
+        de.b = p;
+        std::memset(&de.peer, 0, sizeof(de.peer));
+        launch_sell<kDot, 2>(STREAM, rows, GatherSrc{{peer.base[peer.rank] + peer.xt_off, nullptr, nullptr}, nullptr}, de, pd, halt, &launches_, nullptr, nullptr, pdl);
       }
       if (slot >= 0) ev(slot, 3);
       launch_sell<kDot, 0>(STREAM, cols, GatherSrc{{b.y[0], b.y[1], b.y[2]}, st_in}, ScatterEpi{peer.base[peer.rank] + peer.partial_off, b.primal_scatter}, nullptr, halt, &launches_, nullptr, nullptr, pdl);
@@ -3826,7 +3862,8 @@ void Device::GatherPrimalSlices(const StepBuffers& b, int cur, int prev) {
   // lazily (it then asks for that one vector with cur < 0)
   comm_->GroupStart();
   if (cur >= 0)
-    for (double* v : {b.x[cur], b.kty[cur], b.avg_x}) comm_->AllGatherInPlace(v, b.slice_stride, stream_);
+    for (double* v : {b.x[cur], b.kty[cur], b.avg_x, b.avg_kty})
+      if (v != nullptr) comm_->AllGatherInPlace(v, b.slice_stride, stream_);
   if (prev >= 0) comm_->AllGatherInPlace(b.x[prev], b.slice_stride, stream_);
   comm_->GroupEnd();
 }

@@ -335,6 +335,10 @@ class Device {
     double* x_tilde = nullptr;
     double* avg_x = nullptr;
     double* avg_y = nullptr;
+    // peer-memory exchange only (else nullptr): K x / K^T y of the average, maintained by the step kernels
+    // alongside the averages (avg_kty on this rank's primal slice; all-gathered with avg_x)
+    double* avg_kx = nullptr;
+    double* avg_kty = nullptr;
     const double *c = nullptr, *q = nullptr, *lv = nullptr, *uv = nullptr, *lc = nullptr, *uc = nullptr;
     StepState* state = nullptr;  // device, TWO slots: an attempt reads one, its decision writes the other
     // row-sharded solve only: [n + 1] exchange buffer for the K^T y' partial

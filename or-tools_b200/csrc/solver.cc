@@ -309,7 +309,7 @@ class DeviceSolve {
                    phase_s_[0], phase_s_[1], phase_s_[2], phase_s_[3], phase_s_[4], phase_s_[5]);
     }
     for (int k = 0; k < 3; ++k) { D.Free(buf_.x[k]); D.Free(buf_.y[k]); D.Free(buf_.kty[k]); D.Free(buf_.kx[k]); }
-    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, x0_, y0_, delta_x_, delta_y_, pc_kx_avg_, pc_kty_avg_, polish_x_, polish_y_}) D.Free(v);
+    for (double* v : {buf_.x_tilde, buf_.avg_x, buf_.avg_y, buf_.avg_kx, buf_.avg_kty, x0_, y0_, delta_x_, delta_y_, pc_kx_avg_, pc_kty_avg_, polish_x_, polish_y_}) D.Free(v);
     if (!nested_) { D.Free(dc_); D.Free(dr_); }
     D.Free(buf_.state);
   }
@@ -342,6 +342,12 @@ class DeviceSolve {
     InvalidateProducts(false, true);
     D.Fill(buf_.avg_x, 0.0, P.n());
     D.Fill(buf_.avg_y, 0.0, P.m());
+    if (buf_.avg_kx != nullptr) {
+      D.Fill(buf_.avg_kx, 0.0, P.m());
+      D.Fill(buf_.avg_kty, 0.0, P.n());
+      // valid from an empty average on, as long as every term enters through the peer-exchange step kernels
+      avg_products_ok_ = params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE;
+    }
     avg_x_weight_ = avg_y_weight_ = 0.0;
     avg_x_terms_ = avg_y_terms_ = 0;
     hs_.avg_weight_sum = 0.0;
@@ -353,6 +359,7 @@ class DeviceSolve {
     int& terms = primal ? avg_x_terms_ : avg_y_terms_;
     if (weight > 0.0) {
       InvalidateProducts(false, true);
+      avg_products_ok_ = false;  // (a term added from the host: the maintained products of the average no longer match)
       D.WeightedAverageAdd(primal ? buf_.avg_x : buf_.avg_y, v, weight / (w + weight), primal ? P.n() : P.m());
       w += weight;
     }
@@ -362,6 +369,11 @@ class DeviceSolve {
     ClearAverages();
     AverageAdd(true, X(), 1.0);
     AverageAdd(false, Y(), 1.0);
+    if (buf_.avg_kx != nullptr && params_.linesearch_rule != PDLP_MALITSKY_POCK_LINESEARCH_RULE) {  // the average IS the current iterate
+      D.CopyD2D(buf_.avg_kx, Kx(), P.m());
+      D.CopyD2D(buf_.avg_kty, Kty(), P.n());
+      avg_products_ok_ = true;
+    }
     hs_.avg_weight_sum = 1.0;
     hs_.avg_num_terms = 1;
   }
@@ -474,6 +486,8 @@ class DeviceSolve {
   // K^T y of the current iterate are iterate buffers of the step loop.)
   double *pc_kx_avg_ = nullptr, *pc_kty_avg_ = nullptr;
   bool pc_kx_avg_ok_ = false, pc_kty_avg_ok_ = false;
+  // buf_.avg_kx / buf_.avg_kty (row-sharded peer exchange) hold K x / K^T y of the current averages
+  bool avg_products_ok_ = false;
   // squared distances of the current / average point to the last restart point, as left by BoundsAt
   double dist_cur_[2] = {0, 0}, dist_avg_[2] = {0, 0};
   bool dist_cur_ok_ = false, dist_avg_ok_ = false;
@@ -484,6 +498,7 @@ class DeviceSolve {
   const double* CachedKx(const double* x) {  // nullptr: not one of the cached points
     if (x == X()) return Kx();
     if (x == buf_.avg_x) {
+      if (avg_products_ok_ && buf_.avg_kx != nullptr) return buf_.avg_kx;
       if (!pc_kx_avg_ok_) { P.Kx(x, pc_kx_avg_); pc_kx_avg_ok_ = true; }
       return pc_kx_avg_;
     }
@@ -492,6 +507,7 @@ class DeviceSolve {
   const double* CachedKty(const double* y) {
     if (y == Y()) return Kty();
     if (y == buf_.avg_y) {
+      if (avg_products_ok_ && buf_.avg_kty != nullptr) return buf_.avg_kty;
       if (!pc_kty_avg_ok_) { P.KTy(y, pc_kty_avg_); pc_kty_avg_ok_ = true; }
       return pc_kty_avg_;
     }
@@ -607,8 +623,11 @@ void DeviceSolve::ApplyRestartChoice(int restart) {  // pdhg.cc:2246-2296
       D.CopyD2D(Y(), buf_.avg_y, P.m());
       dist_cur_[0] = dist_avg_[0]; dist_cur_[1] = dist_avg_[1]; dist_cur_ok_ = dist_avg_ok_;
       // the new current iterate is the average: its products are the average's
-      if (pc_kty_avg_ok_) D.CopyD2D(Kty(), pc_kty_avg_, P.n()); else P.KTy(Y(), Kty());
-      if (pc_kx_avg_ok_) D.CopyD2D(Kx(), pc_kx_avg_, P.m()); else P.Kx(X(), Kx());
+      if (avg_products_ok_ && buf_.avg_kty != nullptr) { D.CopyD2D(Kty(), buf_.avg_kty, P.n()); D.CopyD2D(Kx(), buf_.avg_kx, P.m()); }
+      else {
+        if (pc_kty_avg_ok_) D.CopyD2D(Kty(), pc_kty_avg_, P.n()); else P.KTy(Y(), Kty());
+        if (pc_kx_avg_ok_) D.CopyD2D(Kx(), pc_kx_avg_, P.m()); else P.Kx(X(), Kx());
+      }
 
       break;
   }
@@ -1275,6 +1294,10 @@ void DeviceSolve::AllocateIterates() {
   pc_kx_avg_ = P.NewDual();
   pc_kty_avg_ = P.NewPrimal();
   delta_y_ = P.NewDual();
+  if (P.sharded() && P.arena() != nullptr) {  // peer exchange: the step kernels maintain K x / K^T y of the average (device_ops.h)
+    buf_.avg_kx = P.NewDual();
+    buf_.avg_kty = P.NewPrimal();
+  }
   buf_.c = P.c(); buf_.q = P.q(); buf_.lv = P.lv(); buf_.uv = P.uv(); buf_.lc = P.lc(); buf_.uc = P.uc();
   buf_.state = D.AllocState();
   buf_.exchange = P.exchange();
