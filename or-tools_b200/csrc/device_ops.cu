@@ -536,6 +536,7 @@ struct PeerPtrs {
   int world, rank;
   double* base[kMaxPeers];
   int64_t xt_off, partial_off, y_off, scal_off, flags_off, epoch_off, tr_off, cand_off;
+  int tr_barrier;      // barrier index of the trust-region solve using these pointers (3, or 4 for the second of a concurrent pair)
   int64_t row_begin;   // this rank's first position in the box-wide dual order
   long long timeout_cycles;  // a peer that does not arrive within this many SM clocks halts the loop
   int64_t begin, end;  // this rank's slice of the primal vector (begin is even)
@@ -1939,7 +1940,7 @@ __device__ bool tr_round(const TrSolveArgs& g, const PeerPtrs& peer, double* bin
         if (lane < K) dst[lane] = tot[lane];
         if (32 + lane < K) dst[32 + lane] = tot[32 + lane];
       }
-      peer_barrier(peer, 3, g.peer_error);
+      peer_barrier(peer, peer.tr_barrier, g.peer_error);
     }
     __syncthreads();
     if (tid < K) {
@@ -2249,7 +2250,7 @@ __global__ void __launch_bounds__(kThreads, kTrBlocksPerSm) k_tr_solve(TrSolveAr
           if (tid == 0)
             for (int h = 0; h < peer.world; ++h) *reinterpret_cast<volatile long long*>(peer_base(peer, h) + peer.cand_off + kSeg * peer.rank + 3 * kTrFinishCap) = ncand;
           __syncthreads();  // all stores of the block are issued before the (system-scope) fence of the barrier
-          if (warp == 0) peer_barrier(peer, 3, g.peer_error);
+          if (warp == 0) peer_barrier(peer, peer.tr_barrier, g.peer_error);
           nseg = peer.world;
         }
         __syncthreads();
@@ -3168,7 +3169,7 @@ static long long PeerTimeoutCycles() {
   }();
   return v;
 }
-static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_global) {
+static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_global, int set = 0) {
   PeerPtrs pp;
   std::memset(&pp, 0, sizeof(pp));
   if (arena == nullptr) return pp;
@@ -3176,7 +3177,10 @@ static PeerPtrs MakeTrPeerPtrs(const PeerArena* arena, int64_t n, int64_t m_glob
   pp.rank = arena->rank;
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(arena->base[h]);
   const PeerLayout l = PeerLayout::For(n, m_global, pp.world);
-  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off; pp.cand_off = l.cand_off;
+  pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off;
+  pp.tr_off = set == 0 ? l.tr_off : l.tr2_off;
+  pp.cand_off = set == 0 ? l.cand_off : l.cand2_off;
+  pp.tr_barrier = set == 0 ? 3 : 4;
   pp.timeout_cycles = PeerTimeoutCycles();
   return pp;
 }
@@ -3281,15 +3285,20 @@ static int TrSms() {
 // The restart test needs the bounds at the average AND at the current iterate (pdhg.cc:2109-2170):
 // two independent joint problems. One GPU: two persistent launches on two streams, one block per
 // SM each (both co-resident), so the latency-bound rounds of one solve overlap the other's; one
-// host synchronisation for both. Not used on a row-sharded solve (both would exchange through the
-// same arena segments) or with the diagonal solver: returns false and the caller solves them in turn.
+// host synchronisation for both. Row-sharded peer solves: the second solve exchanges through its own
+// arena segments and barrier. Not used with the diagonal solver or the NCCL-only exchange: returns
+// false and the caller solves them in turn.
 bool Device::LocalizedLagrangianBoundsPair(const double* const x[2], const double* const y[2], const double* const kx[2], const double* const kty[2],
                                            const double* c, const double* q, const double* lv, const double* uv, const double* lc, const double* uc,
                                            double primal_weight, int64_t n, int64_t mm, const double* x0, const double* y0, double out[2][3],
                                            double extra_out[2][3]) {
   static const bool enabled = [] { const char* e = std::getenv("PDLP_B200_TR_PAIR"); return !(e != nullptr && e[0] == '0'); }();
-  if (!enabled || comm_ != nullptr || TrLegacy() || x0 == nullptr || y0 == nullptr) return false;
-  const int64_t total = n + mm;
+  const bool use_peer = comm_ != nullptr && peer_arena_ != nullptr && peer_arena_->world > 1;
+  if (!enabled || (comm_ != nullptr && !use_peer) || TrLegacy() || x0 == nullptr || y0 == nullptr) return false;
+  // (row-sharded: every rank counts its own slice of the replicated primal side; the two solves exchange
+  // through their own arena segments and barrier, PeerLayout::tr_off / tr2_off)
+  const int64_t pbeg = PrimalSliceBegin(n), plen = PrimalSliceEnd(n) - pbeg;
+  const int64_t total = plen + mm;
   const int64_t per = ((3 * total + 128 + 3 * kTrFinishCap) + 63) / 64 * 64;
   double* scratch = TrScratch(2 * per);
   if (stream2_ == nullptr) {
@@ -3299,21 +3308,25 @@ bool Device::LocalizedLagrangianBoundsPair(const double* const x[2], const doubl
     for (void*& e : pair_ev_) { cudaEvent_t ev; CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)); e = ev; }
   }
   cudaStream_t s2 = static_cast<cudaStream_t>(stream2_);
-  PeerPtrs no_peer;
-  std::memset(&no_peer, 0, sizeof(no_peer));
   CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(pair_ev_[0]), STREAM));   // (the second stream starts after what the first has queued so far)
   CUDA_OK(cudaStreamWaitEvent(s2, static_cast<cudaEvent_t>(pair_ev_[0]), 0));
+  int32_t* err = reinterpret_cast<int32_t*>(host_results_ + 40);
+  err[0] = err[1] = 0;
   for (int k = 0; k < 2; ++k) {
-    const JointElem el{x[k], y[k], kx[k], kty[k], c, q, lv, uv, lc, uc, primal_weight, n, mm, 0};
+    const JointElem el{x[k], y[k], kx[k], kty[k], c, q, lv, uv, lc, uc, primal_weight, plen, mm, pbeg};
     double* sc = scratch + k * per;
-    if (!tr_solve_persistent<JointElem, true>(k == 0 ? STREAM : s2, nullptr, no_peer, tr_peer_error_, total, el, -1.0, x0, y0, sc, partials_ + k * (kMaxReduceBlocks * 20),
+    const PeerPtrs tr_peer = MakeTrPeerPtrs(use_peer ? peer_arena_ : nullptr, peer_arena_n_, peer_arena_m_, k);
+    cudaStream_t sk = k == 0 ? STREAM : s2;
+    if (!tr_solve_persistent<JointElem, true>(sk, use_peer ? comm_ : nullptr, tr_peer, tr_peer_error_ + k, total, el, -1.0, x0, y0, sc, partials_ + k * (kMaxReduceBlocks * 20),
                                               reinterpret_cast<TrSearchState*>(sc + 3 * total), results_ + 16 * k, &launches_, 1))
       throw std::runtime_error("persistent trust-region launch refused");
-    CUDA_OK(cudaMemcpyAsync(host_results_ + 16 * k, results_ + 16 * k, sizeof(double) * 7, cudaMemcpyDeviceToHost, k == 0 ? STREAM : s2));
+    CUDA_OK(cudaMemcpyAsync(host_results_ + 16 * k, results_ + 16 * k, sizeof(double) * 7, cudaMemcpyDeviceToHost, sk));
+    if (use_peer) CUDA_OK(cudaMemcpyAsync(err + k, tr_peer_error_ + k, sizeof(int32_t), cudaMemcpyDeviceToHost, sk));
   }
   CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(pair_ev_[1]), s2));
   CUDA_OK(cudaStreamWaitEvent(STREAM, static_cast<cudaEvent_t>(pair_ev_[1]), 0));
   Sync();
+  if (err[0] != 0 || err[1] != 0) throw std::runtime_error("peer-memory exchange timed out in the trust-region search: a rank did not arrive");
   for (int k = 0; k < 2; ++k) {
     const double* r = host_results_ + 16 * k;
     const double lagrangian = r[0] + r[1];
@@ -3558,6 +3571,7 @@ static PeerPtrs MakePeerPtrs(const Device::StepBuffers& b) {
   for (int h = 0; h < kMaxPeers; ++h) pp.base[h] = static_cast<double*>(b.arena->base[h]);
   const PeerLayout l = PeerLayout::For(b.n, b.m_global, pp.world);
   pp.xt_off = l.xt_off; pp.partial_off = l.partial_off; pp.y_off = l.y_off; pp.scal_off = l.scal_off; pp.flags_off = l.flags_off; pp.epoch_off = l.epoch_off; pp.tr_off = l.tr_off; pp.cand_off = l.cand_off;
+  pp.tr_barrier = 3;
   pp.row_begin = b.row_begin;
   pp.timeout_cycles = PeerTimeoutCycles();
   pp.begin = b.slice_begin;

@@ -119,6 +119,7 @@ enum { kHaltNone = 0, kHaltCheckpoint = 1, kHaltZeroMovement = 2, kHaltDivergent
 // of every primal vector so that slices can be all-gathered in place.
 struct PeerLayout {
   int64_t stride = 0, n_pad = 0, xt_off = 0, partial_off = 0, y_off = 0, scal_off = 0, flags_off = 0, epoch_off = 0, tr_off = 0, cand_off = 0, doubles = 0;
+  int64_t tr2_off = 0, cand2_off = 0;  // second set of trust-region segments (barrier 4): the two solves of a restart test run concurrently
   static constexpr int64_t kTrCandCap = 4096;                  // = kTrFinishCap of the trust-region solve
   static constexpr int64_t kTrCandSegment = 3 * kTrCandCap + 8;  // per rank: keys, a, b of its candidates + their count
   static PeerLayout For(int64_t n, int64_t m_global, int world) {
@@ -131,10 +132,12 @@ struct PeerLayout {
     l.y_off = 2 * l.n_pad;
     l.scal_off = l.y_off + 2 * ((m_global + 1) / 2) + 2;
     l.flags_off = l.scal_off + 4 * 8;
-    l.epoch_off = l.flags_off + 8 * 4;
-    l.tr_off = l.epoch_off + 4;
+    l.epoch_off = l.flags_off + 8 * 8;   // barriers 0..7 (0 / 1: step loop A / B, 3 / 4: trust-region solves)
+    l.tr_off = l.epoch_off + 8;
     l.cand_off = l.tr_off + 2 * 48 * 8;
-    l.doubles = l.cand_off + kTrCandSegment * 8;
+    l.tr2_off = l.cand_off + kTrCandSegment * 8;
+    l.cand2_off = l.tr2_off + 2 * 48 * 8;
+    l.doubles = l.cand2_off + kTrCandSegment * 8;
     return l;
   }
 };

@@ -409,7 +409,7 @@ void DeviceProblem::ComputeLocalizedLagrangianBounds(const double* x, const doub
 bool DeviceProblem::ComputeLocalizedLagrangianBoundsPair(const double* const x[2], const double* const y[2], const double* const kx[2],
                                                          const double* const kty[2], double primal_weight, bool use_diagonal_solver, const double* x0,
                                                          const double* y0, double out[2][4], double dist_sq[2][2]) {
-  if (use_diagonal_solver || sharded()) return false;
+  if (use_diagonal_solver) return false;
   double r3[2][3], extra[2][3];
   if (!dev_->LocalizedLagrangianBoundsPair(x, y, kx, kty, c_, q_, lv_, uv_, lc_, uc_, primal_weight, n_, m_, x0, y0, r3, extra)) return false;
   for (int k = 0; k < 2; ++k) {
