@@ -1,9 +1,8 @@
 """ctypes mirror of include/pdlp_b200.h (POD structs + function prototypes).
 
-The struct layouts are the interface of the C-ABI boundary; they are shared by
-the product library (prefix ``pdlp_b200_``) and -- in tests only -- by the CPU
-oracle (prefix ``pdlp_oracle_``), which exports the same entry points so parity
-tests call both sides identically.
+The struct layouts are the interface of the C-ABI boundary (entry points with the
+prefix ``pdlp_b200_``); a library that exports the same entry points under another
+prefix can be bound with the same prototypes (``bind(lib, prefix)``).
 """
 import ctypes as C
 

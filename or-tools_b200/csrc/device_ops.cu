@@ -228,6 +228,50 @@ __device__ __forceinline__ double sell_row(const SellDev& a, int64_t slot, const
   return acc;
 }
 
+// The row loop of k_peer_loop: there a phase ends when its LAST slice does, so the latency of one
+// slice counts, not only the throughput. Eight slots per trip, the tail trip masked instead of a
+// serial remainder, software-pipelined like sell_row<., 1>: a 20-entry row is 3 dependent gather
+// round trips instead of 5-6. Same accumulation order as sell_row (j = 0 .. n-1). Gathers at L2
+// (the gathered vector changes inside the launch).
+__device__ __forceinline__ double sell_row8_cg(const SellDev& a, int64_t slot, const double* x) {
+  const int64_t base = a.slice_ptr[slot >> 5] + (slot & 31);
+  const int n = a.slot_len[slot];
+  const double* __restrict__ val = a.val + base;
+  const int32_t* __restrict__ col = a.col + base;
+  constexpr int U = 8;
+  double acc = 0.0;
+  double v[U];
+  int c[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const bool ok = u < n;
+    c[u] = ok ? __ldcs(col + static_cast<int64_t>(u) * 32) : -1;
+    v[u] = ok ? __ldcs(val + static_cast<int64_t>(u) * 32) : 0.0;
+  }
+  for (int j = 0; j < n; j += U) {
+    double xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = c[u] >= 0 ? __ldcg(x + c[u]) : 0.0;
+    double vn[U];
+    int cn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = j + U + u < n;
+      cn[u] = ok ? __ldcs(col + static_cast<int64_t>(j + U + u) * 32) : -1;
+      vn[u] = ok ? __ldcs(val + static_cast<int64_t>(j + U + u) * 32) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (c[u] >= 0) acc = acc + v[u] * xv[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      v[u] = vn[u];
+      c[u] = cn[u];
+    }
+  }
+  return acc;
+}
+
 // Selects one of three kernel-parameter pointers without dynamic indexing of
 // the parameter array (which would force a copy of it to local memory).
 template <class T>
@@ -673,7 +717,12 @@ __global__ void __launch_bounds__(kThreads) k_primal_step(StepPtrs b, PeerPtrs p
 
 // PUSH: the all-gather of y' fused into the producing epilogue -- every new
 // dual value is also stored into every rank's arena at its box-wide position.
-template <bool PUSH, bool AVGK = false>  // AVGK: also maintains K x of the average (StepPtrs::avg_kx; peer exchange only)
+// AVGK: also maintains K x of the average (StepPtrs::avg_kx; peer exchange only). CG: the row-wise vectors
+// may have been written by another SM earlier in the same launch (k_peer_loop hands slices out
+// dynamically): they are read at L2 (ld.global.cg), never through this SM's L1.
+template <bool CG>
+__device__ __forceinline__ double row_ld(const double* p) { return CG ? __ldcg(p) : *p; }
+template <bool PUSH, bool AVGK = false, bool CG = false>
 struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1; nonlinearity of pdhg.cc:2588-2592 on the row side
   StepPtrs b;
   PeerPtrs peer;
@@ -692,18 +741,21 @@ struct DualEpiT {  // pdhg.cc:1912-1930 with theta = 1; nonlinearity of pdhg.cc:
   }
   __device__ __forceinline__ Pre prefetch(const Ctx& c, int64_t pos) const {
     Pre p;
-    p.yc = c.yc[pos];
+    p.yc = row_ld<CG>(c.yc + pos);
     p.lc = __ldg(b.lc + pos);
     p.uc = __ldg(b.uc + pos);
-    p.avg = c.ratio > 0.0 ? b.avg_y[pos] : 0.0;
+    p.avg = c.ratio > 0.0 ? row_ld<CG>(b.avg_y + pos) : 0.0;
     return p;
   }
   // kxt = (K x~)_pos with x~ = 2 x' - x, so K x' = (kxt + K x) / 2 and K (x' - x) = (kxt - K x) / 2
   __device__ __forceinline__ void operator()(const Ctx& c, int64_t pos, double kxt, double* red, const Pre& p) const {
-    const double kxc = c.kxc[pos];  // (loaded here, not prefetched: the row loop is at its register limit)
+    const double kxc = row_ld<CG>(c.kxc + pos);  // (loaded here, not prefetched: the row loop is at its register limit)
     if (c.ratio > 0.0) {
       b.avg_y[pos] = p.avg + c.ratio * (p.yc - p.avg);
-      if (AVGK && b.avg_kx != nullptr) b.avg_kx[pos] += c.ratio * (kxc - b.avg_kx[pos]);
+      if (AVGK && b.avg_kx != nullptr) {
+        const double ak = row_ld<CG>(b.avg_kx + pos);
+        b.avg_kx[pos] = ak + c.ratio * (kxc - ak);
+      }
     }
     const double t = p.yc - c.sigma * kxt;
     const double yn = fmax(fmin(0.0, t + c.sigma * p.uc), t + c.sigma * p.lc);
@@ -1045,14 +1097,15 @@ __global__ void k_clear_pending(StepState* st) { st->pending_ratio = st->pending
 //   T   MODE 0: (K[:,C_g])^T y' from the all-gathered y'; MODE 1: pull slice C_g of every rank's
 //       partial (128-bit peer loads), add in rank order. One warp first takes the step decision
 //       and writes the other state slot.                                        | grid barrier
-// Work is mapped to warps / threads STATICALLY: every row-wise vector is read and written by the
-// same thread in every attempt, and the partial sums do not depend on a schedule. Slices go to
-// the W warps of the grid in rounds of W, in alternating direction (warp w takes slice r W + w in
-// even rounds, r W + W - 1 - w in odd ones): the images are sorted by row length inside windows
-// whose size divides W, so a plain stride-W map would hand one warp the longest slices of every
-// window (measured: +60 % on the K^T y' phase of C2). Data another SM or GPU produced inside the launch
-// (x~, y', K^T y, the partials, the state) is read with ld.global.cg / volatile loads only: the
-// L1 of an SM is not coherent across the phases of one kernel.
+// The elementwise phases (P, the pull of T) are mapped to threads statically. The slices of the
+// row loops (D, T1, T of MODE 0) are handed to warps DYNAMICALLY, one atomic ticket per slice
+// (fetched one slice ahead): the SMs of a B200 do not run a request-bound row loop at the same
+// speed (GPCs of 16 / 18 / 20 SMs share a crossbar port; a static map left the fastest SM idle
+// for 25 % of a phase). Determinism does not depend on the schedule: every slice leaves its
+// {||dy||^2, (K dx).dy} in its own slot, the slots are added per block over fixed ranges after the
+// next grid barrier, the blocks in block order. Data another SM or GPU produced inside the launch
+// (x~, y', K^T y, the row-wise vectors, the partials, the state) is read with ld.global.cg /
+// volatile loads only: the L1 of an SM is not coherent across the phases of one kernel.
 struct PeerLoopArgs {
   StepPtrs p;        // p.state: slot 0 of the two state slots
   PeerPtrs peer;
@@ -1061,67 +1114,76 @@ struct PeerLoopArgs {
   const int32_t* perm;   // MODE 0: column (relative to col0) of a position of the slice image; MODE 1: column of a position
   int64_t col0;
   double* block_partials;  // [blocks][4]: ||dx||^2, ||dy||^2, (K dx).dy
-  unsigned int* sync;      // [0] arrivals [1] generation [2] error (a peer never arrived); zero before the launch
+  double* slice_partials;  // [slices of rows][2]: ||dy||^2, (K dx).dy of a slice
+  unsigned int* sync;      // [0] arrivals [1] generation [2] error (a peer never arrived) [4..6] slice tickets of D / T1 / T; zero before the launch
   int first_slot, max_attempts;
   unsigned long long* trace;  // nullptr, or [0] attempts, [1..6] summed ns of the phases (block 0)
 };
 enum { kLoopSyncPlain = 0, kLoopSyncPeer = 1, kLoopSyncSumsPeer = 2 };
 
 // Grid barrier number `bar` of the launch (all threads of all blocks). The block that arrives last
-// optionally adds the block partials and stores the triple into every arena (kLoopSyncSumsPeer),
-// then meets the other ranks at peer barrier `which` before it releases the grid. Returns true
-// when a peer never arrived.
-__device__ __forceinline__ bool loop_grid_sync(const PeerLoopArgs& g, unsigned& bar, int kind, int which, int* s_err) {
+// optionally (kLoopSyncSumsPeer) adds the partials in a fixed order -- the per-block ones in block
+// order and, when nslices > 0, the per-slice ones of the dual phase in slice order -- and stores
+// the triple into every arena, then meets the other ranks at peer barrier `which` before it
+// releases the grid. Returns true when a peer never arrived.
+template <int BT>
+__device__ __forceinline__ bool loop_grid_sync(const PeerLoopArgs& g, unsigned& bar, int kind, int which, int64_t nslices, int* s_flags, double* s_tot) {
+  // s_flags: [0] error [1] this block arrived last
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    unsigned last = 0;
-    if (lane == 0) {
-      // (cumulative: the block's stores -- local and into the peers' arenas -- ordered by the barrier above)
-      if (kind == kLoopSyncPlain) __threadfence(); else __threadfence_system();
-      const unsigned ticket = atomicAdd(g.sync, 1u);
-      last = ticket == gridDim.x * (bar + 1u) - 1u ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    // (cumulative: the block's stores -- local and into the peers' arenas -- ordered by the barrier above)
+    if (kind == kLoopSyncPlain) __threadfence(); else __threadfence_system();
+    const unsigned ticket = atomicAdd(g.sync, 1u);
+    s_flags[1] = ticket == gridDim.x * (bar + 1u) - 1u ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_flags[1] != 0) {
+    __threadfence();
+    if (kind == kLoopSyncSumsPeer) {
+      double r[3] = {0.0, 0.0, 0.0};
+      for (int k = threadIdx.x; k < static_cast<int>(gridDim.x); k += BT) {
+        r[0] += __ldcg(g.block_partials + 4 * k + 0);
+        if (nslices == 0) {
+          r[1] += __ldcg(g.block_partials + 4 * k + 1);
+          r[2] += __ldcg(g.block_partials + 4 * k + 2);
+        }
+      }
+      for (int64_t k = threadIdx.x; k < nslices; k += BT) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(g.slice_partials) + k);
+        r[1] += v.x;
+        r[2] += v.y;
+      }
+      block_reduce_store<3, 0, BT>(r, nullptr, s_tot);
+      __syncthreads();
     }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last != 0u) {
-      __threadfence();
-      if (kind == kLoopSyncSumsPeer) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) {  // block order: lane-strided, then a shuffle tree
-          s0 += __ldcg(g.block_partials + 4 * b + 0);
-          s1 += __ldcg(g.block_partials + 4 * b + 1);
-          s2 += __ldcg(g.block_partials + 4 * b + 2);
-        }
-        s0 = warp_sum(s0);
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane < g.peer.world) {
-          volatile double* dst = peer_base(g.peer, lane) + g.peer.scal_off + 4 * g.peer.rank;
-          dst[0] = s0;
-          dst[1] = s1;
-          dst[2] = s2;
-        }
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      if (kind == kLoopSyncSumsPeer && lane < g.peer.world) {
+        volatile double* dst = peer_base(g.peer, lane) + g.peer.scal_off + 4 * g.peer.rank;
+        dst[0] = s_tot[0];
+        dst[1] = s_tot[1];
+        dst[2] = s_tot[2];
       }
       if (kind != kLoopSyncPlain) peer_barrier(g.peer, which, reinterpret_cast<int32_t*>(g.sync + 2));
       if (lane == 0) {
         __threadfence();
         *reinterpret_cast<volatile unsigned int*>(g.sync + 1) = bar + 1u;
       }
-    } else if (lane == 0) {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned int*>(g.sync + 1) < bar + 1u) {
-        if (clock64() - t0 > 2 * g.peer.timeout_cycles) {  // (the releasing block itself gives up after timeout_cycles)
-          *reinterpret_cast<volatile int*>(g.sync + 2) = kHaltPeerTimeout;
-          break;
-        }
-      }
-      __threadfence();
     }
-    if (lane == 0) *s_err = *reinterpret_cast<volatile int*>(g.sync + 2);
+  } else if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned int*>(g.sync + 1) < bar + 1u) {
+      if (clock64() - t0 > 2 * g.peer.timeout_cycles) {  // (the releasing block itself gives up after timeout_cycles)
+        *reinterpret_cast<volatile int*>(g.sync + 2) = kHaltPeerTimeout;
+        break;
+      }
+    }
+    __threadfence();
   }
+  if (threadIdx.x == 0) s_flags[0] = *reinterpret_cast<volatile int*>(g.sync + 2);
   __syncthreads();
   ++bar;
-  return *s_err != 0;
+  return s_flags[0] != 0;
 }
 
 // The step decision of k_peer_loop (one thread; run_decide_head of the multi-launch path): the G
@@ -1153,7 +1215,8 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
   constexpr int kWords = static_cast<int>(sizeof(StepState) / sizeof(double));
   static_assert(sizeof(StepState) % sizeof(double) == 0 && kWords <= BT, "the state is copied as doubles");
   __shared__ StepState s_st;
-  __shared__ int s_err;
+  __shared__ int s_flags[2];
+  __shared__ double s_tot[3];
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * BT;
   const int64_t gthread = static_cast<int64_t>(blockIdx.x) * BT + tid;
@@ -1164,7 +1227,7 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
   const bool tracing = g.trace != nullptr && blockIdx.x == 0 && tid == 0;
   const bool decider = gwarp == nwarps - 1;
   unsigned bar = 0;
-  if (tid == 0) s_err = 0;
+  if (tid == 0) s_flags[0] = 0;
   for (int it = 0; it < g.max_attempts; ++it) {
     StepState* st_in = b.state + ((g.first_slot + it) & 1);
     StepState* st_out = b.state + ((g.first_slot + it + 1) & 1);
@@ -1243,16 +1306,18 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
     }
     unsigned long long t1 = 0;
     if (tracing) t1 = loop_now();
-    if (loop_grid_sync(g, bar, kLoopSyncPeer, 0, &s_err)) break;
+    if (loop_grid_sync<BT>(g, bar, kLoopSyncPeer, 0, 0, s_flags, s_tot)) break;
     unsigned long long t2 = 0;
     if (tracing) t2 = loop_now();
 
     // ---- D: K[R_g,:] x~ and the dual update (k_sell + DualEpi) --------------------------
+    if (blockIdx.x == 0 && tid == 0) { g.sync[5] = 0u; g.sync[6] = 0u; }  // (tickets of T1 / T: nobody draws them before the next grid barrier)
     {
-      DualEpiT<MODE == 0, true> epi;
+      typedef DualEpiT<MODE == 0, true, true> Epi;
+      Epi epi;
       epi.b = b;
       epi.peer = peer;
-      typename DualEpiT<MODE == 0, true>::Ctx ctx;
+      typename Epi::Ctx ctx;
       ctx.yc = pick3(b.y, cur);
       ctx.yn = pick3(b.y, cand);
       ctx.kxc = pick3(b.kx, cur);
@@ -1261,48 +1326,72 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
       ctx.ratio = ratio;
       const double* xt = peer.base[peer.rank] + peer.xt_off;
       const SellDev& a = g.rows;
-      const int64_t nsl = a.num_slots >> 5;
-      double red[2] = {0.0, 0.0};
-      for (int64_t r = 0, base = 0; base < nsl; ++r, base += nwarps) {
-        const int64_t sl = base + ((r & 1) ? nwarps - 1 - gwarp : gwarp);  // (see the mapping note above the kernel)
-        if (sl >= nsl) continue;
-        const int64_t slot = (sl << 5) + lane;
+      const unsigned nsl = static_cast<unsigned>(a.num_slots >> 5);
+      unsigned next = 0;
+      if (lane == 0) next = atomicAdd(g.sync + 4, 1u);
+      next = __shfl_sync(0xffffffffu, next, 0);
+      while (next < nsl) {
+        const unsigned sl = next;
+        if (lane == 0) next = atomicAdd(g.sync + 4, 1u);  // (the next ticket travels while this slice is worked on)
+        const int64_t slot = (static_cast<int64_t>(sl) << 5) + lane;
         const int64_t pos = a.num_split + (slot - a.num_virtual_padded);  // (no split rows: the host takes the multi-launch path for those)
         const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
-        typename DualEpiT<MODE == 0, true>::Pre pre;
+        typename Epi::Pre pre;
         if (own_row) pre = epi.prefetch(ctx, pos);
-        const double acc = sell_row<kDot, 1, true>(a, slot, xt);
+        const double acc = sell_row8_cg(a, slot, xt);
+        double red[2] = {0.0, 0.0};
         if (own_row) epi(ctx, pos, acc, red, pre);
+        const double r0 = warp_sum(red[0]), r1 = warp_sum(red[1]);
+        if (lane == 0) *reinterpret_cast<double2*>(g.slice_partials + 2 * static_cast<int64_t>(sl)) = make_double2(r0, r1);
+        next = __shfl_sync(0xffffffffu, next, 0);
       }
-      block_reduce_store<2, 0, BT>(red, nullptr, g.block_partials + 4 * blockIdx.x + 1);
     }
     unsigned long long t3 = 0;
     if (tracing) t3 = loop_now();
     if (MODE == 1) {
+      if (loop_grid_sync<BT>(g, bar, kLoopSyncPlain, 0, 0, s_flags, s_tot)) break;
+      // the slots of a fixed range of slices per block, in a fixed order
+      if (blockIdx.x == 0 && tid == 0) g.sync[4] = 0u;
+      const int64_t nsl = g.rows.num_slots >> 5;
+      const int64_t per = (nsl + gridDim.x - 1) / gridDim.x;
+      const int64_t sb = min(nsl, per * blockIdx.x), se = min(nsl, sb + per);
+      double red[2] = {0.0, 0.0};
+      for (int64_t k = sb + tid; k < se; k += BT) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(g.slice_partials) + k);
+        red[0] += v.x;
+        red[1] += v.y;
+      }
+      block_reduce_store<2, 0, BT>(red, nullptr, g.block_partials + 4 * blockIdx.x + 1);
+    }
+    if (MODE == 1) {
       // ---- T1: the local partial (K[R_g,:])^T y' into the own arena, column order --------
-      if (loop_grid_sync(g, bar, kLoopSyncPlain, 0, &s_err)) break;
       const double* yn = pick3(b.y, cand);
       double* partial = peer.base[peer.rank] + peer.partial_off;
       const SellDev& a = g.cols;
-      const int64_t nsl = a.num_slots >> 5;
-      for (int64_t r = 0, base = 0; base < nsl; ++r, base += nwarps) {
-        const int64_t sl = base + ((r & 1) ? nwarps - 1 - gwarp : gwarp);  // (see the mapping note above the kernel)
-        if (sl >= nsl) continue;
-        const int64_t slot = (sl << 5) + lane;
+      const unsigned nsl = static_cast<unsigned>(a.num_slots >> 5);
+      unsigned next = 0;
+      if (lane == 0) next = atomicAdd(g.sync + 5, 1u);
+      next = __shfl_sync(0xffffffffu, next, 0);
+      while (next < nsl) {
+        const unsigned sl = next;
+        if (lane == 0) next = atomicAdd(g.sync + 5, 1u);
+        const int64_t slot = (static_cast<int64_t>(sl) << 5) + lane;
         const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
         const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
         int32_t dst = 0;
         if (own_row) dst = __ldg(g.perm + pos);
-        const double acc = sell_row<kDot, 1, true>(a, slot, yn);
+        const double acc = sell_row8_cg(a, slot, yn);
         if (own_row) partial[dst] = acc;
+        next = __shfl_sync(0xffffffffu, next, 0);
       }
     }
     unsigned long long t4 = 0;
     if (tracing) t4 = loop_now();
-    if (loop_grid_sync(g, bar, kLoopSyncSumsPeer, 1, &s_err)) break;
+    if (loop_grid_sync<BT>(g, bar, kLoopSyncSumsPeer, 1, MODE == 0 ? (g.rows.num_slots >> 5) : 0, s_flags, s_tot)) break;
     unsigned long long t5 = 0;
     if (tracing) t5 = loop_now();
 
+    if (MODE == 0 && blockIdx.x == 0 && tid == 0) g.sync[4] = 0u;  // (tickets of D: every draw of this attempt is behind the barrier above)
     // ---- the decision (one warp; run_decide_head of the multi-launch path) --------------
     if (decider && lane == 0) loop_decide(st_out, &s_st, peer.base[peer.rank] + peer.scal_off, peer.world);
     // ---- T: K^T y' of the candidate for this rank's column slice -------------------------
@@ -1310,17 +1399,21 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
     if (MODE == 0) {
       const double* yall = peer.base[peer.rank] + peer.y_off;
       const SellDev& a = g.cols;
-      const int64_t nsl = a.num_slots >> 5;
-      for (int64_t r = 0, base = 0; base < nsl; ++r, base += nwarps) {
-        const int64_t sl = base + ((r & 1) ? nwarps - 1 - gwarp : gwarp);  // (see the mapping note above the kernel)
-        if (sl >= nsl) continue;
-        const int64_t slot = (sl << 5) + lane;
+      const unsigned nsl = static_cast<unsigned>(a.num_slots >> 5);
+      unsigned next = 0;
+      if (lane == 0) next = atomicAdd(g.sync + 6, 1u);
+      next = __shfl_sync(0xffffffffu, next, 0);
+      while (next < nsl) {
+        const unsigned sl = next;
+        if (lane == 0) next = atomicAdd(g.sync + 6, 1u);
+        const int64_t slot = (static_cast<int64_t>(sl) << 5) + lane;
         const int64_t pos = a.num_split + (slot - a.num_virtual_padded);
         const bool own_row = slot >= a.num_virtual_padded && pos < a.num_rows;
         int32_t dst = 0;
         if (own_row) dst = __ldg(g.perm + pos);
-        const double acc = sell_row<kDot, 1, true>(a, slot, yall);
+        const double acc = sell_row8_cg(a, slot, yall);
         if (own_row) kc[g.col0 + dst] = acc;
+        next = __shfl_sync(0xffffffffu, next, 0);
       }
     } else {
       for (int64_t i0 = peer.begin + 2 * gthread; i0 < peer.end; i0 += 2 * nthreads) {
@@ -1346,20 +1439,20 @@ __global__ void __launch_bounds__(BT, 1) k_peer_loop(PeerLoopArgs g) {
     }
     unsigned long long t6 = 0;
     if (tracing) t6 = loop_now();
-    if (loop_grid_sync(g, bar, kLoopSyncPlain, 0, &s_err)) break;
+    if (loop_grid_sync<BT>(g, bar, kLoopSyncPlain, 0, 0, s_flags, s_tot)) break;
     if (tracing) {
       const unsigned long long t7 = loop_now();
       g.trace[0] += 1ull;
       g.trace[1] += t1 - t0;  // P
       g.trace[2] += t2 - t1;  // grid + peer barrier A
       g.trace[3] += t3 - t2;  // D
-      g.trace[4] += t4 - t3;  // (MODE 1: grid barrier + T1)
+      g.trace[4] += t4 - t3;  // grid barrier + block sums (+ T1, MODE 1)
       g.trace[5] += t5 - t4;  // sums + grid + peer barrier B
       g.trace[6] += t6 - t5;  // decision + T
       g.trace[7] += t7 - t6;  // closing grid barrier
     }
   }
-  if (s_err != 0 && blockIdx.x == 0 && tid == 0) {  // a peer never arrived: both slots say so, whatever the host reads
+  if (s_flags[0] != 0 && blockIdx.x == 0 && tid == 0) {  // a peer never arrived: both slots say so, whatever the host reads
     b.state[0].halt = kHaltPeerTimeout;
     b.state[1].halt = kHaltPeerTimeout;
   }
@@ -3600,7 +3693,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   const int nd_main = SellGridFor(rows, pair_chunks);
   const int nd_fix = rows.num_split > 0 ? static_cast<int>((rows.num_split * 32 + kThreads - 1) / kThreads) : 0;
   const int nd = b.m > 0 ? nd_main + nd_fix : 0;
-  const int64_t need = std::max<int64_t>(static_cast<int64_t>(np) + 2 * static_cast<int64_t>(nd_main + nd_fix) + 8, 4 * static_cast<int64_t>(num_sms_) + 8);
+  const int64_t need = std::max<int64_t>(static_cast<int64_t>(np) + 2 * static_cast<int64_t>(nd_main + nd_fix) + 8, 4 * static_cast<int64_t>(num_sms_) + 8 + 2 * (rows.num_slots / 32) + 8);
   if (need > step_partials_size_) {
     cudaFree(step_partials_);
     step_partials_ = nullptr;
@@ -3614,16 +3707,15 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
   timing_attempt_idx_.clear();
   timing_peer_ = use_peer;
   auto ev = [&](int slot, int k) { CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(timing_events_[slot * kEvPerSlot + k]), STREAM)); };
-  // k_peer_loop maps slices to warps statically, and the SMs of a B200 do not run a request-bound row loop
-  // at the same speed (GPCs of 16 / 18 / 20 SMs share a crossbar port: measured spread 25 %): it wins
-  // where an attempt is launch- and barrier-bound (at most kPeerLoopRounds slices per warp and image),
-  // the separate launches -- whose blocks the hardware scheduler balances -- win above that.
-  // PDLP_B200_PEER_LOOP=0 / 2 forces the launches / the loop.
+  // k_peer_loop wins where an attempt is launch- and barrier-bound (C2 on 8 GPUs: 5905 against 5396 it/s);
+  // with more work per rank the separate launches are level or ahead (C2 / C4 on 2 GPUs: 4338 against 4252,
+  // 906 against 864 it/s): their row loops are the tuned ones and a phase of the loop ends with the tail of
+  // its last slice. Chosen by the size of the larger image; PDLP_B200_PEER_LOOP=0 / 2 forces the launches /
+  // the loop. Split rows need their fix-up kernel.
   const SellDev& kty_image = b.cols_slice != nullptr ? *b.cols_slice : cols;
-  constexpr int kLoopThreads = 1024;
-  constexpr int64_t kPeerLoopRounds = 3;
-  const int64_t loop_warps = static_cast<int64_t>(num_sms_) * (kLoopThreads / 32);
-  const bool loop_small = std::max(rows.num_slots, kty_image.num_slots) / 32 <= kPeerLoopRounds * loop_warps;
+  constexpr int kLoopThreads = 512;
+  constexpr int64_t kPeerLoopMaxSlices = 16384;
+  const bool loop_small = std::max(rows.num_slots, kty_image.num_slots) / 32 <= kPeerLoopMaxSlices;
   if (use_peer && (PeerLoop() == 2 || (PeerLoop() == 1 && loop_small)) && b.m > 0 && b.n > 0 && rows.num_split == 0 && kty_image.num_split == 0) {
     // the whole chunk of attempts as one persistent cooperative launch (k_peer_loop); it leaves when the
     // decision halts, so rejected steps need no second pass (the cap only bounds a state that never halts)
@@ -3636,6 +3728,7 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
     g.perm = b.cols_slice != nullptr ? b.slice_perm : b.primal_scatter;
     g.col0 = b.slice_begin;
     g.block_partials = step_partials_;
+    g.slice_partials = step_partials_ + 4 * static_cast<int64_t>(num_sms_) + 8;
     g.sync = loop_sync_;
     g.first_slot = first_slot;
     g.max_attempts = count + 64;
