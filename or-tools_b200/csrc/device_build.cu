@@ -429,19 +429,23 @@ struct Scanner {
   int64_t* total_dev = nullptr;
   int64_t* total_host = nullptr;  // pinned
   int64_t sums_cap = 0;
+  // (stream-ordered allocations: cudaMalloc / cudaFree / cudaMallocHost synchronise the device and cost
+  // 0.1-1 ms each; the pinned word for the totals is allocated once per host thread and kept)
   explicit Scanner(cudaStream_t s) : stream(s) {
-    CUDA_OK(cudaMalloc(&total_dev, sizeof(int64_t)));
-    CUDA_OK(cudaMallocHost(&total_host, sizeof(int64_t)));
+    CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&total_dev), sizeof(int64_t) * 8, stream));
+    thread_local int64_t* pinned = nullptr;
+    if (pinned == nullptr) CUDA_OK(cudaMallocHost(&pinned, sizeof(int64_t) * 8));
+    total_host = pinned;
   }
-  ~Scanner() { cudaFree(sums); cudaFree(total_dev); cudaFreeHost(total_host); }
+  ~Scanner() { if (sums != nullptr) cudaFreeAsync(sums, stream); cudaFreeAsync(total_dev, stream); }
   // out[i] = sum in[0..i); returns the total (synchronises).
   int64_t Exclusive(const int64_t* in, int64_t* out, int64_t n, int64_t* launches) {
     if (n <= 0) return 0;
     const int64_t per_block = static_cast<int64_t>(kScanT) * kScanItems;
     const int64_t nb = (n + per_block - 1) / per_block;
     if (nb > sums_cap) {
-      cudaFree(sums);
-      CUDA_OK(cudaMalloc(&sums, sizeof(int64_t) * (nb + 8)));
+      if (sums != nullptr) cudaFreeAsync(sums, stream);
+      CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&sums), sizeof(int64_t) * (nb + 8), stream));
       sums_cap = nb;
     }
     k_scan_blocks<<<static_cast<int>(nb), kScanT, 0, stream>>>(in, out, n, sums);
@@ -521,7 +525,7 @@ void BuildOrientation(cudaStream_t stream, Scanner& scan, Temps& tmp, int64_t ro
   out->slot_len = DevAlloc<int32_t>(num_slots);
   out->virt_pos = DevAlloc<int32_t>(nvp);
   out->split_first = DevAlloc<int32_t>(num_split + 1);
-  CUDA_OK(cudaMalloc(&out->virt_partial, sizeof(double) * (nvp + 32)));
+  out->virt_partial = DevAlloc<double>(nvp + 32);
   o->slot_row = DevAlloc<int32_t>(num_slots);
   o->slot_off = DevAlloc<int64_t>(num_slots);
   o->slot_stride = DevAlloc<int32_t>(num_slots);
@@ -671,9 +675,9 @@ void Device::BuildSellPair(const PdlpProblemView& v, int64_t row_begin, int64_t 
   CUDA_OK(cudaStreamSynchronize(stream));
   if (trace)
     std::fprintf(stderr, "[pdlp_b200 trace] SELL build: device passes %.4f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_build0).count());
-  cudaFree(orow.slot_row);
-  cudaFree(orow.slot_off);
-  cudaFree(orow.slot_stride);
+  cudaFreeAsync(orow.slot_row, stream);
+  cudaFreeAsync(orow.slot_off, stream);
+  cudaFreeAsync(orow.slot_stride, stream);
   *dual_perm = orow.row_of_pos;
   *primal_perm = ocol.row_of_pos;
   info->n = n;
@@ -744,9 +748,9 @@ void Device::BuildColumnSliceImage(const PdlpProblemView& v, int64_t col_begin, 
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(stream));
-  cudaFree(ocol.slot_row);
-  cudaFree(ocol.slot_off);
-  cudaFree(ocol.slot_stride);
+  cudaFreeAsync(ocol.slot_row, stream);
+  cudaFreeAsync(ocol.slot_off, stream);
+  cudaFreeAsync(ocol.slot_stride, stream);
   *row_of_pos_out = ocol.row_of_pos;
 }
 

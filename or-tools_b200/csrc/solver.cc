@@ -1274,9 +1274,19 @@ void DeviceSolve::LogQuadraticProgramStats(const PdlpQuadraticProgramStats& s) c
 
 SolverResultCpp DeviceSolve::PreprocessAndSolve(std::optional<InitialSolution> initial_solution, const volatile int32_t* interrupt_solve,
                                                 const std::string* name) {
+  const char* tr = std::getenv("PDLP_B200_TRACE");
+  const bool trace = tr != nullptr && tr[0] == '1';
+  WallTimer t;
   if (auto err = Prepare(std::move(initial_solution), name); err.has_value()) return std::move(*err);
+  if (trace) D.Sync();
+  const double t_prepare = t.Get();
   auto result = Advance(std::numeric_limits<int>::max(), interrupt_solve);
-  return ConstructOriginalSolverResult(std::move(*result));
+  const double t_advance = t.Get();
+  SolverResultCpp out = ConstructOriginalSolverResult(std::move(*result));
+  if (trace)
+    std::fprintf(stderr, "[pdlp_b200 trace] solve wall seconds: prepare (checks, stats, rescaling) %.4f, loop %.4f, result (unscale, reduced costs, download) %.4f\n",
+                 t_prepare, t_advance - t_prepare, t.Get() - t_advance);
+  return out;
 }
 
 // pdhg.cc:1039-1221
@@ -1362,8 +1372,10 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   if (!P.ObjectiveMatrixIsNonNegative())
     return ErrorSolverResult(PDLP_TERMINATION_REASON_INVALID_PROBLEM,
                              "The objective is not convex (i.e., the objective matrix contains negative or NAN entries).", logger_);
+  const double t_checks = timer.Get();
   solve_log.original_stats = P.ComputeStats();
   solve_log.has_original_stats = true;
+  const double t_stats0 = timer.Get();
   if (auto r = CheckProblemStats(solve_log.original_stats, P.objective_offset(), params_.presolve_use_glop != 0, logger_); r.has_value()) return std::move(*r);
 
   AllocateIterates();
@@ -1392,11 +1404,16 @@ std::optional<SolverResultCpp> DeviceSolve::Prepare(std::optional<InitialSolutio
   D.ClampDual(Y(), P.lc(), P.uc(), m);
 
   // ComputeAndApplyRescaling, pdhg.cc:1325-1339
+  const double t_before_rescaling = timer.Get();
   P.ApplyRescaling(params_.l_inf_ruiz_iterations, params_.l2_norm_rescaling != 0, &dr_, &dc_);
   D.Div(X(), dc_, n);
   D.Div(Y(), dr_, m);
+  const double t_rescaled = timer.Get();
   solve_log.preprocessed_stats = P.ComputeStats();
   solve_log.has_preprocessed_stats = true;
+  if (const char* tr = std::getenv("PDLP_B200_TRACE"); tr != nullptr && tr[0] == '1')
+    std::fprintf(stderr, "[pdlp_b200 trace] prepare wall seconds: bound checks %.4f, stats %.4f, allocate + project %.4f, rescaling (enqueue) %.4f, stats after rescaling %.4f\n",
+                 t_checks, t_stats0 - t_checks, t_before_rescaling - t_stats0, t_rescaled - t_before_rescaling, timer.Get() - t_rescaled);
   if (params_.verbosity_level >= 1) { logger_.Log("Problem stats after rescaling:"); LogQuadraticProgramStats(solve_log.preprocessed_stats); }
 
   double step_size;

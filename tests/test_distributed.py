@@ -107,6 +107,50 @@ def pdhg_reference(k, c, lc, uc, lv, uv, iters, step, weight):
     return x, y, trace
 
 
+def test_maintained_average_products_match_products_of_the_average():
+    """The peer-exchange step kernels keep K x and K^T y of the weighted average up to date with the
+    averages themselves (StepPtrs::avg_kx / avg_kty): avg <- avg + r (v - avg) applied to the iterate
+    and, with the same ratio r = eta / (weight so far + eta), to the iterate's products -- K x' kept by
+    the dual kernel as (K x~ + K x) / 2, K^T y' from the K^T side. Restated in numpy over an adaptive
+    PDHG run: the maintained products equal K avg_x / K^T avg_y (sou.cc:54-79 linearity) to 1e-12."""
+    qp, _ = synthetic.c2(scale=0.001)
+    k = qp.constraint_matrix.tocsr()
+    n, m = k.shape[1], k.shape[0]
+    c, lv, uv = qp.objective_vector, qp.variable_lower_bounds, qp.variable_upper_bounds
+    lc, uc = qp.constraint_lower_bounds, qp.constraint_upper_bounds
+    x, y = np.zeros(n), np.zeros(m)
+    kx, kty = k @ x, k.T @ y
+    avg_x, avg_y, avg_kx, avg_kty = np.zeros(n), np.zeros(m), np.zeros(m), np.zeros(n)
+    wsum, step, weight, total = 0.0, 0.05, 1.0, 0
+    for _ in range(60):
+        while True:
+            total += 1
+            tau, sigma = step / weight, step * weight
+            xn = np.clip(x - tau * (c - kty), lv, uv)
+            kxt = k @ (2 * xn - x)
+            t = y - sigma * kxt
+            yn = np.maximum(np.minimum(0.0, t + sigma * uc), t + sigma * lc)
+            kxn, ktyn = 0.5 * (kxt + kx), k.T @ yn      # what the dual kernel / the K^T side leave
+            dx, dy = xn - x, yn - y
+            movement = 0.5 * weight * (dx @ dx) + 0.5 / weight * (dy @ dy)
+            nonlin = -((0.5 * (kxt - kx)) @ dy)           # (K dx) . dy, the row-side form
+            limit = movement / nonlin if nonlin > 0 else np.inf
+            used = step
+            step = min(limit if np.isinf(limit) else (1 - (total + 1) ** -0.3) * limit, (1 + (total + 1) ** -0.6) * step)
+            if used <= limit:
+                break
+        x, y, kx, kty = xn, yn, kxn, ktyn
+        r = used / (wsum + used)
+        wsum += used
+        avg_x += r * (x - avg_x)
+        avg_y += r * (y - avg_y)
+        avg_kx += r * (kx - avg_kx)
+        avg_kty += r * (kty - avg_kty)
+    assert wsum > 0
+    for got, want in ((avg_kx, k @ avg_x), (avg_kty, k.T @ avg_y)):
+        assert np.linalg.norm(got - want) <= 1e-12 * max(1.0, np.linalg.norm(want))
+
+
 def primal_slice(n, rank, world):
     """Slice of the primal vector rank advances inside the step loop (PeerLayout::For in device_ops.h)."""
     stride = 2 * ((n + 2 * world - 1) // (2 * world))
