@@ -269,8 +269,9 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     names = ["k_primal_step", "k_sell<dot>+DualEpi (K x~, dual update)", "k_sell<dot>+KtyEpi (K^T y', nonlinearity)", "k_step_decide"]
     if world > 1:  # row-sharded: each class includes its part of the fused peer-memory exchange
-        names = ["k_primal_step<PEER> (slice, x~ stores to every arena) + barrier", "k_sell<dot>+DualEpi (row block; y' stores in the all-gather exchange)",
-                 "K^T y' side (barrier + slice product, or partial + barrier + peer pull)", "k_step_decide_peer (scalar slots + barrier)"]
+        # (separate launches, or the phases of the persistent k_peer_loop where that is used: DESIGN.md 5)
+        names = ["primal slice step, x~ stores to every arena, barrier A", "K[R_g,:] x~ + dual update (row block; y' stores in the all-gather exchange)",
+                 "K^T y' side (sums, barrier B, slice product -- or partial, barrier B, peer pull)", "end of the attempt (decision kernel / closing grid barrier)"]
     kern = []
     for i in range(4):
         cnt = st1.kernel_samples[i]

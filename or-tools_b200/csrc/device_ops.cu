@@ -2524,6 +2524,7 @@ Device::Device(int cuda_device) : device_(cuda_device) {
   CUDA_OK(cudaMemset(tile_counters_, 0, 64));
   CUDA_OK(cudaMalloc(&loop_sync_, 256));
   CUDA_OK(cudaMemset(loop_sync_, 0, 256));
+  CUDA_OK(cudaMallocHost(&loop_trace_host_, 8 * sizeof(unsigned long long)));
   CUDA_OK(cudaMalloc(&results_, sizeof(double) * 64));
   CUDA_OK(cudaMallocHost(&host_results_, sizeof(double) * 64));
 }
@@ -2534,6 +2535,7 @@ Device::~Device() {
   cudaFree(tr_peer_error_);
   cudaFree(tile_counters_);
   cudaFree(loop_sync_);
+  cudaFreeHost(loop_trace_host_);
   cudaFree(results_);
   cudaFreeHost(host_results_);
   cudaFree(tr_scratch_);
@@ -3743,6 +3745,8 @@ void Device::EnqueueSteps(const StepBuffers& b, const SellDev& rows, const SellD
     timing_attempt_idx_.clear();
     timing_peer_ = true;
     loop_traced_ = g.trace != nullptr;
+    // (rides on the synchronisation of the state download that follows every batch)
+    if (loop_traced_) CUDA_OK(cudaMemcpyAsync(loop_trace_host_, loop_sync_ + 16, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, STREAM));
     return;
   }
   for (int it = 0; it < count; ++it) {
@@ -3906,9 +3910,7 @@ void Device::CollectStepTimings(int64_t executed_attempts) {
     // k_peer_loop: block 0 summed the phase times of every attempt (globaltimer, ns):
     // [0] attempts, P | barrier A | D | (T1) | sums + barrier B | decision + T | closing barrier
     loop_traced_ = false;
-    unsigned long long h[8];
-    CUDA_OK(cudaMemcpyAsync(h, loop_sync_ + 16, sizeof(h), cudaMemcpyDeviceToHost, STREAM));
-    Sync();
+    const unsigned long long* h = loop_trace_host_;  // copied behind the launch, complete since the state download synchronised
     static const int kLoopClass[7] = {0, 0, 1, 2, 2, 2, 3};
     if (h[0] > 0) {
       for (int k = 0; k < 7; ++k) {

@@ -418,6 +418,7 @@ class Device {
   unsigned int* tile_counters_ = nullptr;  // tile queues of the persistent SpMV pair of the step loop (one per kernel)
   unsigned int* loop_sync_ = nullptr;      // k_peer_loop: [0..2] grid-barrier words, [16..32) phase-time sums (u64)
   bool loop_traced_ = false;               // the last EnqueueSteps launched k_peer_loop with the phase trace on
+  unsigned long long* loop_trace_host_ = nullptr;  // pinned copy of the phase-time sums of the last launch
   int num_sms_ = 148;
   // trust-region scratch (grown on demand)
   double* tr_scratch_ = nullptr;

@@ -44,10 +44,10 @@ for stage in "$@"; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_tr_' -s 4 -c 2 \
         -o /tmp/${TAG}_tr -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_tr.log 2>&1; echo "ncu tr rc=$?"
       python tools/ncu_summary.py /tmp/${TAG}_tr.ncu-rep $OUT/${TAG}_ncu_full_tr_c2.csv
-      # the TMA-staged variant of the same step kernels, for the counter comparison
-      PDLP_B200_SELL_VARIANT=5 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell_tma' -s 60 -c 6 \
+      # the TMA-staged variant of the same step kernels, for the counter comparison (NCU_TMA=0 skips it)
+      [ "${NCU_TMA:-1}" = "1" ] && PDLP_B200_SELL_VARIANT=5 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell_tma' -s 60 -c 6 \
         -o /tmp/${TAG}_step_tma -f python bench.py --steps 40 --warmup 8 --no-e2e --no-cpu > $OUT/${TAG}_ncu_step_tma.log 2>&1; echo "ncu tma rc=$?"
-      python tools/ncu_summary.py /tmp/${TAG}_step_tma.ncu-rep $OUT/${TAG}_ncu_full_step_tma_c2.csv
+      [ "${NCU_TMA:-1}" = "1" ] && python tools/ncu_summary.py /tmp/${TAG}_step_tma.ncu-rep $OUT/${TAG}_ncu_full_step_tma_c2.csv
       ls -la $OUT/${TAG}_ncu_full_*.csv ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $OUT/${TAG}_launches_raw.csv \
