@@ -285,9 +285,12 @@ def run_ours(args):
                 "kernel_share_of_step": (kern[dom]["avg_ms"] / sum(x["avg_ms"] or 0 for x in kern)) if kern[dom]["avg_ms"] else None}
     q_bytes = 0 if qp.objective_matrix is None else 8 * n
     iter_bytes = 2 * nnz * 12 + 4 * (m + 1) + 4 * (n + 1) + 8 * (14 * n + 7 * m) + q_bytes
+    # (N GPUs: the whole problem's bytes per iteration against N times the one-GPU peak)
     iteration_roofline = {"algorithmic_bytes_per_iteration": iter_bytes, "achieved_gbs": iter_bytes * value / 1e9,
-                          "frac_of_peak": iter_bytes * value / 1e9 / peak,
-                          "step_loop_only_frac": (iter_bytes * (iters / (step_ms / 1000.0)) / 1e9 / peak) if step_ms > 0 else None}
+                          "frac_of_peak": iter_bytes * value / 1e9 / (peak * world),
+                          "step_loop_only_frac": (iter_bytes * (iters / (step_ms / 1000.0)) / 1e9 / (peak * world)) if step_ms > 0 else None}
+    if world > 1:
+        iteration_roofline["peak_gbs_all_gpus"] = peak * world
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file) and world == 1:
         try:

@@ -1240,7 +1240,9 @@ void DeviceSolve::FillStatus(PdlpSessionStatus* out) const {
   for (int k = 0; k < 4; ++k) { out->kernel_ms[k] = t.ms[k]; out->kernel_samples[k] = t.samples[k]; }
   // Algorithmic bytes per launch (DESIGN.md "Roofline accounting"):
   //  primal step: reads x, c, K^T y, l_v, u_v (+Q), writes x', x~; deferred average R/W.
-  out->kernel_algorithmic_bytes[0] = 8.0 * (9.0 + qn) * n;
+  //  (peer exchange of a row-sharded solve: a rank advances only its slice of the primal vectors)
+  const double n_step = (P.sharded() && P.arena() != nullptr) ? static_cast<double>(P.slice_end() - P.slice_begin()) : n;
+  out->kernel_algorithmic_bytes[0] = 8.0 * (9.0 + qn) * n_step;
   //  K x~ + dual epilogue: K-by-rows (8 B value + 4 B index per nonzero, 4 B row offset),
   //  gathers x~ once, reads y, l_c, u_c, K x, writes y', K x'; deferred dual average R/W.
   out->kernel_algorithmic_bytes[1] = 12.0 * static_cast<double>(P.nnz()) + 4.0 * (m + 1) + 8.0 * n + 8.0 * 8.0 * m;
