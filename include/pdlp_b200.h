@@ -399,6 +399,14 @@ void pdlp_b200_distributed_destroy(PdlpDistributedContext* context);
  * the equal-mass rule of Sharder (sharder.cc:51-70) applied to the rows of K. */
 int32_t pdlp_b200_row_block(const PdlpProblemView* qp, int32_t rank, int32_t world_size,
                             int64_t* row_begin, int64_t* row_end);
+/* Layout, in doubles, of the peer arena every rank of a row-sharded solve maps
+ * (host-only; diagnostics / tests): out = {slice stride, padded primal length,
+ * x~, K^T y' partial, y', scalar triples, barrier flags, epochs, trust-region
+ * round vectors, trust-region candidates, second trust-region round vectors,
+ * second trust-region candidates, total}. The step-loop exchange replaces the
+ * Sharder's in-process hand-over of x and K^T y (sharder.cc:160-173).         */
+int32_t pdlp_b200_peer_arena_layout(int64_t num_variables, int64_t num_constraints, int32_t world_size,
+                                    int64_t out[13]);
 int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(
     PdlpDistributedContext* context, const PdlpProblemView* qp, const PdlpParams* params,
     const double* initial_primal, int64_t initial_primal_size,

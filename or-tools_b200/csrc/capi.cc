@@ -333,6 +333,13 @@ int32_t pdlp_b200_row_block(const PdlpProblemView* qp, int32_t rank, int32_t wor
     return PDLP_B200_STATUS_BAD_ARGUMENT;
   }
 }
+int32_t pdlp_b200_peer_arena_layout(int64_t num_variables, int64_t num_constraints, int32_t world_size, int64_t out[13]) {
+  if (out == nullptr || num_variables < 0 || num_constraints < 0 || world_size < 1 || world_size > kMaxPeers) return PDLP_B200_STATUS_BAD_ARGUMENT;
+  const PeerLayout l = PeerLayout::For(num_variables, num_constraints, world_size);
+  const int64_t v[13] = {l.stride, l.n_pad, l.xt_off, l.partial_off, l.y_off, l.scal_off, l.flags_off, l.epoch_off, l.tr_off, l.cand_off, l.tr2_off, l.cand2_off, l.doubles};
+  for (int k = 0; k < 13; ++k) out[k] = v[k];
+  return PDLP_B200_STATUS_OK;
+}
 int32_t pdlp_b200_primal_dual_hybrid_gradient_distributed(PdlpDistributedContext* ctx, const PdlpProblemView* qp, const PdlpParams* params,
                                                           const double* initial_primal, int64_t initial_primal_size, const double* initial_dual,
                                                           int64_t initial_dual_size, const volatile int32_t* interrupt_solve,

@@ -151,6 +151,25 @@ def test_maintained_average_products_match_products_of_the_average():
         assert np.linalg.norm(got - want) <= 1e-12 * max(1.0, np.linalg.norm(want))
 
 
+@pytest.mark.parametrize("n,m,world", [(2_000_000, 1_000_000, 8), (4_000_000, 10_000_000, 8), (7, 3, 2), (1, 1, 1), (1001, 0, 3)])
+def test_peer_arena_segments_are_disjoint_and_ordered(n, m, world):
+    """PeerLayout::For (device_ops.h): every segment of the arena the fused exchange writes through starts
+    where the previous one ends or later, the primal slices cover n, the flag / epoch blocks hold the
+    barriers in use (0 / 1 step loop, 3 / 4 the two concurrent trust-region solves), and both sets of
+    trust-region segments are whole."""
+    import ctypes as C
+    out = (C.c_int64 * 13)()
+    assert pdlp.backend().fn("peer_arena_layout")(C.c_int64(n), C.c_int64(m), C.c_int32(world), out) == 0
+    stride, n_pad, xt, partial, y, scal, flags, epoch, tr, cand, tr2, cand2, total = list(out)
+    assert stride % 2 == 0 and stride * world == n_pad >= n
+    assert primal_slice(n, 0, world)[2] == stride
+    assert xt == 0 and partial >= xt + n_pad and y >= partial + n_pad and scal >= y + m
+    assert flags >= scal + 4 * world and epoch >= flags + 8 * 5 and tr >= epoch + 5       # barriers 0..4, 8 ranks each
+    seg = 3 * 4096 + 8
+    assert cand >= tr + 2 * 42 * world and tr2 >= cand + seg * world and cand2 >= tr2 + 2 * 42 * world and total >= cand2 + seg * world
+    assert pdlp.backend().fn("peer_arena_layout")(C.c_int64(n), C.c_int64(m), C.c_int32(9), out) != 0
+
+
 def primal_slice(n, rank, world):
     """Slice of the primal vector rank advances inside the step loop (PeerLayout::For in device_ops.h)."""
     stride = 2 * ((n + 2 * world - 1) // (2 * world))
