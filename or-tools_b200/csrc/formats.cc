@@ -3,6 +3,7 @@
 // QuadraticProgram, the MPS reader / writer and PdlpSolveProto. Host-only code
 // on top of the proto2 codec of proto_codec.cc; the solve itself goes through
 // pdlp_b200_primal_dual_hybrid_gradient (no CPU fallback).
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -457,11 +458,95 @@ bool Encode(const proto::Schema& schema, const std::string& wire, int32_t format
 // ---------------------------------------------------------------------------
 // files
 // ---------------------------------------------------------------------------
-bool ReadFile(const std::string& path, std::string* out, std::string* error) {
-  if (EndsWith(path, ".bz2")) {
-    *error = "bzip2 input is not supported by this build (" + path + "); decompress it first";
+// bzip2 input (quadratic_program_io.cc:50-68 reads .mps.bz2 through the MPS reader's file
+// layer). The image carries libbz2.so.1.0 but not bzlib.h, so the three decompression entry
+// points are bound at run time against a restatement of the public stream record.
+struct BzStream {
+  char* next_in;
+  unsigned int avail_in, total_in_lo32, total_in_hi32;
+  char* next_out;
+  unsigned int avail_out, total_out_lo32, total_out_hi32;
+  void* state;
+  void* (*bzalloc)(void*, int, int);
+  void (*bzfree)(void*, void*);
+  void* opaque;
+};
+struct BzApi {
+  int (*init)(BzStream*, int, int) = nullptr;
+  int (*run)(BzStream*) = nullptr;
+  int (*end)(BzStream*) = nullptr;
+  bool ok = false;
+};
+const BzApi& Bz() {
+  static const BzApi api = [] {
+    BzApi a;
+    void* h = nullptr;
+    for (const char* name : {"libbz2.so.1.0", "libbz2.so.1", "libbz2.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (h != nullptr) break;
+    }
+    if (h == nullptr) return a;
+    a.init = reinterpret_cast<int (*)(BzStream*, int, int)>(dlsym(h, "BZ2_bzDecompressInit"));
+    a.run = reinterpret_cast<int (*)(BzStream*)>(dlsym(h, "BZ2_bzDecompress"));
+    a.end = reinterpret_cast<int (*)(BzStream*)>(dlsym(h, "BZ2_bzDecompressEnd"));
+    a.ok = a.init != nullptr && a.run != nullptr && a.end != nullptr;
+    return a;
+  }();
+  return api;
+}
+
+bool ReadBzip2File(const std::string& path, std::string* out, std::string* error) {
+  const BzApi& bz = Bz();
+  if (!bz.ok) {
+    *error = "cannot read " + path + ": libbz2 was not found on this machine; decompress the file first";
     return false;
   }
+  std::FILE* f = std::fopen(path.c_str(), "rb");
+  if (f == nullptr) {
+    *error = "cannot open " + path;
+    return false;
+  }
+  std::string packed;
+  std::vector<char> buf(1 << 20);
+  for (size_t n; (n = std::fread(buf.data(), 1, buf.size(), f)) > 0;) packed.append(buf.data(), n);
+  const bool read_ok = std::ferror(f) == 0;
+  std::fclose(f);
+  if (!read_ok) {
+    *error = "error while reading " + path;
+    return false;
+  }
+  // a .bz2 file is one or more streams back to back (bzip2 concatenation); an empty file is empty
+  size_t at = 0;
+  while (at < packed.size()) {
+    BzStream s{};
+    if (bz.init(&s, 0, 0) != 0) {
+      *error = "error while reading " + path + ": bzip2 decoder could not start";
+      return false;
+    }
+    int rc = 0;  // BZ_OK
+    while (rc == 0) {
+      const size_t in = std::min<size_t>(packed.size() - at, 1u << 30);
+      s.next_in = packed.data() + at;
+      s.avail_in = static_cast<unsigned int>(in);
+      s.next_out = buf.data();
+      s.avail_out = static_cast<unsigned int>(buf.size());
+      rc = bz.run(&s);
+      at += in - s.avail_in;
+      const size_t produced = buf.size() - s.avail_out;
+      out->append(buf.data(), produced);
+      if (rc == 0 && in == s.avail_in && produced == 0) rc = -7;  // no progress: the stream is cut short (BZ_UNEXPECTED_EOF)
+    }
+    bz.end(&s);
+    if (rc != 4) {  // BZ_STREAM_END
+      *error = "error while reading " + path + ": not a valid bzip2 stream";
+      return false;
+    }
+  }
+  return true;
+}
+
+bool ReadFile(const std::string& path, std::string* out, std::string* error) {
+  if (EndsWith(path, ".bz2")) return ReadBzip2File(path, out, error);
   gzFile f = gzopen(path.c_str(), "rb");  // transparent for files that are not gzipped
   if (f == nullptr) {
     *error = "cannot open " + path;

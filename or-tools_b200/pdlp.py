@@ -990,10 +990,6 @@ def qp_to_mpmodel_proto(qp):
 
 def read_quadratic_program_or_die(filename, include_names=False):
     """ReadQuadraticProgramOrDie (quadratic_program_io.h:28-40; raises instead of dying). Read by the
-    library's own C++ readers (pdlp_b200_read_quadratic_program); .bz2 input, which they refuse, goes
-    through the Python reader."""
-    if str(filename).endswith(".bz2"):
-        from . import qp_io
-        return qp_io.read_quadratic_program(filename, include_names)
+    library's own C++ readers (pdlp_b200_read_quadratic_program), .gz and .bz2 included."""
     from . import native_io
     return native_io.read_quadratic_program(filename, include_names)

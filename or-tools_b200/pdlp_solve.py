@@ -86,7 +86,7 @@ def solve(input_path, params_text="", solve_log_file="", sol_file="", backend=No
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description="Solve an LP / diagonal QP with PDLP on a B200.")
-    ap.add_argument("--input", default="", help="REQUIRED: .mps, .mps.gz, or an MPModelProto [.pb, .textproto, .json, .json.gz] (.bz2 is not supported: no bzip2 in this build)")
+    ap.add_argument("--input", default="", help="REQUIRED: .mps, .mps.gz, .mps.bz2, or an MPModelProto [.pb, .textproto, .json, .json.gz]")
     ap.add_argument("--params", default="", help="PrimalDualHybridGradientParams in text format")
     ap.add_argument("--solve_log_file", default="", help="If non-empty, writes PDLP's SolveLog here (.textproto, .pb or .json)")
     ap.add_argument("--sol_file", default="", help="If non-empty, output the final primal solution in Miplib .sol format")

@@ -146,9 +146,22 @@ def test_read_quadratic_program_or_die(tmp_path):  # quadratic_program_io.h:28-4
     np.testing.assert_array_equal(got.constraint_matrix.toarray(), lp.constraint_matrix.toarray())
     np.testing.assert_array_equal(got.objective_vector, lp.objective_vector)
     assert got.variable_names == lp.variable_names and got.constraint_names == lp.constraint_names and got.problem_name == "lp"
-    with bz2.open(path + ".bz2", "wb") as f:                                      # bzip2 goes through the Python reader
-        f.write(open(path, "rb").read())
-    np.testing.assert_array_equal(pdlp.read_quadratic_program_or_die(path + ".bz2").objective_vector, lp.objective_vector)
+    raw = open(path, "rb").read()
+    with bz2.open(path + ".bz2", "wb") as f:                                      # bzip2: the C++ reader too (libbz2 bound at run time)
+        f.write(raw)
+    got = pdlp.read_quadratic_program_or_die(path + ".bz2", include_names=True)
+    np.testing.assert_array_equal(got.constraint_matrix.toarray(), lp.constraint_matrix.toarray())
+    np.testing.assert_array_equal(got.objective_vector, lp.objective_vector)
+    assert got.variable_names == lp.variable_names
+    cut = raw.index(b"COLUMNS")                                                   # two streams back to back decompress to their concatenation
+    open(str(tmp_path / "two.mps.bz2"), "wb").write(bz2.compress(raw[:cut]) + bz2.compress(raw[cut:]))
+    np.testing.assert_array_equal(pdlp.read_quadratic_program_or_die(str(tmp_path / "two.mps.bz2")).objective_vector, lp.objective_vector)
+    open(str(tmp_path / "cut.mps.bz2"), "wb").write(bz2.compress(raw * 50)[:-20])  # a stream cut short is an error, not a shorter model
+    with pytest.raises(ValueError, match="bzip2"):
+        pdlp.read_quadratic_program_or_die(str(tmp_path / "cut.mps.bz2"))
+    open(str(tmp_path / "bad.mps.bz2"), "wb").write(raw)                          # not bzip2 at all
+    with pytest.raises(ValueError, match="bzip2"):
+        pdlp.read_quadratic_program_or_die(str(tmp_path / "bad.mps.bz2"))
     with pytest.raises(ValueError, match="Invalid filename suffix"):
         pdlp.read_quadratic_program_or_die(str(tmp_path / "lp.txt"))
 
