@@ -14,6 +14,7 @@ through libpdlp_b200.so; there is no CPU fallback.
 import argparse
 import ctypes
 import signal
+import threading
 import sys
 
 from google.protobuf import json_format, text_format
@@ -66,9 +67,31 @@ def solve(input_path, params_text="", solve_log_file="", sol_file="", backend=No
     except ValueError:  # not the main thread
         previous = None
     be = backend if backend is not None else pdlp.backend()
+
+    def run():
+        return be.primal_dual_hybrid_gradient(qp, params, interrupt_solve=interrupted,
+                                              message_callback=lambda m: print(m, file=out, flush=True))
     try:
-        result = be.primal_dual_hybrid_gradient(qp, params, interrupt_solve=interrupted,
-                                                message_callback=lambda m: print(m, file=out, flush=True))
+        if previous is None:
+            result = run()
+        else:
+            # Python runs signal handlers on the main thread between bytecodes, never inside a foreign
+            # call: the solve goes to a worker (ctypes drops the GIL for the call) and the main thread
+            # waits in short joins, so ^C reaches interrupt_solve at any verbosity.
+            box = {}
+
+            def work():
+                try:
+                    box["result"] = run()
+                except BaseException as e:  # re-raised on the main thread
+                    box["error"] = e
+            worker = threading.Thread(target=work, name="pdlp_solve", daemon=True)
+            worker.start()
+            while worker.is_alive():
+                worker.join(0.05)
+            if "error" in box:
+                raise box["error"]
+            result = box["result"]
     finally:
         if previous is not None:
             signal.signal(signal.SIGINT, previous)

@@ -314,6 +314,38 @@ def test_command_line_solve_writes_log_and_sol(tmp_path):
     _run_cli(tmp_path, _oracle())
 
 
+def test_command_line_solve_is_interruptible_without_callbacks(tmp_path):
+    """^C during a solve that prints nothing (verbosity 0: no callback ever hands control back to the
+    interpreter) still reaches interrupt_solve, like the reference binary's signal handler
+    (pdlp_solve.cc:100-108): the solve runs on a worker thread while the main thread takes signals."""
+    import signal
+    import threading
+    import time
+    import scipy.sparse as sps
+    rng = np.random.default_rng(5)
+    m, n = 400, 800
+    lp = pdlp.QuadraticProgram(n, m)
+    lp.constraint_matrix = sps.random(m, n, density=0.02, random_state=7, format="csc", data_rvs=lambda k: rng.normal(size=k))
+    lp.objective_vector = rng.normal(size=n)
+    lp.constraint_lower_bounds, lp.constraint_upper_bounds = np.full(m, -1.0), np.full(m, 1.0)
+    lp.variable_lower_bounds, lp.variable_upper_bounds = np.full(n, -1.0), np.full(n, 1.0)
+    mps = str(tmp_path / "long.mps")
+    qp_io.write_linear_program_to_mps(lp, mps)
+    params = ("verbosity_level: 0 termination_criteria { iteration_limit: 2000000000 simple_optimality_criteria "
+              "{ eps_optimal_absolute: 0 eps_optimal_relative: 0 } }")
+    timer = threading.Timer(0.4, lambda: os.kill(os.getpid(), signal.SIGINT))
+    before = signal.getsignal(signal.SIGINT)
+    start = time.time()
+    timer.start()
+    try:
+        result = pdlp_solve.solve(mps, params, backend=_oracle(), out=open(os.devnull, "w"))
+    finally:
+        timer.cancel()
+    assert result.solve_log.termination_reason == pdlp.TerminationReason.TERMINATION_REASON_INTERRUPTED_BY_USER
+    assert time.time() - start < 20.0 and result.solve_log.iteration_count > 0
+    assert signal.getsignal(signal.SIGINT) is before   # the previous handler is back
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("maximize", [False, True])
 def test_proto_solver_on_the_gpu(b200_backend, maximize):
