@@ -1,5 +1,5 @@
 """Feasibility polishing (primal_dual_hybrid_gradient.cc:2676-3015).
-Transcribed from ``primal_dual_hybrid_gradient_test.cc:1400-1960`` (FeasibilityPolishing*Test):
+Transcribed from ``primal_dual_hybrid_gradient_test.cc:1400-2120`` (every FeasibilityPolishing*Test):
 the two small LPs need ~2500 iterations without polishing and solve at the first polishing
 attempt (iteration 100) with it. Run against the CPU restatement (not gpu) and the CUDA path."""
 import ctypes
@@ -154,3 +154,92 @@ def test_feasibility_polishing_details_in_log(backend):  # :1932-1968
     from ortools_b200 import pdlp_proto
     msg = pdlp_proto.solve_log_to_proto(out.solve_log)
     assert len(msg.feasibility_polishing_details) == len(out.solve_log.feasibility_polishing_details) >= 2
+
+
+def _phases(out):
+    P = pdlp.PolishingPhaseType
+    for phase in out.solve_log.feasibility_polishing_details:
+        assert phase.polishing_phase_type in (P.POLISHING_PHASE_TYPE_PRIMAL_FEASIBILITY, P.POLISHING_PHASE_TYPE_DUAL_FEASIBILITY)
+        yield phase, phase.polishing_phase_type == P.POLISHING_PHASE_TYPE_PRIMAL_FEASIBILITY
+
+
+def test_feasibility_polishing_uses_infinite_tolerances(backend):  # :1962-2001
+    """Each phase's recorded parameters carry detailed criteria in which everything except the
+    residual the phase works on is switched off with infinite tolerances (pdhg.cc:2833-2861)."""
+    out = backend.primal_dual_hybrid_gradient(primal_lp(), polishing_params())
+    seen = 0
+    for phase, primal in _phases(out):
+        c = phase.params.termination_criteria   # the POD mirror is flat: the oneof case is the field's tag
+        assert c.optimality_criteria_case == 10  # has_detailed_optimality_criteria (solvers.proto: tag 10)
+        assert c.eps_optimal_objective_gap_absolute == INF and c.eps_optimal_objective_gap_relative == INF
+        if primal:
+            assert c.eps_optimal_dual_residual_absolute == INF and c.eps_optimal_dual_residual_relative == INF
+            assert c.eps_optimal_primal_residual_absolute == 1.0e-6 and c.eps_optimal_primal_residual_relative == 1.0e-6
+        else:
+            assert c.eps_optimal_primal_residual_absolute == INF and c.eps_optimal_primal_residual_relative == INF
+            assert c.eps_optimal_dual_residual_absolute == 1.0e-6 and c.eps_optimal_dual_residual_relative == 1.0e-6
+        seen += 1
+    assert seen >= 2
+
+
+def test_feasibility_polishing_work_stats_are_correct(backend):  # :2003-2042
+    p = polishing_params()
+    p.record_iteration_stats = True
+    out = backend.primal_dual_hybrid_gradient(primal_lp(), p)
+    assert out.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+    polishing_iterations, polishing_time = 0, 0.0
+    for phase, _ in _phases(out):
+        assert phase.solution_stats.iteration_number == phase.iteration_count
+        assert 0 <= phase.iteration_count <= phase.main_iteration_count // 4
+        polishing_iterations += phase.iteration_count
+        polishing_time += phase.solve_time_sec
+    assert len(out.solve_log.iteration_stats) > 0
+    last = out.solve_log.iteration_stats[-1]
+    assert polishing_iterations >= 1 and last.iteration_number >= 1
+    # iteration_count includes main and polishing iterations; the main loop's iteration_number does not
+    assert last.iteration_number + polishing_iterations == out.solve_log.iteration_count
+    assert polishing_time > 0.0 and last.cumulative_time_sec > 0.0
+    assert polishing_time + last.cumulative_time_sec <= out.solve_log.solve_time_sec
+
+
+def test_feasibility_objectives_are_zero(backend):  # :2044-2078
+    p = polishing_params()
+    p.record_iteration_stats = True
+    out = backend.primal_dual_hybrid_gradient(primal_lp(), p)
+    primal_infos = dual_infos = 0
+    for phase, primal in _phases(out):
+        for stats in phase.iteration_stats:
+            for ci in stats.convergence_information:
+                if primal:
+                    primal_infos += 1
+                    assert ci.primal_objective == 0.0
+                else:
+                    dual_infos += 1
+                    assert ci.dual_objective == 0.0
+    assert primal_infos >= 1 and dual_infos >= 1
+
+
+def test_calls_callback_for_all_three_phases(backend):  # :2080-2100
+    counts, order = {}, []
+
+    def cb(info):
+        counts[info.iteration_type] = counts.get(info.iteration_type, 0) + 1
+        order.append(info.iteration_type)
+
+    backend.primal_dual_hybrid_gradient(primal_lp(), polishing_params(), iteration_stats_callback=cb)
+    T = pdlp.IterationType
+    assert order[-1] == T.FEASIBILITY_POLISHING_TERMINATION
+    assert sorted(counts) == sorted([T.NORMAL, T.PRIMAL_FEASIBILITY, T.DUAL_FEASIBILITY, T.FEASIBILITY_POLISHING_TERMINATION])
+    assert all(v >= 1 for v in counts.values())
+
+
+def test_iteration_limit_includes_feasibility_phases(backend):  # :2102-2120
+    p = polishing_params()
+    p.termination_criteria.iteration_limit = 300
+    p.record_iteration_stats = True
+    out = backend.primal_dual_hybrid_gradient(fx.tiny_lp(), p)
+    assert out.solve_log.termination_reason == TR.TERMINATION_REASON_OPTIMAL
+    polishing_iterations = sum(phase.iteration_count for phase, _ in _phases(out))
+    assert polishing_iterations >= 12   # at least the first, failed, primal polishing attempt
+    assert len(out.solve_log.iteration_stats) > 0
+    assert out.solve_log.iteration_stats[-1].iteration_number + polishing_iterations == out.solve_log.iteration_count
