@@ -86,6 +86,19 @@ void Exercise(const std::string& in) {
   PdlpBlob resp{};
   if (pdlp_b200_solve_proto(data, size, Rand(2), nullptr, &resp) == PDLP_B200_STATUS_OK) pdlp_b200_blob_free(&resp);
 }
+
+// The file layer: the input as the bytes of a .mps.bz2 / .mps.gz file (the bzip2 decoder is bound
+// at run time, formats.cc ReadBzip2File). Mutated compressed streams must end as errors or models.
+void ExerciseFile(const std::string& in, const char* suffix) {
+  char err[256];
+  const std::string path = std::string("build/fuzz_input.mps") + suffix;
+  std::FILE* f = std::fopen(path.c_str(), "wb");
+  if (f == nullptr) return;
+  std::fwrite(in.data(), 1, in.size(), f);
+  std::fclose(f);
+  PdlpModel* model = nullptr;
+  if (pdlp_b200_read_quadratic_program(path.c_str(), Rand(2), &model, err, sizeof err) == PDLP_B200_STATUS_OK) pdlp_b200_model_free(model);
+}
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -101,6 +114,11 @@ int main(int argc, char** argv) {
     std::fclose(f);
     corpus.push_back(s);
   }
+  std::vector<std::string> packed;  // seed files that are compressed streams: fuzzed through the file layer as well
+  for (const std::string& s : corpus) {
+    if (s.size() > 3 && s.compare(0, 3, "BZh") == 0) packed.push_back(s);
+    if (s.size() > 2 && static_cast<unsigned char>(s[0]) == 0x1f && static_cast<unsigned char>(s[1]) == 0x8b) packed.push_back(s);
+  }
   corpus.push_back("");
   corpus.push_back("termination_criteria { simple_optimality_criteria { eps_optimal_absolute: 1e-4 } iteration_limit: 0x10 } random_projection_seeds: [1, 2]");
   corpus.push_back("{\"terminationCriteria\": {\"iterationLimit\": 5, \"timeSecLimit\": \"Infinity\"}, \"randomProjectionSeeds\": [1, 2]}");
@@ -110,6 +128,10 @@ int main(int argc, char** argv) {
     std::string s = Mutate(corpus[static_cast<size_t>(Rand(static_cast<int>(corpus.size())))]);
     Exercise(s);
     if (s.size() < 4096 && Rand(20) == 0) corpus.push_back(s);
+    if (!packed.empty() && it % 8 == 0) {
+      const std::string& seed = packed[static_cast<size_t>(Rand(static_cast<int>(packed.size())))];
+      ExerciseFile(Rand(8) == 0 ? seed : Mutate(seed), seed[0] == 'B' ? ".bz2" : ".gz");
+    }
   }
   std::printf("fuzz ok: %ld inputs, corpus %zu\n", iterations, corpus.size());
   return 0;

@@ -6,5 +6,5 @@ cd "$(dirname "$0")/.."
 mkdir -p build
 g++ -std=c++17 -O1 -g -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer \
     tools/fuzz_formats.cc or-tools_b200/csrc/proto_codec.cc or-tools_b200/csrc/formats.cc or-tools_b200/csrc/params.cc \
-    -lz -o build/fuzz_formats
+    -lz -ldl -o build/fuzz_formats
 exec build/fuzz_formats "$@"
