@@ -195,3 +195,27 @@ def test_diagonal_qp_trust_region_through_the_bounds(oracle, primal_weight, radi
     assert b.lagrangian_value == pytest.approx(-1.0, rel=4e-16)
     assert b.lower_bound == pytest.approx(-1.0 + x * x + 2.0 * x, abs=1e-5)
     assert b.upper_bound == pytest.approx(-1.0 + (y + 1.0), abs=1e-5)
+
+
+# ---------------------------------------------------------- point metadata --
+def test_random_projections_of_the_starting_point(oracle):
+    """RandomProjectionsTest (iteration_stats_test.cc:576-604), reached through the solve log: the projection
+    of a zero vector is 0.0, the projection of a non-zero vector onto a random unit direction is non-zero
+    (almost surely) and no longer than the vector."""
+    from ortools_b200 import pdlp
+    p = pdlp.PrimalDualHybridGradientParams()
+    p.record_iteration_stats = True
+    p.random_projection_seeds = [1, 2]
+    p.termination_criteria.iteration_limit = 1
+    p.l_inf_ruiz_iterations = 0       # the projections are taken of the working problem's iterate (pdhg.cc:1476-1565):
+    p.l2_norm_rescaling = False       # without rescaling that is the caller's
+    lp = fx.test_lp()
+    out = oracle.primal_dual_hybrid_gradient(lp, p)
+    first = out.solve_log.iteration_stats[0]
+    assert first.iteration_number == 0
+    md = [m for m in first.point_metadata if m.point_type == pdlp.PointType.POINT_TYPE_CURRENT_ITERATE][0]
+    x0 = np.clip(np.zeros(4), lp.variable_lower_bounds, lp.variable_upper_bounds)   # the zero start projected onto the bounds
+    norm = float(np.linalg.norm(x0))
+    assert norm > 0.0 and len(md.random_primal_projections) == 2 and len(md.random_dual_projections) == 2
+    assert all(-norm <= v <= norm and v != 0.0 for v in md.random_primal_projections)
+    assert all(v == 0.0 for v in md.random_dual_projections)                          # the dual start is the zero vector
