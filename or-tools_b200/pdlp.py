@@ -767,7 +767,10 @@ _backend = None
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB_NAME)
+    """The in-tree build; PDLP_B200_LIBRARY names another build of the same library (the sanitizer
+    build of tools/asan_host.sh)."""
+    override = os.environ.get("PDLP_B200_LIBRARY", "")
+    return override if override else os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB_NAME)
 
 
 class _ProductBackend(Backend):
