@@ -17,13 +17,16 @@ from ortools_b200 import pdlp
 from ortools_b200 import _capi as capi
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(_DIR, "libpdlp_oracle.so")
+# (PDLP_ORACLE_LIBRARY: another build of the same sources, e.g. the ThreadSanitizer build of tools/tsan_oracle.sh)
+LIB = os.environ.get("PDLP_ORACLE_LIBRARY") or os.path.join(_DIR, "libpdlp_oracle.so")
 SOURCES = [os.path.join(_DIR, "pdlp_cpu_solver.cc"), os.path.join(_DIR, "pdlp_cpu_core.h"),
            os.path.join(_DIR, "..", "include", "pdlp_b200.h")]
 
 
 def build(force=False):
     """Compiles the oracle if it is missing or older than its sources."""
+    if os.environ.get("PDLP_ORACLE_LIBRARY"):
+        return LIB
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in SOURCES if os.path.exists(s)):
         return LIB
     cmd = ["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-shared", "-pthread", SOURCES[0], "-o", LIB]
