@@ -1,7 +1,7 @@
 # Convenience targets; the driver itself calls __graft_entry__.build() / pytest / bench.py directly.
 PY ?= python
 
-.PHONY: build test test-gpu bench bench-reference fuzz properties sanitize clean
+.PHONY: build test test-gpu bench bench-reference fuzz properties sanitize sanitize-host sanitize-oracle clean
 
 build:            ## nvcc (sm_100a) + g++: libpdlp_b200.so, bin/pdlp_solve, the CPU checker
 	$(PY) -c "import __graft_entry__ as g; g.build()"
@@ -26,6 +26,12 @@ properties:       ## long hypothesis campaign (EXAMPLES=3000 make properties)
 
 sanitize:         ## compute-sanitizer passes on the small problems (needs a GPU)
 	tools/sanitize.sh
+
+sanitize-host:    ## the library's host side under ASan + UBSan through its host-only entry points (no GPU)
+	tools/asan_host.sh
+
+sanitize-oracle:  ## the multithreaded CPU checker under ThreadSanitizer, then ASan + UBSan (no GPU)
+	tools/tsan_oracle.sh
 
 clean:
 	rm -rf build or-tools_b200/lib or-tools_b200/bin oracle/libpdlp_oracle.so
