@@ -48,3 +48,14 @@ def test_product_arm_has_no_cpu_fallback():
     r = run_bench("--scale", "0.002", "--steps", "3", "--warmup", "3", "--no-e2e", "--no-cpu")
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr or "no CPU fallback" in r.stderr
+
+
+def test_smoke_fails_loudly_without_a_device():
+    """__graft_entry__.smoke() runs the hot path on cuda:0; without a device it must raise, not fall back."""
+    from ortools_b200 import pdlp
+    if pdlp.backend().device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        entry.smoke()
