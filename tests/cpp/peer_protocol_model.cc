@@ -47,8 +47,9 @@ struct Arena {  // what the peers write into (PeerLayout)
   double y[M];
   double partial[N];
   double scal[4 * G];
-  std::atomic<uint64_t> flags[2][G];
-  uint64_t epoch[2];  // this rank's own epoch counters: touched by whichever block arrives last
+  double tr[2][G][4];  // trust-region round vectors: [round parity][rank][column] (PeerLayout tr_off)
+  std::atomic<uint64_t> flags[3][G];
+  uint64_t epoch[3];  // this rank's own epoch counters: touched by whichever block arrives last
 };
 
 struct Rank {
@@ -219,6 +220,32 @@ void block_main(int g, int blk) {
   }
 }
 
+// ---- the rounds of the trust-region solve (tr_round<PEER> of k_tr_solve) -------------------------
+// Every round each rank stores its vector of totals into slot (round & 1) of every arena, the ranks
+// meet ONCE, and each adds the G vectors in rank order from its own arena. One barrier per round is
+// enough because the slots alternate: a rank can be at most one round ahead of a peer that still
+// reads, and then it writes the other slot. -DTR_SINGLE_SLOT is the negative control.
+constexpr int kTrRounds = 30;
+double tr_result[G][kTrRounds];
+void tr_main(int g) {
+  double carry = 1.0 + g;
+  for (int round = 0; round < kTrRounds; ++round) {
+#ifdef TR_SINGLE_SLOT
+    const int slot = 0;
+#else
+    const int slot = round & 1;
+#endif
+    for (int h = 0; h < G; ++h)
+      for (int c = 0; c < 4; ++c) arena[h].tr[slot][g][c] = carry * (c + 1) + round;
+    peer_barrier(g, 2);
+    double v = 0.0;
+    for (int h = 0; h < G; ++h)
+      for (int c = 0; c < 4; ++c) v += arena[g].tr[slot][h][c];
+    tr_result[g][round] = v;
+    carry = 0.5 * carry + 1e-3 * v;  // (the next round's vector depends on this round's totals, as the bracket does)
+  }
+}
+
 // ---- the same attempts, one thread, no arenas -----------------------------------------------------
 void sequential(double x_out[N]) {
   static double x[3][N], kty[3][N], y[3][M], kx[3][M];
@@ -291,7 +318,8 @@ int main() {
   for (int g = 0; g < G; ++g) {
     std::memset(arena[g].xt, 0, sizeof arena[g].xt); std::memset(arena[g].y, 0, sizeof arena[g].y);
     std::memset(arena[g].partial, 0, sizeof arena[g].partial); std::memset(arena[g].scal, 0, sizeof arena[g].scal);
-    for (int w = 0; w < 2; ++w) { arena[g].epoch[w] = 0; for (int h = 0; h < G; ++h) arena[g].flags[w][h].store(0); }
+    for (int w = 0; w < 3; ++w) { arena[g].epoch[w] = 0; for (int h = 0; h < G; ++h) arena[g].flags[w][h].store(0); }
+    std::memset(arena[g].tr, 0, sizeof arena[g].tr);
     Rank& r = rank_[g];
     std::memset(r.x, 0, sizeof r.x); std::memset(r.kty, 0, sizeof r.kty); std::memset(r.y, 0, sizeof r.y); std::memset(r.kx, 0, sizeof r.kx);
     r.state[0] = State{0, 1, 0, 0.05};
@@ -301,6 +329,9 @@ int main() {
   std::vector<std::thread> threads;
   for (int g = 0; g < G; ++g)
     for (int blk = 0; blk < B; ++blk) threads.emplace_back(block_main, g, blk);
+  for (auto& t : threads) t.join();
+  threads.clear();
+  for (int g = 0; g < G; ++g) threads.emplace_back(tr_main, g);
   for (auto& t : threads) t.join();
   double want[N];
   sequential(want);
@@ -313,6 +344,22 @@ int main() {
         std::printf("rank %d x[%d] = %.17g, sequential %.17g\n", g, i, rank_[g].x[st.cur][i], want[i]);
         bad = 1;
       }
+  }
+  {  // the trust-region rounds: every rank computed the same totals, equal to the sequential ones
+    double carry[G];
+    for (int g = 0; g < G; ++g) carry[g] = 1.0 + g;
+    for (int round = 0; round < kTrRounds; ++round) {
+      double v = 0.0;
+      for (int h = 0; h < G; ++h)
+        for (int c = 0; c < 4; ++c) v += carry[h] * (c + 1) + round;
+      for (int g = 0; g < G; ++g) {
+        if (std::memcmp(&tr_result[g][round], &v, sizeof(double)) != 0) {
+          std::printf("rank %d trust-region round %d: %.17g, sequential %.17g\n", g, round, tr_result[g][round], v);
+          bad = 1;
+        }
+        carry[g] = 0.5 * carry[g] + 1e-3 * v;
+      }
+    }
   }
   std::printf(bad ? "MISMATCH\n" : "model ok: mode %d, %d ranks x %d blocks, %d attempts, bitwise equal to the sequential run\n", MODE, G, B, A);
   return bad;

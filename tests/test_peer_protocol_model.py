@@ -5,7 +5,9 @@ cross-rank barriers of an attempt exactly where the kernel has them, slices hand
 It checks the argument of DESIGN.md 5 mechanically -- no write into an arena can race with a read of
 its previous contents, for any ticket order -- and that the result equals a sequential run bit for
 bit. It models the protocol; the CUDA code itself is exercised by the 2 / 4 / 8-GPU parity tests.
-Negative controls: without the cross-rank part of barrier A or B the same program must fail."""
+The rounds of the trust-region solve (one barrier per round, round vectors in alternating slots) follow
+in the same program. Negative controls: without the cross-rank part of barrier A or B, or with a single
+slot for the round vectors, the same program must fail."""
 import os
 import subprocess
 
@@ -46,9 +48,12 @@ def test_two_cross_rank_barriers_order_every_arena_access(tmp_path, mode):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
-@pytest.mark.parametrize("dropped", ["DROP_PEER_A", "DROP_PEER_B"])
+@pytest.mark.parametrize("dropped", ["DROP_PEER_A", "DROP_PEER_B", "TR_SINGLE_SLOT"])
 def test_the_model_fails_without_either_cross_rank_barrier(tmp_path, mode, dropped):
     exe = build(tmp_path, mode, dropped)
-    p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
-    assert p.returncode != 0
-    assert "ThreadSanitizer: data race" in p.stderr or "MISMATCH" in p.stdout or "timed out" in p.stdout
+    for _ in range(6):  # (a race is reported when both accesses are still in the tool's history: allow a few schedules)
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        if p.returncode != 0:
+            assert "ThreadSanitizer: data race" in p.stderr or "MISMATCH" in p.stdout or "timed out" in p.stdout
+            return
+    pytest.fail("the model passed six times without " + dropped)
