@@ -19,7 +19,8 @@
 // previous contents, for tickets handed out in any order -- and the result is compared bitwise with
 // a sequential run of the same arithmetic. The device's fences become release / acquire operations
 // on the same words (TSan does not model stand-alone fences); -DDROP_PEER_A / -DDROP_PEER_B remove
-// the cross-rank part of one barrier and must make the run fail (negative controls).
+// the cross-rank part of one barrier and must make the run fail (negative controls). The rounds of the
+// trust-region solve follow the attempts (tr_main; -DTR_SINGLE_SLOT is their negative control).
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -85,7 +86,8 @@ void peer_barrier(int g, int which) {
 }
 
 enum { kPlain, kPeer, kSumsPeer };
-// Returns true when this block arrived last (it has then already done the cross-rank part).
+// Grid barrier number `bar` of the rank (loop_grid_sync of the kernel): the block that draws the last ticket
+// adds the partials in a fixed order when asked to, does the cross-rank part, then releases the others.
 void grid_sync(int g, int blk, unsigned& bar, int kind, int which, bool slice_sums) {
   Rank& r = rank_[g];
   const unsigned ticket = r.sync_ticket.fetch_add(1u, std::memory_order_acq_rel);
