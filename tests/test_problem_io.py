@@ -333,17 +333,22 @@ def test_command_line_solve_is_interruptible_without_callbacks(tmp_path):
     qp_io.write_linear_program_to_mps(lp, mps)
     params = ("verbosity_level: 0 termination_criteria { iteration_limit: 2000000000 simple_optimality_criteria "
               "{ eps_optimal_absolute: 0 eps_optimal_relative: 0 } }")
-    timer = threading.Timer(0.4, lambda: os.kill(os.getpid(), signal.SIGINT))
-    before = signal.getsignal(signal.SIGINT)
+    timer = threading.Timer(1.0, lambda: os.kill(os.getpid(), signal.SIGINT))
+    original = signal.getsignal(signal.SIGINT)
+    early = []
+    before = lambda *_: early.append(1)   # (a signal that beat solve()'s own handler must not abort the test session)
+    signal.signal(signal.SIGINT, before)
     start = time.time()
     timer.start()
     try:
         result = pdlp_solve.solve(mps, params, backend=_oracle(), out=open(os.devnull, "w"))
+        assert signal.getsignal(signal.SIGINT) is before   # the previous handler is back
     finally:
         timer.cancel()
+        signal.signal(signal.SIGINT, original)
+    assert not early
     assert result.solve_log.termination_reason == pdlp.TerminationReason.TERMINATION_REASON_INTERRUPTED_BY_USER
     assert time.time() - start < 20.0 and result.solve_log.iteration_count > 0
-    assert signal.getsignal(signal.SIGINT) is before   # the previous handler is back
 
 
 @pytest.mark.gpu
