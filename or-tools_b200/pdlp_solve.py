@@ -19,7 +19,7 @@ import sys
 
 from google.protobuf import json_format, text_format
 
-from . import mp_model, pdlp, pdlp_proto, qp_io
+from . import mp_model, pdlp, pdlp_proto
 
 
 def write_solve_log(path, log_proto):
@@ -59,7 +59,7 @@ def solve(input_path, params_text="", solve_log_file="", sol_file="", backend=No
     except text_format.ParseError as e:
         raise SystemExit("Error parsing --params: %s" % e)
     params = pdlp_proto.params_from_proto(params_msg)
-    qp = qp_io.read_quadratic_program(input_path, include_names=True)  # drops integrality constraints
+    qp = pdlp.read_quadratic_program_or_die(input_path, include_names=True)  # the library's C++ readers; drops integrality constraints
     interrupted = ctypes.c_int32(0)
     previous = signal.getsignal(signal.SIGINT)
     try:
